@@ -1,0 +1,120 @@
+/* sed_b200.h -- C ABI of the B200-native sound-event-detection inference hot path.
+ *
+ * Plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise, `stream`
+ * is a cudaStream_t passed as void*.  Every entry returns 0 on success or one of SED_ERR_*; the
+ * message for the calling thread's last failure is returned by sed_last_error_string().  Nothing here
+ * allocates or frees memory the caller can see, and all work is asynchronous on `stream`.
+ *
+ * The reference (yazdayy/sound-event-detection) has no FFI: its hot path is the Python nn.Module
+ * forward() of pytorch/models.py calling ATen ops.  Each entry below names the reference code it
+ * replaces (file:line under /root/reference).  INTEGRATION.md shows the ctypes binding.
+ */
+#ifndef SED_B200_H_
+#define SED_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SED_OK 0
+#define SED_ERR_BAD_SHAPE 1
+#define SED_ERR_UNSUPPORTED 2
+#define SED_ERR_CUDA 3
+#define SED_ERR_NULL 4
+#define SED_ERR_DRIVER 5
+
+#define SED_DTYPE_F16 0
+#define SED_DTYPE_BF16 1
+
+#define SED_CONV_STORE 0    /* conv -> BN -> ReLU                        (ConvBlock first conv)        */
+#define SED_CONV_POOL 1     /* conv -> BN -> ReLU -> avg_pool2d(2,2)     (ConvBlock second conv)       */
+#define SED_CONV_FREQMEAN 2 /* conv -> BN -> ReLU -> mean over W (W==8)  (conv_block4 + models.py:668) */
+
+/* ABI version of this header (bumped on any signature change). */
+int sed_abi_version(void);
+
+/* Message describing the last non-zero return on the calling thread (host pointer, never NULL). */
+const char* sed_last_error_string(void);
+
+/* Fused front-end: reflect-pad, frame, window, real DFT, power, mel projection, clamped 10*log10,
+ * optional per-mel affine (eval-mode bn0).
+ * Replaces STFT.forward pytorch/stft.py:223-247, Spectrogram.forward :651-670,
+ * LogmelFilterBank.forward + power_to_db :698-734 and bn0 pytorch/models.py:642-644.
+ *   wave [B, L] f32; window [n_fft] f32 (row 0 of the loaded conv_real kernel);
+ *   twiddle [n_fft][2] f32 = exp(-2 pi i k / n_fft); banded mel matrix: for mel bin m the non-zero
+ *   weights melW[mel_lo[m] .. mel_lo[m]+mel_len[m]) are stored at mel_val[mel_off[m] ..];
+ *   db_offset = 10*log10(max(amin, ref)); bn_scale/bn_shift [n_mels] or NULL;
+ *   out [B, T, n_mels] f32 with T = L / hop + 1.  n_fft in {256, 512, 1024}. */
+int sed_frontend_logmel_f32(const float* wave, int B, int L, int n_fft, int hop, const float* window,
+                            const float* twiddle, const int* mel_lo, const int* mel_len, const int* mel_off,
+                            const float* mel_val, int n_mels, float amin, float db_offset, int is_log,
+                            const float* bn_scale, const float* bn_shift, float* out, void* stream);
+
+/* Power spectrogram only.  Replaces Spectrogram.forward pytorch/stft.py:651-670 (power == 2).
+ *   out [B, T, n_fft/2+1] f32 (the reference's [B,1,T,F] layout). */
+int sed_spectrogram_f32(const float* wave, int B, int L, int n_fft, int hop, const float* window,
+                        const float* twiddle, float* out, void* stream);
+
+/* Mel projection + power_to_db on existing spectrogram rows.
+ * Replaces LogmelFilterBank.forward pytorch/stft.py:698-734 (top_db == None).
+ *   spec [rows, F] f32 -> out [rows, n_mels] f32. */
+int sed_logmel_rows_f32(const float* spec, long rows, int F, const int* mel_lo, const int* mel_len,
+                        const int* mel_off, const float* mel_val, int n_mels, float amin, float db_offset,
+                        int is_log, float* out, void* stream);
+
+/* conv_block1.conv1 (Cin = 1) + bn1 + ReLU.  Replaces pytorch/models.py:128 for the first block.
+ *   x [NB, H, 64] f32 (log-mel after bn0); w9 [64][9] f32; scale/shift [64] folded BatchNorm;
+ *   out [NB, H, 64, 64] NHWC 16-bit (dtype). */
+int sed_conv_first_f32(const float* x, int NB, int H, int W, const float* w9, const float* scale,
+                       const float* shift, void* out, int dtype, void* stream);
+
+/* 3x3 stride-1 pad-1 convolution (no bias) + folded BatchNorm + ReLU [+ 2x2 avg-pool | + mean over W]
+ * on the tcgen05 tensor cores.  Replaces ConvBlock.forward pytorch/models.py:125-141 (one conv each
+ * call) and torch.mean(x, dim=3) models.py:668.
+ *   x [NB, H, W, cin] NHWC 16-bit; wpacked [cout][9][cin] 16-bit (tap = 3*kh + kw);
+ *   scale/shift [cout] f32; out NHWC 16-bit: [NB,H,W,cout] | [NB,H/2,W/2,cout] | [NB,H,cout].
+ *   Supported (cin,cout,mode): (64,64,POOL) (64,128,STORE) (128,128,POOL) (128,256,STORE)
+ *   (256,256,POOL) (256,512,STORE) (512,512,FREQMEAN).
+ *   variant 0 = haloed-patch operand reuse, 1 = one TMA box per tap. */
+int sed_conv3x3_bn_relu(const void* x, int NB, int H, int W, int cin, const void* wpacked, const float* scale,
+                        const float* shift, int cout, int mode, void* out, int dtype, int variant, void* stream);
+
+/* out[M, N] = a[M, K] * w[N, K]^T + bias (optional ReLU) on the tensor cores; K in {256, 512},
+ * N % 128 == 0.  Replaces the nn.Linear calls inside nn.GRU (input projection, models.py:670) and
+ * MultiHead (w_qs/w_ks/w_vs/fc, models.py:863-865, 876).
+ *   a16 [M,K], w16 [N,K] 16-bit; bias [N] f32 or NULL; out [M,N] f32; out16 [M,N] 16-bit or NULL. */
+int sed_linear(const void* a16, long M, int K, const void* w16, const float* bias, int N, int relu, float* out,
+               void* out16, int dtype, void* stream);
+
+/* Bidirectional GRU recurrence, hidden 256, gate order r,z,n, h0 = 0.
+ * Replaces nn.GRU.forward pytorch/models.py:670 given the input projections.
+ *   gi [B, T, 1536] f32 = x W_ih^T + b_ih, columns [dir][gate][256];
+ *   whh_packed [2*768, 256] 16-bit, row (dir*768 + 96*q + 32*g + jj) = W_hh[dir][g*256 + 32*q + jj];
+ *   bhh [2][768] f32; out [B, T, 512] f32 = [forward | backward]. */
+int sed_bigru(const float* gi, const void* whh_packed, const float* bhh, int B, int T, float* out, int dtype,
+              void* stream);
+
+/* softmax(q k^T / 8) v for 8 heads of 64.  Replaces ScaledDotProductAttention.forward
+ * pytorch/models.py:808-820 and the head split/merge :863-875.
+ *   qkv [B, T, 1536] f32 = [q | k | v], head h = columns h*64..h*64+63; out16 [B, T, 512] 16-bit. */
+int sed_mha_core(const float* qkv, int B, int T, void* out16, int dtype, void* stream);
+
+/* Frame-attention pooling + framewise interpolation/padding.
+ * Replaces AttBlock.forward pytorch/models.py:161-169, interpolate :84-95, pad_framewise_output :65-81.
+ *   x [B, T, 512] f32; w_att/w_cla [25][512]; b_att/b_cla [25];
+ *   clip [B,25]; frame [B, frames_out, 25] (frames_out >= T*ratio, padded with the last frame);
+ *   cla_t / norm_att_t [B,25,T] or NULL. */
+int sed_attpool(const float* x, int B, int T, const float* w_att, const float* b_att, const float* w_cla,
+                const float* b_cla, int ratio, int frames_out, float* clip, float* frame, float* cla_t,
+                float* norm_att_t, void* stream);
+
+/* Test hook: as sed_conv3x3_bn_relu with an explicit UMMA descriptor base-offset policy for the
+ * haloed-patch variant (0 = none, 1 = (addr >> 7) & 7). */
+int sed_conv3x3_bn_relu_dbg(const void* x, int NB, int H, int W, int cin, const void* wpacked, const float* scale,
+                            const float* shift, int cout, int mode, void* out, int dtype, int variant,
+                            int bo_mode, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SED_B200_H_ */

@@ -1,0 +1,40 @@
+"""Import the UNMODIFIED reference (`/root/reference/pytorch/{stft,models}.py`) in the build container.
+
+TEST INFRASTRUCTURE ONLY -- never imported by the product package.  `/root/reference` exists only in
+the build container (not on the GPU box), so this module is used solely by `oracle/gen_golden.py`
+and by the `not gpu` tests that pin `oracle/sed_oracle.py` against the real reference (they skip
+when the reference tree is absent).  Recipe from SURVEY.md section 8(c).
+"""
+import importlib
+import os
+import sys
+
+REF_ROOT = os.environ.get("SED_REFERENCE_ROOT", "/root/reference")
+_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_shims")
+
+
+def available():
+    return os.path.isfile(os.path.join(REF_ROOT, "pytorch", "models.py"))
+
+
+def load():
+    """Returns (ref_stft_module, ref_models_module)."""
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REF_ROOT)
+    sys.dont_write_bytecode = True  # the reference tree is read-only
+    saved_path = list(sys.path)
+    saved_mods = {k: sys.modules.get(k) for k in ("models", "stft", "librosa", "matplotlib")}
+    try:
+        for k in saved_mods:
+            sys.modules.pop(k, None)
+        sys.path[:0] = [_SHIMS, os.path.join(REF_ROOT, "pytorch"), os.path.join(REF_ROOT, "utils")]
+        ref_stft = importlib.import_module("stft")
+        ref_models = importlib.import_module("models")
+    finally:
+        sys.path[:] = saved_path
+    # keep the reference modules reachable only through the returned handles
+    for k in ("models", "stft"):
+        sys.modules.pop(k, None)
+        if saved_mods[k] is not None:
+            sys.modules[k] = saved_mods[k]
+    return ref_stft, ref_models

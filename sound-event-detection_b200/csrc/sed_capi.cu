@@ -1,0 +1,129 @@
+// extern "C" boundary: see include/sed_b200.h for the contract of every entry.
+#include "../../include/sed_b200.h"
+
+#include <cuda_runtime.h>
+
+#include "sed_kernels.h"
+
+#define SED_ABI_VERSION 1
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+#define SED_REQUIRE(ptr)                                         \
+  do {                                                           \
+    if ((ptr) == nullptr) {                                      \
+      sed::set_error("%s: null pointer argument " #ptr, __func__); \
+      return SED_ERR_NULL;                                       \
+    }                                                            \
+  } while (0)
+
+extern "C" {
+
+int sed_abi_version(void) { return SED_ABI_VERSION; }
+
+const char* sed_last_error_string(void) { return sed::last_error(); }
+
+int sed_frontend_logmel_f32(const float* wave, int B, int L, int n_fft, int hop, const float* window,
+                            const float* twiddle, const int* mel_lo, const int* mel_len, const int* mel_off,
+                            const float* mel_val, int n_mels, float amin, float db_offset, int is_log,
+                            const float* bn_scale, const float* bn_shift, float* out, void* stream) {
+  SED_REQUIRE(wave); SED_REQUIRE(window); SED_REQUIRE(twiddle); SED_REQUIRE(mel_lo); SED_REQUIRE(mel_len);
+  SED_REQUIRE(mel_off); SED_REQUIRE(mel_val); SED_REQUIRE(out);
+  if ((bn_scale == nullptr) != (bn_shift == nullptr)) {
+    sed::set_error("sed_frontend_logmel_f32: bn_scale and bn_shift must both be set or both be NULL");
+    return SED_ERR_NULL;
+  }
+  sed::FrontendArgs a{};
+  a.wave = wave; a.B = B; a.L = L; a.n_fft = n_fft; a.hop = hop;
+  a.T = (hop > 0) ? L / hop + 1 : 0;
+  a.window = window; a.twiddle = twiddle;
+  a.mel_lo = mel_lo; a.mel_len = mel_len; a.mel_off = mel_off; a.mel_val = mel_val; a.n_mels = n_mels;
+  a.amin = amin; a.db_offset = db_offset; a.is_log = is_log;
+  a.bn_scale = bn_scale; a.bn_shift = bn_shift; a.out = out; a.mode = 0;
+  int rc = sed::frontend_launch(a, as_stream(stream));
+  if (rc == SED_ERR_BAD_SHAPE) sed::set_error("sed_frontend_logmel_f32: bad shape B=%d L=%d n_fft=%d hop=%d", B, L, n_fft, hop);
+  if (rc == SED_ERR_UNSUPPORTED) sed::set_error("sed_frontend_logmel_f32: n_fft=%d unsupported (256/512/1024)", n_fft);
+  if (rc == SED_ERR_CUDA) sed::set_error("sed_frontend_logmel_f32: %s", cudaGetErrorString(cudaGetLastError()));
+  return rc;
+}
+
+int sed_spectrogram_f32(const float* wave, int B, int L, int n_fft, int hop, const float* window,
+                        const float* twiddle, float* out, void* stream) {
+  SED_REQUIRE(wave); SED_REQUIRE(window); SED_REQUIRE(twiddle); SED_REQUIRE(out);
+  sed::FrontendArgs a{};
+  a.wave = wave; a.B = B; a.L = L; a.n_fft = n_fft; a.hop = hop;
+  a.T = (hop > 0) ? L / hop + 1 : 0;
+  a.window = window; a.twiddle = twiddle;
+  a.out = out; a.mode = 1;
+  int rc = sed::frontend_launch(a, as_stream(stream));
+  if (rc == SED_ERR_BAD_SHAPE) sed::set_error("sed_spectrogram_f32: bad shape B=%d L=%d n_fft=%d hop=%d", B, L, n_fft, hop);
+  if (rc == SED_ERR_UNSUPPORTED) sed::set_error("sed_spectrogram_f32: n_fft=%d unsupported (256/512/1024)", n_fft);
+  if (rc == SED_ERR_CUDA) sed::set_error("sed_spectrogram_f32: %s", cudaGetErrorString(cudaGetLastError()));
+  return rc;
+}
+
+int sed_logmel_rows_f32(const float* spec, long rows, int F, const int* mel_lo, const int* mel_len,
+                        const int* mel_off, const float* mel_val, int n_mels, float amin, float db_offset,
+                        int is_log, float* out, void* stream) {
+  SED_REQUIRE(spec); SED_REQUIRE(mel_lo); SED_REQUIRE(mel_len); SED_REQUIRE(mel_off); SED_REQUIRE(mel_val);
+  SED_REQUIRE(out);
+  int rc = sed::logmel_rows_launch(spec, rows, F, mel_lo, mel_len, mel_off, mel_val, n_mels, amin, db_offset, is_log,
+                                   out, as_stream(stream));
+  if (rc == SED_ERR_BAD_SHAPE) sed::set_error("sed_logmel_rows_f32: bad shape rows=%ld", rows);
+  return rc;
+}
+
+int sed_conv_first_f32(const float* x, int NB, int H, int W, const float* w9, const float* scale,
+                       const float* shift, void* out, int dtype, void* stream) {
+  SED_REQUIRE(x); SED_REQUIRE(w9); SED_REQUIRE(scale); SED_REQUIRE(shift); SED_REQUIRE(out);
+  if (dtype != SED_DTYPE_F16 && dtype != SED_DTYPE_BF16) {
+    sed::set_error("sed_conv_first_f32: dtype must be SED_DTYPE_F16 or SED_DTYPE_BF16");
+    return SED_ERR_UNSUPPORTED;
+  }
+  return sed::conv_first_launch(x, NB, H, W, w9, scale, shift, out, dtype, as_stream(stream));
+}
+
+int sed_conv3x3_bn_relu_dbg(const void* x, int NB, int H, int W, int cin, const void* wpacked, const float* scale,
+                            const float* shift, int cout, int mode, void* out, int dtype, int variant,
+                            int bo_mode, void* stream) {
+  SED_REQUIRE(x); SED_REQUIRE(wpacked); SED_REQUIRE(scale); SED_REQUIRE(shift); SED_REQUIRE(out);
+  if (variant != 0 && variant != 1) {
+    sed::set_error("sed_conv3x3_bn_relu: variant must be 0 (patch) or 1 (per-tap)");
+    return SED_ERR_UNSUPPORTED;
+  }
+  return sed::conv3x3_launch(x, NB, H, W, cin, wpacked, scale, shift, cout, mode, out, dtype, variant, bo_mode,
+                             as_stream(stream));
+}
+
+int sed_conv3x3_bn_relu(const void* x, int NB, int H, int W, int cin, const void* wpacked, const float* scale,
+                        const float* shift, int cout, int mode, void* out, int dtype, int variant, void* stream) {
+  return sed_conv3x3_bn_relu_dbg(x, NB, H, W, cin, wpacked, scale, shift, cout, mode, out, dtype, variant, 0, stream);
+}
+
+int sed_linear(const void* a16, long M, int K, const void* w16, const float* bias, int N, int relu, float* out,
+               void* out16, int dtype, void* stream) {
+  SED_REQUIRE(a16); SED_REQUIRE(w16); SED_REQUIRE(out);
+  return sed::linear_launch(a16, M, K, w16, bias, N, relu, out, out16, dtype, as_stream(stream));
+}
+
+int sed_bigru(const float* gi, const void* whh_packed, const float* bhh, int B, int T, float* out, int dtype,
+              void* stream) {
+  SED_REQUIRE(gi); SED_REQUIRE(whh_packed); SED_REQUIRE(bhh); SED_REQUIRE(out);
+  return sed::gru_launch(gi, whh_packed, bhh, B, T, out, dtype, as_stream(stream));
+}
+
+int sed_mha_core(const float* qkv, int B, int T, void* out16, int dtype, void* stream) {
+  SED_REQUIRE(qkv); SED_REQUIRE(out16);
+  return sed::mha_core_launch(qkv, B, T, out16, dtype, as_stream(stream));
+}
+
+int sed_attpool(const float* x, int B, int T, const float* w_att, const float* b_att, const float* w_cla,
+                const float* b_cla, int ratio, int frames_out, float* clip, float* frame, float* cla_t,
+                float* norm_att_t, void* stream) {
+  SED_REQUIRE(x); SED_REQUIRE(w_att); SED_REQUIRE(b_att); SED_REQUIRE(w_cla); SED_REQUIRE(b_cla);
+  SED_REQUIRE(clip); SED_REQUIRE(frame);
+  return sed::attpool_launch(x, B, T, w_att, b_att, w_cla, b_cla, ratio, frames_out, clip, frame, cla_t, norm_att_t,
+                             as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,399 @@
+// tcgen05 implicit-GEMM 3x3 convolution (+ folded BatchNorm + ReLU + 2x2 avg-pool / freq-mean) and
+// the plain GEMM ("linear") used by the temporal blocks, for sm_100a.
+//
+// Reference semantics: ConvBlock.forward  pytorch/models.py:125-141 (conv 3x3 s1 p1 no bias -> BN(eval)
+// -> ReLU, twice, then avg_pool2d), freq-mean models.py:668, nn.Linear inside nn.GRU / MultiHead.
+//
+// GEMM view: M = output pixels (one 16(H) x 8(W) spatial patch = 128 rows per tile), N = Cout slice,
+// K = 9 taps x Cin.  Activations are NHWC 16-bit, weights are [Cout][tap][Cin] 16-bit (K-major).
+//
+//  * A operand, PATCH mode: per 64-channel chunk ONE TMA box (64ch x 10w x 18h) brings the haloed
+//    patch into a SWIZZLE_128B buffer (180 pixel rows of 128 B, zero-filled outside the image = conv
+//    padding).  The nine taps are nine UMMA descriptors into that single buffer: start address
+//    + (r*10+s)*128 B, 8-row group stride 1280 B.  A is therefore read from L2 once, not nine times.
+//  * A operand, TAP mode: one (64ch x 8w x 16h) box per tap (used for the GEMM and as fallback).
+//  * B operand: either streamed per (chunk, tap) through a ring, or RESIDENT in shared memory for the
+//    whole persistent CTA when the Cout-slice of the weights fits (weight-stationary).
+//  * NT (1|2) pixel tiles share every B block, accumulators live in TMEM (NT*BN columns per stage).
+//  * Warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps2-5 = epilogue.
+#pragma once
+#include "sed_common.cuh"
+
+namespace sed {
+
+enum : int { EPI_STORE = 0, EPI_POOL = 1, EPI_FREQMEAN = 2, EPI_LINEAR = 3 };
+
+struct ConvParams {
+  int NB, H, W;            // images, rows, cols of the (same-size) convolution; W % 8 == 0
+  int tiles_h, tiles_w;    // ceil(H/16), W/8
+  int num_tiles;           // conv: NB*tiles_h*tiles_w ; linear: ceil(M/128)
+  int cout;                // total output channels (row stride of the output)
+  int nslices;             // cout / BN
+  const float* scale;      // [cout] folded BN scale   (linear: unused)
+  const float* shift;      // [cout] folded BN shift   (linear: bias)
+  void* out;               // EPI 0/1/2: 16-bit NHWC ; EPI 3: float [M, ldc]
+  void* out2;              // EPI 3: optional 16-bit copy [M, ldc] (may be null)
+  int M, ldc, relu;        // linear only
+  int patch_bo_mode;       // PATCH-mode descriptor base_offset policy: 0 = none, 1 = (addr>>7)&7
+};
+
+constexpr int kPatchBytes = 180 * 128;       // 18 x 10 pixels x 64 ch x 2 B
+constexpr int kPatchStride = 23 * 1024;      // padded so every patch starts 1024-aligned
+constexpr int kTileBytes = 128 * 128;        // 128 pixels x 64 ch x 2 B
+
+template <int CIN, int BN, int NT, bool BRES, bool PATCH, int EPI, int SA, int SB>
+struct ConvCfg {
+  static constexpr int TAPS = (EPI == EPI_LINEAR) ? 1 : 9;
+  static constexpr int NCHUNK = CIN / 64;
+  static constexpr int A_STAGE = NT * (PATCH ? kPatchStride : kTileBytes);
+  static constexpr int B_BLOCK = BN * 128;
+  static constexpr int B_BYTES = BRES ? NCHUNK * TAPS * B_BLOCK : SB * B_BLOCK;
+  static constexpr int ACC_COLS = NT * BN;
+  static constexpr int ACC_STAGES = (2 * ACC_COLS <= 512) ? 2 : 1;
+  static constexpr int TMEM_COLS = (ACC_COLS * ACC_STAGES <= 32) ? 32 : (ACC_COLS * ACC_STAGES <= 64) ? 64
+                                   : (ACC_COLS * ACC_STAGES <= 128) ? 128 : (ACC_COLS * ACC_STAGES <= 256) ? 256 : 512;
+  static constexpr int SMEM_A = SA * A_STAGE;
+  static constexpr int SMEM_MISC = 2 * 512 * 4 + 256;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + SMEM_A + B_BYTES + SMEM_MISC;
+  static_assert(CIN % 64 == 0, "CIN must be a multiple of 64");
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N");
+  static_assert(ACC_COLS <= 512, "TMEM columns");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+template <typename T, int CIN, int BN, int NT, bool BRES, bool PATCH, int EPI, int SA, int SB>
+__global__ void __launch_bounds__(192, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const ConvParams p) {
+  using Cfg = ConvCfg<CIN, BN, NT, BRES, PATCH, EPI, SA, SB>;
+  constexpr int TAPS = Cfg::TAPS;
+  constexpr int NCHUNK = Cfg::NCHUNK;
+  constexpr int ACC_STAGES = Cfg::ACC_STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::SMEM_A;
+  float* s_scale = reinterpret_cast<float*>(smem_b + Cfg::B_BYTES);
+  float* s_shift = s_scale + 512;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 512);
+  uint64_t* a_full = bars;             // [SA]
+  uint64_t* a_empty = a_full + SA;     // [SA]
+  uint64_t* b_full = a_empty + SA;     // [SB] (index 0 doubles as "resident weights landed")
+  uint64_t* b_empty = b_full + SB;     // [SB]
+  uint64_t* t_full = b_empty + SB;     // [2]
+  uint64_t* t_empty = t_full + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- work decomposition -------------------------------------------------------------
+  const int groups = (p.num_tiles + NT - 1) / NT;
+  int item_begin, item_stride, item_end;
+  int fixed_slice = 0;
+  if (BRES) {
+    fixed_slice = blockIdx.x % p.nslices;
+    item_begin = blockIdx.x / p.nslices;
+    item_stride = gridDim.x / p.nslices;
+    item_end = groups;
+  } else {
+    item_begin = blockIdx.x;
+    item_stride = gridDim.x;
+    item_end = groups * p.nslices;
+  }
+
+  // ---- one-time setup -------------------------------------------------------------------
+  for (int i = threadIdx.x; i < p.cout && i < 512; i += blockDim.x) {
+    s_scale[i] = (EPI == EPI_LINEAR) ? 1.0f : p.scale[i];
+    s_shift[i] = p.shift ? p.shift[i] : 0.0f;
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_coords = [&](int tile, int& n, int& h0, int& w0) {
+    const int per_img = p.tiles_h * p.tiles_w;
+    n = tile / per_img;
+    const int rem = tile - n * per_img;
+    const int th = rem / p.tiles_w;
+    h0 = th * 16;
+    w0 = (rem - th * p.tiles_w) * 8;
+  };
+
+  if (warp == 0) {
+    // =============================== TMA producer ===========================================
+    if (elect_one()) {
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+      if (BRES) {
+        mbar_expect_tx(&b_full[0], NCHUNK * TAPS * Cfg::B_BLOCK);
+        for (int c = 0; c < NCHUNK; ++c)
+          for (int tap = 0; tap < TAPS; ++tap)
+            tma_load_2d(smem_b + (c * TAPS + tap) * Cfg::B_BLOCK, &tmB, &b_full[0], tap * CIN + c * 64,
+                        fixed_slice * BN);
+      }
+      for (int item = item_begin; item < item_end; item += item_stride) {
+        const int g = BRES ? item : item / p.nslices;
+        const int slice = BRES ? fixed_slice : item - g * p.nslices;
+        for (int c = 0; c < NCHUNK; ++c) {
+          if (PATCH) {
+            mbar_wait(&a_empty[sa], pa ^ 1);
+            mbar_expect_tx(&a_full[sa], NT * kPatchBytes);
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+              int n, h0, w0;
+              tile_coords(g * NT + t, n, h0, w0);  // tiles past the end have n >= NB: fully OOB -> zeros
+              tma_load_4d(smem_a + sa * Cfg::A_STAGE + t * kPatchStride, &tmA, &a_full[sa], c * 64, w0 - 1,
+                          h0 - 1, n);
+            }
+            if (++sa == SA) { sa = 0; pa ^= 1; }
+          }
+          for (int tap = 0; tap < TAPS; ++tap) {
+            if (!PATCH) {
+              mbar_wait(&a_empty[sa], pa ^ 1);
+              mbar_expect_tx(&a_full[sa], NT * kTileBytes);
+#pragma unroll
+              for (int t = 0; t < NT; ++t) {
+                uint8_t* dst = smem_a + sa * Cfg::A_STAGE + t * kTileBytes;
+                if (EPI == EPI_LINEAR) {
+                  tma_load_2d(dst, &tmA, &a_full[sa], c * 64, (g * NT + t) * 128);
+                } else {
+                  int n, h0, w0;
+                  tile_coords(g * NT + t, n, h0, w0);
+                  tma_load_4d(dst, &tmA, &a_full[sa], c * 64, w0 + (tap % 3) - 1, h0 + (tap / 3) - 1, n);
+                }
+              }
+              if (++sa == SA) { sa = 0; pa ^= 1; }
+            }
+            if (!BRES) {
+              mbar_wait(&b_empty[sb], pb ^ 1);
+              mbar_expect_tx(&b_full[sb], Cfg::B_BLOCK);
+              tma_load_2d(smem_b + sb * Cfg::B_BLOCK, &tmB, &b_full[sb], tap * CIN + c * 64, slice * BN);
+              if (++sb == SB) { sb = 0; pb ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer =============================================
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_f16(Elem16<T>::kFmt, 128, BN);
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
+      if (BRES) {
+        mbar_wait(&b_full[0], 0);
+        tc_fence_after();
+      }
+      for (int item = item_begin; item < item_end; item += item_stride) {
+        mbar_wait(&t_empty[acc], pacc ^ 1);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + acc * Cfg::ACC_COLS;
+        for (int c = 0; c < NCHUNK; ++c) {
+          if (PATCH) {
+            mbar_wait(&a_full[sa], pa);
+            tc_fence_after();
+          }
+          for (int tap = 0; tap < TAPS; ++tap) {
+            if (!PATCH) {
+              mbar_wait(&a_full[sa], pa);
+              tc_fence_after();
+            }
+            uint32_t b_addr;
+            if (BRES) {
+              b_addr = smem_u32(smem_b + (c * TAPS + tap) * Cfg::B_BLOCK);
+            } else {
+              mbar_wait(&b_full[sb], pb);
+              tc_fence_after();
+              b_addr = smem_u32(smem_b + sb * Cfg::B_BLOCK);
+            }
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+              uint32_t a_addr;
+              uint32_t a_sbo;
+              if (PATCH) {
+                a_addr = smem_u32(smem_a + sa * Cfg::A_STAGE + t * kPatchStride) + ((tap / 3) * 10 + (tap % 3)) * 128;
+                a_sbo = 1280;
+              } else {
+                a_addr = smem_u32(smem_a + sa * Cfg::A_STAGE + t * kTileBytes);
+                a_sbo = 1024;
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                uint64_t adesc = umma_desc_sw128(a_addr + k * 32, a_sbo);
+                if (PATCH && p.patch_bo_mode == 1) adesc |= static_cast<uint64_t>((a_addr >> 7) & 7u) << 49;
+                umma_f16(d_base + t * BN, adesc, umma_desc_sw128(b_addr + k * 32, 1024), idesc,
+                         (c | tap | k) ? 1u : 0u);
+              }
+            }
+            if (!PATCH) {
+              umma_commit(&a_empty[sa]);
+              if (++sa == SA) { sa = 0; pa ^= 1; }
+            }
+            if (!BRES) {
+              umma_commit(&b_empty[sb]);
+              if (++sb == SB) { sb = 0; pb ^= 1; }
+            }
+          }
+          if (PATCH) {
+            umma_commit(&a_empty[sa]);
+            if (++sa == SA) { sa = 0; pa ^= 1; }
+          }
+        }
+        umma_commit(&t_full[acc]);
+        if (++acc == ACC_STAGES) { acc = 0; pacc ^= 1; }
+      }
+    }
+  } else {
+    // =============================== epilogue (4 warps) =====================================
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int m = quarter * 32 + lane;       // row of the 128-row tile
+    const int hl = m >> 3, wl = m & 7;
+    uint32_t acc = 0, pacc = 0;
+    T* out16 = reinterpret_cast<T*>(p.out);
+    for (int item = item_begin; item < item_end; item += item_stride) {
+      const int g = BRES ? item : item / p.nslices;
+      const int slice = BRES ? fixed_slice : item - g * p.nslices;
+      const int ch0 = slice * BN;
+      mbar_wait(&t_full[acc], pacc);
+      tc_fence_after();
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const int tile = g * NT + t;
+        const bool tile_ok = tile < p.num_tiles;
+        int n = 0, h0 = 0, w0 = 0;
+        if (EPI != EPI_LINEAR) tile_coords(tile, n, h0, w0);
+        const int h = h0 + hl, w = w0 + wl;
+        const uint32_t taddr = tmem_base + acc * Cfg::ACC_COLS + t * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+        for (int cc = 0; cc < BN / 16; ++cc) {
+          uint32_t r[16];
+          tmem_ld16(taddr + cc * 16, r);
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int ch = ch0 + cc * 16 + j;
+            float x = fmaf(__uint_as_float(r[j]), s_scale[ch], s_shift[ch]);
+            if (EPI != EPI_LINEAR || p.relu) x = fmaxf(x, 0.0f);
+            v[j] = x;
+          }
+          if (EPI == EPI_STORE) {
+            if (tile_ok && h < p.H) {
+              uint4 q0, q1;
+              q0.x = Elem16<T>::pack2(v[0], v[1]);   q0.y = Elem16<T>::pack2(v[2], v[3]);
+              q0.z = Elem16<T>::pack2(v[4], v[5]);   q0.w = Elem16<T>::pack2(v[6], v[7]);
+              q1.x = Elem16<T>::pack2(v[8], v[9]);   q1.y = Elem16<T>::pack2(v[10], v[11]);
+              q1.z = Elem16<T>::pack2(v[12], v[13]); q1.w = Elem16<T>::pack2(v[14], v[15]);
+              T* dst = out16 + ((static_cast<size_t>(n) * p.H + h) * p.W + w) * p.cout + ch0 + cc * 16;
+              reinterpret_cast<uint4*>(dst)[0] = q0;
+              reinterpret_cast<uint4*>(dst)[1] = q1;
+            }
+          } else if (EPI == EPI_POOL) {
+            // 2x2 average: partners are lane^1 (w) and lane^8 (h); recursive halving so each lane
+            // finishes with 4 channels of one pooled pixel.
+            float k8[8];
+            const bool wodd = (wl & 1) != 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float send = wodd ? v[j] : v[8 + j];
+              const float keep = wodd ? v[8 + j] : v[j];
+              k8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+            }
+            float k4[4];
+            const bool hodd = (hl & 1) != 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float send = hodd ? k8[j] : k8[4 + j];
+              const float keep = hodd ? k8[4 + j] : k8[j];
+              k4[j] = 0.25f * (keep + __shfl_xor_sync(0xffffffffu, send, 8));
+            }
+            const int Hp = p.H >> 1, Wp = p.W >> 1;
+            const int hp = h >> 1, wp = w >> 1;
+            if (tile_ok && hp < Hp) {
+              const int ch = ch0 + cc * 16 + (wodd ? 8 : 0) + (hodd ? 4 : 0);
+              uint2 q;
+              q.x = Elem16<T>::pack2(k4[0], k4[1]);
+              q.y = Elem16<T>::pack2(k4[2], k4[3]);
+              T* dst = out16 + ((static_cast<size_t>(n) * Hp + hp) * Wp + wp) * p.cout + ch;
+              *reinterpret_cast<uint2*>(dst) = q;
+            }
+          } else if (EPI == EPI_FREQMEAN) {
+            // mean over the 8 frequency columns of a row (W == 8): lanes ^1, ^2, ^4
+            float k8[8];
+            const bool b0 = (wl & 1) != 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float send = b0 ? v[j] : v[8 + j];
+              const float keep = b0 ? v[8 + j] : v[j];
+              k8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+            }
+            float k4[4];
+            const bool b1 = (wl & 2) != 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float send = b1 ? k8[j] : k8[4 + j];
+              const float keep = b1 ? k8[4 + j] : k8[j];
+              k4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+            float k2[2];
+            const bool b2 = (wl & 4) != 0;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const float send = b2 ? k4[j] : k4[2 + j];
+              const float keep = b2 ? k4[2 + j] : k4[j];
+              k2[j] = 0.125f * (keep + __shfl_xor_sync(0xffffffffu, send, 4));
+            }
+            if (tile_ok && h < p.H) {
+              const int ch = ch0 + cc * 16 + (b0 ? 8 : 0) + (b1 ? 4 : 0) + (b2 ? 2 : 0);
+              T* dst = out16 + (static_cast<size_t>(n) * p.H + h) * p.cout + ch;
+              *reinterpret_cast<uint32_t*>(dst) = Elem16<T>::pack2(k2[0], k2[1]);
+            }
+          } else {  // EPI_LINEAR
+            const long row = static_cast<long>(tile) * 128 + m;
+            if (tile_ok && row < p.M) {
+              float* dst = reinterpret_cast<float*>(p.out) + row * p.ldc + ch0 + cc * 16;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              if (p.out2) {
+                uint4 q0, q1;
+                q0.x = Elem16<T>::pack2(v[0], v[1]);   q0.y = Elem16<T>::pack2(v[2], v[3]);
+                q0.z = Elem16<T>::pack2(v[4], v[5]);   q0.w = Elem16<T>::pack2(v[6], v[7]);
+                q1.x = Elem16<T>::pack2(v[8], v[9]);   q1.y = Elem16<T>::pack2(v[10], v[11]);
+                q1.z = Elem16<T>::pack2(v[12], v[13]); q1.w = Elem16<T>::pack2(v[14], v[15]);
+                T* d2 = reinterpret_cast<T*>(p.out2) + row * p.ldc + ch0 + cc * 16;
+                reinterpret_cast<uint4*>(d2)[0] = q0;
+                reinterpret_cast<uint4*>(d2)[1] = q1;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[acc]);
+      if (++acc == ACC_STAGES) { acc = 0; pacc ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace sed

@@ -1,0 +1,54 @@
+// Internal launcher interface between the kernel translation units and the C-ABI (sed_capi.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sed {
+
+struct FrontendArgs {
+  const float* wave;  // [B, L]
+  int B, L, T, n_fft, hop;
+  const float* window;   // [n_fft]
+  const float* twiddle;  // [n_fft][2]  exp(-2 pi i k / n_fft)
+  const int* mel_lo;     // [n_mels] first non-zero frequency bin
+  const int* mel_len;    // [n_mels] band length
+  const int* mel_off;    // [n_mels] offset into mel_val
+  const float* mel_val;  // banded mel weights
+  int n_mels;
+  float amin, db_offset;
+  int is_log;
+  const float* bn_scale;  // [n_mels] or null
+  const float* bn_shift;
+  float* out;
+  int mode;  // 0 = log-mel [B,T,n_mels], 1 = power spectrogram [B,T,F]
+};
+int frontend_launch(const FrontendArgs& a, cudaStream_t stream);
+int logmel_rows_launch(const float* spec, long rows, int F, const int* mel_lo, const int* mel_len, const int* mel_off,
+                       const float* mel_val, int n_mels, float amin, float db_offset, int is_log, float* out,
+                       cudaStream_t stream);
+
+// dtype: 0 = fp16, 1 = bf16 (16-bit activation / weight element type of the tensor-core path)
+int conv_first_launch(const float* x, int NB, int H, int W, const float* w9, const float* scale, const float* shift,
+                      void* out, int dtype, cudaStream_t stream);
+
+// mode: 0 = store NHWC, 1 = 2x2 avg-pool, 2 = freq-mean (W must be 8) ; variant: 0 = patch (halo reuse), 1 = per-tap
+int conv3x3_launch(const void* x, int NB, int H, int W, int cin, const void* wpacked, const float* scale,
+                   const float* shift, int cout, int mode, void* out, int dtype, int variant, int bo_mode,
+                   cudaStream_t stream);
+
+int linear_launch(const void* a16, long M, int K, const void* w16, const float* bias, int N, int relu, float* out,
+                  void* out16, int dtype, cudaStream_t stream);
+
+int gru_launch(const float* gi, const void* whh_packed, const float* bhh, int B, int T, float* out, int dtype,
+               cudaStream_t stream);
+
+int mha_core_launch(const float* qkv, int B, int T, void* out16, int dtype, cudaStream_t stream);
+
+int attpool_launch(const float* x, int B, int T, const float* w_att, const float* b_att, const float* w_cla,
+                   const float* b_cla, int ratio, int frames_out, float* clip, float* frame, float* cla_t,
+                   float* norm_att_t, cudaStream_t stream);
+
+const char* last_error();
+void set_error(const char* fmt, ...);
+
+}  // namespace sed

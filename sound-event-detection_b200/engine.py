@@ -1,0 +1,350 @@
+"""Host-side engine: packs a reference-layout `state_dict` once per device and drives the C ABI.
+
+Data layout in HBM (all allocations are torch tensors; the C ABI only sees raw pointers):
+  waveform [B, L] f32 -> log-mel(+bn0) [mb, T, 64] f32 -> conv activations NHWC 16-bit
+  ([mb,T,64,64] -> [mb,T/2,32,64] -> ... -> [mb,T/8,8,512]) -> freq-mean features [B, T', 512] 16-bit
+  -> GRU: gi [B,T',1536] f32 -> h [B,T',512] f32 | MHA: qkv [B,T',1536] f32 -> ctx 16-bit -> fc [B,T',512] f32
+  -> clipwise [B,25], framewise [B,frames,25], embedding.
+The conv stack runs over micro-batches (default 148 clips = one per SM, which makes every layer's tile
+count a multiple of the persistent grid); the temporal block and the head run once over the batch.
+"""
+import math
+import threading
+
+import numpy as np
+import torch
+
+from . import capi
+
+CONV_LAYERS = (
+    # name, cin, cout, mode
+    ("conv_block1.conv2", 64, 64, capi.CONV_POOL),
+    ("conv_block2.conv1", 64, 128, capi.CONV_STORE),
+    ("conv_block2.conv2", 128, 128, capi.CONV_POOL),
+    ("conv_block3.conv1", 128, 256, capi.CONV_STORE),
+    ("conv_block3.conv2", 256, 256, capi.CONV_POOL),
+    ("conv_block4.conv1", 256, 512, capi.CONV_STORE),
+    ("conv_block4.conv2", 512, 512, capi.CONV_FREQMEAN),
+)
+
+_DTYPES = {"fp16": (capi.SED_DTYPE_F16, torch.float16), "bf16": (capi.SED_DTYPE_BF16, torch.bfloat16)}
+
+
+def fold_bn(sd, prefix, eps=1e-5):
+    """Eval-mode BatchNorm as y = x*scale + shift (float64 fold, float32 result)."""
+    w = sd[prefix + ".weight"].double()
+    b = sd[prefix + ".bias"].double()
+    mean = sd[prefix + ".running_mean"].double()
+    var = sd[prefix + ".running_var"].double()
+    scale = w / torch.sqrt(var + eps)
+    shift = b - mean * scale
+    return scale.float().contiguous(), shift.float().contiguous()
+
+
+def twiddle_table(n_fft):
+    k = np.arange(n_fft, dtype=np.float64)
+    ang = -2.0 * np.pi * k / n_fft
+    return torch.from_numpy(np.stack([np.cos(ang), np.sin(ang)], axis=1).astype(np.float32)).contiguous()
+
+
+def band_mel(melW):
+    """melW [F, M] float32 -> (lo, len, off, val): per mel bin the contiguous span covering all non-zeros."""
+    W = melW.detach().cpu().float().numpy()
+    F, M = W.shape
+    lo = np.zeros(M, np.int32)
+    ln = np.zeros(M, np.int32)
+    off = np.zeros(M, np.int32)
+    vals = []
+    pos = 0
+    for m in range(M):
+        nz = np.nonzero(W[:, m])[0]
+        if nz.size:
+            lo[m] = nz[0]
+            ln[m] = nz[-1] - nz[0] + 1
+        off[m] = pos
+        vals.append(W[lo[m]:lo[m] + ln[m], m])
+        pos += int(ln[m])
+    val = np.concatenate(vals) if pos else np.zeros(1, np.float32)
+    if val.size == 0:
+        val = np.zeros(1, np.float32)
+    return (torch.from_numpy(lo), torch.from_numpy(ln), torch.from_numpy(off),
+            torch.from_numpy(np.ascontiguousarray(val, dtype=np.float32)))
+
+
+def check_windowed_dft(conv_real, conv_imag, n_fft, tol=2e-5):
+    """The fused front-end evaluates the loaded Conv1d kernels as window x DFT.  Verify that the
+    loaded kernels have that structure (stft.py:207-212) and return the window (row 0 of conv_real)."""
+    wr = conv_real.detach().cpu().double().reshape(-1, n_fft)
+    wi = conv_imag.detach().cpu().double().reshape(-1, n_fft)
+    F = n_fft // 2 + 1
+    if wr.shape[0] != F or wi.shape[0] != F:
+        raise NotImplementedError("STFT kernels must have n_fft//2+1 output channels")
+    win = wr[0].clone()
+    kn = (torch.arange(F, dtype=torch.int64)[:, None] * torch.arange(n_fft, dtype=torch.int64)[None, :]) % n_fft
+    ang = -2.0 * math.pi * kn.double() / n_fft
+    err = max((wr - torch.cos(ang) * win).abs().max().item(), (wi - torch.sin(ang) * win).abs().max().item())
+    scale = max(win.abs().max().item(), 1e-30)
+    if err > tol * scale:
+        raise NotImplementedError(
+            "loaded conv_real/conv_imag are not a windowed DFT (max deviation %.3g); the B200 front-end "
+            "only supports the reference's frozen STFT kernels" % err)
+    return win.float().contiguous()
+
+
+class FrontendPlan:
+    """Device-resident constants of the front-end for one (n_fft, hop, melW) configuration."""
+
+    def __init__(self, conv_real, conv_imag, n_fft, hop, melW, device, amin=1e-10, ref=1.0, is_log=True):
+        self.n_fft, self.hop = int(n_fft), int(hop)
+        if self.n_fft not in (256, 512, 1024):
+            raise NotImplementedError("n_fft=%d: only the reference presets 256/512/1024 are built" % n_fft)
+        self.window = check_windowed_dft(conv_real, conv_imag, self.n_fft).to(device)
+        self.twiddle = twiddle_table(self.n_fft).to(device)
+        self.amin = float(amin)
+        self.db_offset = float(10.0 * np.log10(np.maximum(amin, ref)))
+        self.is_log = 1 if is_log else 0
+        self.n_mels = 0
+        if melW is not None:
+            lo, ln, off, val = band_mel(melW)
+            self.mel_lo, self.mel_len, self.mel_off, self.mel_val = (t.to(device) for t in (lo, ln, off, val))
+            self.n_mels = int(melW.shape[1])
+            self.F = int(melW.shape[0])
+
+
+def logmel_forward(plan, wave, bn_scale=None, bn_shift=None, out=None):
+    """wave [B, L] f32 cuda -> [B, T, n_mels] f32."""
+    lib = capi.load()
+    B, L = wave.shape
+    T = L // plan.hop + 1
+    if out is None:
+        out = torch.empty((B, T, plan.n_mels), dtype=torch.float32, device=wave.device)
+    rc = lib.sed_frontend_logmel_f32(capi.ptr(wave), B, L, plan.n_fft, plan.hop, capi.ptr(plan.window),
+                                     capi.ptr(plan.twiddle), capi.ptr(plan.mel_lo), capi.ptr(plan.mel_len),
+                                     capi.ptr(plan.mel_off), capi.ptr(plan.mel_val), plan.n_mels, plan.amin,
+                                     plan.db_offset, plan.is_log, capi.ptr(bn_scale), capi.ptr(bn_shift),
+                                     capi.ptr(out), capi.current_stream(wave.device))
+    capi.check(rc, "sed_frontend_logmel_f32")
+    capi._count()
+    return out
+
+
+def spectrogram_forward(plan, wave):
+    lib = capi.load()
+    B, L = wave.shape
+    T = L // plan.hop + 1
+    out = torch.empty((B, 1, T, plan.n_fft // 2 + 1), dtype=torch.float32, device=wave.device)
+    rc = lib.sed_spectrogram_f32(capi.ptr(wave), B, L, plan.n_fft, plan.hop, capi.ptr(plan.window),
+                                 capi.ptr(plan.twiddle), capi.ptr(out), capi.current_stream(wave.device))
+    capi.check(rc, "sed_spectrogram_f32")
+    capi._count()
+    return out
+
+
+def logmel_rows_forward(plan, spec):
+    lib = capi.load()
+    F = spec.shape[-1]
+    if F != plan.F:
+        raise ValueError("spectrogram has %d bins, mel matrix expects %d" % (F, plan.F))
+    spec_c = spec.contiguous()
+    rows = spec_c.numel() // F
+    out = torch.empty(spec.shape[:-1] + (plan.n_mels,), dtype=torch.float32, device=spec.device)
+    rc = lib.sed_logmel_rows_f32(capi.ptr(spec_c), rows, F, capi.ptr(plan.mel_lo), capi.ptr(plan.mel_len),
+                                 capi.ptr(plan.mel_off), capi.ptr(plan.mel_val), plan.n_mels, plan.amin,
+                                 plan.db_offset, plan.is_log, capi.ptr(out), capi.current_stream(spec.device))
+    capi.check(rc, "sed_logmel_rows_f32")
+    capi._count()
+    return out
+
+
+class PackedModel:
+    """Weights of one model repacked for the kernels, resident on one device."""
+
+    def __init__(self, sd, model_type, n_fft, hop, device, precision="fp16"):
+        if precision not in _DTYPES:
+            raise ValueError("precision must be 'fp16' or 'bf16'")
+        self.model_type = model_type
+        self.device = torch.device(device)
+        self.precision = precision
+        self.dtype_code, self.tdtype = _DTYPES[precision]
+        dev, td = self.device, self.tdtype
+        sd = {k: v.detach().to("cpu") for k, v in sd.items()}
+        self.front = FrontendPlan(sd["spectrogram_extractor.stft.conv_real.weight"],
+                                  sd["spectrogram_extractor.stft.conv_imag.weight"], n_fft, hop,
+                                  sd["logmel_extractor.melW"], dev)
+        if self.front.n_mels != 64:
+            raise NotImplementedError("Cnn_9layers needs mel_bins == 64 (bn0 is BatchNorm2d(64), models.py:607)")
+        s, b = fold_bn(sd, "bn0")
+        self.bn0_scale, self.bn0_shift = s.to(dev), b.to(dev)
+        # conv_block1.conv1 (Cin = 1): float32 CUDA-core layer
+        self.c11_w = sd["conv_block1.conv1.weight"].float().reshape(64, 9).contiguous().to(dev)
+        s, b = fold_bn(sd, "conv_block1.bn1")
+        self.c11_scale, self.c11_shift = s.to(dev), b.to(dev)
+        self.convs = []
+        for name, cin, cout, mode in CONV_LAYERS:
+            w = sd[name + ".weight"].float()
+            if tuple(w.shape) != (cout, cin, 3, 3):
+                raise ValueError("%s.weight has shape %s" % (name, tuple(w.shape)))
+            wp = w.permute(0, 2, 3, 1).reshape(cout, 9 * cin).to(td).contiguous().to(dev)  # [Cout][tap][Cin]
+            s, b = fold_bn(sd, name.replace(".conv", ".bn"))
+            self.convs.append((cin, cout, mode, wp, s.to(dev), b.to(dev)))
+        if model_type == "Cnn_9layers_Gru_FrameAtt":
+            wih = torch.cat([sd["gru.weight_ih_l0"], sd["gru.weight_ih_l0_reverse"]], 0).float()
+            self.gru_wih = wih.to(td).contiguous().to(dev)  # [1536, 512]
+            self.gru_bih = torch.cat([sd["gru.bias_ih_l0"], sd["gru.bias_ih_l0_reverse"]], 0).float().contiguous().to(dev)
+            packed = []
+            for suffix in ("", "_reverse"):
+                whh = sd["gru.weight_hh_l0" + suffix].float()  # [768, 256] rows = [r | z | n]
+                # block q holds hidden units 32q..32q+31 of all three gates (see sed_b200.h: sed_bigru)
+                packed.append(whh.view(3, 8, 32, 256).permute(1, 0, 2, 3).reshape(768, 256))
+            self.gru_whh = torch.cat(packed, 0).to(td).contiguous().to(dev)  # [1536, 256]
+            self.gru_bhh = torch.stack([sd["gru.bias_hh_l0"], sd["gru.bias_hh_l0_reverse"]], 0).float().contiguous().to(dev)
+        elif model_type == "Cnn_9layers_Transformer_FrameAtt":
+            wqkv = torch.cat([sd["multihead.w_qs.weight"], sd["multihead.w_ks.weight"], sd["multihead.w_vs.weight"]], 0)
+            self.mha_wqkv = wqkv.float().to(td).contiguous().to(dev)
+            self.mha_bqkv = torch.cat([sd["multihead.w_qs.bias"], sd["multihead.w_ks.bias"],
+                                       sd["multihead.w_vs.bias"]], 0).float().contiguous().to(dev)
+            self.mha_wfc = sd["multihead.fc.weight"].float().to(td).contiguous().to(dev)
+            self.mha_bfc = sd["multihead.fc.bias"].float().contiguous().to(dev)
+        else:
+            raise NotImplementedError("model_type %r is not built" % (model_type,))
+        self.att_w = sd["att_block.att.weight"].float().reshape(25, 512).contiguous().to(dev)
+        self.att_b = sd["att_block.att.bias"].float().contiguous().to(dev)
+        self.cla_w = sd["att_block.cla.weight"].float().reshape(25, 512).contiguous().to(dev)
+        self.cla_b = sd["att_block.cla.bias"].float().contiguous().to(dev)
+        self._ws = {}
+        self._lock = threading.Lock()
+
+    # ------------------------------------------------------------------ workspaces
+    def _workspace(self, mb, T):
+        key = (mb, T)
+        ws = self._ws.get(key)
+        if ws is None:
+            dev, td = self.device, self.tdtype
+            H1, H2, H3 = T // 2, T // 4, T // 8
+            ws = {
+                "logmel": torch.empty((mb, T, 64), dtype=torch.float32, device=dev),
+                "a1": torch.empty((mb, T, 64, 64), dtype=td, device=dev),
+                "p1": torch.empty((mb, H1, 32, 64), dtype=td, device=dev),
+                "a2": torch.empty((mb, H1, 32, 128), dtype=td, device=dev),
+                "p2": torch.empty((mb, H2, 16, 128), dtype=td, device=dev),
+                "a3": torch.empty((mb, H2, 16, 256), dtype=td, device=dev),
+                "p3": torch.empty((mb, H3, 8, 256), dtype=td, device=dev),
+                "a4": torch.empty((mb, H3, 8, 512), dtype=td, device=dev),
+            }
+            self._ws = {key: ws}  # keep only the most recent shape
+        return ws
+
+    # ------------------------------------------------------------------ stages
+    def conv_stack(self, wave_mb, feat_out, variant=0, stages=None):
+        """wave_mb [mb, L] f32 -> feat_out [mb, T', 512] 16-bit (freq-mean of conv_block4)."""
+        lib = capi.load()
+        mb, L = wave_mb.shape
+        T = L // self.front.hop + 1
+        if T // 8 < 1:
+            raise ValueError("clip too short: %d frames" % T)
+        ws = self._workspace(mb, T)
+        stream = capi.current_stream(self.device)
+        logmel_forward(self.front, wave_mb, self.bn0_scale, self.bn0_shift, out=ws["logmel"])
+        rc = lib.sed_conv_first_f32(capi.ptr(ws["logmel"]), mb, T, 64, capi.ptr(self.c11_w), capi.ptr(self.c11_scale),
+                                    capi.ptr(self.c11_shift), capi.ptr(ws["a1"]), self.dtype_code, stream)
+        capi.check(rc, "sed_conv_first_f32")
+        capi._count()
+        chain = [("a1", "p1"), ("p1", "a2"), ("a2", "p2"), ("p2", "a3"), ("a3", "p3"), ("p3", "a4"), ("a4", None)]
+        for (cin, cout, mode, wp, s, b), (src, dst) in zip(self.convs, chain):
+            x = ws[src]
+            out = feat_out if dst is None else ws[dst]
+            rc = lib.sed_conv3x3_bn_relu(capi.ptr(x), mb, x.shape[1], x.shape[2], cin, capi.ptr(wp), capi.ptr(s),
+                                         capi.ptr(b), cout, mode, capi.ptr(out), self.dtype_code, variant, stream)
+            capi.check(rc, "sed_conv3x3_bn_relu(%d->%d)" % (cin, cout))
+            capi._count()
+        if stages is not None:
+            stages["bn0"] = ws["logmel"].clone()
+            for k in ("a1", "p1", "a2", "p2", "a3", "p3", "a4"):
+                stages[k] = ws[k].clone()
+
+    def linear(self, a16, w16, bias, relu=False, out16=False):
+        lib = capi.load()
+        M, K = a16.shape
+        N = w16.shape[0]
+        out = torch.empty((M, N), dtype=torch.float32, device=self.device)
+        o16 = torch.empty((M, N), dtype=self.tdtype, device=self.device) if out16 else None
+        rc = lib.sed_linear(capi.ptr(a16), M, K, capi.ptr(w16), capi.ptr(bias), N, 1 if relu else 0, capi.ptr(out),
+                            capi.ptr(o16), self.dtype_code, capi.current_stream(self.device))
+        capi.check(rc, "sed_linear")
+        capi._count((N + 511) // 512)
+        return (out, o16) if out16 else out
+
+    def temporal(self, feat16, stages=None):
+        """feat16 [B, T', 512] 16-bit -> [B, T', 512] f32 (GRU or MultiHead output)."""
+        lib = capi.load()
+        B, Tp, _ = feat16.shape
+        stream = capi.current_stream(self.device)
+        flat = feat16.view(B * Tp, 512)
+        if self.model_type == "Cnn_9layers_Gru_FrameAtt":
+            gi = self.linear(flat, self.gru_wih, self.gru_bih)
+            out = torch.empty((B, Tp, 512), dtype=torch.float32, device=self.device)
+            rc = lib.sed_bigru(capi.ptr(gi), capi.ptr(self.gru_whh), capi.ptr(self.gru_bhh), B, Tp, capi.ptr(out),
+                               self.dtype_code, stream)
+            capi.check(rc, "sed_bigru")
+            capi._count()
+            if stages is not None:
+                stages["gi"] = gi
+            return out
+        qkv = self.linear(flat, self.mha_wqkv, self.mha_bqkv)
+        ctx = torch.empty((B * Tp, 512), dtype=self.tdtype, device=self.device)
+        rc = lib.sed_mha_core(capi.ptr(qkv), B, Tp, capi.ptr(ctx), self.dtype_code, stream)
+        capi.check(rc, "sed_mha_core")
+        capi._count()
+        out = self.linear(ctx, self.mha_wfc, self.mha_bfc, relu=True)
+        if stages is not None:
+            stages["qkv"] = qkv
+            stages["ctx"] = ctx
+        return out.view(B, Tp, 512)
+
+    def head(self, x, frames_out, want_cla=True, want_norm_att=False):
+        lib = capi.load()
+        B, Tp, _ = x.shape
+        dev = self.device
+        clip = torch.empty((B, 25), dtype=torch.float32, device=dev)
+        frame = torch.empty((B, frames_out, 25), dtype=torch.float32, device=dev)
+        cla = torch.empty((B, 25, Tp), dtype=torch.float32, device=dev) if want_cla else None
+        natt = torch.empty((B, 25, Tp), dtype=torch.float32, device=dev) if want_norm_att else None
+        rc = lib.sed_attpool(capi.ptr(x), B, Tp, capi.ptr(self.att_w), capi.ptr(self.att_b), capi.ptr(self.cla_w),
+                             capi.ptr(self.cla_b), 8, frames_out, capi.ptr(clip), capi.ptr(frame), capi.ptr(cla),
+                             capi.ptr(natt), capi.current_stream(dev))
+        capi.check(rc, "sed_attpool")
+        capi._count()
+        return clip, frame, cla, natt
+
+    # ------------------------------------------------------------------ whole model
+    def forward(self, wave, micro_batch=148, variant=0, return_stages=False):
+        """wave [B, L] f32 on self.device -> reference output dict (models.py:683-686 / :1072-1075)."""
+        if wave.dim() != 2:
+            raise ValueError("input must be (batch_size, data_length)")
+        if wave.device != self.device:
+            raise ValueError("input is on %s, packed weights are on %s" % (wave.device, self.device))
+        wave = wave.float().contiguous()
+        B, L = wave.shape
+        T = L // self.front.hop + 1
+        Tp = T // 8
+        stages = {} if return_stages else None
+        with self._lock:
+            feat16 = torch.empty((B, Tp, 512), dtype=self.tdtype, device=self.device)
+            for b0 in range(0, B, micro_batch):
+                b1 = min(B, b0 + micro_batch)
+                self.conv_stack(wave[b0:b1], feat16[b0:b1], variant=variant,
+                                stages=stages if (return_stages and b0 == 0) else None)
+            x = self.temporal(feat16, stages)
+            frames = Tp * 8
+            if self.model_type == "Cnn_9layers_Gru_FrameAtt" and frames != 1000:
+                frames = frames if frames % 100 == 0 else frames + 100 - frames % 100  # models.py:62-63, 680-681
+            is_gru = self.model_type == "Cnn_9layers_Gru_FrameAtt"
+            clip, frame, cla, natt = self.head(x, frames, want_cla=is_gru, want_norm_att=return_stages)
+        out = {"framewise_output": frame, "clipwise_output": clip,
+               "embedding": cla if is_gru else x.transpose(1, 2)}
+        if return_stages:
+            stages["feat"] = feat16
+            stages["temporal"] = x
+            stages["norm_att"] = natt
+            return out, stages
+        return out
