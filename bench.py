@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""Headline benchmark: clips/sec (10 s, 16 kHz) of logmel + CRNN inference (BASELINE.json `metric`).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]           # B200 arm (this repo's kernels)
+  python bench.py --impl reference [--steps K] [--warmup W]     # reference algorithm on the host CPU
+
+A step = one pass of the whole hot path (waveform -> log-mel -> Cnn9 -> bi-GRU -> frame-attention pooling)
+over one batch of synthetic clips: BASELINE.json configs[1], Cnn_9layers_Gru_FrameAtt, 16 kHz, batch 1024 per
+GPU.  For N > 1 each rank owns its own 1024-clip shard (weak scaling, no collective on the data path) and the
+framewise/clipwise outputs are gathered to rank 0 with NCCL inside the timed step.  One JSON line on stdout.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODEL_TYPE = "Cnn_9layers_Gru_FrameAtt"
+SR, N_FFT, HOP, FMIN, FMAX = 16000, 512, 160, 25, 7000
+CLIP_SAMPLES = 160000
+CONV_GFLOP_TC = 26.031 - 0.0738  # tensor-core conv layers per clip (SURVEY.md 8d minus conv_block1.conv1)
+METRIC = "clips/sec (10 s, 16 kHz) logmel+CRNN inference"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            pk = json.load(f)
+        return {"tflops_sustained": float(pk.get("bf16_tflops_sustained", 1410.6)),
+                "tflops_burst": float(pk.get("bf16_tflops", 1678.0)), "hbm_gbs": float(pk.get("hbm_gbs", 6537.6)),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops_sustained": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_throughput(steps, warmup, batch=32):
+    """The reference algorithm (oracle port of pytorch/models.py forward) on the host CPU, all cores."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import sed_oracle
+    from sed_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synth.synthetic_state_dict(MODEL_TYPE, SR)
+    wave = synth.synthetic_waveform(batch, CLIP_SAMPLES, seed=1234)
+    for _ in range(warmup):
+        sed_oracle.model_forward(sd, wave, MODEL_TYPE, N_FFT, HOP)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        sed_oracle.model_forward(sd, wave, MODEL_TYPE, N_FFT, HOP)
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": batch * steps / total, "unit": "clips/s", "cores": cores, "kind": "port",
+            "sample": "%d steps of batch %d x 10 s clips, float32 torch CPU ops, %d threads" % (steps, batch, cores),
+            "ms_per_step": 1e3 * total / steps, "batch": batch}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    warmup = max(0, args.warmup)
+    batch = args.ref_batch
+    cb = cpu_reference_throughput(steps, warmup, batch)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "clips/s", "n_gpus": 0, "steps": steps,
+        "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "Cnn_9layers_Gru_FrameAtt logmel 16k, synthetic 10 s clips, batch %d per step "
+                               "(bounded sample of the batch-1024 workload), host CPU" % batch},
+        "cpu_baseline": {"value": cb["value"], "unit": "clips/s", "cores": cb["cores"], "kind": "port",
+                         "sample": cb["sample"]},
+        "e2e": {"value": cb["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from sed_b200 import capi, engine, synth
+    from sed_b200 import dist as sdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the B200 arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    capi.load()
+
+    B = args.batch
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    sd = synth.synthetic_state_dict(MODEL_TYPE, SR)
+    pm = engine.PackedModel(sd, MODEL_TYPE, N_FFT, HOP, dev, precision=args.precision)
+    wave_host = synth.synthetic_waveform(B, CLIP_SAMPLES, seed=1234, rank=rank).pin_memory()
+    wave = wave_host.to(dev)
+
+    def step_device():
+        out = pm.forward(wave, micro_batch=args.micro_batch, variant=args.variant)
+        if world > 1:
+            sdist.gather_outputs(out, dst=0)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(warmup):
+        step_device()
+    barrier()
+
+    # ---------------- timed region 1: inputs resident in HBM ----------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    capi.reset_launches()
+    pm.conv_events = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        step_device()
+    e1.record()
+    barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    launches = capi.launches()
+    conv_ms = sum(a.elapsed_time(b) for a, b, _ in pm.conv_events)
+    conv_clips = sum(n for _, _, n in pm.conv_events)
+    pm.conv_events = None
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = t.item()
+
+    # ---------------- timed region 2: end to end with HOST buffers ----------------
+    def step_host():
+        out = pm.forward_host(wave_host, micro_batch=args.micro_batch, variant=args.variant)
+        return out
+
+    for _ in range(2):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record()
+    for _ in range(steps):
+        res = step_host()
+    h1.record()
+    barrier()
+    e2e_ms = max(h0.elapsed_time(h1), 0.0)
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    t = torch.tensor([max(e2e_ms, wall_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = t.item()
+    d2h = res["clipwise_output"].numel() * 4 + res["framewise_output"].numel() * 4
+
+    if rank == 0:
+        peaks = load_peaks()
+        value = world * B * steps / (elapsed_ms / 1e3)
+        conv_tflops = CONV_GFLOP_TC * 1e9 * conv_clips / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+        n_conv_launch = 7 * len([1 for _ in range(0, B, args.micro_batch)]) * steps
+        line = {
+            "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": elapsed_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": "Cnn_9layers_Gru_FrameAtt logmel 16k batch %d per GPU (BASELINE.json configs[1]), "
+                                   "10 s clips, seeded synthetic checkpoint" % B,
+                       "batch_per_gpu": B, "micro_batch": args.micro_batch, "parallelism": "dp%d (batch shards, "
+                       "NCCL gather of outputs to rank 0)" % world,
+                       "l2": "inputs (%.0f MB/step) and activations (>2 GB/micro-batch) exceed the 126 MB L2" %
+                             (B * CLIP_SAMPLES * 4 / 1e6)},
+            "e2e": {"value": world * B * steps / (e2e_ms / 1e3), "unit": "clips/s",
+                    "h2d_bytes_per_step": B * CLIP_SAMPLES * 4, "d2h_bytes_per_step": d2h,
+                    "api": "PackedModel.forward_host (pinned host waveform in, host clipwise/framewise out)"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": peaks["tflops_sustained"],
+                         "unit": "TFLOP/s", "frac": conv_tflops / peaks["tflops_sustained"],
+                         "traffic": None,
+                         "kernel": "conv_umma_kernel (7 tcgen05 implicit-GEMM launches per micro-batch, "
+                                   "%.3f GFLOP/clip algorithmic)" % CONV_GFLOP_TC,
+                         "peak_source": peaks["source"] + ", sustained bf16; burst %.1f" % peaks["tflops_burst"],
+                         "launches_timed": n_conv_launch, "conv_ms_per_step": conv_ms / steps},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_reference_throughput(steps=3, warmup=1, batch=args.ref_batch)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="clips per GPU per step")
+    ap.add_argument("--micro-batch", type=int, default=148)
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--ref-batch", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -213,6 +213,8 @@ class PackedModel:
         self.cla_b = sd["att_block.cla.bias"].float().contiguous().to(dev)
         self._ws = {}
         self._lock = threading.Lock()
+        self._host = {}
+        self.conv_events = None  # set to [] to collect (start, end) CUDA events around the tensor-core conv launches
 
     # ------------------------------------------------------------------ workspaces
     def _workspace(self, mb, T):
@@ -250,6 +252,9 @@ class PackedModel:
         capi.check(rc, "sed_conv_first_f32")
         capi._count()
         chain = [("a1", "p1"), ("p1", "a2"), ("a2", "p2"), ("p2", "a3"), ("a3", "p3"), ("p3", "a4"), ("a4", None)]
+        if self.conv_events is not None:
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record(torch.cuda.current_stream(self.device))
         for (cin, cout, mode, wp, s, b), (src, dst) in zip(self.convs, chain):
             x = ws[src]
             out = feat_out if dst is None else ws[dst]
@@ -257,6 +262,10 @@ class PackedModel:
                                          capi.ptr(b), cout, mode, capi.ptr(out), self.dtype_code, variant, stream)
             capi.check(rc, "sed_conv3x3_bn_relu(%d->%d)" % (cin, cout))
             capi._count()
+        if self.conv_events is not None:
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record(torch.cuda.current_stream(self.device))
+            self.conv_events.append((ev0, ev1, mb))
         if stages is not None:
             stages["bn0"] = ws["logmel"].clone()
             for k in ("a1", "p1", "a2", "p2", "a3", "p3", "a4"):
@@ -317,7 +326,44 @@ class PackedModel:
         return clip, frame, cla, natt
 
     # ------------------------------------------------------------------ whole model
-    def forward(self, wave, micro_batch=148, variant=0, return_stages=False):
+    def forward_host(self, wave_host, micro_batch=148, variant=0):
+        """End-to-end call with HOST buffers: `wave_host` [B, L] f32 (pinned for full speed) is copied to
+        the device micro-batch by micro-batch on a copy stream that runs ahead of the compute stream, and
+        `clipwise_output` / `framewise_output` come back as host tensors (the reference callers do
+        `.data.cpu().numpy()` on exactly these, pytorch_utils.py:57-62)."""
+        if wave_host.is_cuda or wave_host.dim() != 2:
+            raise ValueError("forward_host expects a (batch_size, data_length) CPU tensor")
+        B, L = wave_host.shape
+        key = (B, L)
+        hb = self._host.get(key)
+        if hb is None:
+            T = L // self.front.hop + 1
+            frames = (T // 8) * 8
+            if self.model_type == "Cnn_9layers_Gru_FrameAtt" and frames != 1000 and frames % 100:
+                frames += 100 - frames % 100
+            hb = {"dev": torch.empty((B, L), dtype=torch.float32, device=self.device),
+                  "clip": torch.empty((B, 25), dtype=torch.float32).pin_memory(),
+                  "frame": torch.empty((B, frames, 25), dtype=torch.float32).pin_memory(),
+                  "copy_stream": torch.cuda.Stream(self.device)}
+            self._host = {key: hb}
+        cs = hb["copy_stream"]
+        compute = torch.cuda.current_stream(self.device)
+        cs.wait_stream(compute)  # the previous call may still be reading the staging buffer
+        events = []
+        with torch.cuda.stream(cs):
+            for b0 in range(0, B, micro_batch):
+                b1 = min(B, b0 + micro_batch)
+                hb["dev"][b0:b1].copy_(wave_host[b0:b1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+                events.append(ev)
+        out = self.forward(hb["dev"], micro_batch=micro_batch, variant=variant, _h2d_events=events)
+        hb["clip"].copy_(out["clipwise_output"], non_blocking=True)
+        hb["frame"].copy_(out["framewise_output"], non_blocking=True)
+        compute.synchronize()
+        return {"clipwise_output": hb["clip"], "framewise_output": hb["frame"]}
+
+    def forward(self, wave, micro_batch=148, variant=0, return_stages=False, _h2d_events=None):
         """wave [B, L] f32 on self.device -> reference output dict (models.py:683-686 / :1072-1075)."""
         if wave.dim() != 2:
             raise ValueError("input must be (batch_size, data_length)")
@@ -330,8 +376,10 @@ class PackedModel:
         stages = {} if return_stages else None
         with self._lock:
             feat16 = torch.empty((B, Tp, 512), dtype=self.tdtype, device=self.device)
-            for b0 in range(0, B, micro_batch):
+            for i, b0 in enumerate(range(0, B, micro_batch)):
                 b1 = min(B, b0 + micro_batch)
+                if _h2d_events is not None:
+                    torch.cuda.current_stream(self.device).wait_event(_h2d_events[i])
                 self.conv_stack(wave[b0:b1], feat16[b0:b1], variant=variant,
                                 stages=stages if (return_stages and b0 == 0) else None)
             x = self.temporal(feat16, stages)

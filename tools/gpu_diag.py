@@ -69,6 +69,10 @@ def run_stage(stage):
             viol = ((got - ref).abs() > tol).float().mean().item()
             print("frontend sr=%d: max|d| vs ref %.3e, viol frac %.3e, ref vs f64 %.3e, got vs f64 %.3e" % (
                 sr, (got - ref).abs().max(), viol, (ref.double() - f64).abs().max(), (got.double() - f64).abs().max()))
+            for c in range(wave.shape[0]):
+                print("     clip %d: vs ref %.3e viol %.3e | got vs f64 %.3e | ref vs f64 %.3e | min dB %.1f" % (
+                    c, (got[c] - ref[c]).abs().max(), ((got[c] - ref[c]).abs() > tol[c]).float().mean(),
+                    (got[c].double() - f64[c]).abs().max(), (ref[c].double() - f64[c]).abs().max(), ref[c].min()))
             gspec = engine.spectrogram_forward(plan, wave.to(dev)).cpu()
             print("   spectrogram rel err %.3e" % rel_err(gspec, spec)[0])
         return
@@ -79,8 +83,9 @@ def run_stage(stage):
         scale = torch.rand(64) + 0.5
         shift = torch.randn(64) * 0.1
         out = torch.empty(2, 37, 64, 64, dtype=td, device=dev)
-        rc = lib.sed_conv_first_f32(capi.ptr(x.to(dev)), 2, 37, 64, capi.ptr(w.reshape(64, 9).contiguous().to(dev)),
-                                    capi.ptr(scale.to(dev)), capi.ptr(shift.to(dev)), capi.ptr(out), code, stream)
+        xd, wd, sc, sh = x.to(dev), w.reshape(64, 9).contiguous().to(dev), scale.to(dev), shift.to(dev)
+        rc = lib.sed_conv_first_f32(capi.ptr(xd), 2, 37, 64, capi.ptr(wd), capi.ptr(sc), capi.ptr(sh), capi.ptr(out),
+                                    code, stream)
         capi.check(rc, "conv_first")
         torch.cuda.synchronize()
         ref = conv_ref(x[..., None], w, scale, shift, 0)
@@ -101,8 +106,9 @@ def run_stage(stage):
                 oshape = {0: (NB, H, W, cout), 1: (NB, H // 2, W // 2, cout), 2: (NB, H, cout)}[mode]
                 out = torch.full(oshape, float("nan"), dtype=td, device=dev)
                 t0 = time.time()
-                rc = lib.sed_conv3x3_bn_relu_dbg(capi.ptr(x.to(dev)), NB, H, W, cin, capi.ptr(wp), capi.ptr(scale.to(dev)),
-                                                 capi.ptr(shift.to(dev)), cout, mode, capi.ptr(out), code, variant, bo,
+                xd, sc, sh = x.to(dev), scale.to(dev), shift.to(dev)
+                rc = lib.sed_conv3x3_bn_relu_dbg(capi.ptr(xd), NB, H, W, cin, capi.ptr(wp), capi.ptr(sc),
+                                                 capi.ptr(sh), cout, mode, capi.ptr(out), code, variant, bo,
                                                  stream)
                 capi.check(rc, name)
                 torch.cuda.synchronize()
@@ -119,7 +125,8 @@ def run_stage(stage):
             w = (torch.randn(N, K) / np.sqrt(K)).to(td)
             bias = torch.randn(N) * 0.1
             out = torch.full((M, N), float("nan"), dtype=torch.float32, device=dev)
-            rc = lib.sed_linear(capi.ptr(a.to(dev)), M, K, capi.ptr(w.to(dev)), capi.ptr(bias.to(dev)), N, relu,
+            ad, wd, bd = a.to(dev), w.to(dev), bias.to(dev)
+            rc = lib.sed_linear(capi.ptr(ad), M, K, capi.ptr(wd), capi.ptr(bd), N, relu,
                                 capi.ptr(out), None, code, stream)
             capi.check(rc, "linear")
             torch.cuda.synchronize()
