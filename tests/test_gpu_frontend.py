@@ -1,0 +1,95 @@
+"""GPU parity of the fused front-end (C ABI: sed_frontend_logmel_f32 / sed_spectrogram_f32 / sed_logmel_rows_f32)
+against the reference fixtures and the CPU oracle.  Tolerance (north_star): |a-b| <= 1e-4 * max(|b|, 1) dB."""
+import numpy as np
+import pytest
+import torch
+
+import sed_oracle as so
+from conftest import load_golden, logmel_close
+from sed_b200 import engine, melbank, stft, synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _plan(sr, melW=None):
+    n_fft, hop, fmin, fmax = synth.PRESETS[sr]
+    wr, wi = melbank.windowed_dft_kernels(n_fft, n_fft, "hann")
+    if melW is None:
+        melW = melbank.mel_filterbank(sr, n_fft, 64, fmin, fmax)
+    return engine.FrontendPlan(wr, wi, n_fft, hop, melW, torch.device(DEV)), (wr, wi, melW)
+
+
+@pytest.mark.parametrize("sr", [8000, 16000, 32000])
+def test_logmel_matches_reference_golden(sr):
+    g = load_golden("frontend_%dk.npz" % (sr // 1000))
+    plan, _ = _plan(sr, torch.from_numpy(g["melW"]))
+    wave = (torch.from_numpy(g["wave_i16"]).float() / 32767.0).to(DEV)
+    got = engine.logmel_forward(plan, wave).cpu().numpy()
+    assert got.shape == g["logmel"].shape
+    ok = logmel_close(got, g["logmel"], rtol=1e-4)
+    assert ok.all(), "violations %.3e, max |d| %.3e dB" % (1 - ok.mean(), np.abs(got - g["logmel"]).max())
+    assert np.all(got[3] == -100.0)  # silence -> exactly 10*log10(amin)
+
+
+@pytest.mark.parametrize("sr", [8000, 16000, 32000])
+def test_logmel_matches_oracle_long_and_ragged(sr):
+    n_fft, hop, _, _ = synth.PRESETS[sr]
+    plan, (wr, wi, melW) = _plan(sr)
+    for L in (sr * 5, sr * 10, sr * 10 + 1, 3 * n_fft + 7):
+        wave = torch.cat([synth.synthetic_waveform(2, L, seed=L % 1000, kind="noise"),
+                          torch.rand(1, L, generator=torch.Generator().manual_seed(3)) * 2 - 1])
+        got = engine.logmel_forward(plan, wave.to(DEV)).cpu().numpy()
+        ref = so.logmel(so.spectrogram(wave, wr, wi, n_fft, hop), melW)[:, 0].numpy()
+        assert got.shape == ref.shape == (3, L // hop + 1, 64)
+        assert logmel_close(got, ref).all(), (sr, L, np.abs(got - ref).max())
+
+
+def test_logmel_vs_float64_fft_is_at_least_as_close_as_the_reference():
+    g = load_golden("frontend_16k.npz")
+    plan, _ = _plan(16000, torch.from_numpy(g["melW"]))
+    wave = torch.from_numpy(g["wave_i16"]).float() / 32767.0
+    got = engine.logmel_forward(plan, wave.to(DEV)).cpu().numpy()
+    f64 = so.logmel_float64_fft(wave.numpy().astype(np.float64), 512, 160, g["melW"])
+    for i in (0, 1):  # noise-like signals
+        assert np.abs(got[i] - f64[i]).max() < 2e-4
+
+
+def test_bn0_affine_is_fused():
+    plan, (wr, wi, melW) = _plan(16000)
+    wave = synth.synthetic_waveform(2, 16000, seed=9)
+    scale = torch.rand(64) + 0.5
+    shift = torch.randn(64)
+    got = engine.logmel_forward(plan, wave.to(DEV), scale.to(DEV), shift.to(DEV)).cpu()
+    ref = so.logmel(so.spectrogram(wave, wr, wi, 512, 160), melW)[:, 0] * scale + shift
+    assert (got - ref).abs().max() < 2e-4
+
+
+def test_spectrogram_and_logmel_modules_are_drop_ins():
+    g = load_golden("frontend_16k.npz")
+    wave = (torch.from_numpy(g["wave_i16"]).float() / 32767.0).to(DEV)
+    spec_mod = stft.Spectrogram(n_fft=512, hop_length=160, win_length=512, window="hann", center=True,
+                                pad_mode="reflect", freeze_parameters=True).to(DEV)
+    mel_mod = stft.LogmelFilterBank(sr=16000, n_fft=512, n_mels=64, fmin=25, fmax=7000, ref=1.0, amin=1e-10,
+                                    top_db=None, freeze_parameters=True).to(DEV)
+    spec = spec_mod(wave)
+    assert spec.shape == (6, 1, 101, 257) and spec.dtype == torch.float32
+    rows = spec[:, 0, ::25].cpu().numpy()
+    # power values: compare relative to each frame's total energy (float32 DFT resolution)
+    scale = np.maximum(g["spec_rows"].max(axis=-1, keepdims=True), 1e-20)
+    assert (np.abs(rows - g["spec_rows"]) / scale).max() < 2e-6
+    lm = mel_mod(spec)
+    assert lm.shape == (6, 1, 101, 64)
+    assert logmel_close(lm[:, 0].cpu().numpy(), g["logmel"]).all()
+    # top_db = 80 (constructor default): batch-global clamp, stft.py:729-732
+    mel80 = stft.LogmelFilterBank(sr=16000, n_fft=512, n_mels=64, fmin=25, fmax=7000).to(DEV)
+    lm80 = mel80(spec)[:, 0].cpu().numpy()
+    assert logmel_close(lm80, g["logmel_top80"]).all()
+
+
+def test_non_dft_kernels_are_rejected_loudly():
+    mod = stft.Spectrogram(n_fft=512, hop_length=160).to(DEV)
+    with torch.no_grad():
+        mod.stft.conv_real.weight.add_(0.01 * torch.randn_like(mod.stft.conv_real.weight))
+    with pytest.raises(NotImplementedError):
+        mod(torch.zeros(1, 16000, device=DEV))

@@ -1,0 +1,168 @@
+"""GPU parity of the individual kernels through the C ABI: conv layers (both operand-staging variants),
+first conv layer, tensor-core linear, GRU, attention core, frame-attention head."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import sed_oracle as so
+from conftest import synthetic_sd
+from sed_b200 import capi, engine
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+DTYPES = {"fp16": (0, torch.float16, 2e-3), "bf16": (1, torch.bfloat16, 1.6e-2)}
+
+
+def conv_ref(x_nhwc, w, scale, shift, mode):
+    y = F.conv2d(x_nhwc.permute(0, 3, 1, 2).float(), w.float(), padding=1)
+    y = torch.relu(y * scale[None, :, None, None] + shift[None, :, None, None])
+    if mode == 1:
+        y = F.avg_pool2d(y, 2)
+    if mode == 2:
+        return y.mean(dim=3).permute(0, 2, 1)
+    return y.permute(0, 2, 3, 1)
+
+
+def run_conv(x, w, scale, shift, mode, code, td, variant):
+    lib = capi.load()
+    NB, H, W, cin = x.shape
+    cout = w.shape[0]
+    xd = x.to(DEV)
+    wp = w.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous().to(DEV)
+    sc, sh = scale.to(DEV), shift.to(DEV)
+    oshape = {0: (NB, H, W, cout), 1: (NB, H // 2, W // 2, cout), 2: (NB, H, cout)}[mode]
+    out = torch.full(oshape, float("nan"), dtype=td, device=DEV)
+    rc = lib.sed_conv3x3_bn_relu(capi.ptr(xd), NB, H, W, cin, capi.ptr(wp), capi.ptr(sc), capi.ptr(sh), cout, mode,
+                                 capi.ptr(out), code, variant, capi.current_stream(DEV))
+    capi.check(rc, "sed_conv3x3_bn_relu")
+    torch.cuda.synchronize()
+    return out.float().cpu()
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("layer", engine.CONV_LAYERS, ids=[l[0] for l in engine.CONV_LAYERS])
+def test_conv_layers_match_cpu_conv(layer, variant):
+    name, cin, cout, mode = layer
+    W = {64: 64 if cout == 64 else 32, 128: 32 if cout == 128 else 16, 256: 16 if cout == 256 else 8, 512: 8}[cin]
+    code, td, tol = DTYPES["fp16"]
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    # ragged heights: 1 row, odd rows (pool floors), non-multiples of the 16-row tile, several images
+    for NB, H in ((1, 16), (3, 37), (2, 2), (1, 125 if cin >= 256 else 63)):
+        if mode == 1 and H < 2:
+            continue
+        x = (torch.randn(NB, H, W, cin, generator=g) * 0.5).to(td)
+        w = (torch.randn(cout, cin, 3, 3, generator=g) / np.sqrt(9 * cin)).to(td)
+        scale = torch.rand(cout, generator=g) + 0.5
+        shift = torch.randn(cout, generator=g) * 0.1
+        got = run_conv(x, w, scale, shift, mode, code, td, variant)
+        ref = conv_ref(x.float(), w.float(), scale, shift, mode)
+        assert not torch.isnan(got).any()
+        err = (got - ref).abs().max().item() / ref.abs().max().item()
+        assert err < tol, (name, NB, H, err)
+
+
+def test_conv_bf16_path():
+    code, td, tol = DTYPES["bf16"]
+    x = (torch.randn(2, 20, 16, 256) * 0.5).to(td)
+    w = (torch.randn(256, 256, 3, 3) / 48).to(td)
+    scale, shift = torch.rand(256) + 0.5, torch.randn(256) * 0.1
+    got = run_conv(x, w, scale, shift, 1, code, td, 0)
+    ref = conv_ref(x.float(), w.float(), scale, shift, 1)
+    assert (got - ref).abs().max().item() / ref.abs().max().item() < tol
+
+
+def test_conv_variants_agree_bitwise():
+    """Haloed-patch and per-tap staging feed the same MMAs in the same order: identical bits."""
+    code, td, _ = DTYPES["fp16"]
+    x = (torch.randn(3, 40, 32, 128) * 0.5).to(td)
+    w = (torch.randn(128, 128, 3, 3) / 34).to(td)
+    scale, shift = torch.rand(128) + 0.5, torch.randn(128) * 0.1
+    a = run_conv(x, w, scale, shift, 1, code, td, 0)
+    b = run_conv(x, w, scale, shift, 1, code, td, 1)
+    assert torch.equal(a, b)
+
+
+def test_conv_rejects_unsupported_layers():
+    lib = capi.load()
+    x = torch.zeros(1, 16, 8, 192, dtype=torch.float16, device=DEV)
+    with pytest.raises(NotImplementedError):
+        rc = lib.sed_conv3x3_bn_relu(capi.ptr(x), 1, 16, 8, 192, capi.ptr(x), capi.ptr(x), capi.ptr(x), 192, 0,
+                                     capi.ptr(x), 0, 0, capi.current_stream(DEV))
+        capi.check(rc, "conv")
+    with pytest.raises(ValueError):
+        rc = lib.sed_conv3x3_bn_relu(capi.ptr(x), 1, 16, 7, 64, capi.ptr(x), capi.ptr(x), capi.ptr(x), 64, 1,
+                                     capi.ptr(x), 0, 0, capi.current_stream(DEV))
+        capi.check(rc, "conv")
+
+
+def test_conv_first_layer():
+    lib = capi.load()
+    for NB, H in ((2, 37), (1, 1001)):
+        x = torch.randn(NB, H, 64)
+        w = torch.randn(64, 1, 3, 3) * 0.3
+        scale, shift = torch.rand(64) + 0.5, torch.randn(64) * 0.1
+        out = torch.empty(NB, H, 64, 64, dtype=torch.float16, device=DEV)
+        xd, wd, sc, sh = x.to(DEV), w.reshape(64, 9).contiguous().to(DEV), scale.to(DEV), shift.to(DEV)
+        rc = lib.sed_conv_first_f32(capi.ptr(xd), NB, H, 64, capi.ptr(wd), capi.ptr(sc), capi.ptr(sh), capi.ptr(out), 0,
+                                    capi.current_stream(DEV))
+        capi.check(rc, "conv_first")
+        ref = conv_ref(x[..., None], w, scale, shift, 0)
+        assert (out.float().cpu() - ref).abs().max().item() < 1e-3 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("M,K,N,relu", [(375, 512, 1536, 0), (300, 512, 512, 1), (128, 256, 768, 0), (1, 512, 512, 0)])
+def test_linear(M, K, N, relu):
+    lib = capi.load()
+    a = (torch.randn(M, K) * 0.5).half()
+    w = (torch.randn(N, K) / np.sqrt(K)).half()
+    bias = torch.randn(N) * 0.1
+    out = torch.full((M, N), float("nan"), dtype=torch.float32, device=DEV)
+    ad, wd, bd = a.to(DEV), w.to(DEV), bias.to(DEV)
+    rc = lib.sed_linear(capi.ptr(ad), M, K, capi.ptr(wd), capi.ptr(bd), N, relu, capi.ptr(out), None, 0,
+                        capi.current_stream(DEV))
+    capi.check(rc, "sed_linear")
+    ref = a.float() @ w.float().t() + bias
+    if relu:
+        ref = torch.relu(ref)
+    assert (out.cpu() - ref).abs().max().item() < 2e-4 * max(ref.abs().max().item(), 1.0)
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (3, 7), (130, 20), (5, 125), (2, 62)])
+def test_bigru_matches_oracle(B, T):
+    mt = "Cnn_9layers_Gru_FrameAtt"
+    sd = synthetic_sd(mt)
+    pm = engine.PackedModel(sd, mt, 512, 160, DEV)
+    x = torch.relu(torch.randn(B, T, 512, generator=torch.Generator().manual_seed(B * 131 + T)) * 0.5).half()
+    got = pm.temporal(x.to(DEV)).cpu()
+    ref = so.bigru(x.float(), sd)
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() < 1.5e-3  # fp16 operands of h W_hh^T over T recurrent steps
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (2, 62), (3, 125), (2, 140)])
+def test_multihead_matches_oracle(B, T):
+    mt = "Cnn_9layers_Transformer_FrameAtt"
+    sd = synthetic_sd(mt)
+    pm = engine.PackedModel(sd, mt, 512, 160, DEV)
+    x = torch.relu(torch.randn(B, T, 512, generator=torch.Generator().manual_seed(B * 17 + T)) * 0.5).half()
+    got = pm.temporal(x.to(DEV)).cpu()
+    ref = so.multihead(x.float(), sd)
+    assert (got - ref).abs().max().item() < 2e-3 * max(ref.abs().max().item(), 1.0)
+
+
+@pytest.mark.parametrize("B,T,frames", [(3, 125, 1000), (2, 62, 500), (2, 62, 496), (1, 1, 100)])
+def test_attpool_matches_oracle(B, T, frames):
+    mt = "Cnn_9layers_Gru_FrameAtt"
+    sd = synthetic_sd(mt)
+    pm = engine.PackedModel(sd, mt, 512, 160, DEV)
+    x = torch.tanh(torch.randn(B, T, 512, generator=torch.Generator().manual_seed(T)))
+    clip, frame, cla, natt = pm.head(x.to(DEV), frames, True, True)
+    rclip, rnatt, rcla = so.att_block(x.transpose(1, 2), sd)
+    rfw = so.interpolate(rcla.transpose(1, 2), 8)
+    if rfw.shape[1] != frames:
+        rfw = so.pad_framewise_output(rfw, frames)
+    assert (clip.cpu() - rclip).abs().max() < 2e-6
+    assert (frame.cpu() - rfw).abs().max() < 2e-6
+    assert (cla.cpu() - rcla).abs().max() < 2e-6
+    assert (natt.cpu() - rnatt).abs().max() < 2e-6

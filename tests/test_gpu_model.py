@@ -1,0 +1,132 @@
+"""Whole hot path on the GPU through the drop-in modules, against reference fixtures and the oracle.
+Tolerances (north_star): probabilities within 2e-3 absolute; thresholded decisions (shipped opt_thresholds)
+identical on >= 99.9 % of frames."""
+import numpy as np
+import pytest
+import torch
+
+import sed_oracle as so
+from conftest import load_golden, synthetic_sd
+from sed_b200 import models, synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ARGS = {sr: (sr,) + synth.PRESETS[sr][:2] + (64,) + synth.PRESETS[sr][2:] + (25, "logmel") for sr in synth.PRESETS}
+
+
+def build(mt, sr=16000, precision="fp16"):
+    model = getattr(models, mt)(*ARGS[sr])
+    model.load_state_dict(synthetic_sd(mt, sr))
+    model.precision = precision
+    return model.to(DEV).eval()
+
+
+def tag(mt):
+    return "gru" if "Gru" in mt else "transformer"
+
+
+@pytest.mark.parametrize("mt", synth.MODEL_TYPES)
+@pytest.mark.parametrize("sr", [16000, 8000, 32000])
+def test_model_matches_reference_golden(mt, sr):
+    g = load_golden("model_%s_%dk.npz" % (tag(mt), sr // 1000))
+    wave = (torch.from_numpy(g["wave_i16"]).float() / 32767.0).to(DEV)
+    out = build(mt, sr)(wave)
+    assert set(out) == {"framewise_output", "clipwise_output", "embedding"}
+    for k in ("framewise_output", "clipwise_output"):
+        got = out[k].cpu().numpy()
+        assert got.shape == g[k].shape and got.dtype == np.float32
+        assert np.abs(got - g[k]).max() <= 2e-3, (k, np.abs(got - g[k]).max())
+    emb = out["embedding"].cpu().numpy()
+    assert emb.shape == g["embedding"].shape
+    tol = 2e-3 if "Gru" in mt else 2e-2  # Transformer embedding = un-squashed ReLU features (|x| up to ~5)
+    assert np.abs(emb - g["embedding"]).max() <= tol
+
+
+@pytest.mark.parametrize("mt", synth.MODEL_TYPES)
+def test_full_size_clips_and_thresholded_decisions(mt, thresholds):
+    g = load_golden("model_%s_full.npz" % tag(mt))
+    thr = np.asarray(thresholds["%s/best_logmel_16k.sed.valid.pkl" % mt]["sed_high_threshold"])
+    low = np.asarray(thresholds["%s/best_logmel_16k.sed.valid.pkl" % mt]["sed_low_threshold"])
+    model = build(mt)
+    for name, L in (("10s", 160000), ("5s", 80000)):
+        wave = torch.cat([synth.synthetic_waveform(2, L, seed=77, kind="events"), synth.synthetic_waveform(1, L, seed=78)])
+        chk = g["wave_checksum_" + name]
+        assert abs(wave.double().sum().item() - chk[0]) < 1e-6 and abs(wave.double().abs().sum().item() - chk[1]) < 1e-6
+        out = model(wave.to(DEV))
+        fw = out["framewise_output"].cpu().numpy()
+        ref = g["framewise_" + name]
+        assert fw.shape == ref.shape  # 1000 / 500 (GRU pads 496 -> 500) / 496 (Transformer)
+        assert np.abs(fw - ref).max() <= 2e-3
+        assert np.abs(out["clipwise_output"].cpu().numpy() - g["clipwise_" + name]).max() <= 2e-3
+        for t in (thr, low):
+            agree = ((fw > t[None, None, :]) == (ref > t[None, None, :])).mean()
+            assert agree >= 0.999, (name, agree)
+
+
+@pytest.mark.parametrize("mt", synth.MODEL_TYPES)
+def test_batch_shards_are_bit_identical(mt):
+    """Clips are independent: run(B) == concat(run(shards)) exactly, for any micro-batch split."""
+    model = build(mt)
+    wave = synth.synthetic_waveform(5, 48000, seed=11, kind="events").to(DEV)
+    full = model(wave)
+    parts = [model(wave[0:2]), model(wave[2:5])]
+    model.micro_batch = 2
+    mb = model(wave)
+    model.micro_batch = 148
+    for k in ("framewise_output", "clipwise_output"):
+        cat = torch.cat([p[k] for p in parts], 0)
+        assert torch.equal(full[k], cat), k
+        assert torch.equal(full[k], mb[k]), k
+    single = model(wave[3:4])
+    assert torch.equal(single["clipwise_output"], full["clipwise_output"][3:4])
+
+
+def test_conv_variants_give_identical_outputs():
+    model = build("Cnn_9layers_Gru_FrameAtt")
+    wave = synth.synthetic_waveform(2, 80000, seed=3, kind="events").to(DEV)
+    a = model(wave)
+    model.conv_variant = 1
+    b = model(wave)
+    assert torch.equal(a["framewise_output"], b["framewise_output"])
+
+
+def test_bf16_operand_mode_is_available_and_looser():
+    mt = "Cnn_9layers_Gru_FrameAtt"
+    g = load_golden("model_gru_16k.npz")
+    wave = (torch.from_numpy(g["wave_i16"]).float() / 32767.0).to(DEV)
+    out = build(mt, precision="bf16")(wave)
+    err = np.abs(out["framewise_output"].cpu().numpy() - g["framewise_output"]).max()
+    assert err <= 5e-2  # bf16 operands: ~8x the fp16 error (precision table)
+
+
+def test_reload_invalidates_packed_weights():
+    mt = "Cnn_9layers_Gru_FrameAtt"
+    model = build(mt)
+    wave = synth.synthetic_waveform(1, 32000, seed=5).to(DEV)
+    a = model(wave)["clipwise_output"].clone()
+    sd2 = synth.synthetic_state_dict(mt, 16000, seed=1)
+    model.load_state_dict(sd2)
+    b = model(wave)["clipwise_output"]
+    ref = so.model_forward(sd2, wave.cpu(), mt, 512, 160)["clipwise_output"]
+    assert not torch.equal(a, b)
+    assert (b.cpu() - ref).abs().max() <= 2e-3
+
+
+def test_host_buffer_entry_matches_device_entry():
+    from sed_b200 import engine
+    mt = "Cnn_9layers_Gru_FrameAtt"
+    pm = engine.PackedModel(synthetic_sd(mt), mt, 512, 160, torch.device(DEV))
+    wave = synth.synthetic_waveform(5, 80000, seed=21).pin_memory()
+    host = pm.forward_host(wave, micro_batch=2)
+    dev = pm.forward(wave.to(DEV), micro_batch=2)
+    assert torch.equal(host["framewise_output"], dev["framewise_output"].cpu())
+    assert torch.equal(host["clipwise_output"], dev["clipwise_output"].cpu())
+
+
+def test_data_parallel_wrapper_single_gpu():
+    """Reference callers wrap the model in torch.nn.DataParallel (main_strong.py:541)."""
+    mt = "Cnn_9layers_Transformer_FrameAtt"
+    model = torch.nn.DataParallel(build(mt), device_ids=[0])
+    wave = synth.synthetic_waveform(2, 32000, seed=8).to(DEV)
+    out = model(wave)
+    assert out["framewise_output"].shape == (2, 200, 25)

@@ -1,0 +1,83 @@
+"""Host-side packing logic (no GPU): BN folding, banded mel matrix, DFT-structure check, GRU weight order."""
+import numpy as np
+import pytest
+import torch
+
+import sed_oracle as so
+from conftest import synthetic_sd
+from sed_b200 import engine, melbank, synth
+from sed_b200 import dist as sdist
+
+
+def test_fold_bn_equals_eval_batchnorm():
+    sd = synthetic_sd("Cnn_9layers_Gru_FrameAtt")
+    x = torch.randn(2, 64, 5, 7)
+    s, b = engine.fold_bn(sd, "conv_block1.bn2")
+    ref = so.bn_eval(x, sd, "conv_block1.bn2")
+    assert torch.allclose(x * s[None, :, None, None] + b[None, :, None, None], ref, atol=2e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("sr", [8000, 16000, 32000])
+def test_band_mel_reconstructs_matrix(sr):
+    n_fft, hop, fmin, fmax = synth.PRESETS[sr]
+    W = melbank.mel_filterbank(sr, n_fft, 64, fmin, fmax)
+    lo, ln, off, val = engine.band_mel(W)
+    R = np.zeros(W.shape, np.float32)
+    for m in range(64):
+        R[lo[m]:lo[m] + ln[m], m] = val[off[m]:off[m] + ln[m]].numpy()
+    assert np.array_equal(R, W.numpy())
+    assert int(ln.sum()) < 0.06 * W.numel()  # triangular filters: ~2.6 % dense
+
+
+def test_band_mel_handles_dense_and_empty_columns():
+    W = torch.rand(17, 5)
+    W[:, 2] = 0
+    lo, ln, off, val = engine.band_mel(W)
+    assert ln[2] == 0 and ln[0] == 17
+
+
+def test_windowed_dft_check_accepts_reference_and_rejects_others():
+    wr, wi = melbank.windowed_dft_kernels(512, 512, "hann")
+    win = engine.check_windowed_dft(wr, wi, 512)
+    assert torch.allclose(win, torch.from_numpy(melbank.hann_periodic(512)).float(), atol=1e-7)
+    with pytest.raises(NotImplementedError):
+        engine.check_windowed_dft(wr + 0.01 * torch.randn_like(wr), wi, 512)
+    # shorter window padded to n_fft is still window x DFT
+    wr2, wi2 = melbank.windowed_dft_kernels(512, 400, "hann")
+    engine.check_windowed_dft(wr2, wi2, 512)
+
+
+def test_twiddle_table():
+    tw = engine.twiddle_table(512).numpy()
+    k = 37
+    assert abs(tw[k, 0] - np.cos(2 * np.pi * k / 512)) < 1e-7 and abs(tw[k, 1] + np.sin(2 * np.pi * k / 512)) < 1e-7
+
+
+def test_gru_weight_block_order():
+    """Row (96*q + 32*g + jj) of the packed recurrent matrix is W_hh[g*256 + 32*q + jj] (sed_b200.h: sed_bigru)."""
+    whh = torch.arange(768 * 256, dtype=torch.float32).view(768, 256)
+    packed = whh.view(3, 8, 32, 256).permute(1, 0, 2, 3).reshape(768, 256)
+    for q, g, jj in ((0, 0, 0), (3, 1, 7), (7, 2, 31)):
+        assert torch.equal(packed[96 * q + 32 * g + jj], whh[g * 256 + 32 * q + jj])
+
+
+def test_shard_bounds_cover_batch_contiguously():
+    for B, n in ((4096, 8), (1024, 3), (5, 8), (7, 2)):
+        spans = [sdist.shard_bounds(B, n, r) for r in range(n)]
+        assert spans[0][0] == 0 and spans[-1][1] == B
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+def test_synthetic_waveform_is_int16_quantised_and_seeded():
+    a = synth.synthetic_waveform(2, 1000, seed=1234, rank=0)
+    b = synth.synthetic_waveform(2, 1000, seed=1234, rank=0)
+    c = synth.synthetic_waveform(2, 1000, seed=1234, rank=1)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    q = a * 32767.0
+    assert torch.allclose(q, torch.round(q), atol=1e-3)
+
+
+def test_flops_per_clip_match_survey():
+    f = so.flops_per_clip(1001, 512)
+    assert abs(f["conv"] - 26.031) < 0.01 and abs(f["total"] - 26.892) < 0.02
