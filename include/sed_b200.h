@@ -86,13 +86,17 @@ int sed_conv3x3_bn_relu(const void* x, int NB, int H, int W, int cin, const void
 int sed_linear(const void* a16, long M, int K, const void* w16, const float* bias, int N, int relu, float* out,
                void* out16, int dtype, void* stream);
 
+/* Bytes of device scratch sed_bigru needs for a batch of B clips (16-bit hidden-state exchange buffer). */
+long sed_bigru_workspace_bytes(int B);
+
 /* Bidirectional GRU recurrence, hidden 256, gate order r,z,n, h0 = 0.
  * Replaces nn.GRU.forward pytorch/models.py:670 given the input projections.
  *   gi [B, T, 1536] f32 = x W_ih^T + b_ih, columns [dir][gate][256];
  *   whh_packed [2*768, 256] 16-bit, row (dir*768 + 96*q + 32*g + jj) = W_hh[dir][g*256 + 32*q + jj];
- *   bhh [2][768] f32; out [B, T, 512] f32 = [forward | backward]. */
-int sed_bigru(const float* gi, const void* whh_packed, const float* bhh, int B, int T, float* out, int dtype,
-              void* stream);
+ *   bhh [2][768] f32; out [B, T, 512] f32 = [forward | backward];
+ *   workspace: sed_bigru_workspace_bytes(B) bytes, 128-byte aligned, contents irrelevant. */
+int sed_bigru(const float* gi, const void* whh_packed, const float* bhh, int B, int T, float* out, void* workspace,
+              int dtype, void* stream);
 
 /* softmax(q k^T / 8) v for 8 heads of 64.  Replaces ScaledDotProductAttention.forward
  * pytorch/models.py:808-820 and the head split/merge :863-875.

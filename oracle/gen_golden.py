@@ -81,7 +81,8 @@ def main():
             seconds = 2.0 if sr == 16000 else 1.5
             L = int(sr * seconds)
             wave = torch.cat([synth.synthetic_waveform(3, L, seed=31, kind="events", sample_rate=sr),
-                              synth.synthetic_waveform(1, L, seed=32, kind="noise"), torch.zeros(1, L)])
+                              synth.synthetic_waveform(1, L, seed=32, kind="noise"),
+                              0.01 * synth.synthetic_waveform(1, L, seed=33, kind="noise"), torch.zeros(1, L)])
             q = torch.round(wave * 32767.0).to(torch.int16)
             wave = q.float() / 32767.0
             with torch.no_grad():

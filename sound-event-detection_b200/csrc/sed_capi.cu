@@ -5,7 +5,7 @@
 
 #include "sed_kernels.h"
 
-#define SED_ABI_VERSION 1
+#define SED_ABI_VERSION 2
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -106,10 +106,12 @@ int sed_linear(const void* a16, long M, int K, const void* w16, const float* bia
   return sed::linear_launch(a16, M, K, w16, bias, N, relu, out, out16, dtype, as_stream(stream));
 }
 
-int sed_bigru(const float* gi, const void* whh_packed, const float* bhh, int B, int T, float* out, int dtype,
-              void* stream) {
-  SED_REQUIRE(gi); SED_REQUIRE(whh_packed); SED_REQUIRE(bhh); SED_REQUIRE(out);
-  return sed::gru_launch(gi, whh_packed, bhh, B, T, out, dtype, as_stream(stream));
+long sed_bigru_workspace_bytes(int B) { return B > 0 ? static_cast<long>(sed::gru_workspace_bytes(B)) : 0; }
+
+int sed_bigru(const float* gi, const void* whh_packed, const float* bhh, int B, int T, float* out, void* workspace,
+              int dtype, void* stream) {
+  SED_REQUIRE(gi); SED_REQUIRE(whh_packed); SED_REQUIRE(bhh); SED_REQUIRE(out); SED_REQUIRE(workspace);
+  return sed::gru_launch(gi, whh_packed, bhh, B, T, out, workspace, dtype, as_stream(stream));
 }
 
 int sed_mha_core(const float* qkv, int B, int T, void* out16, int dtype, void* stream) {

@@ -1,6 +1,7 @@
 // Internal launcher interface between the kernel translation units and the C-ABI (sed_capi.cu).
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 namespace sed {
@@ -39,8 +40,9 @@ int conv3x3_launch(const void* x, int NB, int H, int W, int cin, const void* wpa
 int linear_launch(const void* a16, long M, int K, const void* w16, const float* bias, int N, int relu, float* out,
                   void* out16, int dtype, cudaStream_t stream);
 
-int gru_launch(const float* gi, const void* whh_packed, const float* bhh, int B, int T, float* out, int dtype,
-               cudaStream_t stream);
+size_t gru_workspace_bytes(int B);
+int gru_launch(const float* gi, const void* whh_packed, const float* bhh, int B, int T, float* out, void* workspace,
+               int dtype, cudaStream_t stream);
 
 int mha_core_launch(const float* qkv, int B, int T, void* out16, int dtype, cudaStream_t stream);
 

@@ -1,11 +1,9 @@
 // Temporal blocks and the frame-attention head for sm_100a.
 //
 //  * gru_kernel      : persistent bidirectional GRU recurrence (pytorch/models.py:614-615, 670; gate order
-//                      r, z, n).  One CTA owns 128 clips of one direction for all T steps.  The hidden state
-//                      is the UMMA A operand (16-bit, SWIZZLE_128B, double-buffered in shared memory); the
-//                      recurrent weights stream through a TMA ring in 96-row blocks ordered [r|z|n] x 32
-//                      hidden units, so the gate math for those units runs straight out of TMEM while the
-//                      next block's MMA is in flight.  The float32 state lives in the output tensor.
+//                      r, z, n).  An 8-CTA cluster owns 128 clips of one direction for all T steps; each CTA
+//                      keeps a 96-row [r|z|n] x 32-unit slice of W_hh resident in shared memory and the f32
+//                      state of its units in registers; h_t is exchanged through L2 + TMA once per step.
 //  * mha_core_kernel : softmax(q k^T / sqrt(64)) v per (clip, head)  (models.py:799-820, 863-875), float32,
 //                      one query row per thread, K/V of the head resident in shared memory.
 //  * attpool_kernel  : AttBlock + interpolate + pad_framewise_output (models.py:161-169, 84-95, 65-81).
@@ -15,184 +13,219 @@
 namespace sed {
 
 // =================================================================================================
-// GRU recurrence
+// GRU recurrence: one 8-CTA cluster per (128-clip block, direction)
 // =================================================================================================
-constexpr int kGruChunkRows = 96;    // 32 hidden units x 3 gates per weight block
-constexpr int kGruChunks = 8;        // 256 / 32
-constexpr int kGruABuf = 4 * 16384;  // 128 clips x 256 k x 2 B
-constexpr int kGruBStage = 4 * kGruChunkRows * 128;  // 4 k-chunks x 96 rows x 128 B
-constexpr int kGruSB = 2;
-constexpr int kGruSmem = 1024 + 2 * kGruABuf + kGruSB * kGruBStage + 256;
+// CTA `q` of the cluster owns hidden units 32q..32q+31 of all three gates: its 96x256 slice of W_hh stays
+// resident in shared memory for all T steps and its threads keep the float32 state of those units in
+// registers.  Per step every CTA (1) TMA-loads the full 16-bit h_{t-1} [128 x 256] (the UMMA A operand),
+// (2) issues 16 tcgen05.mma (M=128, N=96, K=256) into TMEM, (3) runs the gate math for its 32 units, writes
+// h_t (f32) to the output and the 16-bit copy to a double-buffered exchange tensor in global memory (L2),
+// and (4) signals the h_ready mbarrier of all 8 CTAs (remote arrive, release/acquire at cluster scope).
+constexpr int kGruCluster = 8;
+constexpr int kGruChunkRows = 96;                    // 32 hidden units x 3 gates
+constexpr int kGruWBytes = 4 * kGruChunkRows * 128;  // 4 k-chunks x 96 rows x 128 B
+constexpr int kGruABytes = 4 * 16384;                // 128 clips x 256 k x 2 B
+constexpr int kGruSmem = 1024 + kGruWBytes + kGruABytes + 512;
+constexpr int kGruThreads = 64 + 256;  // TMA warp, MMA warp, 8 gate-math warps (2 per TMEM lane quarter)
+
+SED_DEVICE_INLINE void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+SED_DEVICE_INLINE void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+SED_DEVICE_INLINE void mbar_arrive_remote(uint64_t* bar, uint32_t cta_rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(cta_rank)
+      : "memory");
+}
+SED_DEVICE_INLINE void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+SED_DEVICE_INLINE float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+SED_DEVICE_INLINE float fast_tanh(float x) {
+  // 1 - 2 / (exp(2x) + 1); |error| ~1e-7 absolute, far below the 16-bit operand rounding of h W_hh^T
+  return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f);
+}
 
 template <typename T>
-__global__ void __launch_bounds__(192, 1)
-gru_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ gi, const float* __restrict__ bhh,
-           int B, int Tn, float* __restrict__ out) {
+__global__ void __cluster_dims__(kGruCluster, 1, 1) __launch_bounds__(kGruThreads, 1)
+gru_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH,
+           const float* __restrict__ gi, const float* __restrict__ bhh, int B, int Bpad, int Tn,
+           float* __restrict__ out, T* __restrict__ hx) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;                       // [2][4][128 rows][128 B]
-  uint8_t* smem_b = smem + 2 * kGruABuf;        // [SB][4][96 rows][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kGruSB * kGruBStage);
-  uint64_t* b_full = bars;            // [2]
-  uint64_t* b_empty = bars + 2;       // [2]
-  uint64_t* acc_full = bars + 4;      // [2]
-  uint64_t* acc_empty = bars + 6;     // [2]
-  uint64_t* h_ready = bars + 8;       // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint8_t* smem_w = smem;                 // [4][96 rows][128 B]   resident W_hh slice
+  uint8_t* smem_a = smem + kGruWBytes;    // [4][128 rows][128 B]  h_{t-1}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + kGruABytes);
+  uint64_t* w_full = bars;
+  uint64_t* a_full = bars + 1;
+  uint64_t* acc_full = bars + 2;
+  uint64_t* h_ready = bars + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  float* s_bias = reinterpret_cast<float*>(bars + 5);  // [3][32] b_hh of this CTA's units
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x % kGruCluster;  // == %cluster_ctarank for cluster dims (8,1,1)
+  const int clip0 = (blockIdx.x / kGruCluster) * 128;
   const int dir = blockIdx.y;
-  const int clip0 = blockIdx.x * 128;
 
   // h_{-1} = 0 (nn.GRU default h0)
-  for (int i = threadIdx.x; i < kGruABuf / 16; i += blockDim.x)
+  for (int i = threadIdx.x; i < kGruABytes / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(smem_a)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
+  if (threadIdx.x < 96)
+    s_bias[threadIdx.x] = bhh[dir * 768 + (threadIdx.x >> 5) * 256 + q * 32 + (threadIdx.x & 31)];
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmW);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&b_full[i], 1);
-      mbar_init(&b_empty[i], 1);
-      mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);
-    }
-    mbar_init(h_ready, 4);
+    tma_prefetch_desc(&tmH);
+    mbar_init(w_full, 1);
+    mbar_init(a_full, 1);
+    mbar_init(acc_full, 1);
+    mbar_init(h_ready, kGruCluster * 8);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, 128);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // every CTA's barriers are initialised before anyone signals them remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (elect_one()) {
-      uint32_t sb = 0, pb = 0;
-      for (int s = 0; s < Tn; ++s) {
-        for (int q = 0; q < kGruChunks; ++q) {
-          mbar_wait(&b_empty[sb], pb ^ 1);
-          mbar_expect_tx(&b_full[sb], kGruBStage);
+      mbar_expect_tx(w_full, kGruWBytes);
 #pragma unroll
-          for (int kc = 0; kc < 4; ++kc)
-            tma_load_2d(smem_b + sb * kGruBStage + kc * (kGruChunkRows * 128), &tmW, &b_full[sb], kc * 64,
-                        dir * 768 + q * kGruChunkRows);
-          if (++sb == kGruSB) { sb = 0; pb ^= 1; }
-        }
+      for (int kc = 0; kc < 4; ++kc)
+        tma_load_2d(smem_w + kc * (kGruChunkRows * 128), &tmW, w_full, kc * 64, dir * 768 + q * kGruChunkRows);
+      for (int s = 1; s < Tn; ++s) {
+        mbar_wait_cluster(h_ready, (s - 1) & 1);  // all 8 slices of h_{s-1} are in the exchange buffer
+        fence_proxy_async_all();                  // generic-proxy global writes -> async-proxy (TMA) reads
+        mbar_expect_tx(a_full, kGruABytes);
+        const int row = (((s - 1) & 1) * 2 + dir) * Bpad + clip0;
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) tma_load_2d(smem_a + kc * 16384, &tmH, a_full, kc * 64, row);
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_f16(Elem16<T>::kFmt, 128, kGruChunkRows);
-      uint32_t sb = 0, pb = 0, acc = 0, pacc = 0;
+      mbar_wait(w_full, 0);
+      const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_w);
       for (int s = 0; s < Tn; ++s) {
-        if (s > 0) {
-          mbar_wait(h_ready, (s - 1) & 1);
-          tc_fence_after();
-        }
-        const uint32_t a_base = smem_u32(smem_a + (s & 1) * kGruABuf);
-        for (int q = 0; q < kGruChunks; ++q) {
-          mbar_wait(&acc_empty[acc], pacc ^ 1);
-          mbar_wait(&b_full[sb], pb);
-          tc_fence_after();
-          const uint32_t b_base = smem_u32(smem_b + sb * kGruBStage);
+        if (s > 0) mbar_wait(a_full, (s - 1) & 1);
+        tc_fence_after();
 #pragma unroll
-          for (int kc = 0; kc < 4; ++kc) {
+        for (int kc = 0; kc < 4; ++kc) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_f16(tmem_base + acc * kGruChunkRows, umma_desc_sw128(a_base + kc * 16384 + k * 32, 1024),
-                       umma_desc_sw128(b_base + kc * (kGruChunkRows * 128) + k * 32, 1024), idesc, (kc | k) ? 1u : 0u);
-            }
+          for (int k = 0; k < 4; ++k) {
+            umma_f16(tmem_base, umma_desc_sw128(a_base + kc * 16384 + k * 32, 1024),
+                     umma_desc_sw128(b_base + kc * (kGruChunkRows * 128) + k * 32, 1024), idesc, (kc | k) ? 1u : 0u);
           }
-          umma_commit(&b_empty[sb]);
-          umma_commit(&acc_full[acc]);
-          if (++sb == kGruSB) { sb = 0; pb ^= 1; }
-          if (++acc == 2) { acc = 0; pacc ^= 1; }
         }
+        umma_commit(acc_full);
       }
     }
   } else {
-    const int quarter = warp & 3;
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;         // which 16 of the CTA's 32 hidden units this warp owns
     const int m = quarter * 32 + lane;
     const int clip = clip0 + m;
     const bool valid = clip < B;
-    const float* bh = bhh + dir * 768;
-    uint32_t acc = 0, pacc = 0;
+    const int u0 = q * 32 + half * 16;        // first hidden unit of this thread
+    float h[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) h[j] = 0.0f;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * 16;
     for (int s = 0; s < Tn; ++s) {
       const int t = dir ? (Tn - 1 - s) : s;
-      const int t_prev = dir ? (t + 1) : (t - 1);
-      const float* gi_row = gi + (static_cast<size_t>(clip) * Tn + t) * 1536 + dir * 768;
-      float* out_row = out + (static_cast<size_t>(clip) * Tn + t) * 512 + dir * 256;
-      const float* prev_row = out + (static_cast<size_t>(clip) * Tn + t_prev) * 512 + dir * 256;
-      uint8_t* a_next = smem_a + ((s + 1) & 1) * kGruABuf;
-      for (int q = 0; q < kGruChunks; ++q) {
-        mbar_wait(&acc_full[acc], pacc);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + acc * kGruChunkRows + (static_cast<uint32_t>(quarter * 32) << 16);
+      const float* gi_row = gi + (static_cast<size_t>(clip) * Tn + t) * 1536 + dir * 768 + u0;
+      float* out_row = out + (static_cast<size_t>(clip) * Tn + t) * 512 + dir * 256 + u0;
+      // input projections for this step: issued before the accumulator wait so they overlap the MMA
+      float4 gr[4], gz[4], gn[4];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t ar[16], az[16], an[16];
-          tmem_ld16(taddr + half * 16, ar);
-          tmem_ld16(taddr + 32 + half * 16, az);
-          tmem_ld16(taddr + 64 + half * 16, an);
-          tmem_ld_wait();
-          const int j0 = q * 32 + half * 16;
-          float hn[16];
-#pragma unroll
-          for (int v4 = 0; v4 < 4; ++v4) {
-            float4 gr = make_float4(0, 0, 0, 0), gz = gr, gn = gr, hp = gr;
-            if (valid) {
-              gr = *reinterpret_cast<const float4*>(gi_row + j0 + v4 * 4);
-              gz = *reinterpret_cast<const float4*>(gi_row + 256 + j0 + v4 * 4);
-              gn = *reinterpret_cast<const float4*>(gi_row + 512 + j0 + v4 * 4);
-              if (s > 0) hp = *reinterpret_cast<const float4*>(prev_row + j0 + v4 * 4);
-            }
-            const float grv[4] = {gr.x, gr.y, gr.z, gr.w}, gzv[4] = {gz.x, gz.y, gz.z, gz.w};
-            const float gnv[4] = {gn.x, gn.y, gn.z, gn.w}, hpv[4] = {hp.x, hp.y, hp.z, hp.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int jj = v4 * 4 + e;
-              const int j = j0 + jj;
-              const float r = 1.0f / (1.0f + expf(-(grv[e] + __uint_as_float(ar[jj]) + __ldg(bh + j))));
-              const float z = 1.0f / (1.0f + expf(-(gzv[e] + __uint_as_float(az[jj]) + __ldg(bh + 256 + j))));
-              const float nn = tanhf(gnv[e] + r * (__uint_as_float(an[jj]) + __ldg(bh + 512 + j)));
-              hn[jj] = (1.0f - z) * nn + z * hpv[e];
-            }
-            if (valid)
-              *reinterpret_cast<float4*>(out_row + j0 + v4 * 4) =
-                  make_float4(hn[v4 * 4], hn[v4 * 4 + 1], hn[v4 * 4 + 2], hn[v4 * 4 + 3]);
-          }
-          // 16-bit copy of h_t into the next step's A operand (SWIZZLE_128B K-major layout)
-          const int kc = j0 >> 6;
-          const int c16 = (j0 & 63) >> 3;
-          uint8_t* rowp = a_next + kc * 16384 + m * 128;
-          uint4 q0, q1;
-          q0.x = Elem16<T>::pack2(hn[0], hn[1]);   q0.y = Elem16<T>::pack2(hn[2], hn[3]);
-          q0.z = Elem16<T>::pack2(hn[4], hn[5]);   q0.w = Elem16<T>::pack2(hn[6], hn[7]);
-          q1.x = Elem16<T>::pack2(hn[8], hn[9]);   q1.y = Elem16<T>::pack2(hn[10], hn[11]);
-          q1.z = Elem16<T>::pack2(hn[12], hn[13]); q1.w = Elem16<T>::pack2(hn[14], hn[15]);
-          if (!valid) { q0 = make_uint4(0, 0, 0, 0); q1 = q0; }
-          *reinterpret_cast<uint4*>(rowp + ((c16 ^ (m & 7)) << 4)) = q0;
-          *reinterpret_cast<uint4*>(rowp + (((c16 + 1) ^ (m & 7)) << 4)) = q1;
+      for (int v = 0; v < 4; ++v) {
+        if (valid) {
+          gr[v] = *reinterpret_cast<const float4*>(gi_row + v * 4);
+          gz[v] = *reinterpret_cast<const float4*>(gi_row + 256 + v * 4);
+          gn[v] = *reinterpret_cast<const float4*>(gi_row + 512 + v * 4);
+        } else {
+          gr[v] = gz[v] = gn[v] = make_float4(0, 0, 0, 0);
         }
+      }
+      mbar_wait(acc_full, s & 1);
+      tc_fence_after();
+      uint32_t ar[16], az[16], an[16];
+      tmem_ld16(taddr, ar);
+      tmem_ld16(taddr + 32, az);
+      tmem_ld16(taddr + 64, an);
+      tmem_ld_wait();
+#pragma unroll
+      for (int v4 = 0; v4 < 4; ++v4) {
+        const float grv[4] = {gr[v4].x, gr[v4].y, gr[v4].z, gr[v4].w};
+        const float gzv[4] = {gz[v4].x, gz[v4].y, gz[v4].z, gz[v4].w};
+        const float gnv[4] = {gn[v4].x, gn[v4].y, gn[v4].z, gn[v4].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int jj = v4 * 4 + e;
+          const int j = half * 16 + jj;
+          const float r = fast_sigmoid(grv[e] + __uint_as_float(ar[jj]) + s_bias[j]);
+          const float z = fast_sigmoid(gzv[e] + __uint_as_float(az[jj]) + s_bias[32 + j]);
+          const float nn = fast_tanh(gnv[e] + r * (__uint_as_float(an[jj]) + s_bias[64 + j]));
+          h[jj] = (1.0f - z) * nn + z * h[jj];
+        }
+      }
+      if (valid) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          *reinterpret_cast<float4*>(out_row + v * 4) = make_float4(h[4 * v], h[4 * v + 1], h[4 * v + 2], h[4 * v + 3]);
+      }
+      if (s + 1 < Tn) {
+        // 16-bit copy of this thread's slice of h_t into exchange buffer (s & 1)
+        T* hx_row = hx + (static_cast<size_t>((s & 1) * 2 + dir) * Bpad + clip) * 256 + u0;
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          uint4 pk;
+          pk.x = Elem16<T>::pack2(h[8 * v], h[8 * v + 1]);
+          pk.y = Elem16<T>::pack2(h[8 * v + 2], h[8 * v + 3]);
+          pk.z = Elem16<T>::pack2(h[8 * v + 4], h[8 * v + 5]);
+          pk.w = Elem16<T>::pack2(h[8 * v + 6], h[8 * v + 7]);
+          reinterpret_cast<uint4*>(hx_row)[v] = pk;
+        }
+        fence_proxy_async_all();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[acc]);
-        if (++acc == 2) { acc = 0; pacc ^= 1; }
+        if (lane == 0) {
+#pragma unroll
+          for (int r = 0; r < kGruCluster; ++r) mbar_arrive_remote(h_ready, r);
+        }
       }
-      fence_proxy_async_smem();  // generic-proxy writes of h_t -> visible to the UMMA (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(h_ready);
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 128);
   }
 }
 
@@ -200,8 +233,25 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int gru_launch(const float* gi, const void* whh_packed, const float* bhh, int B, int Tn, float* out, int dtype,
-               cudaStream_t stream) {
+static int encode_2d(EncodeTiledFn enc, CUtensorMap* m, int dtype, void* base, uint64_t cols, uint64_t rows,
+                     uint32_t box_rows) {
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstr[1] = {cols * 2};
+  const cuuint32_t box[2] = {64, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim,
+                   gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SED_OK : SED_ERR_DRIVER;
+}
+
+size_t gru_workspace_bytes(int B) {
+  const size_t bpad = (static_cast<size_t>(B) + 127) / 128 * 128;
+  return 2 * 2 * bpad * 256 * 2;
+}
+
+int gru_launch(const float* gi, const void* whh_packed, const float* bhh, int B, int Tn, float* out, void* workspace,
+               int dtype, cudaStream_t stream) {
   if (B <= 0 || Tn <= 0) {
     set_error("gru: bad shape B=%d T=%d", B, Tn);
     return SED_ERR_BAD_SHAPE;
@@ -213,27 +263,26 @@ int gru_launch(const float* gi, const void* whh_packed, const float* bhh, int B,
     set_error("cuTensorMapEncodeTiled entry point unavailable");
     return SED_ERR_DRIVER;
   }
-  CUtensorMap tmW;
-  const cuuint64_t gdim[2] = {256, 2 * 768};
-  const cuuint64_t gstr[1] = {256 * 2};
-  const cuuint32_t box[2] = {64, kGruChunkRows};
-  const cuuint32_t estr[2] = {1, 1};
-  CUresult r = reinterpret_cast<EncodeTiledFn>(fp)(
-      &tmW, dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-      const_cast<void*>(whh_packed), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("gru: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(fp);
+  const int Bpad = (B + 127) / 128 * 128;
+  CUtensorMap tmW, tmH;
+  if (encode_2d(enc, &tmW, dtype, const_cast<void*>(whh_packed), 256, 2 * 768, kGruChunkRows) != SED_OK ||
+      encode_2d(enc, &tmH, dtype, workspace, 256, 4ull * Bpad, 128) != SED_OK) {
+    set_error("gru: cuTensorMapEncodeTiled failed");
     return SED_ERR_DRIVER;
   }
-  dim3 grid((B + 127) / 128, 2);
+  dim3 grid(kGruCluster * (Bpad / 128), 2);
   cudaError_t e;
   if (dtype == 0) {
     e = cudaFuncSetAttribute(gru_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGruSmem);
-    if (e == cudaSuccess) gru_kernel<__half><<<grid, 192, kGruSmem, stream>>>(tmW, gi, bhh, B, Tn, out);
+    if (e == cudaSuccess)
+      gru_kernel<__half><<<grid, kGruThreads, kGruSmem, stream>>>(tmW, tmH, gi, bhh, B, Bpad, Tn, out,
+                                                                  reinterpret_cast<__half*>(workspace));
   } else {
     e = cudaFuncSetAttribute(gru_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGruSmem);
-    if (e == cudaSuccess) gru_kernel<__nv_bfloat16><<<grid, 192, kGruSmem, stream>>>(tmW, gi, bhh, B, Tn, out);
+    if (e == cudaSuccess)
+      gru_kernel<__nv_bfloat16><<<grid, kGruThreads, kGruSmem, stream>>>(tmW, tmH, gi, bhh, B, Bpad, Tn, out,
+                                                                         reinterpret_cast<__nv_bfloat16*>(workspace));
   }
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {

@@ -292,8 +292,9 @@ class PackedModel:
         if self.model_type == "Cnn_9layers_Gru_FrameAtt":
             gi = self.linear(flat, self.gru_wih, self.gru_bih)
             out = torch.empty((B, Tp, 512), dtype=torch.float32, device=self.device)
+            ws = torch.empty((lib.sed_bigru_workspace_bytes(B),), dtype=torch.uint8, device=self.device)
             rc = lib.sed_bigru(capi.ptr(gi), capi.ptr(self.gru_whh), capi.ptr(self.gru_bhh), B, Tp, capi.ptr(out),
-                               self.dtype_code, stream)
+                               capi.ptr(ws), self.dtype_code, stream)
             capi.check(rc, "sed_bigru")
             capi._count()
             if stages is not None:

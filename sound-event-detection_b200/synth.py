@@ -147,7 +147,7 @@ def synthetic_state_dict(model_type, sample_rate=16000, seed=0, calib_seconds=3.
         sd["multihead.fc.bias"] = 0.05 * torch.randn(512, generator=g)
 
     # head gain chosen so framewise probabilities span roughly [0.02, 0.98] on the synthetic inputs
-    gain = 1.25 if model_type == "Cnn_9layers_Gru_FrameAtt" else 0.6
+    gain = 1.0 if model_type == "Cnn_9layers_Gru_FrameAtt" else 0.5
     sd["att_block.att.weight"] = _xavier_uniform((25, 512, 1), g, gain=gain)
     sd["att_block.att.bias"] = 0.3 * torch.randn(25, generator=g)
     sd["att_block.cla.weight"] = _xavier_uniform((25, 512, 1), g, gain=gain)

@@ -9,7 +9,7 @@ from sed_b200 import capi
 def _declared_functions():
     src = open(capi.HEADER_PATH).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    decls = re.findall(r"\b(?:int|const char\s*\*)\s+(sed_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", src, flags=re.S)
+    decls = re.findall(r"\b(?:int|long|const char\s*\*)\s+(sed_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", src, flags=re.S)
     out = {}
     for name, args in decls:
         args = args.strip()
@@ -35,7 +35,7 @@ def test_binding_matches_header():
     for name, nargs in decl.items():
         assert len(capi.SIGNATURES[name][0]) == nargs, name
     lib = capi.load()
-    assert lib.sed_abi_version() == 1
+    assert lib.sed_abi_version() == 2
     assert isinstance(lib.sed_last_error_string(), bytes)
 
 

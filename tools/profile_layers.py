@@ -67,8 +67,9 @@ def main():
         rows.append(("gru input projection (B=%d)" % B, t * mb / B, 2.0 * mb * 125 * 1536 * 512, 0))
         gi = pm.linear(featB.view(-1, 512), pm.gru_wih, pm.gru_bih)
         out = torch.empty((B, 125, 512), dtype=torch.float32, device=dev)
+        gws = torch.empty((lib.sed_bigru_workspace_bytes(B),), dtype=torch.uint8, device=dev)
         t = timeit(lambda: lib.sed_bigru(capi.ptr(gi), capi.ptr(pm.gru_whh), capi.ptr(pm.gru_bhh), B, 125, capi.ptr(out),
-                                         pm.dtype_code, stream))
+                                         capi.ptr(gws), pm.dtype_code, stream))
         rows.append(("gru recurrence (B=%d)" % B, t * mb / B, 2.0 * mb * 125 * 2 * 768 * 256, 0))
         x = out
     else:
