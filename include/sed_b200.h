@@ -112,12 +112,6 @@ int sed_attpool(const float* x, int B, int T, const float* w_att, const float* b
                 const float* b_cla, int ratio, int frames_out, float* clip, float* frame, float* cla_t,
                 float* norm_att_t, void* stream);
 
-/* Test hook: as sed_conv3x3_bn_relu with an explicit UMMA descriptor base-offset policy for the
- * haloed-patch variant (0 = none, 1 = (addr >> 7) & 7). */
-int sed_conv3x3_bn_relu_dbg(const void* x, int NB, int H, int W, int cin, const void* wpacked, const float* scale,
-                            const float* shift, int cout, int mode, void* out, int dtype, int variant,
-                            int bo_mode, void* stream);
-
 #ifdef __cplusplus
 }
 #endif

@@ -83,21 +83,15 @@ int sed_conv_first_f32(const float* x, int NB, int H, int W, const float* w9, co
   return sed::conv_first_launch(x, NB, H, W, w9, scale, shift, out, dtype, as_stream(stream));
 }
 
-int sed_conv3x3_bn_relu_dbg(const void* x, int NB, int H, int W, int cin, const void* wpacked, const float* scale,
-                            const float* shift, int cout, int mode, void* out, int dtype, int variant,
-                            int bo_mode, void* stream) {
+int sed_conv3x3_bn_relu(const void* x, int NB, int H, int W, int cin, const void* wpacked, const float* scale,
+                        const float* shift, int cout, int mode, void* out, int dtype, int variant, void* stream) {
   SED_REQUIRE(x); SED_REQUIRE(wpacked); SED_REQUIRE(scale); SED_REQUIRE(shift); SED_REQUIRE(out);
   if (variant != 0 && variant != 1) {
     sed::set_error("sed_conv3x3_bn_relu: variant must be 0 (patch) or 1 (per-tap)");
     return SED_ERR_UNSUPPORTED;
   }
-  return sed::conv3x3_launch(x, NB, H, W, cin, wpacked, scale, shift, cout, mode, out, dtype, variant, bo_mode,
+  return sed::conv3x3_launch(x, NB, H, W, cin, wpacked, scale, shift, cout, mode, out, dtype, variant,
                              as_stream(stream));
-}
-
-int sed_conv3x3_bn_relu(const void* x, int NB, int H, int W, int cin, const void* wpacked, const float* scale,
-                        const float* shift, int cout, int mode, void* out, int dtype, int variant, void* stream) {
-  return sed_conv3x3_bn_relu_dbg(x, NB, H, W, cin, wpacked, scale, shift, cout, mode, out, dtype, variant, 0, stream);
 }
 
 int sed_linear(const void* a16, long M, int K, const void* w16, const float* bias, int N, int relu, float* out,

@@ -173,7 +173,7 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
     const long items = static_cast<long>(groups) * p.nslices;
     grid = items < num_sms() ? static_cast<int>(items) : num_sms();
   }
-  kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("conv_umma launch: %s", cudaGetErrorString(e));
@@ -206,8 +206,7 @@ static int conv3x3_dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, Conv
 }
 
 int conv3x3_launch(const void* x, int NB, int H, int W, int cin, const void* wpacked, const float* scale,
-                   const float* shift, int cout, int mode, void* out, int dtype, int variant, int bo_mode,
-                   cudaStream_t stream) {
+                   const float* shift, int cout, int mode, void* out, int dtype, int variant, cudaStream_t stream) {
   if (NB <= 0 || H <= 0 || W <= 0 || (W % 8) != 0 || (cin % 64) != 0) {
     set_error("conv3x3: bad shape NB=%d H=%d W=%d cin=%d", NB, H, W, cin);
     return SED_ERR_BAD_SHAPE;
@@ -250,7 +249,6 @@ int conv3x3_launch(const void* x, int NB, int H, int W, int cin, const void* wpa
   p.scale = scale; p.shift = shift;
   p.out = out; p.out2 = nullptr;
   p.M = 0; p.ldc = 0; p.relu = 1;
-  p.patch_bo_mode = bo_mode;
   if (dtype == 0) return conv3x3_dispatch<__half>(tmA, tmB, p, cin, cout, mode, variant, stream);
   if (dtype == 1) return conv3x3_dispatch<__nv_bfloat16>(tmA, tmB, p, cin, cout, mode, variant, stream);
   set_error("conv3x3: dtype must be 0 (fp16) or 1 (bf16)");

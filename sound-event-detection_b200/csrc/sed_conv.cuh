@@ -34,7 +34,6 @@ struct ConvParams {
   void* out;               // EPI 0/1/2: 16-bit NHWC ; EPI 3: float [M, ldc]
   void* out2;              // EPI 3: optional 16-bit copy [M, ldc] (may be null)
   int M, ldc, relu;        // linear only
-  int patch_bo_mode;       // PATCH-mode descriptor base_offset policy: 0 = none, 1 = (addr>>7)&7
 };
 
 constexpr int kPatchBytes = 180 * 128;       // 18 x 10 pixels x 64 ch x 2 B
@@ -43,6 +42,10 @@ constexpr int kTileBytes = 128 * 128;        // 128 pixels x 64 ch x 2 B
 
 template <int CIN, int BN, int NT, bool BRES, bool PATCH, int EPI, int SA, int SB>
 struct ConvCfg {
+  // epilogue warps: 2 per TMEM lane quarter when the accumulator cannot be double-buffered (the drain is
+  // then on the critical path), else 1 per quarter
+  static constexpr int EW = (2 * NT * BN <= 512) ? 4 : 8;
+  static constexpr int THREADS = 64 + 32 * EW;
   static constexpr int TAPS = (EPI == EPI_LINEAR) ? 1 : 9;
   static constexpr int NCHUNK = CIN / 64;
   static constexpr int A_STAGE = NT * (PATCH ? kPatchStride : kTileBytes);
@@ -61,8 +64,22 @@ struct ConvCfg {
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
+// UMMA shared-memory descriptor split into its constant high word and an address-carrying low word:
+// consecutive operands differ only by a small addend on the low word (addresses are < 256 KB, so the
+// 14-bit start-address field never carries), which keeps the single issuing thread at ~2 integer
+// instructions per tcgen05.mma.
+SED_DEVICE_INLINE constexpr uint32_t desc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+SED_DEVICE_INLINE uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+SED_DEVICE_INLINE uint64_t desc_join(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+
 template <typename T, int CIN, int BN, int NT, bool BRES, bool PATCH, int EPI, int SA, int SB>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(ConvCfg<CIN, BN, NT, BRES, PATCH, EPI, SA, SB>::THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const ConvParams p) {
   using Cfg = ConvCfg<CIN, BN, NT, BRES, PATCH, EPI, SA, SB>;
@@ -113,7 +130,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], Cfg::EW); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -192,6 +209,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // =============================== MMA issuer =============================================
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_f16(Elem16<T>::kFmt, 128, BN);
+      constexpr uint32_t a_hi = desc_hi_sw128(PATCH ? 1280 : 1024);
+      constexpr uint32_t b_hi = desc_hi_sw128(1024);
+      constexpr uint32_t a_tile_step = (PATCH ? kPatchStride : kTileBytes) >> 4;
+      const uint32_t a_lo0 = desc_lo(smem_u32(smem_a));
+      const uint32_t b_lo0 = desc_lo(smem_u32(smem_b));
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
       if (BRES) {
         mbar_wait(&b_full[0], 0);
@@ -202,40 +224,35 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         const uint32_t d_base = tmem_base + acc * Cfg::ACC_COLS;
         for (int c = 0; c < NCHUNK; ++c) {
+          uint32_t a_lo = 0;
           if (PATCH) {
             mbar_wait(&a_full[sa], pa);
             tc_fence_after();
+            a_lo = a_lo0 + sa * (Cfg::A_STAGE >> 4);
           }
+#pragma unroll
           for (int tap = 0; tap < TAPS; ++tap) {
             if (!PATCH) {
               mbar_wait(&a_full[sa], pa);
               tc_fence_after();
+              a_lo = a_lo0 + sa * (Cfg::A_STAGE >> 4);
             }
-            uint32_t b_addr;
+            uint32_t b_lo;
             if (BRES) {
-              b_addr = smem_u32(smem_b + (c * TAPS + tap) * Cfg::B_BLOCK);
+              b_lo = b_lo0 + (c * TAPS + tap) * (Cfg::B_BLOCK >> 4);
             } else {
               mbar_wait(&b_full[sb], pb);
               tc_fence_after();
-              b_addr = smem_u32(smem_b + sb * Cfg::B_BLOCK);
+              b_lo = b_lo0 + sb * (Cfg::B_BLOCK >> 4);
             }
+            // PATCH: tap (r, s) is the same haloed buffer shifted by (r*10 + s) pixel rows of 128 B
+            const uint32_t tap_off = PATCH ? ((tap / 3) * 10 + (tap % 3)) * 8 : 0;
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
-              uint32_t a_addr;
-              uint32_t a_sbo;
-              if (PATCH) {
-                a_addr = smem_u32(smem_a + sa * Cfg::A_STAGE + t * kPatchStride) + ((tap / 3) * 10 + (tap % 3)) * 128;
-                a_sbo = 1280;
-              } else {
-                a_addr = smem_u32(smem_a + sa * Cfg::A_STAGE + t * kTileBytes);
-                a_sbo = 1024;
-              }
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                uint64_t adesc = umma_desc_sw128(a_addr + k * 32, a_sbo);
-                if (PATCH && p.patch_bo_mode == 1) adesc |= static_cast<uint64_t>((a_addr >> 7) & 7u) << 49;
-                umma_f16(d_base + t * BN, adesc, umma_desc_sw128(b_addr + k * 32, 1024), idesc,
-                         (c | tap | k) ? 1u : 0u);
+                umma_f16(d_base + t * BN, desc_join(a_lo + t * a_tile_step + tap_off + k * 2, a_hi),
+                         desc_join(b_lo + k * 2, b_hi), idesc, (c | tap | k) ? 1u : 0u);
               }
             }
             if (!PATCH) {
@@ -257,8 +274,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    // =============================== epilogue (4 warps) =====================================
+    // =============================== epilogue (EW warps) =====================================
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int chalf = (warp - 2) >> 2;       // EW == 8: which half of the BN columns this warp drains
+    constexpr int CPW = BN / (Cfg::EW / 4);  // columns per warp
+    constexpr int LDB = (CPW >= 64) ? 4 : CPW / 16;  // 16-column TMEM loads in flight per wait
     const int m = quarter * 32 + lane;       // row of the 128-row tile
     const int hl = m >> 3, wl = m & 7;
     uint32_t acc = 0, pacc = 0;
@@ -276,11 +296,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int n = 0, h0 = 0, w0 = 0;
         if (EPI != EPI_LINEAR) tile_coords(tile, n, h0, w0);
         const int h = h0 + hl, w = w0 + wl;
-        const uint32_t taddr = tmem_base + acc * Cfg::ACC_COLS + t * BN + (static_cast<uint32_t>(quarter * 32) << 16);
-        for (int cc = 0; cc < BN / 16; ++cc) {
-          uint32_t r[16];
-          tmem_ld16(taddr + cc * 16, r);
+        const uint32_t taddr = tmem_base + acc * Cfg::ACC_COLS + t * BN + chalf * CPW +
+                               (static_cast<uint32_t>(quarter * 32) << 16);
+        for (int cb = 0; cb < CPW / 16; cb += LDB) {
+          uint32_t rr[LDB][16];
+#pragma unroll
+          for (int u = 0; u < LDB; ++u) tmem_ld16(taddr + (cb + u) * 16, rr[u]);
           tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < LDB; ++u) {
+          const int cc = chalf * (CPW / 16) + cb + u;
+          const uint32_t(&r)[16] = rr[u];
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -378,6 +404,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 reinterpret_cast<uint4*>(d2)[1] = q1;
               }
             }
+          }
           }
         }
       }

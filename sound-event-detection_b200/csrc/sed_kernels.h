@@ -34,8 +34,7 @@ int conv_first_launch(const float* x, int NB, int H, int W, const float* w9, con
 
 // mode: 0 = store NHWC, 1 = 2x2 avg-pool, 2 = freq-mean (W must be 8) ; variant: 0 = patch (halo reuse), 1 = per-tap
 int conv3x3_launch(const void* x, int NB, int H, int W, int cin, const void* wpacked, const float* scale,
-                   const float* shift, int cout, int mode, void* out, int dtype, int variant, int bo_mode,
-                   cudaStream_t stream);
+                   const float* shift, int cout, int mode, void* out, int dtype, int variant, cudaStream_t stream);
 
 int linear_launch(const void* a16, long M, int K, const void* w16, const float* bias, int N, int relu, float* out,
                   void* out16, int dtype, cudaStream_t stream);

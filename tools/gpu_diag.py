@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
-STAGES = ["frontend", "conv_first", "conv_tap", "conv_patch", "conv_patch_bo1", "linear", "gru", "mha", "attpool",
+STAGES = ["frontend", "conv_first", "conv_tap", "conv_patch", "linear", "gru", "mha", "attpool",
           "model_gru", "model_tr"]
 
 
@@ -92,9 +92,8 @@ def run_stage(stage):
         print("conv_first rel/abs err", rel_err(out.float(), ref))
         return
 
-    if stage in ("conv_tap", "conv_patch", "conv_patch_bo1"):
+    if stage in ("conv_tap", "conv_patch"):
         variant = 1 if stage == "conv_tap" else 0
-        bo = 1 if stage == "conv_patch_bo1" else 0
         for (name, cin, cout, mode) in engine.CONV_LAYERS:
             W = {64: 64 if cout == 64 else 32, 128: 32 if cout == 128 else 16, 256: 16 if cout == 256 else 8, 512: 8}[cin]
             for (NB, H) in ((1, 16), (3, 37)):
@@ -107,9 +106,8 @@ def run_stage(stage):
                 out = torch.full(oshape, float("nan"), dtype=td, device=dev)
                 t0 = time.time()
                 xd, sc, sh = x.to(dev), scale.to(dev), shift.to(dev)
-                rc = lib.sed_conv3x3_bn_relu_dbg(capi.ptr(xd), NB, H, W, cin, capi.ptr(wp), capi.ptr(sc),
-                                                 capi.ptr(sh), cout, mode, capi.ptr(out), code, variant, bo,
-                                                 stream)
+                rc = lib.sed_conv3x3_bn_relu(capi.ptr(xd), NB, H, W, cin, capi.ptr(wp), capi.ptr(sc),
+                                             capi.ptr(sh), cout, mode, capi.ptr(out), code, variant, stream)
                 capi.check(rc, name)
                 torch.cuda.synchronize()
                 ref = conv_ref(x.float(), w.float(), scale, shift, mode)
