@@ -79,59 +79,149 @@ static int num_sms() {
 }
 
 // ---------------------------------------------------------------------------------------------
-// conv_block1.conv1 (Cin = 1): CUDA cores, float32 in, 16-bit NHWC out.  models.py:128 (first conv)
-// Each thread owns 8 output channels (weights in registers) and walks over pixels; a warp writes
-// 4 pixels x 128 B contiguous per store instruction.
+// conv_block1.conv1 (Cin = 1, K = 9 taps) + bn1 + ReLU.  pytorch/models.py:128 (first conv of block 1)
+//
+// Float32-grade accuracy on the tensor cores: the 3x3 neighbourhood of each output pixel (9 taps padded
+// to K = 16) and the weights are split into fp16 hi + lo parts and three tcgen05.mma (hi*hi + lo*hi +
+// hi*lo, M = 128 pixels, N = 64 channels, K = 16) accumulate in fp32 TMEM -- the dropped lo*lo term is
+// ~2^-22 relative.  Each CTA loops over tiles of 2 rows x 64 mel bins: its 128 threads gather the taps
+// straight from the log-mel tensor (L1/L2 resident), write the K-major SWIZZLE_32B operand rows, one thread
+// issues the MMAs, then every thread drains its own TMEM lane (one pixel, 64 channels), applies the folded
+// BatchNorm + ReLU and stores 128 contiguous bytes of NHWC output.  Two CTAs per SM overlap the phases.
 // ---------------------------------------------------------------------------------------------
+SED_DEVICE_INLINE constexpr uint32_t desc_hi_sw32(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (6u << 29);  // layout_type 6 = SWIZZLE_32B
+}
+
 template <typename T>
-__global__ void __launch_bounds__(256)
-conv_first_kernel(const float* __restrict__ x, int H, int W, const float* __restrict__ w9,
-                  const float* __restrict__ scale, const float* __restrict__ shift, T* __restrict__ out) {
-  constexpr int ROWS = 8;
-  __shared__ float s_in[ROWS + 2][72];  // W == 64 plus one zero column each side
-  const int n = blockIdx.y;
-  const int h_base = blockIdx.x * ROWS;
-  for (int i = threadIdx.x; i < (ROWS + 2) * 66; i += blockDim.x) {
-    const int r = i / 66, c = i % 66;
-    const int h = h_base + r - 1, w = c - 1;
-    float v = 0.0f;
-    if (h >= 0 && h < H && w >= 0 && w < W) v = x[(static_cast<size_t>(n) * H + h) * W + w];
-    s_in[r][c] = v;
-  }
-  const int cg = threadIdx.x & 7;   // channels cg*8 .. cg*8+7
-  const int pl = threadIdx.x >> 3;  // 0..31
-  float wr[8][9], sc[8], sh[8];
+__global__ void __launch_bounds__(128, 2)
+conv_first_umma_kernel(const float* __restrict__ x, int NB, int H, const float* __restrict__ w9,
+                       const float* __restrict__ scale, const float* __restrict__ shift, T* __restrict__ out) {
+  constexpr int W = 64;
+  __shared__ __align__(1024) uint8_t s_a[2][128 * 32];   // A hi / lo: 128 pixel rows x 16 taps (32 B)
+  __shared__ __align__(1024) uint8_t s_b[2][64 * 32];    // B hi / lo: 64 channel rows x 16 taps
+  __shared__ float s_scale[64], s_shift[64];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  // ---- weights -> split fp16 operand rows (row = channel, 32 B, 16-byte chunk j stored at j ^ bit2(row)) ----
+  if (tid < 64) {
+    float wv[16];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    sc[j] = scale[cg * 8 + j];
-    sh[j] = shift[cg * 8 + j];
+    for (int t = 0; t < 16; ++t) wv[t] = (t < 9) ? w9[tid * 9 + t] : 0.0f;
+    uint32_t hi[8], lo[8];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) wr[j][t] = w9[(cg * 8 + j) * 9 + t];
-  }
-  __syncthreads();
-  for (int pix = pl; pix < ROWS * 64; pix += 32) {
-    const int r = pix >> 6, c = pix & 63;
-    const int h = h_base + r;
-    if (h >= H) break;
-    float in[9];
-#pragma unroll
-    for (int dr = 0; dr < 3; ++dr)
-#pragma unroll
-      for (int dc = 0; dc < 3; ++dc) in[dr * 3 + dc] = s_in[r + dr][c + dc];
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float a = 0.0f;
-#pragma unroll
-      for (int t = 0; t < 9; ++t) a = fmaf(in[t], wr[j][t], a);
-      v[j] = fmaxf(fmaf(a, sc[j], sh[j]), 0.0f);
+    for (int t = 0; t < 8; ++t) {
+      const __half h0 = __float2half_rn(wv[2 * t]), h1 = __float2half_rn(wv[2 * t + 1]);
+      const __half l0 = __float2half_rn(wv[2 * t] - __half2float(h0));
+      const __half l1 = __float2half_rn(wv[2 * t + 1] - __half2float(h1));
+      hi[t] = static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
+      lo[t] = static_cast<uint32_t>(__half_as_ushort(l0)) | (static_cast<uint32_t>(__half_as_ushort(l1)) << 16);
     }
-    uint4 q;
-    q.x = Elem16<T>::pack2(v[0], v[1]);
-    q.y = Elem16<T>::pack2(v[2], v[3]);
-    q.z = Elem16<T>::pack2(v[4], v[5]);
-    q.w = Elem16<T>::pack2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * H + h) * W + c) * 64 + cg * 8) = q;
+    const int sw = (tid >> 2) & 1;
+    *reinterpret_cast<uint4*>(&s_b[0][tid * 32 + ((0 ^ sw) << 4)]) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(&s_b[0][tid * 32 + ((1 ^ sw) << 4)]) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    *reinterpret_cast<uint4*>(&s_b[1][tid * 32 + ((0 ^ sw) << 4)]) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(&s_b[1][tid * 32 + ((1 ^ sw) << 4)]) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    s_scale[tid] = scale[tid];
+    s_shift[tid] = shift[tid];
+  }
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&s_tmem, 64);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+  // only fp16 operands here: the fp32-grade split needs the 11-bit significand of fp16 in both parts
+  constexpr uint32_t idesc = umma_idesc_f16(0, 128, 64);
+  constexpr uint32_t d_hi = desc_hi_sw32(256);
+  const uint32_t a_lo_hi = desc_lo(smem_u32(&s_a[0][0])), a_lo_lo = desc_lo(smem_u32(&s_a[1][0]));
+  const uint32_t b_lo_hi = desc_lo(smem_u32(&s_b[0][0])), b_lo_lo = desc_lo(smem_u32(&s_b[1][0]));
+
+  const int tiles_h = (H + 1) >> 1;
+  const int num_tiles = NB * tiles_h;
+  const int hl = tid >> 6, w = tid & 63;
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int n = tile / tiles_h;
+    const int h = (tile - n * tiles_h) * 2 + hl;
+    // ---- gather the 3x3 neighbourhood (zero outside the image: conv padding=1) ----
+    float in[9];
+    const float* xn = x + static_cast<size_t>(n) * H * W;
+#pragma unroll
+    for (int dr = 0; dr < 3; ++dr) {
+      const int hh = h + dr - 1;
+      const bool rok = hh >= 0 && hh < H;
+#pragma unroll
+      for (int dc = 0; dc < 3; ++dc) {
+        const int ww = w + dc - 1;
+        in[dr * 3 + dc] = (rok && ww >= 0 && ww < W) ? __ldg(xn + hh * W + ww) : 0.0f;
+      }
+    }
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const float v0 = (2 * t < 9) ? in[2 * t] : 0.0f;
+      const float v1 = (2 * t + 1 < 9) ? in[2 * t + 1] : 0.0f;
+      const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+      const __half l0 = __float2half_rn(v0 - __half2float(h0)), l1 = __float2half_rn(v1 - __half2float(h1));
+      hi[t] = static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
+      lo[t] = static_cast<uint32_t>(__half_as_ushort(l0)) | (static_cast<uint32_t>(__half_as_ushort(l1)) << 16);
+    }
+    const int sw = (tid >> 2) & 1;
+    *reinterpret_cast<uint4*>(&s_a[0][tid * 32 + ((0 ^ sw) << 4)]) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(&s_a[0][tid * 32 + ((1 ^ sw) << 4)]) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    *reinterpret_cast<uint4*>(&s_a[1][tid * 32 + ((0 ^ sw) << 4)]) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(&s_a[1][tid * 32 + ((1 ^ sw) << 4)]) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();  // operands written by all threads; previous tile's TMEM reads are complete
+    if (tid == 0) {
+      tc_fence_after();
+      umma_f16(tmem_base, desc_join(a_lo_hi, d_hi), desc_join(b_lo_hi, d_hi), idesc, 0u);
+      umma_f16(tmem_base, desc_join(a_lo_lo, d_hi), desc_join(b_lo_hi, d_hi), idesc, 1u);
+      umma_f16(tmem_base, desc_join(a_lo_hi, d_hi), desc_join(b_lo_lo, d_hi), idesc, 1u);
+      umma_commit(&s_bar);
+    }
+    mbar_wait(&s_bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- drain: thread = TMEM lane = pixel (hl, w); 64 channels ----
+    uint32_t r[4][16];
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) tmem_ld16(taddr + u * 16, r[u]);
+    tmem_ld_wait();
+    if (h < H) {
+      T* dst = out + ((static_cast<size_t>(n) * H + h) * W + w) * 64;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = u * 16 + 2 * j;
+          const float v0 = fmaxf(fmaf(__uint_as_float(r[u][2 * j]), s_scale[c], s_shift[c]), 0.0f);
+          const float v1 = fmaxf(fmaf(__uint_as_float(r[u][2 * j + 1]), s_scale[c + 1], s_shift[c + 1]), 0.0f);
+          pk[j] = Elem16<T>::pack2(v0, v1);
+        }
+        reinterpret_cast<uint4*>(dst)[2 * u] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        reinterpret_cast<uint4*>(dst)[2 * u + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
   }
 }
 
@@ -141,12 +231,13 @@ int conv_first_launch(const float* x, int NB, int H, int W, const float* w9, con
     set_error("conv_first: W must be 64 (got %d)", W);
     return SED_ERR_BAD_SHAPE;
   }
-  dim3 grid((H + 7) / 8, NB);
+  const long tiles = static_cast<long>(NB) * ((H + 1) / 2);
+  const int grid = static_cast<int>(tiles < 2L * num_sms() ? tiles : 2L * num_sms());
   if (dtype == 0)
-    conv_first_kernel<__half><<<grid, 256, 0, stream>>>(x, H, W, w9, scale, shift, reinterpret_cast<__half*>(out));
+    conv_first_umma_kernel<__half><<<grid, 128, 0, stream>>>(x, NB, H, w9, scale, shift, reinterpret_cast<__half*>(out));
   else
-    conv_first_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(x, H, W, w9, scale, shift,
-                                                               reinterpret_cast<__nv_bfloat16*>(out));
+    conv_first_umma_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(x, NB, H, w9, scale, shift,
+                                                                    reinterpret_cast<__nv_bfloat16*>(out));
   return cudaGetLastError() == cudaSuccess ? SED_OK : SED_ERR_CUDA;
 }
 

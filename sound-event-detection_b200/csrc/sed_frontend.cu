@@ -27,7 +27,55 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-// One Stockham pass of radix R over N complex points held in shared memory, executed by one warp.
+// Shared-memory FFT buffers are padded by one complex element per 8 so the strided writes of the
+// Stockham passes spread over the banks.
+__device__ __forceinline__ int pidx(int i) { return i + (i >> 3); }
+
+template <int R>
+__device__ __forceinline__ void butterfly(float2 (&v)[R]);
+
+template <>
+__device__ __forceinline__ void butterfly<2>(float2 (&v)[2]) {
+  const float2 a0 = v[0], a1 = v[1];
+  v[0] = make_float2(a0.x + a1.x, a0.y + a1.y);
+  v[1] = make_float2(a0.x - a1.x, a0.y - a1.y);
+}
+
+template <>
+__device__ __forceinline__ void butterfly<4>(float2 (&v)[4]) {
+  const float2 a0 = make_float2(v[0].x + v[2].x, v[0].y + v[2].y);
+  const float2 a1 = make_float2(v[0].x - v[2].x, v[0].y - v[2].y);
+  const float2 a2 = make_float2(v[1].x + v[3].x, v[1].y + v[3].y);
+  const float2 a3 = make_float2(v[1].x - v[3].x, v[1].y - v[3].y);
+  v[0] = make_float2(a0.x + a2.x, a0.y + a2.y);
+  v[1] = make_float2(a1.x + a3.y, a1.y - a3.x);  // a1 - i*a3
+  v[2] = make_float2(a0.x - a2.x, a0.y - a2.y);
+  v[3] = make_float2(a1.x - a3.y, a1.y + a3.x);  // a1 + i*a3
+}
+
+template <>
+__device__ __forceinline__ void butterfly<8>(float2 (&v)[8]) {
+  constexpr float kS = 0.70710678118654752440f;
+  float2 a[4], b[4];
+#pragma unroll
+  for (int n = 0; n < 4; ++n) {
+    a[n] = make_float2(v[n].x + v[n + 4].x, v[n].y + v[n + 4].y);
+    b[n] = make_float2(v[n].x - v[n + 4].x, v[n].y - v[n + 4].y);
+  }
+  // b[n] *= W8^n  (W8 = exp(-2 pi i / 8))
+  b[1] = make_float2((b[1].x + b[1].y) * kS, (b[1].y - b[1].x) * kS);
+  b[2] = make_float2(b[2].y, -b[2].x);
+  b[3] = make_float2((b[3].y - b[3].x) * kS, -(b[3].x + b[3].y) * kS);
+  butterfly<4>(a);
+  butterfly<4>(b);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    v[2 * k] = a[k];
+    v[2 * k + 1] = b[k];
+  }
+}
+
+// One Stockham pass of radix R over N complex points held in (padded) shared memory, executed by one warp.
 // src == nullptr means "first pass": inputs come from the windowed frame pair (re = frame a, im = frame b).
 template <int N, int R>
 __device__ __forceinline__ void fft_pass(const float2* __restrict__ src, float2* __restrict__ dst, int Ns,
@@ -45,7 +93,7 @@ __device__ __forceinline__ void fft_pass(const float2* __restrict__ src, float2*
         const float w = win[idx];
         v[r] = make_float2(w * seg_a[idx], w * seg_b[idx]);
       } else {
-        v[r] = src[idx];
+        v[r] = src[pidx(idx)];
       }
     }
     if (Ns > 1) {
@@ -53,24 +101,10 @@ __device__ __forceinline__ void fft_pass(const float2* __restrict__ src, float2*
 #pragma unroll
       for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tw[r * k * tstride]);
     }
-    if (R == 4) {
-      const float2 a0 = make_float2(v[0].x + v[2].x, v[0].y + v[2].y);
-      const float2 a1 = make_float2(v[0].x - v[2].x, v[0].y - v[2].y);
-      const float2 a2 = make_float2(v[1].x + v[3].x, v[1].y + v[3].y);
-      const float2 a3 = make_float2(v[1].x - v[3].x, v[1].y - v[3].y);
-      // multiply a3 by -i (forward transform): (x, y) -> (y, -x)
-      v[0] = make_float2(a0.x + a2.x, a0.y + a2.y);
-      v[1] = make_float2(a1.x + a3.y, a1.y - a3.x);
-      v[2] = make_float2(a0.x - a2.x, a0.y - a2.y);
-      v[3] = make_float2(a1.x - a3.y, a1.y + a3.x);
-    } else {
-      const float2 a0 = v[0], a1 = v[1];
-      v[0] = make_float2(a0.x + a1.x, a0.y + a1.y);
-      v[1] = make_float2(a0.x - a1.x, a0.y - a1.y);
-    }
+    butterfly<R>(v);
     const int j0 = (j / Ns) * Ns * R + k;
 #pragma unroll
-    for (int r = 0; r < R; ++r) dst[j0 + r * Ns] = v[r];
+    for (int r = 0; r < R; ++r) dst[pidx(j0 + r * Ns)] = v[r];
   }
   __syncwarp();
 }
@@ -91,7 +125,7 @@ frontend_kernel(const float* __restrict__ wave, int L, int T, int hop, const flo
   float* s_seg = smem_f;                                            // [seg_len]
   float* s_win = s_seg + ((seg_len + 3) & ~3);                      // [NFFT]
   float2* s_tw = reinterpret_cast<float2*>(s_win + NFFT);           // [NFFT]
-  float2* s_buf = s_tw + NFFT;                                      // [WARPS][2][NFFT]
+  float2* s_buf = s_tw + NFFT;                                      // [WARPS][2][NFFT + NFFT/8]
 
   const int b = blockIdx.y;
   const int f_base = blockIdx.x * FPB;
@@ -112,8 +146,9 @@ frontend_kernel(const float* __restrict__ wave, int L, int T, int hop, const flo
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float2* buf0 = s_buf + warp * 2 * NFFT;
-  float2* buf1 = buf0 + NFFT;
+  constexpr int BUF = NFFT + NFFT / 8;  // padded (see pidx)
+  float2* buf0 = s_buf + warp * 2 * BUF;
+  float2* buf1 = buf0 + BUF;
 
   for (int pair = warp; pair < FPB / 2; pair += WARPS) {
     const int fa = f_base + 2 * pair;
@@ -122,29 +157,34 @@ frontend_kernel(const float* __restrict__ wave, int L, int T, int hop, const flo
     const float* seg_b = seg_a + hop;
 
     // ---- 2 real frames -> 1 complex FFT of size NFFT (Stockham autosort, natural-order output) ----
+    // radix schedule: 256 = 4*8*8, 512 = 8*8*8, 1024 = 2*8*8*8
     float2* src = nullptr;
     float2* dst = buf0;
     int Ns = 1;
-    constexpr bool kOddLog2 = (NFFT == 512 || NFFT == 2048 || NFFT == 128);
-    if (kOddLog2) {
+    if (NFFT == 1024) {
       fft_pass<NFFT, 2>(src, dst, Ns, s_tw, seg_a, seg_b, s_win, lane);
       Ns = 2;
       src = dst;
       dst = (dst == buf0) ? buf1 : buf0;
-    }
-    while (Ns < NFFT) {
+    } else if (NFFT == 256) {
       fft_pass<NFFT, 4>(src, dst, Ns, s_tw, seg_a, seg_b, s_win, lane);
-      Ns *= 4;
+      Ns = 4;
       src = dst;
       dst = (dst == buf0) ? buf1 : buf0;
     }
-    const float2* Z = src;                        // spectrum of (a + i b)
+    while (Ns < NFFT) {
+      fft_pass<NFFT, 8>(src, dst, Ns, s_tw, seg_a, seg_b, s_win, lane);
+      Ns *= 8;
+      src = dst;
+      dst = (dst == buf0) ? buf1 : buf0;
+    }
+    const float2* Z = src;                        // spectrum of (a + i b), padded indexing
     float* P = reinterpret_cast<float*>(dst);     // P[0..F) = |A|^2, P[F..2F) = |B|^2  (2F <= 2*NFFT floats)
 
     // ---- split the two real spectra and take the power (stft.py:663) ----
     for (int k = lane; k < F; k += 32) {
-      const float2 zk = Z[k & (NFFT - 1)];
-      const float2 zn = Z[(NFFT - k) & (NFFT - 1)];
+      const float2 zk = Z[pidx(k & (NFFT - 1))];
+      const float2 zn = Z[pidx((NFFT - k) & (NFFT - 1))];
       const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
       const float br = 0.5f * (zk.y + zn.y), bi = 0.5f * (zn.x - zk.x);
       P[k] = ar * ar + ai * ai;
@@ -162,7 +202,11 @@ frontend_kernel(const float* __restrict__ wave, int L, int T, int hop, const flo
         for (int k = lane; k < F; k += 32) o[k] = Pf[k];
       } else {
         float* o = out + (static_cast<size_t>(b) * T + f) * n_mels;
-        for (int m = lane; m < n_mels; m += 32) {
+        // bins are visited as (lane, n_mels-1-lane, lane+32, ...): narrow low bands pair with wide high bands
+        for (int mi = lane; mi < n_mels; mi += 32) {
+          const int pr = mi >> 5;
+          const int m = (pr & 1) ? (n_mels - 1 - (mi - 32 * pr) - 32 * (pr >> 1)) : (lane + 32 * (pr >> 1));
+          if (m < 0 || m >= n_mels) continue;
           const int lo = mel_lo[m], len = mel_len[m];
           const float* mv = mel_val + mel_off[m];
           float acc = 0.0f;
@@ -202,7 +246,8 @@ static int launch_frontend(const FrontendArgs& a, cudaStream_t stream) {
   constexpr int WARPS = FrontCfg<NFFT>::WARPS;
   constexpr int FPB = FrontCfg<NFFT>::FPB;
   const int seg_len = (FPB - 1) * a.hop + NFFT;
-  const size_t smem = sizeof(float) * (((seg_len + 3) & ~3) + NFFT) + sizeof(float2) * (NFFT + WARPS * 2 * NFFT);
+  const size_t smem = sizeof(float) * (((seg_len + 3) & ~3) + NFFT) +
+                      sizeof(float2) * (NFFT + WARPS * 2 * (NFFT + NFFT / 8));
   if (smem > 227 * 1024) return SED_ERR_UNSUPPORTED;
   cudaError_t e = cudaFuncSetAttribute(frontend_kernel<NFFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return SED_ERR_CUDA;
