@@ -1,6 +1,7 @@
 // Host-side launchers for the conv stack and the tensor-core GEMM, plus the CUDA-core first layer.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "sed_conv.cuh"
@@ -94,10 +95,12 @@ SED_DEVICE_INLINE constexpr uint32_t desc_hi_sw32(uint32_t sbo_bytes) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(128, 2)
-conv_first_umma_kernel(const float* __restrict__ x, int NB, int H, const float* __restrict__ w9,
-                       const float* __restrict__ scale, const float* __restrict__ shift, T* __restrict__ out) {
+__global__ void __launch_bounds__(128, 4)
+conv_first_umma_kernel(const __grid_constant__ CUtensorMap tmO, const float* __restrict__ x, int NB, int H,
+                       const float* __restrict__ w9, const float* __restrict__ scale,
+                       const float* __restrict__ shift) {
   constexpr int W = 64;
+  __shared__ __align__(1024) uint8_t s_stg[128 * 128];   // output tile, SWIZZLE_128B, TMA-stored
   __shared__ __align__(1024) uint8_t s_a[2][128 * 32];   // A hi / lo: 128 pixel rows x 16 taps (32 B)
   __shared__ __align__(1024) uint8_t s_b[2][64 * 32];    // B hi / lo: 64 channel rows x 16 taps
   __shared__ float s_scale[64], s_shift[64];
@@ -183,6 +186,7 @@ conv_first_umma_kernel(const float* __restrict__ x, int NB, int H, const float* 
     *reinterpret_cast<uint4*>(&s_a[1][tid * 32 + ((1 ^ sw) << 4)]) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
     fence_proxy_async_smem();
     tc_fence_before();
+    if (tid == 0) bulk_wait_read0();  // the previous tile's TMA store has finished reading s_stg
     __syncthreads();  // operands written by all threads; previous tile's TMEM reads are complete
     if (tid == 0) {
       tc_fence_after();
@@ -200,8 +204,8 @@ conv_first_umma_kernel(const float* __restrict__ x, int NB, int H, const float* 
 #pragma unroll
     for (int u = 0; u < 4; ++u) tmem_ld16(taddr + u * 16, r[u]);
     tmem_ld_wait();
-    if (h < H) {
-      T* dst = out + ((static_cast<size_t>(n) * H + h) * W + w) * 64;
+    {
+      uint8_t* rowp = s_stg + tid * 128;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         uint32_t pk[8];
@@ -212,11 +216,18 @@ conv_first_umma_kernel(const float* __restrict__ x, int NB, int H, const float* 
           const float v1 = fmaxf(fmaf(__uint_as_float(r[u][2 * j + 1]), s_scale[c + 1], s_shift[c + 1]), 0.0f);
           pk[j] = Elem16<T>::pack2(v0, v1);
         }
-        reinterpret_cast<uint4*>(dst)[2 * u] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        reinterpret_cast<uint4*>(dst)[2 * u + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        *reinterpret_cast<uint4*>(rowp + (((2 * u) ^ (tid & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(rowp + (((2 * u + 1) ^ (tid & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       }
     }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {  // rows past H (odd H) are clipped by the tensor map
+      tma_store_4d(&tmO, s_stg, 0, 0, (tile - n * tiles_h) * 2, n);
+      bulk_commit();
+    }
   }
+  if (tid == 0) bulk_wait_all0();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -231,13 +242,20 @@ int conv_first_launch(const float* x, int NB, int H, int W, const float* w9, con
     set_error("conv_first: W must be 64 (got %d)", W);
     return SED_ERR_BAD_SHAPE;
   }
+  CUtensorMap tmO;
+  {
+    const uint64_t dims[4] = {64, 64, (uint64_t)H, (uint64_t)NB};
+    const uint64_t str[3] = {64 * 2, 64 * 64 * 2, (uint64_t)H * 64 * 64 * 2};
+    const uint32_t box[4] = {64, 64, 2, 1};
+    int rc = make_map(&tmO, dtype, 4, out, dims, str, box);
+    if (rc) return rc;
+  }
   const long tiles = static_cast<long>(NB) * ((H + 1) / 2);
-  const int grid = static_cast<int>(tiles < 2L * num_sms() ? tiles : 2L * num_sms());
+  const int grid = static_cast<int>(tiles < 4L * num_sms() ? tiles : 4L * num_sms());
   if (dtype == 0)
-    conv_first_umma_kernel<__half><<<grid, 128, 0, stream>>>(x, NB, H, w9, scale, shift, reinterpret_cast<__half*>(out));
+    conv_first_umma_kernel<__half><<<grid, 128, 0, stream>>>(tmO, x, NB, H, w9, scale, shift);
   else
-    conv_first_umma_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(x, NB, H, w9, scale, shift,
-                                                                    reinterpret_cast<__nv_bfloat16*>(out));
+    conv_first_umma_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(tmO, x, NB, H, w9, scale, shift);
   return cudaGetLastError() == cudaSuccess ? SED_OK : SED_ERR_CUDA;
 }
 
@@ -245,7 +263,8 @@ int conv_first_launch(const float* x, int NB, int H, int W, const float* w9, con
 // tcgen05 conv / linear launch
 // ---------------------------------------------------------------------------------------------
 template <typename T, int CIN, int BN, int NT, bool BRES, bool PATCH, int EPI, int SA, int SB>
-static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
+static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvParams& p,
+                      cudaStream_t stream) {
   using Cfg = ConvCfg<CIN, BN, NT, BRES, PATCH, EPI, SA, SB>;
   auto kern = conv_umma_kernel<T, CIN, BN, NT, BRES, PATCH, EPI, SA, SB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -264,7 +283,7 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
     const long items = static_cast<long>(groups) * p.nslices;
     grid = items < num_sms() ? static_cast<int>(items) : num_sms();
   }
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmO, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("conv_umma launch: %s", cudaGetErrorString(e));
@@ -274,22 +293,23 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
 }
 
 template <typename T>
-static int conv3x3_dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvParams& p, int cin, int cout, int mode,
-                            int variant, cudaStream_t stream) {
+static int conv3x3_dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, ConvParams& p,
+                            int cin, int cout, int mode, int variant, cudaStream_t stream) {
   // (cin, cout, mode) are the seven tensor-core layers of Cnn_9layers.
 #define SED_CASE(CIN_, COUT_, MODE_, BN_, NT_, BRES_, SA_P, SB_P, SA_T, SB_T)                                     \
   if (cin == CIN_ && cout == COUT_ && mode == MODE_) {                                                             \
     p.nslices = COUT_ / BN_;                                                                                       \
-    if (variant == 0) return launch_cfg<T, CIN_, BN_, NT_, BRES_, true, MODE_, SA_P, SB_P>(tmA, tmB, p, stream);   \
-    return launch_cfg<T, CIN_, BN_, NT_, BRES_, false, MODE_, SA_T, SB_T>(tmA, tmB, p, stream);                    \
+    if (variant == 0)                                                                                              \
+      return launch_cfg<T, CIN_, BN_, NT_, BRES_, true, MODE_, SA_P, SB_P>(tmA, tmB, tmO, p, stream);              \
+    return launch_cfg<T, CIN_, BN_, NT_, BRES_, false, MODE_, SA_T, SB_T>(tmA, tmB, tmO, p, stream);               \
   }
   //        cin cout mode           BN  NT bres  SA/SB patch  SA/SB tap
   SED_CASE(64, 64, EPI_POOL, 64, 1, true, 4, 1, 6, 1)       // conv_block1.conv2 : weights resident (72 KB)
-  SED_CASE(64, 128, EPI_STORE, 128, 1, true, 3, 1, 4, 1)    // conv_block2.conv1 : weights resident (144 KB)
+  SED_CASE(64, 128, EPI_STORE, 128, 1, true, 2, 1, 2, 1)    // conv_block2.conv1 : weights resident (144 KB)
   SED_CASE(128, 128, EPI_POOL, 64, 1, true, 3, 1, 4, 1)     // conv_block2.conv2 : 2 Cout slices resident
-  SED_CASE(128, 256, EPI_STORE, 64, 1, true, 3, 1, 4, 1)    // conv_block3.conv1 : 4 Cout slices resident
+  SED_CASE(128, 256, EPI_STORE, 64, 1, true, 2, 1, 3, 1)    // conv_block3.conv1 : 4 Cout slices resident
   SED_CASE(256, 256, EPI_POOL, 256, 2, false, 2, 3, 3, 3)   // conv_block3.conv2 : weights streamed, 2 tiles/CTA
-  SED_CASE(256, 512, EPI_STORE, 256, 2, false, 2, 3, 3, 3)  // conv_block4.conv1
+  SED_CASE(256, 512, EPI_STORE, 256, 2, false, 2, 3, 2, 3)  // conv_block4.conv1
   SED_CASE(512, 512, EPI_FREQMEAN, 256, 2, false, 2, 3, 3, 3)  // conv_block4.conv2 (+ freq mean, models.py:668)
 #undef SED_CASE
   set_error("conv3x3: unsupported layer (cin=%d, cout=%d, mode=%d)", cin, cout, mode);
@@ -331,6 +351,14 @@ int conv3x3_launch(const void* x, int NB, int H, int W, int cin, const void* wpa
     int rc = make_map(&tmB, dtype, 2, const_cast<void*>(wpacked), dims, str, box);
     if (rc) return rc;
   }
+  CUtensorMap tmO = tmA;  // only read by the EPI_STORE epilogue
+  if (mode == EPI_STORE) {
+    const uint64_t dims[4] = {(uint64_t)cout, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
+    const uint64_t str[3] = {(uint64_t)cout * 2, (uint64_t)W * cout * 2, (uint64_t)H * W * cout * 2};
+    const uint32_t box[4] = {64, 8, 16, 1};
+    int rc = make_map(&tmO, dtype, 4, out, dims, str, box);
+    if (rc) return rc;
+  }
   ConvParams p{};
   p.NB = NB; p.H = H; p.W = W;
   p.tiles_h = (H + 15) / 16;
@@ -340,8 +368,12 @@ int conv3x3_launch(const void* x, int NB, int H, int W, int cin, const void* wpa
   p.scale = scale; p.shift = shift;
   p.out = out; p.out2 = nullptr;
   p.M = 0; p.ldc = 0; p.relu = 1;
-  if (dtype == 0) return conv3x3_dispatch<__half>(tmA, tmB, p, cin, cout, mode, variant, stream);
-  if (dtype == 1) return conv3x3_dispatch<__nv_bfloat16>(tmA, tmB, p, cin, cout, mode, variant, stream);
+  {
+    const char* e = getenv("SED_CONV_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
+  if (dtype == 0) return conv3x3_dispatch<__half>(tmA, tmB, tmO, p, cin, cout, mode, variant, stream);
+  if (dtype == 1) return conv3x3_dispatch<__nv_bfloat16>(tmA, tmB, tmO, p, cin, cout, mode, variant, stream);
   set_error("conv3x3: dtype must be 0 (fp16) or 1 (bf16)");
   return SED_ERR_UNSUPPORTED;
 }
@@ -393,11 +425,11 @@ int linear_launch(const void* a16, long M, int K, const void* w16, const float* 
     p.out2 = out16 ? (void*)((char*)out16 + (size_t)n0 * 2) : nullptr;
     p.M = (int)M; p.ldc = N; p.relu = relu;
     if (K == 512) {
-      rc = dtype == 0 ? launch_cfg<__half, 512, 128, 1, false, false, EPI_LINEAR, 4, 4>(tmA, tmBp, p, stream)
-                      : launch_cfg<__nv_bfloat16, 512, 128, 1, false, false, EPI_LINEAR, 4, 4>(tmA, tmBp, p, stream);
+      rc = dtype == 0 ? launch_cfg<__half, 512, 128, 1, false, false, EPI_LINEAR, 4, 4>(tmA, tmBp, tmA, p, stream)
+                      : launch_cfg<__nv_bfloat16, 512, 128, 1, false, false, EPI_LINEAR, 4, 4>(tmA, tmBp, tmA, p, stream);
     } else {
-      rc = dtype == 0 ? launch_cfg<__half, 256, 128, 1, false, false, EPI_LINEAR, 4, 4>(tmA, tmBp, p, stream)
-                      : launch_cfg<__nv_bfloat16, 256, 128, 1, false, false, EPI_LINEAR, 4, 4>(tmA, tmBp, p, stream);
+      rc = dtype == 0 ? launch_cfg<__half, 256, 128, 1, false, false, EPI_LINEAR, 4, 4>(tmA, tmBp, tmA, p, stream)
+                      : launch_cfg<__nv_bfloat16, 256, 128, 1, false, false, EPI_LINEAR, 4, 4>(tmA, tmBp, tmA, p, stream);
     }
   }
   return rc;

@@ -34,6 +34,7 @@ struct ConvParams {
   void* out;               // EPI 0/1/2: 16-bit NHWC ; EPI 3: float [M, ldc]
   void* out2;              // EPI 3: optional 16-bit copy [M, ldc] (may be null)
   int M, ldc, relu;        // linear only
+  int dbg;                 // profiling experiments only (SED_CONV_DBG): 1 = no stores, 2 = no drain, 4 = no MMA
 };
 
 constexpr int kPatchBytes = 180 * 128;       // 18 x 10 pixels x 64 ch x 2 B
@@ -42,10 +43,12 @@ constexpr int kTileBytes = 128 * 128;        // 128 pixels x 64 ch x 2 B
 
 template <int CIN, int BN, int NT, bool BRES, bool PATCH, int EPI, int SA, int SB>
 struct ConvCfg {
-  // epilogue warps: 2 per TMEM lane quarter when the accumulator cannot be double-buffered (the drain is
-  // then on the critical path), else 1 per quarter
-  static constexpr int EW = (2 * NT * BN <= 512) ? 4 : 8;
+  // 8 epilogue warps: two per TMEM lane quarter, each draining half of the BN accumulator columns
+  static constexpr int EW = 8;
   static constexpr int THREADS = 64 + 32 * EW;
+  static constexpr int CPW = BN / 2;                                  // accumulator columns per epilogue warp
+  static constexpr int NSTG = (EPI == EPI_STORE) ? (CPW >= 64 ? 2 : 1) : 0;  // 16 KB TMA-store staging tiles
+  static constexpr int SS = BRES ? BN : 512;                          // cached scale/shift entries
   static constexpr int TAPS = (EPI == EPI_LINEAR) ? 1 : 9;
   static constexpr int NCHUNK = CIN / 64;
   static constexpr int A_STAGE = NT * (PATCH ? kPatchStride : kTileBytes);
@@ -56,8 +59,9 @@ struct ConvCfg {
   static constexpr int TMEM_COLS = (ACC_COLS * ACC_STAGES <= 32) ? 32 : (ACC_COLS * ACC_STAGES <= 64) ? 64
                                    : (ACC_COLS * ACC_STAGES <= 128) ? 128 : (ACC_COLS * ACC_STAGES <= 256) ? 256 : 512;
   static constexpr int SMEM_A = SA * A_STAGE;
-  static constexpr int SMEM_MISC = 2 * 512 * 4 + 256;
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + SMEM_A + B_BYTES + SMEM_MISC;
+  static constexpr int SMEM_STG = NSTG * kTileBytes;
+  static constexpr int SMEM_MISC = 2 * SS * 4 + 256;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + SMEM_A + B_BYTES + SMEM_STG + SMEM_MISC;
   static_assert(CIN % 64 == 0, "CIN must be a multiple of 64");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N");
   static_assert(ACC_COLS <= 512, "TMEM columns");
@@ -81,7 +85,7 @@ SED_DEVICE_INLINE uint64_t desc_join(uint32_t lo, uint32_t hi) {
 template <typename T, int CIN, int BN, int NT, bool BRES, bool PATCH, int EPI, int SA, int SB>
 __global__ void __launch_bounds__(ConvCfg<CIN, BN, NT, BRES, PATCH, EPI, SA, SB>::THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const ConvParams p) {
+                 const __grid_constant__ CUtensorMap tmO, const ConvParams p) {
   using Cfg = ConvCfg<CIN, BN, NT, BRES, PATCH, EPI, SA, SB>;
   constexpr int TAPS = Cfg::TAPS;
   constexpr int NCHUNK = Cfg::NCHUNK;
@@ -91,9 +95,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::SMEM_A;
-  float* s_scale = reinterpret_cast<float*>(smem_b + Cfg::B_BYTES);
-  float* s_shift = s_scale + 512;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 512);
+  uint8_t* smem_stg = smem_b + Cfg::B_BYTES;  // [NSTG][128 px][128 B] SWIZZLE_128B staging for TMA stores
+  float* s_scale = reinterpret_cast<float*>(smem_stg + Cfg::SMEM_STG);
+  float* s_shift = s_scale + Cfg::SS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + Cfg::SS);
   uint64_t* a_full = bars;             // [SA]
   uint64_t* a_empty = a_full + SA;     // [SA]
   uint64_t* b_full = a_empty + SA;     // [SB] (index 0 doubles as "resident weights landed")
@@ -121,13 +126,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 
   // ---- one-time setup -------------------------------------------------------------------
-  for (int i = threadIdx.x; i < p.cout && i < 512; i += blockDim.x) {
-    s_scale[i] = (EPI == EPI_LINEAR) ? 1.0f : p.scale[i];
-    s_shift[i] = p.shift ? p.shift[i] : 0.0f;
+  // folded BatchNorm scale / shift (linear: 1 / bias); resident-weight CTAs only cache their own slice
+  const int ss_base = BRES ? fixed_slice * BN : 0;
+  for (int i = threadIdx.x; i < Cfg::SS && ss_base + i < p.cout; i += blockDim.x) {
+    s_scale[i] = (EPI == EPI_LINEAR) ? 1.0f : p.scale[ss_base + i];
+    s_shift[i] = p.shift ? p.shift[ss_base + i] : 0.0f;
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (EPI == EPI_STORE) tma_prefetch_desc(&tmO);
     for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], Cfg::EW); }
@@ -251,8 +259,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int t = 0; t < NT; ++t) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                umma_f16(d_base + t * BN, desc_join(a_lo + t * a_tile_step + tap_off + k * 2, a_hi),
-                         desc_join(b_lo + k * 2, b_hi), idesc, (c | tap | k) ? 1u : 0u);
+                if (!(p.dbg & 4))
+                  umma_f16(d_base + t * BN, desc_join(a_lo + t * a_tile_step + tap_off + k * 2, a_hi),
+                           desc_join(b_lo + k * 2, b_hi), idesc, (c | tap | k) ? 1u : 0u);
               }
             }
             if (!PATCH) {
@@ -276,9 +285,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // =============================== epilogue (EW warps) =====================================
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-    const int chalf = (warp - 2) >> 2;       // EW == 8: which half of the BN columns this warp drains
-    constexpr int CPW = BN / (Cfg::EW / 4);  // columns per warp
+    const int chalf = (warp - 2) >> 2;       // which half of the BN columns this warp drains
+    constexpr int CPW = Cfg::CPW;            // columns per warp
     constexpr int LDB = (CPW >= 64) ? 4 : CPW / 16;  // 16-column TMEM loads in flight per wait
+    // TMA-store staging (EPI_STORE): with CPW >= 64 each column half owns a staging tile and a 128-thread
+    // named barrier; with CPW == 32 all 8 warps fill one 64-channel tile together.
+    constexpr bool kSplitStg = CPW >= 64;
+    const int stg_group = kSplitStg ? chalf : 0;
+    const int stg_threads = kSplitStg ? 128 : 256;
+    const bool stg_leader = (lane == 0) && (warp == (kSplitStg ? 2 + 4 * chalf : 2));
+    uint8_t* stg = smem_stg + stg_group * kTileBytes;
     const int m = quarter * 32 + lane;       // row of the 128-row tile
     const int hl = m >> 3, wl = m & 7;
     uint32_t acc = 0, pacc = 0;
@@ -291,8 +307,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
+        if (p.dbg & 2) break;
         const int tile = g * NT + t;
-        const bool tile_ok = tile < p.num_tiles;
+        const bool tile_ok = (tile < p.num_tiles) && !(p.dbg & 1);
         int n = 0, h0 = 0, w0 = 0;
         if (EPI != EPI_LINEAR) tile_coords(tile, n, h0, w0);
         const int h = h0 + hl, w = w0 + wl;
@@ -310,21 +327,33 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int ch = ch0 + cc * 16 + j;
+            const int ch = (BRES ? 0 : ch0) + cc * 16 + j;
             float x = fmaf(__uint_as_float(r[j]), s_scale[ch], s_shift[ch]);
             if (EPI != EPI_LINEAR || p.relu) x = fmaxf(x, 0.0f);
             v[j] = x;
           }
           if (EPI == EPI_STORE) {
-            if (tile_ok && h < p.H) {
-              uint4 q0, q1;
-              q0.x = Elem16<T>::pack2(v[0], v[1]);   q0.y = Elem16<T>::pack2(v[2], v[3]);
-              q0.z = Elem16<T>::pack2(v[4], v[5]);   q0.w = Elem16<T>::pack2(v[6], v[7]);
-              q1.x = Elem16<T>::pack2(v[8], v[9]);   q1.y = Elem16<T>::pack2(v[10], v[11]);
-              q1.z = Elem16<T>::pack2(v[12], v[13]); q1.w = Elem16<T>::pack2(v[14], v[15]);
-              T* dst = out16 + ((static_cast<size_t>(n) * p.H + h) * p.W + w) * p.cout + ch0 + cc * 16;
-              reinterpret_cast<uint4*>(dst)[0] = q0;
-              reinterpret_cast<uint4*>(dst)[1] = q1;
+            // stage this row's 16 channels in the SWIZZLE_128B tile; one TMA store per 64-channel chunk
+            if (u == 0) {
+              if (stg_leader) bulk_wait_read0();          // previous store has finished reading the tile
+              named_bar_sync(1 + stg_group, stg_threads);
+            }
+            uint4 q0, q1;
+            q0.x = Elem16<T>::pack2(v[0], v[1]);   q0.y = Elem16<T>::pack2(v[2], v[3]);
+            q0.z = Elem16<T>::pack2(v[4], v[5]);   q0.w = Elem16<T>::pack2(v[6], v[7]);
+            q1.x = Elem16<T>::pack2(v[8], v[9]);   q1.y = Elem16<T>::pack2(v[10], v[11]);
+            q1.z = Elem16<T>::pack2(v[12], v[13]); q1.w = Elem16<T>::pack2(v[14], v[15]);
+            const int c16 = ((cc * 16) & 63) >> 3;         // 16-byte chunk of the 64-channel row
+            uint8_t* rowp = stg + m * 128;
+            *reinterpret_cast<uint4*>(rowp + ((c16 ^ (m & 7)) << 4)) = q0;
+            *reinterpret_cast<uint4*>(rowp + (((c16 + 1) ^ (m & 7)) << 4)) = q1;
+            if (u == LDB - 1) {
+              fence_proxy_async_smem();
+              named_bar_sync(1 + stg_group, stg_threads);
+              if (stg_leader && tile_ok) {
+                tma_store_4d(&tmO, stg, ch0 + ((cc * 16) & ~63), w0, h0, n);
+                bulk_commit();
+              }
             }
           } else if (EPI == EPI_POOL) {
             // 2x2 average: partners are lane^1 (w) and lane^8 (h); recursive halving so each lane
@@ -413,6 +442,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (lane == 0) mbar_arrive(&t_empty[acc]);
       if (++acc == ACC_STAGES) { acc = 0; pacc ^= 1; }
     }
+    if (EPI == EPI_STORE && stg_leader) bulk_wait_all0();  // staging tiles must outlive their stores
   }
 
   tc_fence_before();
