@@ -86,8 +86,8 @@ int sed_conv_first_f32(const float* x, int NB, int H, int W, const float* w9, co
 int sed_conv3x3_bn_relu(const void* x, int NB, int H, int W, int cin, const void* wpacked, const float* scale,
                         const float* shift, int cout, int mode, void* out, int dtype, int variant, void* stream) {
   SED_REQUIRE(x); SED_REQUIRE(wpacked); SED_REQUIRE(scale); SED_REQUIRE(shift); SED_REQUIRE(out);
-  if (variant != 0 && variant != 1) {
-    sed::set_error("sed_conv3x3_bn_relu: variant must be 0 (patch) or 1 (per-tap)");
+  if (variant < 0 || variant > 2) {
+    sed::set_error("sed_conv3x3_bn_relu: variant must be 0 (patch), 1 (per-tap) or 2 (CTA pairs)");
     return SED_ERR_UNSUPPORTED;
   }
   return sed::conv3x3_launch(x, NB, H, W, cin, wpacked, scale, shift, cout, mode, out, dtype, variant,

@@ -292,10 +292,42 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   return SED_OK;
 }
 
+template <typename T, int CIN, int BN, int EPI, int SA>
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvParams& p,
+                       cudaStream_t stream) {
+  using Cfg = Conv2Cfg<CIN, BN, EPI, SA>;
+  auto kern = conv_umma2_kernel<T, CIN, BN, EPI, SA>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(pair, smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+    return SED_ERR_CUDA;
+  }
+  const int items = (p.num_tiles + 1) / 2;
+  int pairs_per_slice = (num_sms() / 2) / p.nslices;
+  if (pairs_per_slice > items) pairs_per_slice = items;
+  if (pairs_per_slice < 1) pairs_per_slice = 1;
+  const int grid = 2 * pairs_per_slice * p.nslices;
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmO, p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("conv_umma2 launch: %s", cudaGetErrorString(e));
+    return SED_ERR_CUDA;
+  }
+  return SED_OK;
+}
+
 template <typename T>
 static int conv3x3_dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, ConvParams& p,
                             int cin, int cout, int mode, int variant, cudaStream_t stream) {
   // (cin, cout, mode) are the seven tensor-core layers of Cnn_9layers.
+  // variant 2: CTA-pair (cta_group::2) kernels for the weight-stationary layers
+  if (variant == 2) {
+    if (cin == 64 && cout == 64 && mode == EPI_POOL) { p.nslices = 1; return launch_pair<T, 64, 64, EPI_POOL, 4>(tmA, tmB, tmO, p, stream); }
+    if (cin == 64 && cout == 128 && mode == EPI_STORE) { p.nslices = 1; return launch_pair<T, 64, 128, EPI_STORE, 4>(tmA, tmB, tmO, p, stream); }
+    if (cin == 128 && cout == 128 && mode == EPI_POOL) { p.nslices = 1; return launch_pair<T, 128, 128, EPI_POOL, 3>(tmA, tmB, tmO, p, stream); }
+    if (cin == 128 && cout == 256 && mode == EPI_STORE) { p.nslices = 2; return launch_pair<T, 128, 128, EPI_STORE, 2>(tmA, tmB, tmO, p, stream); }
+    variant = 0;  // streamed-weight layers have no pair variant
+  }
 #define SED_CASE(CIN_, COUT_, MODE_, BN_, NT_, BRES_, SA_P, SB_P, SA_T, SB_T)                                     \
   if (cin == CIN_ && cout == COUT_ && mode == MODE_) {                                                             \
     p.nslices = COUT_ / BN_;                                                                                       \
@@ -336,7 +368,7 @@ int conv3x3_launch(const void* x, int NB, int H, int W, int cin, const void* wpa
     const uint64_t str[3] = {(uint64_t)cin * 2, (uint64_t)W * cin * 2, (uint64_t)H * W * cin * 2};
     const uint32_t box_patch[4] = {64, 10, 18, 1};
     const uint32_t box_tap[4] = {64, 8, 16, 1};
-    int rc = make_map(&tmA, dtype, 4, const_cast<void*>(x), dims, str, variant == 0 ? box_patch : box_tap);
+    int rc = make_map(&tmA, dtype, 4, const_cast<void*>(x), dims, str, variant != 1 ? box_patch : box_tap);
     if (rc) return rc;
   }
   int bn = 0;
@@ -344,6 +376,7 @@ int conv3x3_launch(const void* x, int NB, int H, int W, int cin, const void* wpa
   else if (cin == 64 && cout == 128) bn = 128;
   else if (cin == 128) bn = 64;
   else bn = 256;
+  if (variant == 2 && cin <= 128) bn = (cout == 64) ? 32 : 64;  // each CTA of a pair loads half of the N rows
   {
     const uint64_t dims[2] = {(uint64_t)9 * cin, (uint64_t)cout};
     const uint64_t str[1] = {(uint64_t)9 * cin * 2};

@@ -68,6 +68,151 @@ struct ConvCfg {
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
+// Drain one 128 x BN accumulator tile: this warp handles TMEM lane quarter (warp & 3) and column half
+// `chalf`.  Applies y = max(acc * scale + shift, 0) and the layer's output transform (store / 2x2 avg-pool /
+// mean over the 8 frequency columns / plain GEMM row store).
+template <typename T, int BN, bool BRES, int EPI>
+SED_DEVICE_INLINE void conv_epilogue_tile(const uint32_t taddr, const int chalf, const int warp, const int lane,
+                                          const float* s_scale, const float* s_shift, const int ch0,
+                                          const int tile, const bool tile_ok, const int n, const int h0, const int w0,
+                                          const ConvParams& p, uint8_t* smem_stg, const CUtensorMap* tmO_ptr) {
+  constexpr int CPW = BN / 2;
+  constexpr int LDB = (CPW >= 64) ? 4 : CPW / 16;  // 16-column TMEM loads in flight per wait
+  // TMA-store staging (EPI_STORE): with CPW >= 64 each column half owns a staging tile and a 128-thread
+  // named barrier; with CPW == 32 all 8 warps fill one 64-channel tile together.
+  constexpr bool kSplitStg = CPW >= 64;
+  const int stg_group = kSplitStg ? chalf : 0;
+  const int stg_threads = kSplitStg ? 128 : 256;
+  const bool stg_leader = (lane == 0) && (warp == (kSplitStg ? 2 + 4 * chalf : 2));
+  uint8_t* stg = smem_stg + stg_group * kTileBytes;
+  const int m = (warp & 3) * 32 + lane;  // row of the 128-row tile
+  const int hl = m >> 3, wl = m & 7;
+  const int h = h0 + hl, w = w0 + wl;
+  T* out16 = reinterpret_cast<T*>(p.out);
+  (void)w; (void)out16; (void)stg; (void)stg_leader; (void)stg_threads;
+        for (int cb = 0; cb < CPW / 16; cb += LDB) {
+          uint32_t rr[LDB][16];
+#pragma unroll
+          for (int u = 0; u < LDB; ++u) tmem_ld16(taddr + (cb + u) * 16, rr[u]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < LDB; ++u) {
+          const int cc = chalf * (CPW / 16) + cb + u;
+          const uint32_t(&r)[16] = rr[u];
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int ch = (BRES ? 0 : ch0) + cc * 16 + j;
+            float x = fmaf(__uint_as_float(r[j]), s_scale[ch], s_shift[ch]);
+            if (EPI != EPI_LINEAR || p.relu) x = fmaxf(x, 0.0f);
+            v[j] = x;
+          }
+          if (EPI == EPI_STORE) {
+            // stage this row's 16 channels in the SWIZZLE_128B tile; one TMA store per 64-channel chunk
+            if (u == 0) {
+              if (stg_leader) bulk_wait_read0();          // previous store has finished reading the tile
+              named_bar_sync(1 + stg_group, stg_threads);
+            }
+            uint4 q0, q1;
+            q0.x = Elem16<T>::pack2(v[0], v[1]);   q0.y = Elem16<T>::pack2(v[2], v[3]);
+            q0.z = Elem16<T>::pack2(v[4], v[5]);   q0.w = Elem16<T>::pack2(v[6], v[7]);
+            q1.x = Elem16<T>::pack2(v[8], v[9]);   q1.y = Elem16<T>::pack2(v[10], v[11]);
+            q1.z = Elem16<T>::pack2(v[12], v[13]); q1.w = Elem16<T>::pack2(v[14], v[15]);
+            const int c16 = ((cc * 16) & 63) >> 3;         // 16-byte chunk of the 64-channel row
+            uint8_t* rowp = stg + m * 128;
+            *reinterpret_cast<uint4*>(rowp + ((c16 ^ (m & 7)) << 4)) = q0;
+            *reinterpret_cast<uint4*>(rowp + (((c16 + 1) ^ (m & 7)) << 4)) = q1;
+            if (u == LDB - 1) {
+              fence_proxy_async_smem();
+              named_bar_sync(1 + stg_group, stg_threads);
+              if (stg_leader && tile_ok) {
+                tma_store_4d(tmO_ptr, stg, ch0 + ((cc * 16) & ~63), w0, h0, n);
+                bulk_commit();
+              }
+            }
+          } else if (EPI == EPI_POOL) {
+            // 2x2 average: partners are lane^1 (w) and lane^8 (h); recursive halving so each lane
+            // finishes with 4 channels of one pooled pixel.
+            float k8[8];
+            const bool wodd = (wl & 1) != 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float send = wodd ? v[j] : v[8 + j];
+              const float keep = wodd ? v[8 + j] : v[j];
+              k8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+            }
+            float k4[4];
+            const bool hodd = (hl & 1) != 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float send = hodd ? k8[j] : k8[4 + j];
+              const float keep = hodd ? k8[4 + j] : k8[j];
+              k4[j] = 0.25f * (keep + __shfl_xor_sync(0xffffffffu, send, 8));
+            }
+            const int Hp = p.H >> 1, Wp = p.W >> 1;
+            const int hp = h >> 1, wp = w >> 1;
+            if (tile_ok && hp < Hp) {
+              const int ch = ch0 + cc * 16 + (wodd ? 8 : 0) + (hodd ? 4 : 0);
+              uint2 q;
+              q.x = Elem16<T>::pack2(k4[0], k4[1]);
+              q.y = Elem16<T>::pack2(k4[2], k4[3]);
+              T* dst = out16 + ((static_cast<size_t>(n) * Hp + hp) * Wp + wp) * p.cout + ch;
+              *reinterpret_cast<uint2*>(dst) = q;
+            }
+          } else if (EPI == EPI_FREQMEAN) {
+            // mean over the 8 frequency columns of a row (W == 8): lanes ^1, ^2, ^4
+            float k8[8];
+            const bool b0 = (wl & 1) != 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float send = b0 ? v[j] : v[8 + j];
+              const float keep = b0 ? v[8 + j] : v[j];
+              k8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+            }
+            float k4[4];
+            const bool b1 = (wl & 2) != 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float send = b1 ? k8[j] : k8[4 + j];
+              const float keep = b1 ? k8[4 + j] : k8[j];
+              k4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+            float k2[2];
+            const bool b2 = (wl & 4) != 0;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const float send = b2 ? k4[j] : k4[2 + j];
+              const float keep = b2 ? k4[2 + j] : k4[j];
+              k2[j] = 0.125f * (keep + __shfl_xor_sync(0xffffffffu, send, 4));
+            }
+            if (tile_ok && h < p.H) {
+              const int ch = ch0 + cc * 16 + (b0 ? 8 : 0) + (b1 ? 4 : 0) + (b2 ? 2 : 0);
+              T* dst = out16 + (static_cast<size_t>(n) * p.H + h) * p.cout + ch;
+              *reinterpret_cast<uint32_t*>(dst) = Elem16<T>::pack2(k2[0], k2[1]);
+            }
+          } else {  // EPI_LINEAR
+            const long row = static_cast<long>(tile) * 128 + m;
+            if (tile_ok && row < p.M) {
+              float* dst = reinterpret_cast<float*>(p.out) + row * p.ldc + ch0 + cc * 16;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              if (p.out2) {
+                uint4 q0, q1;
+                q0.x = Elem16<T>::pack2(v[0], v[1]);   q0.y = Elem16<T>::pack2(v[2], v[3]);
+                q0.z = Elem16<T>::pack2(v[4], v[5]);   q0.w = Elem16<T>::pack2(v[6], v[7]);
+                q1.x = Elem16<T>::pack2(v[8], v[9]);   q1.y = Elem16<T>::pack2(v[10], v[11]);
+                q1.z = Elem16<T>::pack2(v[12], v[13]); q1.w = Elem16<T>::pack2(v[14], v[15]);
+                T* d2 = reinterpret_cast<T*>(p.out2) + row * p.ldc + ch0 + cc * 16;
+                reinterpret_cast<uint4*>(d2)[0] = q0;
+                reinterpret_cast<uint4*>(d2)[1] = q1;
+              }
+            }
+          }
+          }
+        }
+}
+
 // UMMA shared-memory descriptor split into its constant high word and an address-carrying low word:
 // consecutive operands differ only by a small addend on the low word (addresses are < 256 KB, so the
 // 14-bit start-address field never carries), which keeps the single issuing thread at ~2 integer
@@ -287,18 +432,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
     const int chalf = (warp - 2) >> 2;       // which half of the BN columns this warp drains
     constexpr int CPW = Cfg::CPW;            // columns per warp
-    constexpr int LDB = (CPW >= 64) ? 4 : CPW / 16;  // 16-column TMEM loads in flight per wait
-    // TMA-store staging (EPI_STORE): with CPW >= 64 each column half owns a staging tile and a 128-thread
-    // named barrier; with CPW == 32 all 8 warps fill one 64-channel tile together.
-    constexpr bool kSplitStg = CPW >= 64;
-    const int stg_group = kSplitStg ? chalf : 0;
-    const int stg_threads = kSplitStg ? 128 : 256;
-    const bool stg_leader = (lane == 0) && (warp == (kSplitStg ? 2 + 4 * chalf : 2));
-    uint8_t* stg = smem_stg + stg_group * kTileBytes;
-    const int m = quarter * 32 + lane;       // row of the 128-row tile
-    const int hl = m >> 3, wl = m & 7;
+    const bool stg_leader = (lane == 0) && (warp == ((CPW >= 64) ? 2 + 4 * chalf : 2));
     uint32_t acc = 0, pacc = 0;
-    T* out16 = reinterpret_cast<T*>(p.out);
     for (int item = item_begin; item < item_end; item += item_stride) {
       const int g = BRES ? item : item / p.nslices;
       const int slice = BRES ? fixed_slice : item - g * p.nslices;
@@ -312,130 +447,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool tile_ok = (tile < p.num_tiles) && !(p.dbg & 1);
         int n = 0, h0 = 0, w0 = 0;
         if (EPI != EPI_LINEAR) tile_coords(tile, n, h0, w0);
-        const int h = h0 + hl, w = w0 + wl;
         const uint32_t taddr = tmem_base + acc * Cfg::ACC_COLS + t * BN + chalf * CPW +
                                (static_cast<uint32_t>(quarter * 32) << 16);
-        for (int cb = 0; cb < CPW / 16; cb += LDB) {
-          uint32_t rr[LDB][16];
-#pragma unroll
-          for (int u = 0; u < LDB; ++u) tmem_ld16(taddr + (cb + u) * 16, rr[u]);
-          tmem_ld_wait();
-#pragma unroll
-          for (int u = 0; u < LDB; ++u) {
-          const int cc = chalf * (CPW / 16) + cb + u;
-          const uint32_t(&r)[16] = rr[u];
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int ch = (BRES ? 0 : ch0) + cc * 16 + j;
-            float x = fmaf(__uint_as_float(r[j]), s_scale[ch], s_shift[ch]);
-            if (EPI != EPI_LINEAR || p.relu) x = fmaxf(x, 0.0f);
-            v[j] = x;
-          }
-          if (EPI == EPI_STORE) {
-            // stage this row's 16 channels in the SWIZZLE_128B tile; one TMA store per 64-channel chunk
-            if (u == 0) {
-              if (stg_leader) bulk_wait_read0();          // previous store has finished reading the tile
-              named_bar_sync(1 + stg_group, stg_threads);
-            }
-            uint4 q0, q1;
-            q0.x = Elem16<T>::pack2(v[0], v[1]);   q0.y = Elem16<T>::pack2(v[2], v[3]);
-            q0.z = Elem16<T>::pack2(v[4], v[5]);   q0.w = Elem16<T>::pack2(v[6], v[7]);
-            q1.x = Elem16<T>::pack2(v[8], v[9]);   q1.y = Elem16<T>::pack2(v[10], v[11]);
-            q1.z = Elem16<T>::pack2(v[12], v[13]); q1.w = Elem16<T>::pack2(v[14], v[15]);
-            const int c16 = ((cc * 16) & 63) >> 3;         // 16-byte chunk of the 64-channel row
-            uint8_t* rowp = stg + m * 128;
-            *reinterpret_cast<uint4*>(rowp + ((c16 ^ (m & 7)) << 4)) = q0;
-            *reinterpret_cast<uint4*>(rowp + (((c16 + 1) ^ (m & 7)) << 4)) = q1;
-            if (u == LDB - 1) {
-              fence_proxy_async_smem();
-              named_bar_sync(1 + stg_group, stg_threads);
-              if (stg_leader && tile_ok) {
-                tma_store_4d(&tmO, stg, ch0 + ((cc * 16) & ~63), w0, h0, n);
-                bulk_commit();
-              }
-            }
-          } else if (EPI == EPI_POOL) {
-            // 2x2 average: partners are lane^1 (w) and lane^8 (h); recursive halving so each lane
-            // finishes with 4 channels of one pooled pixel.
-            float k8[8];
-            const bool wodd = (wl & 1) != 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float send = wodd ? v[j] : v[8 + j];
-              const float keep = wodd ? v[8 + j] : v[j];
-              k8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-            }
-            float k4[4];
-            const bool hodd = (hl & 1) != 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float send = hodd ? k8[j] : k8[4 + j];
-              const float keep = hodd ? k8[4 + j] : k8[j];
-              k4[j] = 0.25f * (keep + __shfl_xor_sync(0xffffffffu, send, 8));
-            }
-            const int Hp = p.H >> 1, Wp = p.W >> 1;
-            const int hp = h >> 1, wp = w >> 1;
-            if (tile_ok && hp < Hp) {
-              const int ch = ch0 + cc * 16 + (wodd ? 8 : 0) + (hodd ? 4 : 0);
-              uint2 q;
-              q.x = Elem16<T>::pack2(k4[0], k4[1]);
-              q.y = Elem16<T>::pack2(k4[2], k4[3]);
-              T* dst = out16 + ((static_cast<size_t>(n) * Hp + hp) * Wp + wp) * p.cout + ch;
-              *reinterpret_cast<uint2*>(dst) = q;
-            }
-          } else if (EPI == EPI_FREQMEAN) {
-            // mean over the 8 frequency columns of a row (W == 8): lanes ^1, ^2, ^4
-            float k8[8];
-            const bool b0 = (wl & 1) != 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float send = b0 ? v[j] : v[8 + j];
-              const float keep = b0 ? v[8 + j] : v[j];
-              k8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-            }
-            float k4[4];
-            const bool b1 = (wl & 2) != 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float send = b1 ? k8[j] : k8[4 + j];
-              const float keep = b1 ? k8[4 + j] : k8[j];
-              k4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-            }
-            float k2[2];
-            const bool b2 = (wl & 4) != 0;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const float send = b2 ? k4[j] : k4[2 + j];
-              const float keep = b2 ? k4[2 + j] : k4[j];
-              k2[j] = 0.125f * (keep + __shfl_xor_sync(0xffffffffu, send, 4));
-            }
-            if (tile_ok && h < p.H) {
-              const int ch = ch0 + cc * 16 + (b0 ? 8 : 0) + (b1 ? 4 : 0) + (b2 ? 2 : 0);
-              T* dst = out16 + (static_cast<size_t>(n) * p.H + h) * p.cout + ch;
-              *reinterpret_cast<uint32_t*>(dst) = Elem16<T>::pack2(k2[0], k2[1]);
-            }
-          } else {  // EPI_LINEAR
-            const long row = static_cast<long>(tile) * 128 + m;
-            if (tile_ok && row < p.M) {
-              float* dst = reinterpret_cast<float*>(p.out) + row * p.ldc + ch0 + cc * 16;
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-              if (p.out2) {
-                uint4 q0, q1;
-                q0.x = Elem16<T>::pack2(v[0], v[1]);   q0.y = Elem16<T>::pack2(v[2], v[3]);
-                q0.z = Elem16<T>::pack2(v[4], v[5]);   q0.w = Elem16<T>::pack2(v[6], v[7]);
-                q1.x = Elem16<T>::pack2(v[8], v[9]);   q1.y = Elem16<T>::pack2(v[10], v[11]);
-                q1.z = Elem16<T>::pack2(v[12], v[13]); q1.w = Elem16<T>::pack2(v[14], v[15]);
-                T* d2 = reinterpret_cast<T*>(p.out2) + row * p.ldc + ch0 + cc * 16;
-                reinterpret_cast<uint4*>(d2)[0] = q0;
-                reinterpret_cast<uint4*>(d2)[1] = q1;
-              }
-            }
-          }
-          }
-        }
+        conv_epilogue_tile<T, BN, BRES, EPI>(taddr, chalf, warp, lane, s_scale, s_shift, ch0, tile, tile_ok, n, h0, w0, p,
+                                             smem_stg, &tmO);
       }
       tc_fence_before();
       __syncwarp();
@@ -450,6 +465,200 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// =================================================================================================
+// CTA-pair variant (tcgen05 cta_group::2) for the weight-stationary layers.
+//
+// With the accumulator N of a single-CTA MMA limited to the layer's Cout slice (64 or 128), each
+// K=16 MMA step reads 4 KB of A plus N*32 B of B from shared memory in N/2 cycles -- more than the
+// 128 B/clk the shared-memory pipe delivers, so those layers ran at half the tensor rate.  A CTA pair
+// computes M = 256 pixels (one 16x8 tile per CTA) against the SAME N columns; each CTA keeps only half of
+// the weight rows (N/2) resident and the hardware shares the halves, so the per-CTA shared-memory traffic
+// per MMA drops to 4 KB + N*16 B and the weight-resident footprint halves as well.
+//
+// Roles per CTA: warp0 = TMA producer (own haloed patch; completion is signalled on the LEADER's mbarrier),
+// warp1 = TMEM allocation (+ MMA issue on the leader only, commits multicast to both CTAs),
+// warps2-9 = epilogue of the CTA's own 128 accumulator rows.
+// =================================================================================================
+template <int CIN, int BN, int EPI, int SA>
+struct Conv2Cfg {
+  static constexpr int NCHUNK = CIN / 64;
+  static constexpr int TAPS = 9;
+  static constexpr int B_HALF = (BN / 2) * 128;                       // one (chunk, tap) block of this CTA's rows
+  static constexpr int B_BYTES = NCHUNK * TAPS * B_HALF;
+  static constexpr int SMEM_A = SA * kPatchStride;
+  static constexpr int CPW = BN / 2;
+  static constexpr int NSTG = (EPI == EPI_STORE) ? (CPW >= 64 ? 2 : 1) : 0;
+  static constexpr int SMEM_STG = NSTG * kTileBytes;
+  static constexpr int SMEM_MISC = 2 * BN * 4 + 256;
+  static constexpr int SMEM_BYTES = 1024 + SMEM_A + B_BYTES + SMEM_STG + SMEM_MISC;
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
+                                   : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int THREADS = 64 + 32 * 8;
+  static_assert(BN % 32 == 0 && BN <= 256, "pair MMA: N multiple of 16 per CTA half");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+template <typename T, int CIN, int BN, int EPI, int SA>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Conv2Cfg<CIN, BN, EPI, SA>::THREADS, 1)
+conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmO, const ConvParams p) {
+  using Cfg = Conv2Cfg<CIN, BN, EPI, SA>;
+  constexpr int TAPS = Cfg::TAPS;
+  constexpr int NCHUNK = Cfg::NCHUNK;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::SMEM_A;
+  uint8_t* smem_stg = smem_b + Cfg::B_BYTES;
+  float* s_scale = reinterpret_cast<float*>(smem_stg + Cfg::SMEM_STG);
+  float* s_shift = s_scale + BN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + BN);
+  uint64_t* a_full = bars;            // [SA]  leader's copy is the live one
+  uint64_t* a_empty = a_full + SA;    // [SA]  per CTA (multicast commit)
+  uint64_t* b_full = a_empty + SA;    // [1]   leader's copy
+  uint64_t* t_full = b_full + 1;      // [2]   per CTA (multicast commit)
+  uint64_t* t_empty = t_full + 2;     // [2]   leader's copy, 16 arrivals (8 warps x 2 CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  // ---- work decomposition: pair `pr` of `npairs`, Cout slice fixed per pair ----
+  const int pr = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int fixed_slice = pr % p.nslices;
+  const int item_begin = pr / p.nslices, item_stride = npairs / p.nslices;
+  const int items = (p.num_tiles + 1) >> 1;  // two tiles (one per CTA) per item
+  const int ch0 = fixed_slice * BN;
+
+  for (int i = threadIdx.x; i < BN; i += blockDim.x) {
+    s_scale[i] = p.scale[ch0 + i];
+    s_shift[i] = p.shift[ch0 + i];
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (EPI == EPI_STORE) tma_prefetch_desc(&tmO);
+    for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    mbar_init(b_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 16); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc2(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // peer barriers / TMEM are ready before any cross-CTA signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_coords = [&](int tile, int& n, int& h0, int& w0) {
+    const int per_img = p.tiles_h * p.tiles_w;
+    n = tile / per_img;
+    const int rem = tile - n * per_img;
+    const int th = rem / p.tiles_w;
+    h0 = th * 16;
+    w0 = (rem - th * p.tiles_w) * 8;
+  };
+
+  if (warp == 0) {
+    // =============================== TMA producer (both CTAs) ===============================
+    if (elect_one()) {
+      const uint32_t bfull_leader = map_to_cta(b_full, 0);
+      if (leader) mbar_expect_tx(b_full, 2 * Cfg::B_BYTES);
+      for (int c = 0; c < NCHUNK; ++c)
+        for (int tap = 0; tap < TAPS; ++tap)
+          tma_load_2d_2sm(smem_b + (c * TAPS + tap) * Cfg::B_HALF, &tmB, bfull_leader, tap * CIN + c * 64,
+                          ch0 + rank * (BN / 2));
+      uint32_t sa = 0, pa = 0;
+      for (int item = item_begin; item < items; item += item_stride) {
+        int n, h0, w0;
+        tile_coords(item * 2 + rank, n, h0, w0);  // past-the-end tiles have n >= NB: fully OOB -> zeros
+        for (int c = 0; c < NCHUNK; ++c) {
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          if (leader) mbar_expect_tx(&a_full[sa], 2 * kPatchBytes);
+          tma_load_4d_2sm(smem_a + sa * kPatchStride, &tmA, map_to_cta(&a_full[sa], 0), c * 64, w0 - 1, h0 - 1, n);
+          if (++sa == SA) { sa = 0; pa ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer (leader CTA only) ===========================
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_f16(Elem16<T>::kFmt, 256, BN);
+      constexpr uint32_t a_hi = desc_hi_sw128(1280);
+      constexpr uint32_t b_hi = desc_hi_sw128(1024);
+      const uint32_t a_lo0 = desc_lo(smem_u32(smem_a));
+      const uint32_t b_lo0 = desc_lo(smem_u32(smem_b));
+      uint32_t sa = 0, pa = 0, acc = 0, pacc = 0;
+      mbar_wait_cluster(b_full, 0);
+      tc_fence_after();
+      for (int item = item_begin; item < items; item += item_stride) {
+        mbar_wait_cluster(&t_empty[acc], pacc ^ 1);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + acc * BN;
+        for (int c = 0; c < NCHUNK; ++c) {
+          mbar_wait_cluster(&a_full[sa], pa);
+          tc_fence_after();
+          const uint32_t a_lo = a_lo0 + sa * (kPatchStride >> 4);
+#pragma unroll
+          for (int tap = 0; tap < TAPS; ++tap) {
+            const uint32_t b_lo = b_lo0 + (c * TAPS + tap) * (Cfg::B_HALF >> 4);
+            const uint32_t tap_off = ((tap / 3) * 10 + (tap % 3)) * 8;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (!(p.dbg & 4))
+                umma_f16_2sm(d_base, desc_join(a_lo + tap_off + k * 2, a_hi), desc_join(b_lo + k * 2, b_hi), idesc,
+                             (c | tap | k) ? 1u : 0u);
+            }
+          }
+          umma_commit_2sm(&a_empty[sa], 3);
+          if (++sa == SA) { sa = 0; pa ^= 1; }
+        }
+        umma_commit_2sm(&t_full[acc], 3);
+        if (++acc == 2) { acc = 0; pacc ^= 1; }
+      }
+    }
+  } else {
+    // =============================== epilogue (8 warps, both CTAs) ==========================
+    const int quarter = warp & 3;
+    const int chalf = (warp - 2) >> 2;
+    constexpr int CPW = Cfg::CPW;
+    const bool stg_leader = (lane == 0) && (warp == ((CPW >= 64) ? 2 + 4 * chalf : 2));
+    uint32_t acc = 0, pacc = 0;
+    for (int item = item_begin; item < items; item += item_stride) {
+      mbar_wait(&t_full[acc], pacc);
+      tc_fence_after();
+      if (!(p.dbg & 2)) {
+        const int tile = item * 2 + rank;
+        const bool tile_ok = (tile < p.num_tiles) && !(p.dbg & 1);
+        int n, h0, w0;
+        tile_coords(tile, n, h0, w0);
+        const uint32_t taddr = tmem_base + acc * BN + chalf * CPW + (static_cast<uint32_t>(quarter * 32) << 16);
+        conv_epilogue_tile<T, BN, true, EPI>(taddr, chalf, warp, lane, s_scale, s_shift, ch0, tile, tile_ok, n, h0, w0,
+                                             p, smem_stg, &tmO);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&t_empty[acc], 0);
+      if (++acc == 2) { acc = 0; pacc ^= 1; }
+    }
+    if (EPI == EPI_STORE && stg_leader) bulk_wait_all0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the leader's MMAs read the peer's shared memory: nobody leaves early
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
   }
 }
 

@@ -28,34 +28,6 @@ constexpr int kGruABytes = 4 * 16384;                // 128 clips x 256 k x 2 B
 constexpr int kGruSmem = 1024 + kGruWBytes + kGruABytes + 512;
 constexpr int kGruThreads = 64 + 256;  // TMA warp, MMA warp, 8 gate-math warps (2 per TMEM lane quarter)
 
-SED_DEVICE_INLINE void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-SED_DEVICE_INLINE void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  }
-}
-SED_DEVICE_INLINE void mbar_arrive_remote(uint64_t* bar, uint32_t cta_rank) {
-  asm volatile(
-      "{\n\t"
-      ".reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(cta_rank)
-      : "memory");
-}
-SED_DEVICE_INLINE void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 SED_DEVICE_INLINE float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 SED_DEVICE_INLINE float fast_tanh(float x) {
   // 1 - 2 / (exp(2x) + 1); |error| ~1e-7 absolute, far below the 16-bit operand rounding of h W_hh^T

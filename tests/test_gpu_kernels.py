@@ -40,7 +40,7 @@ def run_conv(x, w, scale, shift, mode, code, td, variant):
     return out.float().cpu()
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("layer", engine.CONV_LAYERS, ids=[l[0] for l in engine.CONV_LAYERS])
 def test_conv_layers_match_cpu_conv(layer, variant):
     name, cin, cout, mode = layer
@@ -80,7 +80,9 @@ def test_conv_variants_agree_bitwise():
     scale, shift = torch.rand(128) + 0.5, torch.randn(128) * 0.1
     a = run_conv(x, w, scale, shift, 1, code, td, 0)
     b = run_conv(x, w, scale, shift, 1, code, td, 1)
+    c = run_conv(x, w, scale, shift, 1, code, td, 2)  # CTA-pair kernel: same K order per output
     assert torch.equal(a, b)
+    assert torch.equal(a, c)
 
 
 def test_conv_rejects_unsupported_layers():

@@ -53,12 +53,14 @@ def main():
     for (name, _, _, _), (cin, cout, mode, wp, s, b), (src, dst) in zip(engine.CONV_LAYERS, pm.convs, chain):
         x = ws[src]
         out = feat if dst is None else ws[dst]
-        for variant in ((0, 1) if args.variant == 0 else (1,)):
+        for variant in (0, 2):
             t = timeit(lambda: lib.sed_conv3x3_bn_relu(capi.ptr(x), mb, x.shape[1], x.shape[2], cin, capi.ptr(wp),
                                                        capi.ptr(s), capi.ptr(b), cout, mode, capi.ptr(out),
                                                        pm.dtype_code, variant, stream))
             flops = 2.0 * mb * x.shape[1] * x.shape[2] * 9 * cin * cout
-            rows.append(("%s %d->%d %s" % (name, cin, cout, "patch" if variant == 0 else "tap"), t, flops,
+            if variant == 2 and cin > 128:
+                continue
+            rows.append(("%s %d->%d %s" % (name, cin, cout, {0: "patch", 1: "tap", 2: "pair"}[variant]), t, flops,
                          x.numel() * 2 + out.numel() * 2))
     B = args.batch
     featB = torch.randn(B, 125, 512, device=dev).to(pm.tdtype)
@@ -81,7 +83,7 @@ def main():
     tot = 0.0
     print("per micro-batch of %d clips (temporal/head rows scaled from B=%d)" % (mb, B))
     for name, t, fl, by in rows:
-        if name.endswith("tap") and args.variant == 0:
+        if name.endswith("pair"):
             tag = "   (alt)"
         else:
             tag = ""
