@@ -267,7 +267,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="clips per GPU per step")
     ap.add_argument("--micro-batch", type=int, default=148)
-    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--variant", type=int, default=2)
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--ref-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")

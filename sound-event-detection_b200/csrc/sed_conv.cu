@@ -292,11 +292,11 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   return SED_OK;
 }
 
-template <typename T, int CIN, int BN, int EPI, int SA>
+template <typename T, int CIN, int BN, int EPI, int SA, int ACC>
 static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvParams& p,
                        cudaStream_t stream) {
-  using Cfg = Conv2Cfg<CIN, BN, EPI, SA>;
-  auto kern = conv_umma2_kernel<T, CIN, BN, EPI, SA>;
+  using Cfg = Conv2Cfg<CIN, BN, EPI, SA, ACC>;
+  auto kern = conv_umma2_kernel<T, CIN, BN, EPI, SA, ACC>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(pair, smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
@@ -322,10 +322,10 @@ static int conv3x3_dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   // (cin, cout, mode) are the seven tensor-core layers of Cnn_9layers.
   // variant 2: CTA-pair (cta_group::2) kernels for the weight-stationary layers
   if (variant == 2) {
-    if (cin == 64 && cout == 64 && mode == EPI_POOL) { p.nslices = 1; return launch_pair<T, 64, 64, EPI_POOL, 4>(tmA, tmB, tmO, p, stream); }
-    if (cin == 64 && cout == 128 && mode == EPI_STORE) { p.nslices = 1; return launch_pair<T, 64, 128, EPI_STORE, 4>(tmA, tmB, tmO, p, stream); }
-    if (cin == 128 && cout == 128 && mode == EPI_POOL) { p.nslices = 1; return launch_pair<T, 128, 128, EPI_POOL, 3>(tmA, tmB, tmO, p, stream); }
-    if (cin == 128 && cout == 256 && mode == EPI_STORE) { p.nslices = 2; return launch_pair<T, 128, 128, EPI_STORE, 2>(tmA, tmB, tmO, p, stream); }
+    if (cin == 64 && cout == 64 && mode == EPI_POOL) { p.nslices = 1; return launch_pair<T, 64, 64, EPI_POOL, 6, 4>(tmA, tmB, tmO, p, stream); }
+    if (cin == 64 && cout == 128 && mode == EPI_STORE) { p.nslices = 1; return launch_pair<T, 64, 128, EPI_STORE, 4, 4>(tmA, tmB, tmO, p, stream); }
+    if (cin == 128 && cout == 128 && mode == EPI_POOL) { p.nslices = 1; return launch_pair<T, 128, 128, EPI_POOL, 3, 2>(tmA, tmB, tmO, p, stream); }
+    if (cin == 128 && cout == 256 && mode == EPI_STORE) { p.nslices = 2; return launch_pair<T, 128, 128, EPI_STORE, 2, 2>(tmA, tmB, tmO, p, stream); }
     variant = 0;  // streamed-weight layers have no pair variant
   }
 #define SED_CASE(CIN_, COUT_, MODE_, BN_, NT_, BRES_, SA_P, SB_P, SA_T, SB_T)                                     \

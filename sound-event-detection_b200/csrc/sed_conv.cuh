@@ -482,7 +482,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // warp1 = TMEM allocation (+ MMA issue on the leader only, commits multicast to both CTAs),
 // warps2-9 = epilogue of the CTA's own 128 accumulator rows.
 // =================================================================================================
-template <int CIN, int BN, int EPI, int SA>
+template <int CIN, int BN, int EPI, int SA, int ACC>
 struct Conv2Cfg {
   static constexpr int NCHUNK = CIN / 64;
   static constexpr int TAPS = 9;
@@ -494,18 +494,19 @@ struct Conv2Cfg {
   static constexpr int SMEM_STG = NSTG * kTileBytes;
   static constexpr int SMEM_MISC = 2 * BN * 4 + 256;
   static constexpr int SMEM_BYTES = 1024 + SMEM_A + B_BYTES + SMEM_STG + SMEM_MISC;
-  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
-                                   : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int TMEM_COLS = (ACC * BN <= 32) ? 32 : (ACC * BN <= 64) ? 64 : (ACC * BN <= 128) ? 128
+                                   : (ACC * BN <= 256) ? 256 : 512;
+  static_assert(ACC * BN <= 512, "TMEM columns");
   static constexpr int THREADS = 64 + 32 * 8;
   static_assert(BN % 32 == 0 && BN <= 256, "pair MMA: N multiple of 16 per CTA half");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-template <typename T, int CIN, int BN, int EPI, int SA>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Conv2Cfg<CIN, BN, EPI, SA>::THREADS, 1)
+template <typename T, int CIN, int BN, int EPI, int SA, int ACC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Conv2Cfg<CIN, BN, EPI, SA, ACC>::THREADS, 1)
 conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmO, const ConvParams p) {
-  using Cfg = Conv2Cfg<CIN, BN, EPI, SA>;
+  using Cfg = Conv2Cfg<CIN, BN, EPI, SA, ACC>;
   constexpr int TAPS = Cfg::TAPS;
   constexpr int NCHUNK = Cfg::NCHUNK;
 
@@ -520,9 +521,9 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* a_full = bars;            // [SA]  leader's copy is the live one
   uint64_t* a_empty = a_full + SA;    // [SA]  per CTA (multicast commit)
   uint64_t* b_full = a_empty + SA;    // [1]   leader's copy
-  uint64_t* t_full = b_full + 1;      // [2]   per CTA (multicast commit)
-  uint64_t* t_empty = t_full + 2;     // [2]   leader's copy, 16 arrivals (8 warps x 2 CTAs)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  uint64_t* t_full = b_full + 1;      // [ACC] per CTA (multicast commit)
+  uint64_t* t_empty = t_full + ACC;   // [ACC] leader's copy, 16 arrivals (8 warps x 2 CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + ACC);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -546,7 +547,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (EPI == EPI_STORE) tma_prefetch_desc(&tmO);
     for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     mbar_init(b_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 16); }
+    for (int i = 0; i < ACC; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 16); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -598,14 +599,14 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t a_lo0 = desc_lo(smem_u32(smem_a));
       const uint32_t b_lo0 = desc_lo(smem_u32(smem_b));
       uint32_t sa = 0, pa = 0, acc = 0, pacc = 0;
-      mbar_wait_cluster(b_full, 0);
+      mbar_wait(b_full, 0);
       tc_fence_after();
       for (int item = item_begin; item < items; item += item_stride) {
-        mbar_wait_cluster(&t_empty[acc], pacc ^ 1);
+        mbar_wait(&t_empty[acc], pacc ^ 1);
         tc_fence_after();
         const uint32_t d_base = tmem_base + acc * BN;
         for (int c = 0; c < NCHUNK; ++c) {
-          mbar_wait_cluster(&a_full[sa], pa);
+          mbar_wait(&a_full[sa], pa);
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + sa * (kPatchStride >> 4);
 #pragma unroll
@@ -623,7 +624,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (++sa == SA) { sa = 0; pa ^= 1; }
         }
         umma_commit_2sm(&t_full[acc], 3);
-        if (++acc == 2) { acc = 0; pacc ^= 1; }
+        if (++acc == ACC) { acc = 0; pacc ^= 1; }
       }
     }
   } else {
@@ -647,8 +648,8 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_remote(&t_empty[acc], 0);
-      if (++acc == 2) { acc = 0; pacc ^= 1; }
+      if (lane == 0) mbar_arrive_remote_light(&t_empty[acc], 0);
+      if (++acc == ACC) { acc = 0; pacc ^= 1; }
     }
     if (EPI == EPI_STORE && stg_leader) bulk_wait_all0();
   }

@@ -237,7 +237,7 @@ class PackedModel:
         return ws
 
     # ------------------------------------------------------------------ stages
-    def conv_stack(self, wave_mb, feat_out, variant=0, stages=None):
+    def conv_stack(self, wave_mb, feat_out, variant=2, stages=None):
         """wave_mb [mb, L] f32 -> feat_out [mb, T', 512] 16-bit (freq-mean of conv_block4)."""
         lib = capi.load()
         mb, L = wave_mb.shape
@@ -327,7 +327,7 @@ class PackedModel:
         return clip, frame, cla, natt
 
     # ------------------------------------------------------------------ whole model
-    def forward_host(self, wave_host, micro_batch=148, variant=0):
+    def forward_host(self, wave_host, micro_batch=148, variant=2):
         """End-to-end call with HOST buffers: `wave_host` [B, L] f32 (pinned for full speed) is copied to
         the device micro-batch by micro-batch on a copy stream that runs ahead of the compute stream, and
         `clipwise_output` / `framewise_output` come back as host tensors (the reference callers do
@@ -364,7 +364,7 @@ class PackedModel:
         compute.synchronize()
         return {"clipwise_output": hb["clip"], "framewise_output": hb["frame"]}
 
-    def forward(self, wave, micro_batch=148, variant=0, return_stages=False, _h2d_events=None):
+    def forward(self, wave, micro_batch=148, variant=2, return_stages=False, _h2d_events=None):
         """wave [B, L] f32 on self.device -> reference output dict (models.py:683-686 / :1072-1075)."""
         if wave.dim() != 2:
             raise ValueError("input must be (batch_size, data_length)")

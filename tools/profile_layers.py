@@ -29,7 +29,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mb", type=int, default=148)
     ap.add_argument("--batch", type=int, default=1024)
-    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--variant", type=int, default=2)
     ap.add_argument("--model", default="Cnn_9layers_Gru_FrameAtt")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -83,7 +83,7 @@ def main():
     tot = 0.0
     print("per micro-batch of %d clips (temporal/head rows scaled from B=%d)" % (mb, B))
     for name, t, fl, by in rows:
-        if name.endswith("pair"):
+        if name.endswith("patch") and ("pair" in [r[0].split()[-1] for r in rows if r[0].split()[0] == name.split()[0]]):
             tag = "   (alt)"
         else:
             tag = ""
