@@ -98,6 +98,11 @@ long sed_bigru_workspace_bytes(int B);
 int sed_bigru(const float* gi, const void* whh_packed, const float* bhh, int B, int T, float* out, void* workspace,
               int dtype, void* stream);
 
+/* Profiling hook: sed_bigru that also records clock64() stamps of CTA 0 for recurrence steps 8..15
+ * (stamps: device buffer of 8*12 long long).  Developer tool (tools/gru_stamps.py). */
+int sed_bigru_profile(const float* gi, const void* whh_packed, const float* bhh, int B, int T, float* out,
+                      void* workspace, int dtype, long long* stamps, void* stream);
+
 /* softmax(q k^T / 8) v for 8 heads of 64.  Replaces ScaledDotProductAttention.forward
  * pytorch/models.py:808-820 and the head split/merge :863-875.
  *   qkv [B, T, 1536] f32 = [q | k | v], head h = columns h*64..h*64+63; out16 [B, T, 512] 16-bit. */

@@ -108,6 +108,12 @@ int sed_bigru(const float* gi, const void* whh_packed, const float* bhh, int B, 
   return sed::gru_launch(gi, whh_packed, bhh, B, T, out, workspace, dtype, as_stream(stream));
 }
 
+int sed_bigru_profile(const float* gi, const void* whh_packed, const float* bhh, int B, int T, float* out,
+                      void* workspace, int dtype, long long* stamps, void* stream) {
+  SED_REQUIRE(gi); SED_REQUIRE(whh_packed); SED_REQUIRE(bhh); SED_REQUIRE(out); SED_REQUIRE(workspace); SED_REQUIRE(stamps);
+  return sed::gru_launch(gi, whh_packed, bhh, B, T, out, workspace, dtype, as_stream(stream), stamps);
+}
+
 int sed_mha_core(const float* qkv, int B, int T, void* out16, int dtype, void* stream) {
   SED_REQUIRE(qkv); SED_REQUIRE(out16);
   return sed::mha_core_launch(qkv, B, T, out16, dtype, as_stream(stream));

@@ -41,7 +41,7 @@ int linear_launch(const void* a16, long M, int K, const void* w16, const float* 
 
 size_t gru_workspace_bytes(int B);
 int gru_launch(const float* gi, const void* whh_packed, const float* bhh, int B, int T, float* out, void* workspace,
-               int dtype, cudaStream_t stream);
+               int dtype, cudaStream_t stream, long long* stamps = nullptr);
 
 int mha_core_launch(const float* qkv, int B, int T, void* out16, int dtype, cudaStream_t stream);
 

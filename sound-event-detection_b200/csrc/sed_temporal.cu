@@ -38,10 +38,16 @@ template <typename T>
 __global__ void __cluster_dims__(kGruCluster, 1, 1) __launch_bounds__(kGruThreads, 1)
 gru_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH,
            const float* __restrict__ gi, const float* __restrict__ bhh, int B, int Bpad, int Tn,
-           float* __restrict__ out, T* __restrict__ hx) {
+           float* __restrict__ out, T* __restrict__ hx, long long* __restrict__ stamps) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_w = smem;                 // [4][96 rows][128 B]   resident W_hh slice
+  // profiling hook (stamps != nullptr): CTA 0 records clock64() at 12 points of steps 8..15
+  const bool prof = stamps != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+#define GRU_STAMP(step, slot)                                                       \
+  do {                                                                               \
+    if (prof && (step) >= 8 && (step) < 16) stamps[((step) - 8) * 12 + (slot)] = clock64(); \
+  } while (0)
   uint8_t* smem_a = smem + kGruWBytes;    // [4][128 rows][128 B]  h_{t-1}
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + kGruABytes);
   uint64_t* w_full = bars;
@@ -68,7 +74,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
     mbar_init(w_full, 1);
     mbar_init(a_full, 1);
     mbar_init(acc_full, 1);
-    mbar_init(h_ready, kGruCluster * 8);
+    mbar_init(h_ready, kGruCluster);  // one arrival per source CTA
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -89,7 +95,8 @@ gru_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
         tma_load_2d(smem_w + kc * (kGruChunkRows * 128), &tmW, w_full, kc * 64, dir * 768 + q * kGruChunkRows);
       for (int s = 1; s < Tn; ++s) {
         mbar_wait_cluster(h_ready, (s - 1) & 1);  // all 8 slices of h_{s-1} are in the exchange buffer
-        fence_proxy_async_all();                  // generic-proxy global writes -> async-proxy (TMA) reads
+        GRU_STAMP(s, 0);  // (the writers issued fence.proxy.async before their release-arrive)
+        GRU_STAMP(s, 1);
         mbar_expect_tx(a_full, kGruABytes);
         const int row = (((s - 1) & 1) * 2 + dir) * Bpad + clip0;
 #pragma unroll
@@ -103,6 +110,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
       const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_w);
       for (int s = 0; s < Tn; ++s) {
         if (s > 0) mbar_wait(a_full, (s - 1) & 1);
+        GRU_STAMP(s, 2);
         tc_fence_after();
 #pragma unroll
         for (int kc = 0; kc < 4; ++kc) {
@@ -113,6 +121,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
           }
         }
         umma_commit(acc_full);
+        GRU_STAMP(s, 3);
       }
     }
   } else {
@@ -142,7 +151,9 @@ gru_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
           gr[v] = gz[v] = gn[v] = make_float4(0, 0, 0, 0);
         }
       }
+      if (warp == 2 && lane == 0) GRU_STAMP(s, 4);
       mbar_wait(acc_full, s & 1);
+      if (warp == 2 && lane == 0) GRU_STAMP(s, 5);
       tc_fence_after();
       uint32_t ar[16], az[16], an[16];
       tmem_ld16(taddr, ar);
@@ -164,6 +175,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
           h[jj] = (1.0f - z) * nn + z * h[jj];
         }
       }
+      if (warp == 2 && lane == 0) GRU_STAMP(s, 6);
       if (valid) {
 #pragma unroll
         for (int v = 0; v < 4; ++v)
@@ -181,13 +193,17 @@ gru_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
           pk.w = Elem16<T>::pack2(h[8 * v + 6], h[8 * v + 7]);
           reinterpret_cast<uint4*>(hx_row)[v] = pk;
         }
-        fence_proxy_async_all();
+        if (warp == 2 && lane == 0) GRU_STAMP(s, 7);
         tc_fence_before();
-        __syncwarp();
+        named_bar_sync(1, 256);  // all 8 gate warps have written their slice of h_t (and drained TMEM)
+        if (warp == 2 && lane == 0) GRU_STAMP(s, 8);
+        // warp (2 + r) publishes to CTA r: proxy fence (generic global writes -> the peers' TMA reads), then a
+        // release-arrive at cluster scope; the eight destinations are signalled in parallel
         if (lane == 0) {
-#pragma unroll
-          for (int r = 0; r < kGruCluster; ++r) mbar_arrive_remote(h_ready, r);
+          fence_proxy_async_all();
+          mbar_arrive_remote(h_ready, warp - 2);
         }
+        if (warp == 2 && lane == 0) GRU_STAMP(s, 9);
       }
     }
   }
@@ -223,7 +239,7 @@ size_t gru_workspace_bytes(int B) {
 }
 
 int gru_launch(const float* gi, const void* whh_packed, const float* bhh, int B, int Tn, float* out, void* workspace,
-               int dtype, cudaStream_t stream) {
+               int dtype, cudaStream_t stream, long long* stamps) {
   if (B <= 0 || Tn <= 0) {
     set_error("gru: bad shape B=%d T=%d", B, Tn);
     return SED_ERR_BAD_SHAPE;
@@ -249,12 +265,12 @@ int gru_launch(const float* gi, const void* whh_packed, const float* bhh, int B,
     e = cudaFuncSetAttribute(gru_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGruSmem);
     if (e == cudaSuccess)
       gru_kernel<__half><<<grid, kGruThreads, kGruSmem, stream>>>(tmW, tmH, gi, bhh, B, Bpad, Tn, out,
-                                                                  reinterpret_cast<__half*>(workspace));
+                                                                  reinterpret_cast<__half*>(workspace), stamps);
   } else {
     e = cudaFuncSetAttribute(gru_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGruSmem);
     if (e == cudaSuccess)
       gru_kernel<__nv_bfloat16><<<grid, kGruThreads, kGruSmem, stream>>>(tmW, tmH, gi, bhh, B, Bpad, Tn, out,
-                                                                         reinterpret_cast<__nv_bfloat16*>(workspace));
+                                                                         reinterpret_cast<__nv_bfloat16*>(workspace), stamps);
   }
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
