@@ -12,6 +12,8 @@
 // is read from the loaded conv_real kernel (row 0), so a checkpoint's window is honoured; the host
 // wrapper verifies that the loaded kernels are a windowed DFT before selecting this path.
 // The mel projection uses the loaded melW in banded form (first/last non-zero per mel bin).
+#include <cstdlib>
+
 #include "sed_common.cuh"
 #include "sed_kernels.h"
 
@@ -19,8 +21,10 @@ namespace sed {
 
 template <int NFFT>
 struct FrontCfg {
-  static constexpr int WARPS = (NFFT >= 1024) ? 4 : 8;
-  static constexpr int FPB = 32;  // frames per block (even: frames are transformed in pairs)
+  static constexpr int WARPS = 4;
+  static constexpr int FPB = 16;  // frames per block (even: frames are transformed in pairs); small blocks so
+                                  // that several are resident per SM and their load phases overlap
+  static constexpr int MELV = 1024;  // banded mel weights cached in shared memory (falls back to global beyond)
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -75,36 +79,45 @@ __device__ __forceinline__ void butterfly<8>(float2 (&v)[8]) {
   }
 }
 
-// One Stockham pass of radix R over N complex points held in (padded) shared memory, executed by one warp.
-// src == nullptr means "first pass": inputs come from the windowed frame pair (re = frame a, im = frame b).
+// One Stockham pass of radix R over N complex points, IN PLACE in (padded) shared memory, executed by one warp:
+// every lane first pulls the inputs of all its butterflies into registers, the warp synchronises, then the
+// autosorted outputs are written back.  first == true: inputs come from the windowed frame pair instead
+// (re = frame a, im = frame b).
 template <int N, int R>
-__device__ __forceinline__ void fft_pass(const float2* __restrict__ src, float2* __restrict__ dst, int Ns,
-                                         const float2* __restrict__ tw, const float* __restrict__ seg_a,
-                                         const float* __restrict__ seg_b, const float* __restrict__ win,
-                                         int lane) {
+__device__ __forceinline__ void fft_pass(float2* __restrict__ buf, bool first, int Ns, const float2* __restrict__ tw,
+                                         const float* __restrict__ seg_a, const float* __restrict__ seg_b,
+                                         const float* __restrict__ win, int lane) {
   constexpr int NB = N / R;
-  for (int j = lane; j < NB; j += 32) {
-    const int k = j % Ns;
-    float2 v[R];
+  constexpr int BPL = NB / 32;  // butterflies per lane
+  float2 v[BPL][R];
+#pragma unroll
+  for (int q = 0; q < BPL; ++q) {
+    const int j = lane + 32 * q;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int idx = j + r * NB;
-      if (src == nullptr) {
+      if (first) {
         const float w = win[idx];
-        v[r] = make_float2(w * seg_a[idx], w * seg_b[idx]);
+        v[q][r] = make_float2(w * seg_a[idx], w * seg_b[idx]);
       } else {
-        v[r] = src[pidx(idx)];
+        v[q][r] = buf[pidx(idx)];
       }
     }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < BPL; ++q) {
+    const int j = lane + 32 * q;
+    const int k = j % Ns;
     if (Ns > 1) {
       const int tstride = N / (Ns * R);
 #pragma unroll
-      for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tw[r * k * tstride]);
+      for (int r = 1; r < R; ++r) v[q][r] = cmul(v[q][r], tw[r * k * tstride]);
     }
-    butterfly<R>(v);
+    butterfly<R>(v[q]);
     const int j0 = (j / Ns) * Ns * R + k;
 #pragma unroll
-    for (int r = 0; r < R; ++r) dst[pidx(j0 + r * Ns)] = v[r];
+    for (int r = 0; r < R; ++r) buf[pidx(j0 + r * Ns)] = v[q][r];
   }
   __syncwarp();
 }
@@ -116,7 +129,7 @@ frontend_kernel(const float* __restrict__ wave, int L, int T, int hop, const flo
                 const float2* __restrict__ twiddle, const int* __restrict__ mel_lo, const int* __restrict__ mel_len,
                 const int* __restrict__ mel_off, const float* __restrict__ mel_val, int n_mels, float amin,
                 float db_offset, int is_log, const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
-                float* __restrict__ out, int mode) {
+                float* __restrict__ out, int mode, int dbg) {
   constexpr int WARPS = FrontCfg<NFFT>::WARPS;
   constexpr int FPB = FrontCfg<NFFT>::FPB;
   constexpr int F = NFFT / 2 + 1;
@@ -125,7 +138,10 @@ frontend_kernel(const float* __restrict__ wave, int L, int T, int hop, const flo
   float* s_seg = smem_f;                                            // [seg_len]
   float* s_win = s_seg + ((seg_len + 3) & ~3);                      // [NFFT]
   float2* s_tw = reinterpret_cast<float2*>(s_win + NFFT);           // [NFFT]
-  float2* s_buf = s_tw + NFFT;                                      // [WARPS][2][NFFT + NFFT/8]
+  float2* s_buf = s_tw + NFFT;                                      // [WARPS][NFFT + NFFT/8]
+  constexpr int BUF = NFFT + NFFT / 8;                              // padded (see pidx)
+  float* s_melv = reinterpret_cast<float*>(s_buf + WARPS * BUF);    // [MELV] banded mel weights
+  int* s_meli = reinterpret_cast<int*>(s_melv + FrontCfg<NFFT>::MELV);  // [3][n_mels] lo, len, off
 
   const int b = blockIdx.y;
   const int f_base = blockIdx.x * FPB;
@@ -143,12 +159,22 @@ frontend_kernel(const float* __restrict__ wave, int L, int T, int hop, const flo
     s_win[i] = window[i];
     s_tw[i] = twiddle[i];
   }
+  int mel_total = 0;
+  if (mode == 0) {
+    mel_total = mel_off[n_mels - 1] + mel_len[n_mels - 1];
+    for (int i = threadIdx.x; i < n_mels; i += blockDim.x) {
+      s_meli[i] = mel_lo[i];
+      s_meli[n_mels + i] = mel_len[i];
+      s_meli[2 * n_mels + i] = mel_off[i];
+    }
+    if (mel_total <= FrontCfg<NFFT>::MELV)
+      for (int i = threadIdx.x; i < mel_total; i += blockDim.x) s_melv[i] = mel_val[i];
+  }
+  const bool mel_in_smem = mel_total <= FrontCfg<NFFT>::MELV;
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int BUF = NFFT + NFFT / 8;  // padded (see pidx)
-  float2* buf0 = s_buf + warp * 2 * BUF;
-  float2* buf1 = buf0 + BUF;
+  float2* buf = s_buf + warp * BUF;
 
   for (int pair = warp; pair < FPB / 2; pair += WARPS) {
     const int fa = f_base + 2 * pair;
@@ -158,37 +184,48 @@ frontend_kernel(const float* __restrict__ wave, int L, int T, int hop, const flo
 
     // ---- 2 real frames -> 1 complex FFT of size NFFT (Stockham autosort, natural-order output) ----
     // radix schedule: 256 = 4*8*8, 512 = 8*8*8, 1024 = 2*8*8*8
-    float2* src = nullptr;
-    float2* dst = buf0;
     int Ns = 1;
+    bool first = true;
     if (NFFT == 1024) {
-      fft_pass<NFFT, 2>(src, dst, Ns, s_tw, seg_a, seg_b, s_win, lane);
+      fft_pass<NFFT, 2>(buf, first, Ns, s_tw, seg_a, seg_b, s_win, lane);
       Ns = 2;
-      src = dst;
-      dst = (dst == buf0) ? buf1 : buf0;
+      first = false;
     } else if (NFFT == 256) {
-      fft_pass<NFFT, 4>(src, dst, Ns, s_tw, seg_a, seg_b, s_win, lane);
+      fft_pass<NFFT, 4>(buf, first, Ns, s_tw, seg_a, seg_b, s_win, lane);
       Ns = 4;
-      src = dst;
-      dst = (dst == buf0) ? buf1 : buf0;
+      first = false;
     }
     while (Ns < NFFT) {
-      fft_pass<NFFT, 8>(src, dst, Ns, s_tw, seg_a, seg_b, s_win, lane);
+      if ((dbg & 1) && Ns > 1) break;
+      fft_pass<NFFT, 8>(buf, first, Ns, s_tw, seg_a, seg_b, s_win, lane);
       Ns *= 8;
-      src = dst;
-      dst = (dst == buf0) ? buf1 : buf0;
+      first = false;
     }
-    const float2* Z = src;                        // spectrum of (a + i b), padded indexing
-    float* P = reinterpret_cast<float*>(dst);     // P[0..F) = |A|^2, P[F..2F) = |B|^2  (2F <= 2*NFFT floats)
-
-    // ---- split the two real spectra and take the power (stft.py:663) ----
-    for (int k = lane; k < F; k += 32) {
-      const float2 zk = Z[pidx(k & (NFFT - 1))];
-      const float2 zn = Z[pidx((NFFT - k) & (NFFT - 1))];
-      const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
-      const float br = 0.5f * (zk.y + zn.y), bi = 0.5f * (zn.x - zk.x);
-      P[k] = ar * ar + ai * ai;
-      P[F + k] = br * br + bi * bi;
+    // ---- split the two real spectra and take the power (stft.py:663), in place: P[0..F) = |A|^2,
+    //      P[F..2F) = |B|^2 overwrite the spectrum after every lane has read its bins ----
+    constexpr int KPL = (F + 31) / 32;
+    float pa[KPL], pb[KPL];
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+      const int k = lane + 32 * i;
+      if (k < F) {
+        const float2 zk = buf[pidx(k & (NFFT - 1))];
+        const float2 zn = buf[pidx((NFFT - k) & (NFFT - 1))];
+        const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
+        const float br = 0.5f * (zk.y + zn.y), bi = 0.5f * (zn.x - zk.x);
+        pa[i] = ar * ar + ai * ai;
+        pb[i] = br * br + bi * bi;
+      }
+    }
+    __syncwarp();
+    float* P = reinterpret_cast<float*>(buf);
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+      const int k = lane + 32 * i;
+      if (k < F) {
+        P[k] = pa[i];
+        P[F + k] = pb[i];
+      }
     }
     __syncwarp();
 
@@ -197,7 +234,9 @@ frontend_kernel(const float* __restrict__ wave, int L, int T, int hop, const flo
       const int f = fa + which;
       if (f >= T) break;
       const float* Pf = P + which * F;
-      if (mode == 1) {
+      if (dbg & 2) {
+        if (lane == 0) out[(static_cast<size_t>(b) * T + f) * n_mels] = Pf[3];
+      } else if (mode == 1) {
         float* o = out + (static_cast<size_t>(b) * T + f) * F;
         for (int k = lane; k < F; k += 32) o[k] = Pf[k];
       } else {
@@ -207,10 +246,21 @@ frontend_kernel(const float* __restrict__ wave, int L, int T, int hop, const flo
           const int pr = mi >> 5;
           const int m = (pr & 1) ? (n_mels - 1 - (mi - 32 * pr) - 32 * (pr >> 1)) : (lane + 32 * (pr >> 1));
           if (m < 0 || m >= n_mels) continue;
-          const int lo = mel_lo[m], len = mel_len[m];
-          const float* mv = mel_val + mel_off[m];
-          float acc = 0.0f;
-          for (int i = 0; i < len; ++i) acc = fmaf(Pf[lo + i], __ldg(mv + i), acc);  // stft.py:709
+          const int lo = s_meli[m], len = s_meli[n_mels + m], off = s_meli[2 * n_mels + m];
+          float acc = 0.0f, acc2 = 0.0f;  // stft.py:709 restricted to the band of non-zero weights
+          if (mel_in_smem) {
+            const float* mv = s_melv + off;
+            int i = 0;
+            for (; i + 1 < len; i += 2) {
+              acc = fmaf(Pf[lo + i], mv[i], acc);
+              acc2 = fmaf(Pf[lo + i + 1], mv[i + 1], acc2);
+            }
+            if (i < len) acc = fmaf(Pf[lo + i], mv[i], acc);
+          } else {
+            const float* mv = mel_val + off;
+            for (int i = 0; i < len; ++i) acc = fmaf(Pf[lo + i], __ldg(mv + i), acc);
+          }
+          acc += acc2;
           float y = acc;
           if (is_log) y = 10.0f * log10f(fmaxf(acc, amin)) - db_offset;  // stft.py:726-727
           if (bn_scale != nullptr) y = fmaf(y, bn_scale[m], bn_shift[m]);  // models.py:642-644
@@ -246,15 +296,17 @@ static int launch_frontend(const FrontendArgs& a, cudaStream_t stream) {
   constexpr int WARPS = FrontCfg<NFFT>::WARPS;
   constexpr int FPB = FrontCfg<NFFT>::FPB;
   const int seg_len = (FPB - 1) * a.hop + NFFT;
-  const size_t smem = sizeof(float) * (((seg_len + 3) & ~3) + NFFT) +
-                      sizeof(float2) * (NFFT + WARPS * 2 * (NFFT + NFFT / 8));
+  const size_t smem = sizeof(float) * (((seg_len + 3) & ~3) + NFFT + FrontCfg<NFFT>::MELV) +
+                      sizeof(float2) * (NFFT + WARPS * (NFFT + NFFT / 8)) + sizeof(int) * 3 * (a.n_mels > 0 ? a.n_mels : 1);
   if (smem > 227 * 1024) return SED_ERR_UNSUPPORTED;
   cudaError_t e = cudaFuncSetAttribute(frontend_kernel<NFFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return SED_ERR_CUDA;
   dim3 grid((a.T + FPB - 1) / FPB, a.B);
+  const char* e_dbg = getenv("SED_FE_DBG");
+  const int dbg = e_dbg ? atoi(e_dbg) : 0;
   frontend_kernel<NFFT><<<grid, WARPS * 32, smem, stream>>>(
       a.wave, a.L, a.T, a.hop, a.window, reinterpret_cast<const float2*>(a.twiddle), a.mel_lo, a.mel_len, a.mel_off,
-      a.mel_val, a.n_mels, a.amin, a.db_offset, a.is_log, a.bn_scale, a.bn_shift, a.out, a.mode);
+      a.mel_val, a.n_mels, a.amin, a.db_offset, a.is_log, a.bn_scale, a.bn_shift, a.out, a.mode, dbg);
   return cudaGetLastError() == cudaSuccess ? SED_OK : SED_ERR_CUDA;
 }
 
