@@ -39,16 +39,19 @@ const char* sed_last_error_string(void);
 /* Fused front-end: reflect-pad, frame, window, real DFT, power, mel projection, clamped 10*log10,
  * optional per-mel affine (eval-mode bn0).
  * Replaces STFT.forward pytorch/stft.py:223-247, Spectrogram.forward :651-670,
- * LogmelFilterBank.forward + power_to_db :698-734 and bn0 pytorch/models.py:642-644.
- *   wave [B, L] f32; window [n_fft] f32 (row 0 of the loaded conv_real kernel);
- *   twiddle [n_fft][2] f32 = exp(-2 pi i k / n_fft); banded mel matrix: for mel bin m the non-zero
- *   weights melW[mel_lo[m] .. mel_lo[m]+mel_len[m]) are stored at mel_val[mel_off[m] ..];
- *   db_offset = 10*log10(max(amin, ref)); bn_scale/bn_shift [n_mels] or NULL;
+ * LogmelFilterBank.forward + power_to_db :698-734 and bn0 pytorch/models.py:642-644; with wave_dtype = 1 also
+ * int16_to_float32 utils/utilities.py:78-79 (x = q / 32767); with clip_stride < L also the window slicing +
+ * pad_truncate_sequence of the streaming loop pytorch/predict.py:302-305.
+ *   wave: clip b = wave + b*clip_stride, L samples, f32 (wave_dtype 0) or int16 PCM (wave_dtype 1); samples at
+ *   index >= total_len (counted from `wave`) read as zero.  Dense batch: clip_stride = L, total_len = B*L.
+ *   window [n_fft] f32 (row 0 of the loaded conv_real kernel); twiddle [n_fft][2] f32 = exp(-2 pi i k / n_fft);
+ *   banded mel matrix: for mel bin m the non-zero weights melW[mel_lo[m] .. mel_lo[m]+mel_len[m]) are stored at
+ *   mel_val[mel_off[m] ..]; db_offset = 10*log10(max(amin, ref)); bn_scale/bn_shift [n_mels] or NULL;
  *   out [B, T, n_mels] f32 with T = L / hop + 1.  n_fft in {256, 512, 1024}. */
-int sed_frontend_logmel_f32(const float* wave, int B, int L, int n_fft, int hop, const float* window,
-                            const float* twiddle, const int* mel_lo, const int* mel_len, const int* mel_off,
-                            const float* mel_val, int n_mels, float amin, float db_offset, int is_log,
-                            const float* bn_scale, const float* bn_shift, float* out, void* stream);
+int sed_frontend_logmel(const void* wave, int wave_dtype, int B, int L, long clip_stride, long total_len, int n_fft,
+                        int hop, const float* window, const float* twiddle, const int* mel_lo, const int* mel_len,
+                        const int* mel_off, const float* mel_val, int n_mels, float amin, float db_offset, int is_log,
+                        const float* bn_scale, const float* bn_shift, float* out, void* stream);
 
 /* Power spectrogram only.  Replaces Spectrogram.forward pytorch/stft.py:651-670 (power == 2).
  *   out [B, T, n_fft/2+1] f32 (the reference's [B,1,T,F] layout). */
@@ -97,6 +100,14 @@ long sed_bigru_workspace_bytes(int B);
  *   workspace: sed_bigru_workspace_bytes(B) bytes, 128-byte aligned, contents irrelevant. */
 int sed_bigru(const float* gi, const void* whh_packed, const float* bhh, int B, int T, float* out, void* workspace,
               int dtype, void* stream);
+
+/* Overlap-add of per-window framewise outputs followed by the reference's block-wise averaging.
+ * Replaces merge + avg_merge utils/utilities.py:405-446 as driven by pytorch/predict.py:323-349 (bug-compatible:
+ * the first and last overlap_interval frames are never divided, inner blocks use the reference's divisor rule).
+ *   frames [n_windows, frames_per_window, classes] f32; window k starts at frame k*overlap_interval;
+ *   merged [(n_windows-1)*overlap_interval + frames_per_window, classes] f32. */
+int sed_window_merge_avg(const float* frames, int n_windows, int frames_per_window, int classes, int overlap_interval,
+                         int sample_duration, float* merged, void* stream);
 
 /* Profiling hook: sed_bigru that also records clock64() stamps of CTA 0 for recurrence steps 8..15
  * (stamps: device buffer of 8*12 long long).  Developer tool (tools/gru_stamps.py). */

@@ -104,6 +104,29 @@ def main():
             res["wave_checksum_" + name] = np.array([wave.double().sum().item(), wave.double().abs().sum().item()])
         np.savez_compressed(os.path.join(GOLD, "model_%s_full.npz" % ("gru" if "Gru" in mt else "transformer")), **res)
 
+    # ---- streaming post-processing goldens: reference merge / avg_merge (utils/utilities.py:405-446) ----
+    ref_util, ref_vad = ref_import.load_utilities()
+    rng = np.random.RandomState(20260101)
+    stream = {}
+    for fpw in (500, 496):
+        for (ov, dur) in ((1, 5), (0.5, 6)):
+            for nw in (1, 2, 3, 5, 6, 8):
+                frames = rng.rand(nw, fpw, 5).astype(np.float32)  # regenerated from the seed by the tests
+                merged = prev = None
+                for k in range(nw):
+                    curr = frames[k:k + 1]
+                    if k + 1 == 2:
+                        merged = ref_util.merge(prev, curr, dur, k + 1, ov)
+                    elif k + 1 > 2:
+                        merged = ref_util.merge(merged, curr, dur, k + 1, ov)
+                    else:
+                        merged = curr.copy()
+                    prev = curr
+                merged = ref_util.avg_merge(merged.copy(), dur, ov)
+                key = "f%d_ov%s_d%d_n%d" % (fpw, str(ov).replace(".", "p"), dur, nw)
+                stream[key] = merged
+    np.savez_compressed(os.path.join(GOLD, "stream_merge.npz"), **stream)
+
     # ---- shipped thresholds (opt_thresholds/**/best_*.pkl) as a JSON fixture ----
     thr = {}
     base = os.path.join(ref_import.REF_ROOT, "opt_thresholds")

@@ -38,3 +38,26 @@ def load():
         if saved_mods[k] is not None:
             sys.modules[k] = saved_mods[k]
     return ref_stft, ref_models
+
+
+def load_utilities():
+    """Returns the reference's utils/utilities.py module (merge, avg_merge, ...) and utils/vad.py."""
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REF_ROOT)
+    sys.dont_write_bytecode = True
+    saved_path = list(sys.path)
+    names = ("utilities", "vad", "config", "librosa", "matplotlib", "sed_eval", "h5py", "prettytable")
+    saved_mods = {k: sys.modules.get(k) for k in names}
+    try:
+        for k in names:
+            sys.modules.pop(k, None)
+        sys.path[:0] = [_SHIMS, os.path.join(REF_ROOT, "utils")]
+        ref_utilities = importlib.import_module("utilities")
+        ref_vad = importlib.import_module("vad")
+    finally:
+        sys.path[:] = saved_path
+    for k in names:
+        sys.modules.pop(k, None)
+        if saved_mods[k] is not None:
+            sys.modules[k] = saved_mods[k]
+    return ref_utilities, ref_vad

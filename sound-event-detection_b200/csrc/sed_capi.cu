@@ -5,7 +5,7 @@
 
 #include "sed_kernels.h"
 
-#define SED_ABI_VERSION 2
+#define SED_ABI_VERSION 3
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -23,27 +23,31 @@ int sed_abi_version(void) { return SED_ABI_VERSION; }
 
 const char* sed_last_error_string(void) { return sed::last_error(); }
 
-int sed_frontend_logmel_f32(const float* wave, int B, int L, int n_fft, int hop, const float* window,
-                            const float* twiddle, const int* mel_lo, const int* mel_len, const int* mel_off,
-                            const float* mel_val, int n_mels, float amin, float db_offset, int is_log,
-                            const float* bn_scale, const float* bn_shift, float* out, void* stream) {
+int sed_frontend_logmel(const void* wave, int wave_dtype, int B, int L, long clip_stride, long total_len, int n_fft,
+                        int hop, const float* window, const float* twiddle, const int* mel_lo, const int* mel_len,
+                        const int* mel_off, const float* mel_val, int n_mels, float amin, float db_offset, int is_log,
+                        const float* bn_scale, const float* bn_shift, float* out, void* stream) {
   SED_REQUIRE(wave); SED_REQUIRE(window); SED_REQUIRE(twiddle); SED_REQUIRE(mel_lo); SED_REQUIRE(mel_len);
   SED_REQUIRE(mel_off); SED_REQUIRE(mel_val); SED_REQUIRE(out);
   if ((bn_scale == nullptr) != (bn_shift == nullptr)) {
-    sed::set_error("sed_frontend_logmel_f32: bn_scale and bn_shift must both be set or both be NULL");
+    sed::set_error("sed_frontend_logmel: bn_scale and bn_shift must both be set or both be NULL");
     return SED_ERR_NULL;
   }
   sed::FrontendArgs a{};
-  a.wave = wave; a.B = B; a.L = L; a.n_fft = n_fft; a.hop = hop;
+  a.wave = wave; a.wave_dtype = wave_dtype; a.clip_stride = clip_stride; a.total_len = total_len;
+  a.B = B; a.L = L; a.n_fft = n_fft; a.hop = hop;
   a.T = (hop > 0) ? L / hop + 1 : 0;
   a.window = window; a.twiddle = twiddle;
   a.mel_lo = mel_lo; a.mel_len = mel_len; a.mel_off = mel_off; a.mel_val = mel_val; a.n_mels = n_mels;
   a.amin = amin; a.db_offset = db_offset; a.is_log = is_log;
   a.bn_scale = bn_scale; a.bn_shift = bn_shift; a.out = out; a.mode = 0;
   int rc = sed::frontend_launch(a, as_stream(stream));
-  if (rc == SED_ERR_BAD_SHAPE) sed::set_error("sed_frontend_logmel_f32: bad shape B=%d L=%d n_fft=%d hop=%d", B, L, n_fft, hop);
-  if (rc == SED_ERR_UNSUPPORTED) sed::set_error("sed_frontend_logmel_f32: n_fft=%d unsupported (256/512/1024)", n_fft);
-  if (rc == SED_ERR_CUDA) sed::set_error("sed_frontend_logmel_f32: %s", cudaGetErrorString(cudaGetLastError()));
+  if (rc == SED_ERR_BAD_SHAPE)
+    sed::set_error("sed_frontend_logmel: bad shape B=%d L=%d stride=%ld total=%ld n_fft=%d hop=%d", B, L, clip_stride,
+                   total_len, n_fft, hop);
+  if (rc == SED_ERR_UNSUPPORTED)
+    sed::set_error("sed_frontend_logmel: n_fft=%d (256/512/1024) or wave_dtype=%d (0/1) unsupported", n_fft, wave_dtype);
+  if (rc == SED_ERR_CUDA) sed::set_error("sed_frontend_logmel: %s", cudaGetErrorString(cudaGetLastError()));
   return rc;
 }
 
@@ -51,7 +55,8 @@ int sed_spectrogram_f32(const float* wave, int B, int L, int n_fft, int hop, con
                         const float* twiddle, float* out, void* stream) {
   SED_REQUIRE(wave); SED_REQUIRE(window); SED_REQUIRE(twiddle); SED_REQUIRE(out);
   sed::FrontendArgs a{};
-  a.wave = wave; a.B = B; a.L = L; a.n_fft = n_fft; a.hop = hop;
+  a.wave = wave; a.wave_dtype = 0; a.clip_stride = L; a.total_len = static_cast<long>(B) * L;
+  a.B = B; a.L = L; a.n_fft = n_fft; a.hop = hop;
   a.T = (hop > 0) ? L / hop + 1 : 0;
   a.window = window; a.twiddle = twiddle;
   a.out = out; a.mode = 1;
@@ -60,6 +65,13 @@ int sed_spectrogram_f32(const float* wave, int B, int L, int n_fft, int hop, con
   if (rc == SED_ERR_UNSUPPORTED) sed::set_error("sed_spectrogram_f32: n_fft=%d unsupported (256/512/1024)", n_fft);
   if (rc == SED_ERR_CUDA) sed::set_error("sed_spectrogram_f32: %s", cudaGetErrorString(cudaGetLastError()));
   return rc;
+}
+
+int sed_window_merge_avg(const float* frames, int n_windows, int frames_per_window, int classes, int overlap_interval,
+                         int sample_duration, float* merged, void* stream) {
+  SED_REQUIRE(frames); SED_REQUIRE(merged);
+  return sed::window_merge_launch(frames, n_windows, frames_per_window, classes, overlap_interval, sample_duration,
+                                  merged, as_stream(stream));
 }
 
 int sed_logmel_rows_f32(const float* spec, long rows, int F, const int* mel_lo, const int* mel_len,

@@ -123,9 +123,18 @@ __device__ __forceinline__ void fft_pass(float2* __restrict__ buf, bool first, i
 }
 
 // mode 0: out = log-mel (+ optional bn0 affine) [B, T, n_mels];  mode 1: out = power spectrogram [B, T, F]
-template <int NFFT>
+// int16 PCM input follows the reference's HDF5 path: x = q / 32767 (utils/utilities.py:78-79); the float32
+// division is correctly rounded and equals numpy's float64-then-float32 result for every int16 q.
+__device__ __forceinline__ float load_sample(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float load_sample(const short* p) { return static_cast<float>(__ldg(p)) / 32767.0f; }
+
+// Clip b starts at wave + b * clip_stride and is L samples long; samples at or beyond total_len (counted from
+// `wave`) read as zero (pad_truncate_sequence, utils/utilities.py:66-70).  clip_stride < L gives overlapping
+// windows of one long recording (predict.py:297-307) without materialising them.
+template <int NFFT, typename TIn>
 __global__ void __launch_bounds__(FrontCfg<NFFT>::WARPS * 32)
-frontend_kernel(const float* __restrict__ wave, int L, int T, int hop, const float* __restrict__ window,
+frontend_kernel(const TIn* __restrict__ wave, long clip_stride, long total_len, int L, int T, int hop,
+                const float* __restrict__ window,
                 const float2* __restrict__ twiddle, const int* __restrict__ mel_lo, const int* __restrict__ mel_len,
                 const int* __restrict__ mel_off, const float* __restrict__ mel_val, int n_mels, float amin,
                 float db_offset, int is_log, const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
@@ -145,7 +154,8 @@ frontend_kernel(const float* __restrict__ wave, int L, int T, int hop, const flo
 
   const int b = blockIdx.y;
   const int f_base = blockIdx.x * FPB;
-  const float* w = wave + static_cast<size_t>(b) * L;
+  const long clip_base = static_cast<long>(b) * clip_stride;
+  const TIn* w = wave + clip_base;
 
   // stage the waveform segment with reflect padding (stft.py:236-237)
   const long q0 = static_cast<long>(f_base) * hop - NFFT / 2;
@@ -153,7 +163,7 @@ frontend_kernel(const float* __restrict__ wave, int L, int T, int hop, const flo
     long i = q0 + s;
     if (i < 0) i = -i;
     if (i >= L) i = 2L * (L - 1) - i;
-    s_seg[s] = (i >= 0 && i < L) ? __ldg(w + i) : 0.0f;
+    s_seg[s] = (i >= 0 && i < L && clip_base + i < total_len) ? load_sample(w + i) : 0.0f;
   }
   for (int i = threadIdx.x; i < NFFT; i += blockDim.x) {
     s_win[i] = window[i];
@@ -291,27 +301,35 @@ __global__ void logmel_rows_kernel(const float* __restrict__ spec, long rows, in
   }
 }
 
-template <int NFFT>
-static int launch_frontend(const FrontendArgs& a, cudaStream_t stream) {
+template <int NFFT, typename TIn>
+static int launch_frontend_t(const FrontendArgs& a, cudaStream_t stream) {
   constexpr int WARPS = FrontCfg<NFFT>::WARPS;
   constexpr int FPB = FrontCfg<NFFT>::FPB;
   const int seg_len = (FPB - 1) * a.hop + NFFT;
   const size_t smem = sizeof(float) * (((seg_len + 3) & ~3) + NFFT + FrontCfg<NFFT>::MELV) +
                       sizeof(float2) * (NFFT + WARPS * (NFFT + NFFT / 8)) + sizeof(int) * 3 * (a.n_mels > 0 ? a.n_mels : 1);
   if (smem > 227 * 1024) return SED_ERR_UNSUPPORTED;
-  cudaError_t e = cudaFuncSetAttribute(frontend_kernel<NFFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e =
+      cudaFuncSetAttribute(frontend_kernel<NFFT, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return SED_ERR_CUDA;
   dim3 grid((a.T + FPB - 1) / FPB, a.B);
   const char* e_dbg = getenv("SED_FE_DBG");
   const int dbg = e_dbg ? atoi(e_dbg) : 0;
-  frontend_kernel<NFFT><<<grid, WARPS * 32, smem, stream>>>(
-      a.wave, a.L, a.T, a.hop, a.window, reinterpret_cast<const float2*>(a.twiddle), a.mel_lo, a.mel_len, a.mel_off,
+  frontend_kernel<NFFT, TIn><<<grid, WARPS * 32, smem, stream>>>(
+      reinterpret_cast<const TIn*>(a.wave), a.clip_stride, a.total_len, a.L, a.T, a.hop, a.window, reinterpret_cast<const float2*>(a.twiddle), a.mel_lo, a.mel_len, a.mel_off,
       a.mel_val, a.n_mels, a.amin, a.db_offset, a.is_log, a.bn_scale, a.bn_shift, a.out, a.mode, dbg);
   return cudaGetLastError() == cudaSuccess ? SED_OK : SED_ERR_CUDA;
 }
 
+template <int NFFT>
+static int launch_frontend(const FrontendArgs& a, cudaStream_t stream) {
+  if (a.wave_dtype == 1) return launch_frontend_t<NFFT, short>(a, stream);
+  return launch_frontend_t<NFFT, float>(a, stream);
+}
+
 int frontend_launch(const FrontendArgs& a, cudaStream_t stream) {
-  if (a.B <= 0 || a.L <= a.n_fft / 2 || a.hop <= 0) return SED_ERR_BAD_SHAPE;
+  if (a.B <= 0 || a.L <= a.n_fft / 2 || a.hop <= 0 || a.clip_stride <= 0 || a.total_len <= 0) return SED_ERR_BAD_SHAPE;
+  if (a.wave_dtype != 0 && a.wave_dtype != 1) return SED_ERR_UNSUPPORTED;
   switch (a.n_fft) {
     case 256: return launch_frontend<256>(a, stream);
     case 512: return launch_frontend<512>(a, stream);

@@ -7,7 +7,10 @@
 namespace sed {
 
 struct FrontendArgs {
-  const float* wave;  // [B, L]
+  const void* wave;   // clip b = wave + b*clip_stride, L samples (f32 or i16)
+  int wave_dtype;     // 0 = float32, 1 = int16 PCM (x = q / 32767)
+  long clip_stride;   // samples between clip starts (== L for a dense batch)
+  long total_len;     // samples readable from `wave`; beyond -> 0
   int B, L, T, n_fft, hop;
   const float* window;   // [n_fft]
   const float* twiddle;  // [n_fft][2]  exp(-2 pi i k / n_fft)
@@ -42,6 +45,9 @@ int linear_launch(const void* a16, long M, int K, const void* w16, const float* 
 size_t gru_workspace_bytes(int B);
 int gru_launch(const float* gi, const void* whh_packed, const float* bhh, int B, int T, float* out, void* workspace,
                int dtype, cudaStream_t stream, long long* stamps = nullptr);
+
+int window_merge_launch(const float* frames, int n_windows, int frames_per_window, int classes, int overlap_interval,
+                        int sample_duration, float* merged, cudaStream_t stream);
 
 int mha_core_launch(const float* qkv, int B, int T, void* out16, int dtype, cudaStream_t stream);
 

@@ -111,21 +111,57 @@ class FrontendPlan:
             self.F = int(melW.shape[0])
 
 
-def logmel_forward(plan, wave, bn_scale=None, bn_shift=None, out=None):
-    """wave [B, L] f32 cuda -> [B, T, n_mels] f32."""
+def _wave_dtype_code(wave):
+    if wave.dtype == torch.float32:
+        return 0
+    if wave.dtype == torch.int16:
+        return 1  # PCM: x = q / 32767 (utils/utilities.py:78-79), converted inside the kernel
+    raise TypeError("waveform must be float32 or int16, got %s" % (wave.dtype,))
+
+
+def logmel_forward(plan, wave, bn_scale=None, bn_shift=None, out=None, windows=None):
+    """wave [B, L] (f32 or int16 PCM) cuda -> [B, T, n_mels] f32.
+
+    windows=(n_windows, L, stride): `wave` is one 1-D recording; window k = wave[k*stride : k*stride + L], zero
+    padded past the end (the slicing of predict.py:302-305) -- read in place, never materialised."""
     lib = capi.load()
-    B, L = wave.shape
+    code = _wave_dtype_code(wave)
+    if windows is None:
+        if wave.dim() != 2 or not wave.is_contiguous():
+            raise ValueError("waveform batch must be a contiguous (batch_size, data_length) tensor")
+        B, L = wave.shape
+        stride, total = L, B * L
+    else:
+        if wave.dim() != 1 or not wave.is_contiguous():
+            raise ValueError("windowed input must be a contiguous 1-D recording")
+        B, L, stride = (int(v) for v in windows)
+        total = wave.numel()
     T = L // plan.hop + 1
     if out is None:
         out = torch.empty((B, T, plan.n_mels), dtype=torch.float32, device=wave.device)
-    rc = lib.sed_frontend_logmel_f32(capi.ptr(wave), B, L, plan.n_fft, plan.hop, capi.ptr(plan.window),
-                                     capi.ptr(plan.twiddle), capi.ptr(plan.mel_lo), capi.ptr(plan.mel_len),
-                                     capi.ptr(plan.mel_off), capi.ptr(plan.mel_val), plan.n_mels, plan.amin,
-                                     plan.db_offset, plan.is_log, capi.ptr(bn_scale), capi.ptr(bn_shift),
-                                     capi.ptr(out), capi.current_stream(wave.device))
-    capi.check(rc, "sed_frontend_logmel_f32")
+    rc = lib.sed_frontend_logmel(capi.ptr(wave), code, B, L, stride, total, plan.n_fft, plan.hop,
+                                 capi.ptr(plan.window), capi.ptr(plan.twiddle), capi.ptr(plan.mel_lo),
+                                 capi.ptr(plan.mel_len), capi.ptr(plan.mel_off), capi.ptr(plan.mel_val), plan.n_mels,
+                                 plan.amin, plan.db_offset, plan.is_log, capi.ptr(bn_scale), capi.ptr(bn_shift),
+                                 capi.ptr(out), capi.current_stream(wave.device))
+    capi.check(rc, "sed_frontend_logmel")
     capi._count()
     return out
+
+
+def window_merge_avg(frames, overlap_interval, sample_duration):
+    """frames [n_windows, frames_per_window, classes] f32 cuda -> merged [1, total_frames, classes]
+    (merge + avg_merge, utils/utilities.py:405-446)."""
+    lib = capi.load()
+    frames = frames.contiguous()
+    nw, fpw, ncls = frames.shape
+    total = (nw - 1) * overlap_interval + fpw
+    merged = torch.empty((1, total, ncls), dtype=torch.float32, device=frames.device)
+    rc = lib.sed_window_merge_avg(capi.ptr(frames), nw, fpw, ncls, int(overlap_interval), int(sample_duration),
+                                  capi.ptr(merged), capi.current_stream(frames.device))
+    capi.check(rc, "sed_window_merge_avg")
+    capi._count()
+    return merged
 
 
 def spectrogram_forward(plan, wave):
@@ -237,16 +273,20 @@ class PackedModel:
         return ws
 
     # ------------------------------------------------------------------ stages
-    def conv_stack(self, wave_mb, feat_out, variant=2, stages=None):
-        """wave_mb [mb, L] f32 -> feat_out [mb, T', 512] 16-bit (freq-mean of conv_block4)."""
+    def conv_stack(self, wave_mb, feat_out, variant=2, stages=None, windows=None):
+        """wave_mb [mb, L] (f32 / int16) -> feat_out [mb, T', 512] 16-bit (freq-mean of conv_block4).
+        windows=(mb, L, stride): wave_mb is a 1-D recording read as overlapping windows."""
         lib = capi.load()
-        mb, L = wave_mb.shape
+        if windows is None:
+            mb, L = wave_mb.shape
+        else:
+            mb, L = int(windows[0]), int(windows[1])
         T = L // self.front.hop + 1
         if T // 8 < 1:
             raise ValueError("clip too short: %d frames" % T)
         ws = self._workspace(mb, T)
         stream = capi.current_stream(self.device)
-        logmel_forward(self.front, wave_mb, self.bn0_scale, self.bn0_shift, out=ws["logmel"])
+        logmel_forward(self.front, wave_mb, self.bn0_scale, self.bn0_shift, out=ws["logmel"], windows=windows)
         rc = lib.sed_conv_first_f32(capi.ptr(ws["logmel"]), mb, T, 64, capi.ptr(self.c11_w), capi.ptr(self.c11_scale),
                                     capi.ptr(self.c11_shift), capi.ptr(ws["a1"]), self.dtype_code, stream)
         capi.check(rc, "sed_conv_first_f32")
@@ -332,17 +372,17 @@ class PackedModel:
         the device micro-batch by micro-batch on a copy stream that runs ahead of the compute stream, and
         `clipwise_output` / `framewise_output` come back as host tensors (the reference callers do
         `.data.cpu().numpy()` on exactly these, pytorch_utils.py:57-62)."""
-        if wave_host.is_cuda or wave_host.dim() != 2:
-            raise ValueError("forward_host expects a (batch_size, data_length) CPU tensor")
+        if wave_host.is_cuda or wave_host.dim() != 2 or wave_host.dtype not in (torch.float32, torch.int16):
+            raise ValueError("forward_host expects a (batch_size, data_length) float32 or int16 CPU tensor")
         B, L = wave_host.shape
-        key = (B, L)
+        key = (B, L, wave_host.dtype)
         hb = self._host.get(key)
         if hb is None:
             T = L // self.front.hop + 1
             frames = (T // 8) * 8
             if self.model_type == "Cnn_9layers_Gru_FrameAtt" and frames != 1000 and frames % 100:
                 frames += 100 - frames % 100
-            hb = {"dev": torch.empty((B, L), dtype=torch.float32, device=self.device),
+            hb = {"dev": torch.empty((B, L), dtype=wave_host.dtype, device=self.device),
                   "clip": torch.empty((B, 25), dtype=torch.float32).pin_memory(),
                   "frame": torch.empty((B, frames, 25), dtype=torch.float32).pin_memory(),
                   "copy_stream": torch.cuda.Stream(self.device)}
@@ -364,13 +404,40 @@ class PackedModel:
         compute.synchronize()
         return {"clipwise_output": hb["clip"], "framewise_output": hb["frame"]}
 
+    def forward_windows(self, recording, window_samples, stride_samples, n_windows, micro_batch=148, variant=2):
+        """Run the model on `n_windows` overlapping windows of one 1-D recording (f32 or int16, on device):
+        window k = recording[k*stride : k*stride + window_samples], zero padded past the end.  Returns the same
+        dict as forward() with batch dimension = windows (the per-window calls of predict.py:311-313 as one batch)."""
+        if recording.dim() != 1 or recording.device != self.device:
+            raise ValueError("recording must be a 1-D tensor on %s" % (self.device,))
+        if recording.dtype != torch.int16:
+            recording = recording.float()
+        recording = recording.contiguous()
+        T = window_samples // self.front.hop + 1
+        Tp = T // 8
+        with self._lock:
+            feat16 = torch.empty((n_windows, Tp, 512), dtype=self.tdtype, device=self.device)
+            for b0 in range(0, n_windows, micro_batch):
+                b1 = min(n_windows, b0 + micro_batch)
+                sub = recording[b0 * stride_samples:]
+                self.conv_stack(sub, feat16[b0:b1], variant=variant, windows=(b1 - b0, window_samples, stride_samples))
+            x = self.temporal(feat16)
+            frames = Tp * 8
+            is_gru = self.model_type == "Cnn_9layers_Gru_FrameAtt"
+            if is_gru and frames != 1000:
+                frames = frames if frames % 100 == 0 else frames + 100 - frames % 100
+            clip, frame, cla, _ = self.head(x, frames, want_cla=is_gru)
+        return {"framewise_output": frame, "clipwise_output": clip, "embedding": cla if is_gru else x.transpose(1, 2)}
+
     def forward(self, wave, micro_batch=148, variant=2, return_stages=False, _h2d_events=None):
         """wave [B, L] f32 on self.device -> reference output dict (models.py:683-686 / :1072-1075)."""
         if wave.dim() != 2:
             raise ValueError("input must be (batch_size, data_length)")
         if wave.device != self.device:
             raise ValueError("input is on %s, packed weights are on %s" % (wave.device, self.device))
-        wave = wave.float().contiguous()
+        if wave.dtype != torch.int16:  # int16 PCM is consumed as is (x = q / 32767 inside the front-end)
+            wave = wave.float()
+        wave = wave.contiguous()
         B, L = wave.shape
         T = L // self.front.hop + 1
         Tp = T // 8

@@ -1,0 +1,93 @@
+"""GPU parity of the widened rows: int16 PCM input and the batched streaming path with device
+merge / avg_merge (8f-1, BASELINE config 4)."""
+import numpy as np
+import pytest
+import torch
+
+import stream_oracle
+from conftest import load_golden, synthetic_sd
+from sed_b200 import engine, models, streaming, synth
+from test_stream_oracle import CASES, golden_frames, key
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def build(mt, sr=16000):
+    n_fft, hop, fmin, fmax = synth.PRESETS[sr]
+    model = getattr(models, mt)(sr, n_fft, hop, 64, fmin, fmax, 25, "logmel")
+    model.load_state_dict(synthetic_sd(mt, sr))
+    return model.to(DEV).eval()
+
+
+def test_device_merge_avg_merge_bit_exact_with_reference_golden():
+    g = load_golden("stream_merge.npz")
+    frames = golden_frames()
+    for case in CASES:
+        fpw, ov, dur, nw = case
+        got = engine.window_merge_avg(torch.from_numpy(frames[case]).to(DEV), int(100 * ov), dur).cpu().numpy()
+        assert np.array_equal(got, g[key(*case)]), case
+
+
+def test_int16_input_equals_float_input_bitwise():
+    """x = q / 32767 inside the kernel == numpy's int16_to_float32 on the host (utilities.py:78-79)."""
+    model = build("Cnn_9layers_Gru_FrameAtt")
+    q = torch.round(synth.synthetic_waveform(3, 48000, seed=13, kind="events") * 32767.0).to(torch.int16)
+    wave_f = torch.from_numpy((q.numpy() / 32767.).astype(np.float32))
+    a = model(wave_f.to(DEV))
+    b = model(q.to(DEV))
+    for k in ("framewise_output", "clipwise_output"):
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_int16_frontend_full_range():
+    from sed_b200 import melbank
+    wr, wi = melbank.windowed_dft_kernels(512, 512, "hann")
+    plan = engine.FrontendPlan(wr, wi, 512, 160, melbank.mel_filterbank(16000, 512, 64, 25, 7000), torch.device(DEV))
+    q = torch.arange(-32768, 32768, dtype=torch.int32).to(torch.int16).repeat(2)[None]  # every int16 value
+    wave_f = torch.from_numpy((q.numpy() / 32767.).astype(np.float32))
+    a = engine.logmel_forward(plan, wave_f.to(DEV))
+    b = engine.logmel_forward(plan, q.to(DEV))
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("mt", synth.MODEL_TYPES)
+def test_streaming_matches_window_by_window_oracle(mt):
+    """13.4 s recording -> 9 windows of 5 s at 1 s stride; batched GPU path vs the reference loop (B = 1 per window)."""
+    sr = 16000
+    rec = synth.synthetic_waveform(1, int(13.4 * sr), seed=41, kind="events")[0]
+    merged_ref, frames_ref = stream_oracle.streaming_predict(synthetic_sd(mt), rec.numpy(), mt, sr, 512, 160, 5, 1)
+    model = build(mt)
+    merged, out = streaming.predict_framewise(model, rec.to(DEV), sr, 5, 1, return_windows=True)
+    assert out["framewise_output"].shape == frames_ref.shape  # 9 x 500 (GRU, padded) or 9 x 496 (Transformer)
+    assert np.abs(out["framewise_output"].cpu().numpy() - frames_ref).max() <= 2e-3
+    assert merged.shape == merged_ref.shape
+    assert np.abs(merged.cpu().numpy() - merged_ref).max() <= 2e-3
+    # the device merge of the GPU frames equals the numpy merge of the same frames exactly
+    again = stream_oracle.merge_windows(out["framewise_output"].cpu().numpy(), 5, 1)
+    assert np.array_equal(merged.cpu().numpy(), again)
+
+
+def test_streaming_short_recording_and_32k_preset():
+    mt = "Cnn_9layers_Gru_FrameAtt"
+    sr = 32000
+    rec = synth.synthetic_waveform(1, int(3.3 * sr), seed=5, kind="events", sample_rate=sr)[0]
+    merged_ref, _ = stream_oracle.streaming_predict(synthetic_sd(mt, sr), rec.numpy(), mt, sr, 1024, 320, 5, 1)
+    merged = streaming.predict_framewise(build(mt, sr), rec.to(DEV), sr, 5, 1)
+    assert merged.shape == (1, 500, 25)  # a single zero-padded window
+    assert np.abs(merged.cpu().numpy() - merged_ref).max() <= 2e-3
+
+
+def test_windowed_frontend_reads_in_place():
+    """Strided windows of one recording == the same windows materialised as a batch."""
+    mt = "Cnn_9layers_Gru_FrameAtt"
+    pm = engine.PackedModel(synthetic_sd(mt), mt, 512, 160, torch.device(DEV))
+    rec = synth.synthetic_waveform(1, 16000 * 9 + 123, seed=2)[0].to(DEV)
+    n, L, stride = 6, 80000, 16000
+    batch = torch.zeros(n, L, device=DEV)
+    for k in range(n):
+        seg = rec[k * stride:k * stride + L]
+        batch[k, :seg.numel()] = seg
+    a = pm.forward(batch)
+    b = pm.forward_windows(rec, L, stride, n)
+    assert torch.equal(a["framewise_output"], b["framewise_output"])
