@@ -109,6 +109,16 @@ int sed_bigru(const float* gi, const void* whh_packed, const float* bhh, int B, 
 int sed_window_merge_avg(const float* frames, int n_windows, int frames_per_window, int classes, int overlap_interval,
                          int sample_duration, float* merged, void* stream);
 
+/* Frame-wise probabilities -> sound events per (clip, class): double-threshold hysteresis, smoothing, salt removal.
+ * Replaces activity_detection utils/vad.py:11-45 (+ helpers :108-199) as called per clip and class by
+ * frame_prediction_to_event_prediction utils/utilities.py:82-153 / pytorch/predict.py:57-121 (quirks kept:
+ * asymmetric +1 on gap boundaries, low-threshold extension, smooth(1) then smooth(n_smooth), fin-bgn <= n_salt dropped).
+ *   frames [n_clips, n_frames, classes] f32; high/low [classes] f64 (low may be NULL); n_smooth/n_salt [classes] i32;
+ *   events [n_clips, classes, max_events, 2] i32 = (bgn, fin) in frames; counts [n_clips, classes] i32 = number of
+ *   events found (may exceed max_events; only the first max_events are stored). */
+int sed_events(const float* frames, int n_clips, int n_frames, int classes, const double* high, const double* low,
+               const int* n_smooth, const int* n_salt, int max_events, int* events, int* counts, void* stream);
+
 /* Profiling hook: sed_bigru that also records clock64() stamps of CTA 0 for recurrence steps 8..15
  * (stamps: device buffer of 8*12 long long).  Developer tool (tools/gru_stamps.py). */
 int sed_bigru_profile(const float* gi, const void* whh_packed, const float* bhh, int B, int T, float* out,

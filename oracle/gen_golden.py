@@ -127,6 +127,35 @@ def main():
                 stream[key] = merged
     np.savez_compressed(os.path.join(GOLD, "stream_merge.npz"), **stream)
 
+    # ---- event extraction goldens: reference vad.activity_detection on seeded smooth random sequences ----
+    ev = {"cases": []}
+    ev_x = {}
+    rng = np.random.RandomState(77)
+    for case in range(40):
+        n_frames = int(rng.choice([100, 500, 1000, 1237]))
+        base = rng.rand(n_frames + 40)
+        width = int(rng.choice([1, 3, 9, 25]))
+        x = np.convolve(base, np.ones(width) / width, mode="same")[:n_frames]
+        x = ((x - x.min()) / (x.max() - x.min() + 1e-9)).astype(np.float32)
+        if case % 7 == 0:
+            x[-1] = 1.0  # event touching the end
+        if case % 5 == 0:
+            x[0] = 1.0
+        hi = float(rng.uniform(0.3, 0.8)); lo = float(rng.uniform(-0.2, hi))
+        ns = int(rng.choice([0, 1, 3, 10])); nsalt = int(rng.choice([0, 1, 5, 10]))
+        use_low = bool(case % 4 != 3)
+        try:
+            pairs = ref_vad.activity_detection(x, np.float64(hi), np.float64(lo) if use_low else None, ns, nsalt)
+        except IndexError:
+            continue  # the reference itself crashes when a non-first event starts on the last frame
+        ev_x["x%d" % len(ev["cases"])] = x
+        ev["cases"].append({"seed_case": case, "hi": hi, "lo": lo if use_low else None,
+                            "n_smooth": ns, "n_salt": nsalt, "pairs": [[int(a), int(b)] for a, b in pairs]})
+    ev["example"] = ref_vad.find_bgn_fin_pairs([3, 4, 5, 9, 10, 20])
+    with open(os.path.join(GOLD, "events.json"), "w") as fh:
+        json.dump(ev, fh)
+    np.savez_compressed(os.path.join(GOLD, "events_x.npz"), **ev_x)
+
     # ---- shipped thresholds (opt_thresholds/**/best_*.pkl) as a JSON fixture ----
     thr = {}
     base = os.path.join(ref_import.REF_ROOT, "opt_thresholds")

@@ -88,3 +88,62 @@ def streaming_predict(sd, audio_full, model_type, sample_rate, n_fft, hop, sampl
         outs.append(out["framewise_output"].numpy())
     frames = np.concatenate(outs, axis=0)
     return merge_windows(frames, sample_duration, overlap_value), frames
+
+
+# ----------------------------------------------------------------------------------------------
+# Event extraction: utils/vad.py:11-45 activity_detection and helpers :108-199
+# ----------------------------------------------------------------------------------------------
+def find_bgn_fin_pairs(locts):
+    """vad.py:108-130.  Gap handling adds +1 to the closing fin AND to the next bgn; the last fin has no +1."""
+    if len(locts) == 0:
+        return []
+    bgns, fins = [locts[0]], []
+    for i in range(1, len(locts)):
+        if locts[i] - locts[i - 1] > 1:
+            fins.append(locts[i - 1] + 1)
+            bgns.append(locts[i] + 1)
+    fins.append(locts[-1])
+    return [[b, f] for b, f in zip(bgns, fins)]
+
+
+def smooth(pairs, n_smooth):
+    """vad.py:159-184"""
+    if len(pairs) == 0:
+        return []
+    out = []
+    mem_bgn, fin = pairs[0]
+    for n in range(1, len(pairs)):
+        pre_fin = pairs[n - 1][1]
+        bgn, fin = pairs[n]
+        if bgn - pre_fin > n_smooth:
+            out.append([mem_bgn, pre_fin])
+            mem_bgn = bgn
+    out.append([mem_bgn, fin])
+    return out
+
+
+def second_threshold(x, pairs, thres):
+    """vad.py:133-156 (the reference raises IndexError when a pair starts at len(x); treated as a stop here)."""
+    out = []
+    for bgn, fin in pairs:
+        while bgn != -1:
+            if bgn >= len(x) or x[bgn] < thres:
+                break
+            bgn -= 1
+        while fin != len(x):
+            if x[fin] < thres:
+                break
+            fin += 1
+        out.append([bgn + 1, fin])
+    return smooth(out, 1)
+
+
+def activity_detection(x, thres, low_thres=None, n_smooth=1, n_salt=0):
+    """vad.py:11-45"""
+    x = np.asarray(x)
+    locts = np.where(x > thres)[0]
+    pairs = find_bgn_fin_pairs([int(v) for v in locts])
+    if low_thres is not None:
+        pairs = second_threshold(x, pairs, low_thres)
+    pairs = smooth(pairs, n_smooth)
+    return [[b, f] for b, f in pairs if f - b > n_salt]  # remove_salt_noise vad.py:187-199

@@ -5,7 +5,7 @@
 
 #include "sed_kernels.h"
 
-#define SED_ABI_VERSION 3
+#define SED_ABI_VERSION 4
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -72,6 +72,14 @@ int sed_window_merge_avg(const float* frames, int n_windows, int frames_per_wind
   SED_REQUIRE(frames); SED_REQUIRE(merged);
   return sed::window_merge_launch(frames, n_windows, frames_per_window, classes, overlap_interval, sample_duration,
                                   merged, as_stream(stream));
+}
+
+int sed_events(const float* frames, int n_clips, int n_frames, int classes, const double* high, const double* low,
+               const int* n_smooth, const int* n_salt, int max_events, int* events, int* counts, void* stream) {
+  SED_REQUIRE(frames); SED_REQUIRE(high); SED_REQUIRE(n_smooth); SED_REQUIRE(n_salt); SED_REQUIRE(events);
+  SED_REQUIRE(counts);
+  return sed::events_launch(frames, n_clips, n_frames, classes, high, low, n_smooth, n_salt, max_events, events, counts,
+                            as_stream(stream));
 }
 
 int sed_logmel_rows_f32(const float* spec, long rows, int F, const int* mel_lo, const int* mel_len,

@@ -49,6 +49,10 @@ int gru_launch(const float* gi, const void* whh_packed, const float* bhh, int B,
 int window_merge_launch(const float* frames, int n_windows, int frames_per_window, int classes, int overlap_interval,
                         int sample_duration, float* merged, cudaStream_t stream);
 
+int events_launch(const float* frames, int n_clips, int n_frames, int classes, const double* high, const double* low,
+                  const int* n_smooth, const int* n_salt, int max_events, int* events, int* counts,
+                  cudaStream_t stream);
+
 int mha_core_launch(const float* qkv, int B, int T, void* out16, int dtype, cudaStream_t stream);
 
 int attpool_launch(const float* x, int B, int T, const float* w_att, const float* b_att, const float* w_cla,

@@ -192,6 +192,41 @@ def logmel_rows_forward(plan, spec):
     return out
 
 
+def extract_events(frames, high, low, n_smooth, n_salt, max_events=64):
+    """frames [n_clips, n_frames, classes] f32 cuda; per-class thresholds (sequences or scalars).
+    Returns (events [n_clips, classes, max_events, 2] int32, counts [n_clips, classes] int32) on the device
+    (activity_detection, utils/vad.py:11-45, for every clip and class)."""
+    lib = capi.load()
+    frames = frames.contiguous()
+    n_clips, n_frames, classes = frames.shape
+    dev = frames.device
+
+    def per_class(v, dtype):
+        if v is None:
+            return None
+        t = torch.as_tensor(np.asarray(v, dtype=np.float64 if dtype == torch.float64 else np.int64))
+        if t.dim() == 0:
+            t = t.repeat(classes)
+        if t.numel() != classes:
+            raise ValueError("expected %d per-class values, got %d" % (classes, t.numel()))
+        return t.to(dtype).contiguous().to(dev)
+
+    hi, lo = per_class(high, torch.float64), per_class(low, torch.float64)
+    ns, nsalt = per_class(n_smooth, torch.int32), per_class(n_salt, torch.int32)
+    while True:
+        events = torch.zeros((n_clips, classes, max_events, 2), dtype=torch.int32, device=dev)
+        counts = torch.zeros((n_clips, classes), dtype=torch.int32, device=dev)
+        rc = lib.sed_events(capi.ptr(frames), n_clips, n_frames, classes, capi.ptr(hi), capi.ptr(lo), capi.ptr(ns),
+                            capi.ptr(nsalt), max_events, capi.ptr(events), capi.ptr(counts),
+                            capi.current_stream(dev))
+        capi.check(rc, "sed_events")
+        capi._count()
+        most = int(counts.max().item())
+        if most <= max_events:
+            return events, counts
+        max_events = most  # rare: more events than the buffer holds -> rerun once with the exact capacity
+
+
 class PackedModel:
     """Weights of one model repacked for the kernels, resident on one device."""
 

@@ -47,3 +47,32 @@ def predict_framewise(model, recording, sample_rate, sample_duration=5, overlap_
     if return_windows:
         return merged, out
     return merged
+
+
+# Class names of the 25-class strong-label task (utils/config.py:26)
+LABELS = ['Applause', 'Breathing', 'Chatter', 'Cheering', 'Child_speech_kid_speaking', 'Clapping', 'Conversation',
+          'Cough', 'Crowd', 'Crying_sobbing', 'Female_speech_woman_speaking', 'Laughter',
+          'Male_speech_man_speaking', 'Run', 'Screaming', 'Shout', 'Sneeze', 'Walk_footsteps', 'Whispering',
+          'Air_horn_truck_horn', 'Car_alarm', 'Emergency_vehicle', 'Explosion', 'Gunshot_gunfire', 'Siren']
+
+
+def frame_prediction_to_event_prediction(framewise_output, sed_params_dict, frames_per_second=100, audio_names=None,
+                                         labels=LABELS):
+    """Device version of utils/utilities.py:82-153 (and predict.py:57-121, which uses filename 'test').
+
+    framewise_output: (audios_num, frames_num, classes_num) float32 CUDA tensor; sed_params_dict as loaded from the
+    shipped opt_thresholds pickles or the scalar defaults of predict.py:252-257.  Returns the reference's list of
+    {'filename', 'onset', 'offset', 'event_label'} dicts in the reference's order (clip-major, class, event)."""
+    events, counts = engine.extract_events(framewise_output, sed_params_dict['sed_high_threshold'],
+                                           sed_params_dict.get('sed_low_threshold'), sed_params_dict['n_smooth'],
+                                           sed_params_dict['n_salt'])
+    events = events.cpu().numpy()
+    counts = counts.cpu().numpy()
+    event_list = []
+    for n in range(events.shape[0]):
+        name = 'test' if audio_names is None else audio_names[n]
+        for k in range(events.shape[1]):
+            for e in range(int(counts[n, k])):
+                event_list.append({'filename': name, 'onset': events[n, k, e, 0] / float(frames_per_second),
+                                   'offset': events[n, k, e, 1] / float(frames_per_second), 'event_label': labels[k]})
+    return event_list
