@@ -292,21 +292,28 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   return SED_OK;
 }
 
-template <typename T, int CIN, int BN, int EPI, int SA, int ACC>
+template <typename T, int CIN, int BN, int EPI, int SA, int ACC, bool BRES, int NT, int SB>
 static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvParams& p,
                        cudaStream_t stream) {
-  using Cfg = Conv2Cfg<CIN, BN, EPI, SA, ACC>;
-  auto kern = conv_umma2_kernel<T, CIN, BN, EPI, SA, ACC>;
+  using Cfg = Conv2Cfg<CIN, BN, EPI, SA, ACC, BRES, NT, SB>;
+  auto kern = conv_umma2_kernel<T, CIN, BN, EPI, SA, ACC, BRES, NT, SB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(pair, smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
     return SED_ERR_CUDA;
   }
-  const int items = (p.num_tiles + 1) / 2;
-  int pairs_per_slice = (num_sms() / 2) / p.nslices;
-  if (pairs_per_slice > items) pairs_per_slice = items;
-  if (pairs_per_slice < 1) pairs_per_slice = 1;
-  const int grid = 2 * pairs_per_slice * p.nslices;
+  const int items = (p.num_tiles + 2 * NT - 1) / (2 * NT);
+  int grid;
+  if (BRES) {
+    int pairs_per_slice = (num_sms() / 2) / p.nslices;
+    if (pairs_per_slice > items) pairs_per_slice = items;
+    if (pairs_per_slice < 1) pairs_per_slice = 1;
+    grid = 2 * pairs_per_slice * p.nslices;
+  } else {
+    const long work = static_cast<long>(items) * p.nslices;
+    const int pairs = num_sms() / 2;
+    grid = 2 * static_cast<int>(work < pairs ? work : pairs);
+  }
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmO, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -322,11 +329,15 @@ static int conv3x3_dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   // (cin, cout, mode) are the seven tensor-core layers of Cnn_9layers.
   // variant 2: CTA-pair (cta_group::2) kernels for the weight-stationary layers
   if (variant == 2) {
-    if (cin == 64 && cout == 64 && mode == EPI_POOL) { p.nslices = 1; return launch_pair<T, 64, 64, EPI_POOL, 6, 4>(tmA, tmB, tmO, p, stream); }
-    if (cin == 64 && cout == 128 && mode == EPI_STORE) { p.nslices = 1; return launch_pair<T, 64, 128, EPI_STORE, 4, 4>(tmA, tmB, tmO, p, stream); }
-    if (cin == 128 && cout == 128 && mode == EPI_POOL) { p.nslices = 1; return launch_pair<T, 128, 128, EPI_POOL, 3, 2>(tmA, tmB, tmO, p, stream); }
-    if (cin == 128 && cout == 256 && mode == EPI_STORE) { p.nslices = 2; return launch_pair<T, 128, 128, EPI_STORE, 2, 2>(tmA, tmB, tmO, p, stream); }
-    variant = 0;  // streamed-weight layers have no pair variant
+    if (cin == 64 && cout == 64 && mode == EPI_POOL) { p.nslices = 1; return launch_pair<T, 64, 64, EPI_POOL, 6, 4, true, 1, 1>(tmA, tmB, tmO, p, stream); }
+    if (cin == 64 && cout == 128 && mode == EPI_STORE) { p.nslices = 1; return launch_pair<T, 64, 128, EPI_STORE, 4, 4, true, 1, 1>(tmA, tmB, tmO, p, stream); }
+    if (cin == 128 && cout == 128 && mode == EPI_POOL) { p.nslices = 1; return launch_pair<T, 128, 128, EPI_POOL, 3, 2, true, 1, 1>(tmA, tmB, tmO, p, stream); }
+    if (cin == 128 && cout == 256 && mode == EPI_STORE) { p.nslices = 2; return launch_pair<T, 128, 128, EPI_STORE, 2, 2, true, 1, 1>(tmA, tmB, tmO, p, stream); }
+    // streamed weights: each CTA loads half of every 256-row weight block, two pixel tiles per CTA share it
+    if (cin == 256 && cout == 256 && mode == EPI_POOL) { p.nslices = 2; return launch_pair<T, 256, 128, EPI_POOL, 2, 2, false, 2, 6>(tmA, tmB, tmO, p, stream); }
+    if (cin == 256 && cout == 512 && mode == EPI_STORE) { p.nslices = 4; return launch_pair<T, 256, 128, EPI_STORE, 2, 2, false, 2, 6>(tmA, tmB, tmO, p, stream); }
+    if (cin == 512 && cout == 512 && mode == EPI_FREQMEAN) { p.nslices = 4; return launch_pair<T, 512, 128, EPI_FREQMEAN, 2, 2, false, 2, 6>(tmA, tmB, tmO, p, stream); }
+    variant = 0;
   }
 #define SED_CASE(CIN_, COUT_, MODE_, BN_, NT_, BRES_, SA_P, SB_P, SA_T, SB_T)                                     \
   if (cin == CIN_ && cout == COUT_ && mode == MODE_) {                                                             \
@@ -376,7 +387,7 @@ int conv3x3_launch(const void* x, int NB, int H, int W, int cin, const void* wpa
   else if (cin == 64 && cout == 128) bn = 128;
   else if (cin == 128) bn = 64;
   else bn = 256;
-  if (variant == 2 && cin <= 128) bn = (cout == 64) ? 32 : 64;  // each CTA of a pair loads half of the N rows
+  if (variant == 2) bn = (cout == 64) ? 32 : 64;  // each CTA of a pair loads half of the N rows
   {
     const uint64_t dims[2] = {(uint64_t)9 * cin, (uint64_t)cout};
     const uint64_t str[1] = {(uint64_t)9 * cin * 2};

@@ -482,31 +482,35 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // warp1 = TMEM allocation (+ MMA issue on the leader only, commits multicast to both CTAs),
 // warps2-9 = epilogue of the CTA's own 128 accumulator rows.
 // =================================================================================================
-template <int CIN, int BN, int EPI, int SA, int ACC>
+template <int CIN, int BN, int EPI, int SA, int ACC, bool BRES, int NT, int SB>
 struct Conv2Cfg {
   static constexpr int NCHUNK = CIN / 64;
   static constexpr int TAPS = 9;
   static constexpr int B_HALF = (BN / 2) * 128;                       // one (chunk, tap) block of this CTA's rows
-  static constexpr int B_BYTES = NCHUNK * TAPS * B_HALF;
-  static constexpr int SMEM_A = SA * kPatchStride;
+  static constexpr int B_BYTES = BRES ? NCHUNK * TAPS * B_HALF : SB * B_HALF;
+  static constexpr int A_STAGE = NT * kPatchStride;
+  static constexpr int SMEM_A = SA * A_STAGE;
   static constexpr int CPW = BN / 2;
   static constexpr int NSTG = (EPI == EPI_STORE) ? (CPW >= 64 ? 2 : 1) : 0;
   static constexpr int SMEM_STG = NSTG * kTileBytes;
-  static constexpr int SMEM_MISC = 2 * BN * 4 + 256;
+  static constexpr int SS = BRES ? BN : 512;
+  static constexpr int SMEM_MISC = 2 * SS * 4 + 256;
   static constexpr int SMEM_BYTES = 1024 + SMEM_A + B_BYTES + SMEM_STG + SMEM_MISC;
-  static constexpr int TMEM_COLS = (ACC * BN <= 32) ? 32 : (ACC * BN <= 64) ? 64 : (ACC * BN <= 128) ? 128
-                                   : (ACC * BN <= 256) ? 256 : 512;
-  static_assert(ACC * BN <= 512, "TMEM columns");
+  static constexpr int ACC_COLS = NT * BN;
+  static constexpr int TMEM_COLS = (ACC * ACC_COLS <= 32) ? 32 : (ACC * ACC_COLS <= 64) ? 64
+                                   : (ACC * ACC_COLS <= 128) ? 128 : (ACC * ACC_COLS <= 256) ? 256 : 512;
   static constexpr int THREADS = 64 + 32 * 8;
+  static_assert(ACC * ACC_COLS <= 512, "TMEM columns");
   static_assert(BN % 32 == 0 && BN <= 256, "pair MMA: N multiple of 16 per CTA half");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-template <typename T, int CIN, int BN, int EPI, int SA, int ACC>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Conv2Cfg<CIN, BN, EPI, SA, ACC>::THREADS, 1)
+template <typename T, int CIN, int BN, int EPI, int SA, int ACC, bool BRES, int NT, int SB>
+__global__ void __cluster_dims__(2, 1, 1)
+__launch_bounds__(Conv2Cfg<CIN, BN, EPI, SA, ACC, BRES, NT, SB>::THREADS, 1)
 conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmO, const ConvParams p) {
-  using Cfg = Conv2Cfg<CIN, BN, EPI, SA, ACC>;
+  using Cfg = Conv2Cfg<CIN, BN, EPI, SA, ACC, BRES, NT, SB>;
   constexpr int TAPS = Cfg::TAPS;
   constexpr int NCHUNK = Cfg::NCHUNK;
 
@@ -516,12 +520,13 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* smem_b = smem + Cfg::SMEM_A;
   uint8_t* smem_stg = smem_b + Cfg::B_BYTES;
   float* s_scale = reinterpret_cast<float*>(smem_stg + Cfg::SMEM_STG);
-  float* s_shift = s_scale + BN;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + BN);
+  float* s_shift = s_scale + Cfg::SS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + Cfg::SS);
   uint64_t* a_full = bars;            // [SA]  leader's copy is the live one
   uint64_t* a_empty = a_full + SA;    // [SA]  per CTA (multicast commit)
-  uint64_t* b_full = a_empty + SA;    // [1]   leader's copy
-  uint64_t* t_full = b_full + 1;      // [ACC] per CTA (multicast commit)
+  uint64_t* b_full = a_empty + SA;    // [SB]  leader's copy (index 0 = "resident weights landed")
+  uint64_t* b_empty = b_full + SB;    // [SB]  per CTA (multicast commit)
+  uint64_t* t_full = b_empty + SB;    // [ACC] per CTA (multicast commit)
   uint64_t* t_empty = t_full + ACC;   // [ACC] leader's copy, 16 arrivals (8 warps x 2 CTAs)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + ACC);
 
@@ -530,23 +535,32 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
 
-  // ---- work decomposition: pair `pr` of `npairs`, Cout slice fixed per pair ----
+  // ---- work decomposition: an item = 2*NT tiles (NT per CTA of the pair) of one Cout slice ----
   const int pr = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int fixed_slice = pr % p.nslices;
-  const int item_begin = pr / p.nslices, item_stride = npairs / p.nslices;
-  const int items = (p.num_tiles + 1) >> 1;  // two tiles (one per CTA) per item
-  const int ch0 = fixed_slice * BN;
+  const int items = (p.num_tiles + 2 * NT - 1) / (2 * NT);
+  int work_begin, work_stride, work_end, fixed_slice = 0;
+  if (BRES) {
+    fixed_slice = pr % p.nslices;
+    work_begin = pr / p.nslices;
+    work_stride = npairs / p.nslices;
+    work_end = items;
+  } else {
+    work_begin = pr;
+    work_stride = npairs;
+    work_end = items * p.nslices;
+  }
 
-  for (int i = threadIdx.x; i < BN; i += blockDim.x) {
-    s_scale[i] = p.scale[ch0 + i];
-    s_shift[i] = p.shift[ch0 + i];
+  const int ss_base = BRES ? fixed_slice * BN : 0;
+  for (int i = threadIdx.x; i < Cfg::SS && ss_base + i < p.cout; i += blockDim.x) {
+    s_scale[i] = p.scale[ss_base + i];
+    s_shift[i] = p.shift[ss_base + i];
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (EPI == EPI_STORE) tma_prefetch_desc(&tmO);
     for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    mbar_init(b_full, 1);
+    for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < ACC; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 16); }
     fence_barrier_init();
   }
@@ -572,21 +586,39 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0) {
     // =============================== TMA producer (both CTAs) ===============================
     if (elect_one()) {
-      const uint32_t bfull_leader = map_to_cta(b_full, 0);
-      if (leader) mbar_expect_tx(b_full, 2 * Cfg::B_BYTES);
-      for (int c = 0; c < NCHUNK; ++c)
-        for (int tap = 0; tap < TAPS; ++tap)
-          tma_load_2d_2sm(smem_b + (c * TAPS + tap) * Cfg::B_HALF, &tmB, bfull_leader, tap * CIN + c * 64,
-                          ch0 + rank * (BN / 2));
-      uint32_t sa = 0, pa = 0;
-      for (int item = item_begin; item < items; item += item_stride) {
-        int n, h0, w0;
-        tile_coords(item * 2 + rank, n, h0, w0);  // past-the-end tiles have n >= NB: fully OOB -> zeros
+      if (BRES) {
+        const uint32_t bfull_leader = map_to_cta(&b_full[0], 0);
+        if (leader) mbar_expect_tx(&b_full[0], 2 * Cfg::B_BYTES);
+        for (int c = 0; c < NCHUNK; ++c)
+          for (int tap = 0; tap < TAPS; ++tap)
+            tma_load_2d_2sm(smem_b + (c * TAPS + tap) * Cfg::B_HALF, &tmB, bfull_leader, tap * CIN + c * 64,
+                            fixed_slice * BN + rank * (BN / 2));
+      }
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+      for (int w = work_begin; w < work_end; w += work_stride) {
+        const int item = BRES ? w : w / p.nslices;
+        const int slice = BRES ? fixed_slice : w - item * p.nslices;
         for (int c = 0; c < NCHUNK; ++c) {
           mbar_wait(&a_empty[sa], pa ^ 1);
-          if (leader) mbar_expect_tx(&a_full[sa], 2 * kPatchBytes);
-          tma_load_4d_2sm(smem_a + sa * kPatchStride, &tmA, map_to_cta(&a_full[sa], 0), c * 64, w0 - 1, h0 - 1, n);
+          if (leader) mbar_expect_tx(&a_full[sa], 2 * NT * kPatchBytes);
+          const uint32_t afull_leader = map_to_cta(&a_full[sa], 0);
+#pragma unroll
+          for (int t = 0; t < NT; ++t) {
+            int n, h0, w0;
+            tile_coords((item * 2 + rank) * NT + t, n, h0, w0);  // past-the-end tiles: n >= NB -> zeros
+            tma_load_4d_2sm(smem_a + sa * Cfg::A_STAGE + t * kPatchStride, &tmA, afull_leader, c * 64, w0 - 1, h0 - 1,
+                            n);
+          }
           if (++sa == SA) { sa = 0; pa ^= 1; }
+          if (!BRES) {
+            for (int tap = 0; tap < TAPS; ++tap) {
+              mbar_wait(&b_empty[sb], pb ^ 1);
+              if (leader) mbar_expect_tx(&b_full[sb], 2 * Cfg::B_HALF);
+              tma_load_2d_2sm(smem_b + sb * Cfg::B_HALF, &tmB, map_to_cta(&b_full[sb], 0), tap * CIN + c * 64,
+                              slice * BN + rank * (BN / 2));
+              if (++sb == SB) { sb = 0; pb ^= 1; }
+            }
+          }
         }
       }
     }
@@ -598,26 +630,42 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       constexpr uint32_t b_hi = desc_hi_sw128(1024);
       const uint32_t a_lo0 = desc_lo(smem_u32(smem_a));
       const uint32_t b_lo0 = desc_lo(smem_u32(smem_b));
-      uint32_t sa = 0, pa = 0, acc = 0, pacc = 0;
-      mbar_wait(b_full, 0);
-      tc_fence_after();
-      for (int item = item_begin; item < items; item += item_stride) {
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
+      if (BRES) {
+        mbar_wait(&b_full[0], 0);
+        tc_fence_after();
+      }
+      for (int w = work_begin; w < work_end; w += work_stride) {
         mbar_wait(&t_empty[acc], pacc ^ 1);
         tc_fence_after();
-        const uint32_t d_base = tmem_base + acc * BN;
+        const uint32_t d_base = tmem_base + acc * Cfg::ACC_COLS;
         for (int c = 0; c < NCHUNK; ++c) {
           mbar_wait(&a_full[sa], pa);
           tc_fence_after();
-          const uint32_t a_lo = a_lo0 + sa * (kPatchStride >> 4);
+          const uint32_t a_lo = a_lo0 + sa * (Cfg::A_STAGE >> 4);
 #pragma unroll
           for (int tap = 0; tap < TAPS; ++tap) {
-            const uint32_t b_lo = b_lo0 + (c * TAPS + tap) * (Cfg::B_HALF >> 4);
+            uint32_t b_lo;
+            if (BRES) {
+              b_lo = b_lo0 + (c * TAPS + tap) * (Cfg::B_HALF >> 4);
+            } else {
+              mbar_wait(&b_full[sb], pb);
+              tc_fence_after();
+              b_lo = b_lo0 + sb * (Cfg::B_HALF >> 4);
+            }
             const uint32_t tap_off = ((tap / 3) * 10 + (tap % 3)) * 8;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (!(p.dbg & 4))
-                umma_f16_2sm(d_base, desc_join(a_lo + tap_off + k * 2, a_hi), desc_join(b_lo + k * 2, b_hi), idesc,
-                             (c | tap | k) ? 1u : 0u);
+            for (int t = 0; t < NT; ++t) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (!(p.dbg & 4))
+                  umma_f16_2sm(d_base + t * BN, desc_join(a_lo + t * (kPatchStride >> 4) + tap_off + k * 2, a_hi),
+                               desc_join(b_lo + k * 2, b_hi), idesc, (c | tap | k) ? 1u : 0u);
+              }
+            }
+            if (!BRES) {
+              umma_commit_2sm(&b_empty[sb], 3);
+              if (++sb == SB) { sb = 0; pb ^= 1; }
             }
           }
           umma_commit_2sm(&a_empty[sa], 3);
@@ -634,16 +682,22 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     constexpr int CPW = Cfg::CPW;
     const bool stg_leader = (lane == 0) && (warp == ((CPW >= 64) ? 2 + 4 * chalf : 2));
     uint32_t acc = 0, pacc = 0;
-    for (int item = item_begin; item < items; item += item_stride) {
+    for (int w = work_begin; w < work_end; w += work_stride) {
+      const int item = BRES ? w : w / p.nslices;
+      const int slice = BRES ? fixed_slice : w - item * p.nslices;
+      const int ch0 = slice * BN;
       mbar_wait(&t_full[acc], pacc);
       tc_fence_after();
-      if (!(p.dbg & 2)) {
-        const int tile = item * 2 + rank;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        if (p.dbg & 2) break;
+        const int tile = (item * 2 + rank) * NT + t;
         const bool tile_ok = (tile < p.num_tiles) && !(p.dbg & 1);
         int n, h0, w0;
         tile_coords(tile, n, h0, w0);
-        const uint32_t taddr = tmem_base + acc * BN + chalf * CPW + (static_cast<uint32_t>(quarter * 32) << 16);
-        conv_epilogue_tile<T, BN, true, EPI>(taddr, chalf, warp, lane, s_scale, s_shift, ch0, tile, tile_ok, n, h0, w0,
+        const uint32_t taddr = tmem_base + acc * Cfg::ACC_COLS + t * BN + chalf * CPW +
+                               (static_cast<uint32_t>(quarter * 32) << 16);
+        conv_epilogue_tile<T, BN, BRES, EPI>(taddr, chalf, warp, lane, s_scale, s_shift, ch0, tile, tile_ok, n, h0, w0,
                                              p, smem_stg, &tmO);
       }
       tc_fence_before();

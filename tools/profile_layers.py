@@ -58,8 +58,6 @@ def main():
                                                        capi.ptr(s), capi.ptr(b), cout, mode, capi.ptr(out),
                                                        pm.dtype_code, variant, stream))
             flops = 2.0 * mb * x.shape[1] * x.shape[2] * 9 * cin * cout
-            if variant == 2 and cin > 128:
-                continue
             rows.append(("%s %d->%d %s" % (name, cin, cout, {0: "patch", 1: "tap", 2: "pair"}[variant]), t, flops,
                          x.numel() * 2 + out.numel() * 2))
     B = args.batch
