@@ -27,6 +27,15 @@ CONV_GFLOP_TC = 26.031 - 0.0738  # tensor-core conv layers per clip (SURVEY.md 8
 METRIC = "clips/sec (10 s, 16 kHz) logmel+CRNN inference"
 
 
+def load_conv_traffic():
+    """DRAM bytes of the seven conv launches of one 148-clip micro-batch, from the committed ncu --set full capture."""
+    path = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return json.load(f)
+    return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -239,6 +248,7 @@ def run_b200(args):
 
     if rank == 0:
         peaks = load_peaks()
+        traffic = load_conv_traffic()
         value = world * B * steps / (elapsed_ms / 1e3)
         conv_tflops = CONV_GFLOP_TC * 1e9 * conv_clips / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
         n_conv_launch = 7 * len([1 for _ in range(0, B, args.micro_batch)]) * steps
@@ -261,9 +271,12 @@ def run_b200(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": peaks["tflops_sustained"],
                          "unit": "TFLOP/s", "frac": conv_tflops / peaks["tflops_sustained"],
-                         "traffic": None,
-                         "kernel": "conv_umma_kernel (7 tcgen05 implicit-GEMM launches per micro-batch, "
-                                   "%.3f GFLOP/clip algorithmic)" % CONV_GFLOP_TC,
+                         "traffic": traffic["dram_bytes_total"] if traffic else None,
+                         "traffic_note": "dram__bytes_read+write summed over the 7 conv launches of one 148-clip "
+                                         "micro-batch (profiles/r01_ncu_full_conv_umma2_raw.csv); algorithmic "
+                                         "activation bytes (each layer input read once + output written once) for the same group: %.3e" % (148 * 29832192.0),
+                         "kernel": "conv_umma2_kernel (7 tcgen05 cta_group::2 implicit-GEMM launches per 148-clip "
+                                   "micro-batch, %.3f GFLOP/clip algorithmic)" % CONV_GFLOP_TC,
                          "peak_source": peaks["source"] + ", sustained bf16; burst %.1f" % peaks["tflops_burst"],
                          "launches_timed": n_conv_launch, "conv_ms_per_step": conv_ms / steps},
         }
