@@ -75,12 +75,14 @@ int sed_conv_first_f32(const float* x, int NB, int H, int W, const float* w9, co
  * on the tcgen05 tensor cores.  Replaces ConvBlock.forward pytorch/models.py:125-141 (one conv each
  * call) and torch.mean(x, dim=3) models.py:668.
  *   x [NB, H, W, cin] NHWC 16-bit; wpacked [cout][9][cin] 16-bit (tap = 3*kh + kw);
- *   scale/shift [cout] f32; out NHWC 16-bit: [NB,H,W,cout] | [NB,H/2,W/2,cout] | [NB,H,cout].
+ *   scale/shift [cout] f32; out NHWC 16-bit: [NB,H,W,cout] | [NB,H/2,W/2,cout] | [NB,H,cout];
+ *   out_f32: optional float32 copy [NB,H,cout] of the FREQMEAN result (NULL otherwise).
  *   Supported (cin,cout,mode): (64,64,POOL) (64,128,STORE) (128,128,POOL) (128,256,STORE)
  *   (256,256,POOL) (256,512,STORE) (512,512,FREQMEAN).
- *   variant 0 = haloed-patch operand reuse, 1 = one TMA box per tap. */
+ *   variant 0 = single-CTA haloed-patch operand reuse, 1 = one TMA box per tap, 2 = CTA pairs (cta_group::2). */
 int sed_conv3x3_bn_relu(const void* x, int NB, int H, int W, int cin, const void* wpacked, const float* scale,
-                        const float* shift, int cout, int mode, void* out, int dtype, int variant, void* stream);
+                        const float* shift, int cout, int mode, void* out, void* out_f32, int dtype, int variant,
+                        void* stream);
 
 /* out[M, N] = a[M, K] * w[N, K]^T + bias (optional ReLU) on the tensor cores; K in {256, 512},
  * N % 128 == 0.  Replaces the nn.Linear calls inside nn.GRU (input projection, models.py:670) and
@@ -100,6 +102,13 @@ long sed_bigru_workspace_bytes(int B);
  *   workspace: sed_bigru_workspace_bytes(B) bytes, 128-byte aligned, contents irrelevant. */
 int sed_bigru(const float* gi, const void* whh_packed, const float* bhh, int B, int T, float* out, void* workspace,
               int dtype, void* stream);
+
+/* Linear(512 -> classes) + sigmoid per frame, x`ratio` interpolation, clipwise mean (use_max = 0) or max (1)
+ * over frames: the head of Cnn_9layers_FrameAvg / FrameMax / Gru_FrameAvg / Transformer_FrameAvg
+ * (pytorch/models.py:276-288, 361-373, 547-556, 963-972).
+ *   x [B, T, 512] f32; w [classes, 512]; b [classes]; classes <= 32; clip [B, classes]; frame [B, T*ratio, classes]. */
+int sed_fcpool(const float* x, int B, int T, const float* w, const float* b, int classes, int ratio, int use_max,
+               float* clip, float* frame, void* stream);
 
 /* Overlap-add of per-window framewise outputs followed by the reference's block-wise averaging.
  * Replaces merge + avg_merge utils/utilities.py:405-446 as driven by pytorch/predict.py:323-349 (bug-compatible:

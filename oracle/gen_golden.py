@@ -42,10 +42,37 @@ def frontend_signals(sr, seconds=1.0):
     return q
 
 
+def sibling_goldens(rm):
+    """The five sibling heads of the Cnn_9layers trunk (models.py:213-561, 880-978) at 16 kHz, one file."""
+    res = {}
+    L = 24000
+    wave = torch.cat([synth.synthetic_waveform(2, L, seed=41, kind="events"), synth.synthetic_waveform(1, L, seed=42),
+                      torch.zeros(1, L)])
+    q = torch.round(wave * 32767.0).to(torch.int16)
+    wave = q.float() / 32767.0
+    res["wave_i16"] = q.numpy()
+    for mt in synth.SIBLING_TYPES:
+        classes = 10 if mt == "Cnn_9layers_FrameMax" else 25  # fc heads honour classes_num (models.py:247)
+        sd = synth.synthetic_state_dict(mt, 16000, classes_num=classes)
+        args = PRESET_ARGS[16000][:6] + (classes,)
+        if mt in ("Cnn_9layers_Gru_FrameAvg", "Cnn_9layers_Transformer_FrameAvg"):
+            args = args + ("logmel",)
+        model = getattr(rm, mt)(*args).eval()
+        model.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            out = model(wave)
+        for k in ("framewise_output", "clipwise_output", "embedding"):
+            res["%s.%s" % (mt, k)] = out[k].numpy()
+    np.savez_compressed(os.path.join(GOLD, "model_siblings_16k.npz"), **res)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     rs, rm = ref_import.load()
     torch.set_num_threads(8)
+    sibling_goldens(rm)
+    if "--only-siblings" in sys.argv:
+        return
     meta = {"torch": torch.__version__, "state_dict_keys": {}, "ckpt_fingerprint": {}}
 
     # ---- front-end goldens (reference Spectrogram + LogmelFilterBank, top_db=None as in the models) ----

@@ -204,11 +204,46 @@ def pad_framewise_output(fw, frames_num):
 # --------------------------------------------------------------------------------------
 # whole-model forward (models.py:625-688 GRU, :1029-1077 Transformer), eval mode only
 # --------------------------------------------------------------------------------------
+# sibling heads on the same trunk: model_type -> (temporal, head)
+SIBLING_PLANS = {
+    "Cnn_9layers_FrameMax": (None, "max"),               # models.py:213-295
+    "Cnn_9layers_FrameAvg": (None, "avg"),               # models.py:298-380
+    "Cnn_9layers_FrameAtt": (None, "att"),               # models.py:383-463
+    "Cnn_9layers_Gru_FrameAvg": ("gru", "avg"),          # models.py:466-561
+    "Cnn_9layers_Transformer_FrameAvg": ("mha", "avg"),  # models.py:880-978
+}
+
+
+def sibling_forward(sd, wave, model_type, n_fft, hop):
+    """The five alternative heads of the Cnn_9layers trunk; same output dict."""
+    temporal, head = SIBLING_PLANS[model_type]
+    with torch.no_grad():
+        spec = spectrogram(wave, sd["spectrogram_extractor.stft.conv_real.weight"],
+                           sd["spectrogram_extractor.stft.conv_imag.weight"], n_fft, hop)
+        x = conv_stack(bn0(logmel(spec, sd["logmel_extractor.melW"], top_db=None), sd), sd)
+        x = torch.mean(x, dim=3)  # [B,512,T']   models.py:275, 360, 445, 543, 959
+        if temporal == "gru":
+            x = bigru(x.transpose(1, 2), sd).transpose(1, 2)  # models.py:544-546
+        elif temporal == "mha":
+            x = multihead(x.transpose(1, 2), sd).transpose(1, 2)  # models.py:960-962
+        if head == "att":
+            clip, _, cla = att_block(x, sd)  # models.py:448
+            fw = interpolate(cla.transpose(1, 2), 8)  # models.py:452-453 (no padding)
+            return {"framewise_output": fw, "clipwise_output": clip, "embedding": cla}
+        fw = torch.sigmoid(F.linear(x.transpose(1, 2), sd["fc.weight"], sd["fc.bias"]))  # models.py:280, 365, 551
+        fw = interpolate(fw, 8)
+        clip = torch.max(fw, dim=1)[0] if head == "max" else torch.mean(fw, dim=1)  # models.py:284 / 369
+        return {"framewise_output": fw, "clipwise_output": clip, "embedding": x}
+
+
 def model_forward(sd, wave, model_type, n_fft, hop, return_stages=False):
     """sd: reference-layout state_dict (float32 CPU tensors); wave [B,L] float32.
 
-    model_type in {'Cnn_9layers_Gru_FrameAtt', 'Cnn_9layers_Transformer_FrameAtt'}.
+    model_type in {'Cnn_9layers_Gru_FrameAtt', 'Cnn_9layers_Transformer_FrameAtt'} (with stages) or one of
+    SIBLING_PLANS (outputs only).
     """
+    if model_type in SIBLING_PLANS and not return_stages:
+        return sibling_forward(sd, wave, model_type, n_fft, hop)
     stages = {}
     with torch.no_grad():
         spec = spectrogram(wave, sd["spectrogram_extractor.stft.conv_real.weight"],

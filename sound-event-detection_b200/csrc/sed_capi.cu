@@ -5,7 +5,7 @@
 
 #include "sed_kernels.h"
 
-#define SED_ABI_VERSION 4
+#define SED_ABI_VERSION 5
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -104,13 +104,14 @@ int sed_conv_first_f32(const float* x, int NB, int H, int W, const float* w9, co
 }
 
 int sed_conv3x3_bn_relu(const void* x, int NB, int H, int W, int cin, const void* wpacked, const float* scale,
-                        const float* shift, int cout, int mode, void* out, int dtype, int variant, void* stream) {
+                        const float* shift, int cout, int mode, void* out, void* out_f32, int dtype, int variant,
+                        void* stream) {
   SED_REQUIRE(x); SED_REQUIRE(wpacked); SED_REQUIRE(scale); SED_REQUIRE(shift); SED_REQUIRE(out);
   if (variant < 0 || variant > 2) {
     sed::set_error("sed_conv3x3_bn_relu: variant must be 0 (patch), 1 (per-tap) or 2 (CTA pairs)");
     return SED_ERR_UNSUPPORTED;
   }
-  return sed::conv3x3_launch(x, NB, H, W, cin, wpacked, scale, shift, cout, mode, out, dtype, variant,
+  return sed::conv3x3_launch(x, NB, H, W, cin, wpacked, scale, shift, cout, mode, out, out_f32, dtype, variant,
                              as_stream(stream));
 }
 
@@ -132,6 +133,12 @@ int sed_bigru_profile(const float* gi, const void* whh_packed, const float* bhh,
                       void* workspace, int dtype, long long* stamps, void* stream) {
   SED_REQUIRE(gi); SED_REQUIRE(whh_packed); SED_REQUIRE(bhh); SED_REQUIRE(out); SED_REQUIRE(workspace); SED_REQUIRE(stamps);
   return sed::gru_launch(gi, whh_packed, bhh, B, T, out, workspace, dtype, as_stream(stream), stamps);
+}
+
+int sed_fcpool(const float* x, int B, int T, const float* w, const float* b, int classes, int ratio, int use_max,
+               float* clip, float* frame, void* stream) {
+  SED_REQUIRE(x); SED_REQUIRE(w); SED_REQUIRE(b); SED_REQUIRE(clip); SED_REQUIRE(frame);
+  return sed::fcpool_launch(x, B, T, w, b, classes, ratio, use_max, clip, frame, as_stream(stream));
 }
 
 int sed_mha_core(const float* qkv, int B, int T, void* out16, int dtype, void* stream) {

@@ -360,7 +360,8 @@ static int conv3x3_dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
 }
 
 int conv3x3_launch(const void* x, int NB, int H, int W, int cin, const void* wpacked, const float* scale,
-                   const float* shift, int cout, int mode, void* out, int dtype, int variant, cudaStream_t stream) {
+                   const float* shift, int cout, int mode, void* out, void* out_f32, int dtype, int variant,
+                   cudaStream_t stream) {
   if (NB <= 0 || H <= 0 || W <= 0 || (W % 8) != 0 || (cin % 64) != 0) {
     set_error("conv3x3: bad shape NB=%d H=%d W=%d cin=%d", NB, H, W, cin);
     return SED_ERR_BAD_SHAPE;
@@ -410,7 +411,7 @@ int conv3x3_launch(const void* x, int NB, int H, int W, int cin, const void* wpa
   p.num_tiles = NB * p.tiles_h * p.tiles_w;
   p.cout = cout;
   p.scale = scale; p.shift = shift;
-  p.out = out; p.out2 = nullptr;
+  p.out = out; p.out2 = (mode == EPI_FREQMEAN) ? out_f32 : nullptr;
   p.M = 0; p.ldc = 0; p.relu = 1;
   {
     const char* e = getenv("SED_CONV_DBG");

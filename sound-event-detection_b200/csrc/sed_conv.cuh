@@ -32,7 +32,7 @@ struct ConvParams {
   const float* scale;      // [cout] folded BN scale   (linear: unused)
   const float* shift;      // [cout] folded BN shift   (linear: bias)
   void* out;               // EPI 0/1/2: 16-bit NHWC ; EPI 3: float [M, ldc]
-  void* out2;              // EPI 3: optional 16-bit copy [M, ldc] (may be null)
+  void* out2;              // EPI 3: optional 16-bit copy [M, ldc]; EPI 2: optional f32 copy [NB,H,cout] (may be null)
   int M, ldc, relu;        // linear only
   int dbg;                 // profiling experiments only (SED_CONV_DBG): 1 = no stores, 2 = no drain, 4 = no MMA
 };
@@ -189,6 +189,9 @@ SED_DEVICE_INLINE void conv_epilogue_tile(const uint32_t taddr, const int chalf,
               const int ch = ch0 + cc * 16 + (b0 ? 8 : 0) + (b1 ? 4 : 0) + (b2 ? 2 : 0);
               T* dst = out16 + (static_cast<size_t>(n) * p.H + h) * p.cout + ch;
               *reinterpret_cast<uint32_t*>(dst) = Elem16<T>::pack2(k2[0], k2[1]);
+              if (p.out2)  // optional float32 copy of the features (heads without a temporal block)
+                *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.out2) +
+                                           (static_cast<size_t>(n) * p.H + h) * p.cout + ch) = make_float2(k2[0], k2[1]);
             }
           } else {  // EPI_LINEAR
             const long row = static_cast<long>(tile) * 128 + m;

@@ -37,7 +37,8 @@ int conv_first_launch(const float* x, int NB, int H, int W, const float* w9, con
 
 // mode: 0 = store NHWC, 1 = 2x2 avg-pool, 2 = freq-mean (W must be 8) ; variant: 0 = patch (halo reuse), 1 = per-tap
 int conv3x3_launch(const void* x, int NB, int H, int W, int cin, const void* wpacked, const float* scale,
-                   const float* shift, int cout, int mode, void* out, int dtype, int variant, cudaStream_t stream);
+                   const float* shift, int cout, int mode, void* out, void* out_f32, int dtype, int variant,
+                   cudaStream_t stream);
 
 int linear_launch(const void* a16, long M, int K, const void* w16, const float* bias, int N, int relu, float* out,
                   void* out16, int dtype, cudaStream_t stream);
@@ -58,6 +59,9 @@ int mha_core_launch(const float* qkv, int B, int T, void* out16, int dtype, cuda
 int attpool_launch(const float* x, int B, int T, const float* w_att, const float* b_att, const float* w_cla,
                    const float* b_cla, int ratio, int frames_out, float* clip, float* frame, float* cla_t,
                    float* norm_att_t, cudaStream_t stream);
+
+int fcpool_launch(const float* x, int B, int T, const float* w, const float* b, int C, int ratio, int use_max,
+                  float* clip, float* frame, cudaStream_t stream);
 
 const char* last_error();
 void set_error(const char* fmt, ...);

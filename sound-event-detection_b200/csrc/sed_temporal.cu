@@ -485,4 +485,76 @@ int attpool_launch(const float* x, int B, int Tn, const float* w_att, const floa
   return SED_OK;
 }
 
+// =================================================================================================
+// Linear + sigmoid + mean/max pooling head of the sibling models
+// (Cnn_9layers_FrameAvg / FrameMax / Gru_FrameAvg / Transformer_FrameAvg, pytorch/models.py:276-288, 361-373,
+//  547-556, 963-972): framewise = interpolate(sigmoid(fc(x)), 8); clipwise = mean | max over frames.
+// =================================================================================================
+constexpr int kFcMaxCls = 32;
+
+__global__ void __launch_bounds__(128)
+fcpool_kernel(const float* __restrict__ x, int Tn, const float* __restrict__ w, const float* __restrict__ b, int C,
+              int ratio, int use_max, float* __restrict__ clip, float* __restrict__ frame) {
+  extern __shared__ float smem_h[];
+  float* s_w = smem_h;                        // [32][512], rows >= C are zero
+  float* s_p = s_w + kFcMaxCls * 512;         // [Tn][C]
+  float* s_b = s_p + Tn * C;                  // [32]
+  const int bidx = blockIdx.x;
+  for (int i = threadIdx.x; i < kFcMaxCls * 512; i += blockDim.x) s_w[i] = (i < C * 512) ? w[i] : 0.0f;
+  if (threadIdx.x < kFcMaxCls) s_b[threadIdx.x] = (threadIdx.x < C) ? b[threadIdx.x] : 0.0f;
+  __syncthreads();
+  for (int t = threadIdx.x; t < Tn; t += blockDim.x) {
+    float acc[kFcMaxCls];
+#pragma unroll
+    for (int c = 0; c < kFcMaxCls; ++c) acc[c] = s_b[c];
+    const float4* xr = reinterpret_cast<const float4*>(x + (static_cast<size_t>(bidx) * Tn + t) * 512);
+    for (int k4 = 0; k4 < 128; ++k4) {
+      const float4 xv = xr[k4];
+#pragma unroll
+      for (int c = 0; c < kFcMaxCls; ++c) {
+        const float4 wv = *reinterpret_cast<const float4*>(s_w + c * 512 + k4 * 4);
+        acc[c] = fmaf(xv.x, wv.x, acc[c]);
+        acc[c] = fmaf(xv.y, wv.y, acc[c]);
+        acc[c] = fmaf(xv.z, wv.z, acc[c]);
+        acc[c] = fmaf(xv.w, wv.w, acc[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < kFcMaxCls; ++c)
+      if (c < C) s_p[t * C + c] = 1.0f / (1.0f + expf(-acc[c]));
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    const int c = threadIdx.x;
+    float r = use_max ? -INFINITY : 0.0f;
+    for (int t = 0; t < Tn; ++t) {
+      const float v = s_p[t * C + c];
+      r = use_max ? fmaxf(r, v) : r + v;
+    }
+    clip[bidx * C + c] = use_max ? r : r / static_cast<float>(Tn);
+  }
+  float* fr = frame + static_cast<size_t>(bidx) * Tn * ratio * C;
+  for (int i = threadIdx.x; i < Tn * ratio * C; i += blockDim.x) {
+    const int f = i / C, c = i - f * C;
+    fr[i] = s_p[(f / ratio) * C + c];
+  }
+}
+
+int fcpool_launch(const float* x, int B, int Tn, const float* w, const float* b, int C, int ratio, int use_max,
+                  float* clip, float* frame, cudaStream_t stream) {
+  const size_t smem = sizeof(float) * (kFcMaxCls * 512 + static_cast<size_t>(Tn) * C + kFcMaxCls);
+  if (B <= 0 || Tn <= 0 || C <= 0 || C > kFcMaxCls || ratio <= 0 || smem > 220 * 1024) {
+    set_error("fcpool: unsupported shape B=%d T=%d classes=%d (max %d) ratio=%d", B, Tn, C, kFcMaxCls, ratio);
+    return SED_ERR_BAD_SHAPE;
+  }
+  cudaError_t e = cudaFuncSetAttribute(fcpool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) fcpool_kernel<<<B, 128, smem, stream>>>(x, Tn, w, b, C, ratio, use_max, clip, frame);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("fcpool launch: %s", cudaGetErrorString(e));
+    return SED_ERR_CUDA;
+  }
+  return SED_OK;
+}
+
 }  // namespace sed

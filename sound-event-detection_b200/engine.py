@@ -29,6 +29,19 @@ CONV_LAYERS = (
 
 _DTYPES = {"fp16": (capi.SED_DTYPE_F16, torch.float16), "bf16": (capi.SED_DTYPE_BF16, torch.bfloat16)}
 
+# model_type -> (temporal block, pooling head); the trunk (front-end + conv stack) is shared.
+#   temporal: 'gru' (models.py:614-615) | 'mha' (models.py:1015-1020) | None
+#   head: 'att' = AttBlock (models.py:144-175) | 'avg' / 'max' = Linear + sigmoid + mean / max over frames
+MODEL_PLANS = {
+    "Cnn_9layers_Gru_FrameAtt": ("gru", "att"),            # models.py:564-688
+    "Cnn_9layers_Transformer_FrameAtt": ("mha", "att"),    # models.py:981-1077
+    "Cnn_9layers_FrameMax": (None, "max"),                 # models.py:213-295
+    "Cnn_9layers_FrameAvg": (None, "avg"),                 # models.py:298-380
+    "Cnn_9layers_FrameAtt": (None, "att"),                 # models.py:383-463
+    "Cnn_9layers_Gru_FrameAvg": ("gru", "avg"),            # models.py:466-561
+    "Cnn_9layers_Transformer_FrameAvg": ("mha", "avg"),    # models.py:880-978
+}
+
 
 def fold_bn(sd, prefix, eps=1e-5):
     """Eval-mode BatchNorm as y = x*scale + shift (float64 fold, float32 result)."""
@@ -233,7 +246,12 @@ class PackedModel:
     def __init__(self, sd, model_type, n_fft, hop, device, precision="fp16"):
         if precision not in _DTYPES:
             raise ValueError("precision must be 'fp16' or 'bf16'")
+        if model_type not in MODEL_PLANS:
+            raise NotImplementedError("model_type %r is not built" % (model_type,))
         self.model_type = model_type
+        self.temporal_kind, self.head_kind = MODEL_PLANS[model_type]
+        # only Cnn_9layers_Gru_FrameAtt pads the framewise output to 100-frame blocks (models.py:680-681)
+        self.pads_frames = model_type == "Cnn_9layers_Gru_FrameAtt"
         self.device = torch.device(device)
         self.precision = precision
         self.dtype_code, self.tdtype = _DTYPES[precision]
@@ -258,7 +276,7 @@ class PackedModel:
             wp = w.permute(0, 2, 3, 1).reshape(cout, 9 * cin).to(td).contiguous().to(dev)  # [Cout][tap][Cin]
             s, b = fold_bn(sd, name.replace(".conv", ".bn"))
             self.convs.append((cin, cout, mode, wp, s.to(dev), b.to(dev)))
-        if model_type == "Cnn_9layers_Gru_FrameAtt":
+        if self.temporal_kind == "gru":
             wih = torch.cat([sd["gru.weight_ih_l0"], sd["gru.weight_ih_l0_reverse"]], 0).float()
             self.gru_wih = wih.to(td).contiguous().to(dev)  # [1536, 512]
             self.gru_bih = torch.cat([sd["gru.bias_ih_l0"], sd["gru.bias_ih_l0_reverse"]], 0).float().contiguous().to(dev)
@@ -269,19 +287,25 @@ class PackedModel:
                 packed.append(whh.view(3, 8, 32, 256).permute(1, 0, 2, 3).reshape(768, 256))
             self.gru_whh = torch.cat(packed, 0).to(td).contiguous().to(dev)  # [1536, 256]
             self.gru_bhh = torch.stack([sd["gru.bias_hh_l0"], sd["gru.bias_hh_l0_reverse"]], 0).float().contiguous().to(dev)
-        elif model_type == "Cnn_9layers_Transformer_FrameAtt":
+        elif self.temporal_kind == "mha":
             wqkv = torch.cat([sd["multihead.w_qs.weight"], sd["multihead.w_ks.weight"], sd["multihead.w_vs.weight"]], 0)
             self.mha_wqkv = wqkv.float().to(td).contiguous().to(dev)
             self.mha_bqkv = torch.cat([sd["multihead.w_qs.bias"], sd["multihead.w_ks.bias"],
                                        sd["multihead.w_vs.bias"]], 0).float().contiguous().to(dev)
             self.mha_wfc = sd["multihead.fc.weight"].float().to(td).contiguous().to(dev)
             self.mha_bfc = sd["multihead.fc.bias"].float().contiguous().to(dev)
+        if self.head_kind == "att":
+            self.classes = 25  # hard-coded in the reference (models.py:617)
+            self.att_w = sd["att_block.att.weight"].float().reshape(25, 512).contiguous().to(dev)
+            self.att_b = sd["att_block.att.bias"].float().contiguous().to(dev)
+            self.cla_w = sd["att_block.cla.weight"].float().reshape(25, 512).contiguous().to(dev)
+            self.cla_b = sd["att_block.cla.bias"].float().contiguous().to(dev)
         else:
-            raise NotImplementedError("model_type %r is not built" % (model_type,))
-        self.att_w = sd["att_block.att.weight"].float().reshape(25, 512).contiguous().to(dev)
-        self.att_b = sd["att_block.att.bias"].float().contiguous().to(dev)
-        self.cla_w = sd["att_block.cla.weight"].float().reshape(25, 512).contiguous().to(dev)
-        self.cla_b = sd["att_block.cla.bias"].float().contiguous().to(dev)
+            self.fc_w = sd["fc.weight"].float().contiguous().to(dev)  # [classes_num, 512]
+            self.fc_b = sd["fc.bias"].float().contiguous().to(dev)
+            self.classes = int(self.fc_w.shape[0])
+            if self.fc_w.shape[1] != 512 or self.classes > 32:
+                raise NotImplementedError("fc head: need Linear(512 -> classes_num <= 32)")
         self._ws = {}
         self._lock = threading.Lock()
         self._host = {}
@@ -308,9 +332,10 @@ class PackedModel:
         return ws
 
     # ------------------------------------------------------------------ stages
-    def conv_stack(self, wave_mb, feat_out, variant=2, stages=None, windows=None):
+    def conv_stack(self, wave_mb, feat_out, variant=2, stages=None, windows=None, feat32=None):
         """wave_mb [mb, L] (f32 / int16) -> feat_out [mb, T', 512] 16-bit (freq-mean of conv_block4).
-        windows=(mb, L, stride): wave_mb is a 1-D recording read as overlapping windows."""
+        windows=(mb, L, stride): wave_mb is a 1-D recording read as overlapping windows.
+        feat32: optional [mb, T', 512] f32 copy of the features (models without a temporal block)."""
         lib = capi.load()
         if windows is None:
             mb, L = wave_mb.shape
@@ -334,7 +359,8 @@ class PackedModel:
             x = ws[src]
             out = feat_out if dst is None else ws[dst]
             rc = lib.sed_conv3x3_bn_relu(capi.ptr(x), mb, x.shape[1], x.shape[2], cin, capi.ptr(wp), capi.ptr(s),
-                                         capi.ptr(b), cout, mode, capi.ptr(out), self.dtype_code, variant, stream)
+                                         capi.ptr(b), cout, mode, capi.ptr(out),
+                                         capi.ptr(feat32) if dst is None else None, self.dtype_code, variant, stream)
             capi.check(rc, "sed_conv3x3_bn_relu(%d->%d)" % (cin, cout))
             capi._count()
         if self.conv_events is not None:
@@ -364,7 +390,7 @@ class PackedModel:
         B, Tp, _ = feat16.shape
         stream = capi.current_stream(self.device)
         flat = feat16.view(B * Tp, 512)
-        if self.model_type == "Cnn_9layers_Gru_FrameAtt":
+        if self.temporal_kind == "gru":
             gi = self.linear(flat, self.gru_wih, self.gru_bih)
             out = torch.empty((B, Tp, 512), dtype=torch.float32, device=self.device)
             ws = torch.empty((lib.sed_bigru_workspace_bytes(B),), dtype=torch.uint8, device=self.device)
@@ -375,6 +401,8 @@ class PackedModel:
             if stages is not None:
                 stages["gi"] = gi
             return out
+        if self.temporal_kind != "mha":
+            raise RuntimeError("%s has no temporal block" % self.model_type)
         qkv = self.linear(flat, self.mha_wqkv, self.mha_bqkv)
         ctx = torch.empty((B * Tp, 512), dtype=self.tdtype, device=self.device)
         rc = lib.sed_mha_core(capi.ptr(qkv), B, Tp, capi.ptr(ctx), self.dtype_code, stream)
@@ -386,23 +414,49 @@ class PackedModel:
             stages["ctx"] = ctx
         return out.view(B, Tp, 512)
 
+    def frames_for(self, Tp):
+        """Number of framewise rows the model returns for T' pooled steps (x8 interpolation; only
+        Cnn_9layers_Gru_FrameAtt pads to the next multiple of 100 when != 1000, models.py:62-63, 680-681)."""
+        frames = Tp * 8
+        if self.pads_frames and frames != 1000 and frames % 100:
+            frames += 100 - frames % 100
+        return frames
+
     def head(self, x, frames_out, want_cla=True, want_norm_att=False, out=None):
+        """x [B, T', 512] f32 -> (clipwise [B,C], framewise [B,frames_out,C], cla | None, norm_att | None)."""
         lib = capi.load()
         B, Tp, _ = x.shape
         dev = self.device
+        C = self.classes
         if out is not None:
-            clip, frame = out  # preallocated [B,25] / [B,frames_out,25] (contiguous slices)
+            clip, frame = out  # preallocated [B,C] / [B,frames_out,C] (contiguous slices)
         else:
-            clip = torch.empty((B, 25), dtype=torch.float32, device=dev)
-            frame = torch.empty((B, frames_out, 25), dtype=torch.float32, device=dev)
-        cla = torch.empty((B, 25, Tp), dtype=torch.float32, device=dev) if want_cla else None
-        natt = torch.empty((B, 25, Tp), dtype=torch.float32, device=dev) if want_norm_att else None
-        rc = lib.sed_attpool(capi.ptr(x), B, Tp, capi.ptr(self.att_w), capi.ptr(self.att_b), capi.ptr(self.cla_w),
-                             capi.ptr(self.cla_b), 8, frames_out, capi.ptr(clip), capi.ptr(frame), capi.ptr(cla),
-                             capi.ptr(natt), capi.current_stream(dev))
-        capi.check(rc, "sed_attpool")
+            clip = torch.empty((B, C), dtype=torch.float32, device=dev)
+            frame = torch.empty((B, frames_out, C), dtype=torch.float32, device=dev)
+        if self.head_kind == "att":
+            cla = torch.empty((B, C, Tp), dtype=torch.float32, device=dev) if want_cla else None
+            natt = torch.empty((B, C, Tp), dtype=torch.float32, device=dev) if want_norm_att else None
+            rc = lib.sed_attpool(capi.ptr(x), B, Tp, capi.ptr(self.att_w), capi.ptr(self.att_b), capi.ptr(self.cla_w),
+                                 capi.ptr(self.cla_b), 8, frames_out, capi.ptr(clip), capi.ptr(frame), capi.ptr(cla),
+                                 capi.ptr(natt), capi.current_stream(dev))
+            capi.check(rc, "sed_attpool")
+            capi._count()
+            return clip, frame, cla, natt
+        if frames_out != Tp * 8:
+            raise ValueError("fc heads return exactly 8 x T' frames")
+        rc = lib.sed_fcpool(capi.ptr(x), B, Tp, capi.ptr(self.fc_w), capi.ptr(self.fc_b), C, 8,
+                            1 if self.head_kind == "max" else 0, capi.ptr(clip), capi.ptr(frame),
+                            capi.current_stream(dev))
+        capi.check(rc, "sed_fcpool")
         capi._count()
-        return clip, frame, cla, natt
+        return clip, frame, None, None
+
+    def _embedding(self, x, cla, feat32):
+        """The reference's 'embedding' entry: cla for the two *_FrameAtt models that expose it (models.py:686, 460),
+        else the [B, 512, T'] input of the head (models.py:1075, 288, 553, 970)."""
+        if self.model_type in ("Cnn_9layers_Gru_FrameAtt", "Cnn_9layers_FrameAtt"):
+            return cla
+        return (x if self.temporal_kind else feat32).transpose(1, 2)
 
     # ------------------------------------------------------------------ whole model
     def forward_host(self, wave_host, micro_batch=148, variant=2, head_chunk=256):
@@ -415,16 +469,16 @@ class PackedModel:
         B, L = wave_host.shape
         key = (B, L, wave_host.dtype)
         hb = self._host.get(key)
+        T = L // self.front.hop + 1
+        Tp = T // 8
+        frames = self.frames_for(Tp)
+        C = self.classes
         if hb is None:
-            T = L // self.front.hop + 1
-            frames = (T // 8) * 8
-            if self.model_type == "Cnn_9layers_Gru_FrameAtt" and frames != 1000 and frames % 100:
-                frames += 100 - frames % 100
             hb = {"dev": torch.empty((B, L), dtype=wave_host.dtype, device=self.device),
-                  "clip": torch.empty((B, 25), dtype=torch.float32).pin_memory(),
-                  "frame": torch.empty((B, frames, 25), dtype=torch.float32).pin_memory(),
-                  "clip_dev": torch.empty((B, 25), dtype=torch.float32, device=self.device),
-                  "frame_dev": torch.empty((B, frames, 25), dtype=torch.float32, device=self.device),
+                  "clip": torch.empty((B, C), dtype=torch.float32).pin_memory(),
+                  "frame": torch.empty((B, frames, C), dtype=torch.float32).pin_memory(),
+                  "clip_dev": torch.empty((B, C), dtype=torch.float32, device=self.device),
+                  "frame_dev": torch.empty((B, frames, C), dtype=torch.float32, device=self.device),
                   "copy_stream": torch.cuda.Stream(self.device), "d2h_stream": torch.cuda.Stream(self.device)}
             self._host = {key: hb}
         cs, ds = hb["copy_stream"], hb["d2h_stream"]
@@ -440,16 +494,14 @@ class PackedModel:
                 ev = torch.cuda.Event()
                 ev.record(cs)
                 events.append(ev)
-        T = L // self.front.hop + 1
-        Tp = T // 8
-        frames = hb["frame"].shape[1]
-        is_gru = self.model_type == "Cnn_9layers_Gru_FrameAtt"
         with self._lock:
             feat16 = torch.empty((B, Tp, 512), dtype=self.tdtype, device=self.device)
+            feat32 = None if self.temporal_kind else torch.empty((B, Tp, 512), dtype=torch.float32, device=self.device)
             for (b0, b1), ev in zip(spans, events):
                 compute.wait_event(ev)
-                self.conv_stack(hb["dev"][b0:b1], feat16[b0:b1], variant=variant)
-            x = self.temporal(feat16)
+                self.conv_stack(hb["dev"][b0:b1], feat16[b0:b1], variant=variant,
+                                feat32=None if feat32 is None else feat32[b0:b1])
+            x = self.temporal(feat16) if self.temporal_kind else feat32
             # pooling head in chunks: the device->host copy of chunk i overlaps the head kernel of chunk i+1
             for c0 in range(0, B, head_chunk):
                 c1 = min(B, c0 + head_chunk)
@@ -463,6 +515,18 @@ class PackedModel:
         ds.synchronize()
         return {"clipwise_output": hb["clip"], "framewise_output": hb["frame"]}
 
+    def _run(self, n, Tp, conv_call, stages=None, want_norm_att=False):
+        """Shared tail of forward / forward_windows: conv stack per micro-batch (conv_call(b0, b1, feat16, feat32,
+        stages)), temporal block and head over the whole batch."""
+        feat16 = torch.empty((n, Tp, 512), dtype=self.tdtype, device=self.device)
+        feat32 = None if self.temporal_kind else torch.empty((n, Tp, 512), dtype=torch.float32, device=self.device)
+        conv_call(feat16, feat32)
+        x = self.temporal(feat16, stages) if self.temporal_kind else feat32
+        wants_cla = self.model_type in ("Cnn_9layers_Gru_FrameAtt", "Cnn_9layers_FrameAtt")
+        clip, frame, cla, natt = self.head(x, self.frames_for(Tp), want_cla=wants_cla, want_norm_att=want_norm_att)
+        out = {"framewise_output": frame, "clipwise_output": clip, "embedding": self._embedding(x, cla, feat32)}
+        return out, feat16, x, natt
+
     def forward_windows(self, recording, window_samples, stride_samples, n_windows, micro_batch=148, variant=2):
         """Run the model on `n_windows` overlapping windows of one 1-D recording (f32 or int16, on device):
         window k = recording[k*stride : k*stride + window_samples], zero padded past the end.  Returns the same
@@ -473,20 +537,16 @@ class PackedModel:
             recording = recording.float()
         recording = recording.contiguous()
         T = window_samples // self.front.hop + 1
-        Tp = T // 8
-        with self._lock:
-            feat16 = torch.empty((n_windows, Tp, 512), dtype=self.tdtype, device=self.device)
+
+        def conv_call(feat16, feat32):
             for b0 in range(0, n_windows, micro_batch):
                 b1 = min(n_windows, b0 + micro_batch)
-                sub = recording[b0 * stride_samples:]
-                self.conv_stack(sub, feat16[b0:b1], variant=variant, windows=(b1 - b0, window_samples, stride_samples))
-            x = self.temporal(feat16)
-            frames = Tp * 8
-            is_gru = self.model_type == "Cnn_9layers_Gru_FrameAtt"
-            if is_gru and frames != 1000:
-                frames = frames if frames % 100 == 0 else frames + 100 - frames % 100
-            clip, frame, cla, _ = self.head(x, frames, want_cla=is_gru)
-        return {"framewise_output": frame, "clipwise_output": clip, "embedding": cla if is_gru else x.transpose(1, 2)}
+                self.conv_stack(recording[b0 * stride_samples:], feat16[b0:b1], variant=variant,
+                                windows=(b1 - b0, window_samples, stride_samples),
+                                feat32=None if feat32 is None else feat32[b0:b1])
+
+        with self._lock:
+            return self._run(n_windows, T // 8, conv_call)[0]
 
     def forward(self, wave, micro_batch=148, variant=2, return_stages=False):
         """wave [B, L] f32 on self.device -> reference output dict (models.py:683-686 / :1072-1075)."""
@@ -499,22 +559,17 @@ class PackedModel:
         wave = wave.contiguous()
         B, L = wave.shape
         T = L // self.front.hop + 1
-        Tp = T // 8
         stages = {} if return_stages else None
-        with self._lock:
-            feat16 = torch.empty((B, Tp, 512), dtype=self.tdtype, device=self.device)
+
+        def conv_call(feat16, feat32):
             for b0 in range(0, B, micro_batch):
                 b1 = min(B, b0 + micro_batch)
                 self.conv_stack(wave[b0:b1], feat16[b0:b1], variant=variant,
-                                stages=stages if (return_stages and b0 == 0) else None)
-            x = self.temporal(feat16, stages)
-            frames = Tp * 8
-            if self.model_type == "Cnn_9layers_Gru_FrameAtt" and frames != 1000:
-                frames = frames if frames % 100 == 0 else frames + 100 - frames % 100  # models.py:62-63, 680-681
-            is_gru = self.model_type == "Cnn_9layers_Gru_FrameAtt"
-            clip, frame, cla, natt = self.head(x, frames, want_cla=is_gru, want_norm_att=return_stages)
-        out = {"framewise_output": frame, "clipwise_output": clip,
-               "embedding": cla if is_gru else x.transpose(1, 2)}
+                                stages=stages if (return_stages and b0 == 0) else None,
+                                feat32=None if feat32 is None else feat32[b0:b1])
+
+        with self._lock:
+            out, feat16, x, natt = self._run(B, T // 8, conv_call, stages, want_norm_att=return_stages)
         if return_stages:
             stages["feat"] = feat16
             stages["temporal"] = x

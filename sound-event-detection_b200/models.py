@@ -15,8 +15,10 @@ import torch.nn as nn
 from . import engine
 from .stft import LogmelFilterBank, Spectrogram
 
-__all__ = ["Cnn_9layers_Gru_FrameAtt", "Cnn_9layers_Transformer_FrameAtt", "ConvBlock", "AttBlock", "MultiHead",
-           "Spectrogram", "LogmelFilterBank"]
+__all__ = ["Cnn_9layers_Gru_FrameAtt", "Cnn_9layers_Transformer_FrameAtt", "Cnn_9layers_FrameMax",
+           "Cnn_9layers_FrameAvg", "Cnn_9layers_FrameAtt", "Cnn_9layers_Gru_FrameAvg",
+           "Cnn_9layers_Transformer_FrameAvg", "ConvBlock", "AttBlock", "MultiHead", "Spectrogram",
+           "LogmelFilterBank"]
 
 
 def _xavier(layer):
@@ -133,29 +135,36 @@ class _Cnn9Base(nn.Module):
             return packed.forward(input, micro_batch=self.micro_batch, variant=self.conv_variant)
 
 
+def _make_gru():
+    """nn.GRU(512, 256, bidirectional) with the distributions of reference init_gru (models.py:35-60)."""
+    gru = nn.GRU(input_size=512, hidden_size=256, num_layers=1, bias=True, batch_first=True, bidirectional=True)
+    for name, p in gru.named_parameters():
+        if "bias" in name:
+            nn.init.constant_(p, 0)
+        else:
+            fan_in = p.shape[1]
+            for g in range(3):
+                blk = p.data[g * 256:(g + 1) * 256]
+                if "weight_hh" in name and g == 2:
+                    nn.init.orthogonal_(blk)
+                else:
+                    nn.init.uniform_(blk, -math.sqrt(3 / fan_in), math.sqrt(3 / fan_in))
+    return gru
+
+
+def _make_fc(classes_num):
+    fc = nn.Linear(512, classes_num, bias=True)
+    _xavier(fc)
+    return fc
+
+
 class Cnn_9layers_Gru_FrameAtt(_Cnn9Base):
     MODEL_TYPE = "Cnn_9layers_Gru_FrameAtt"
 
     def __init__(self, sample_rate, window_size, hop_size, mel_bins, fmin, fmax, classes_num, feature_type):
         super().__init__(sample_rate, window_size, hop_size, mel_bins, fmin, fmax, classes_num, feature_type)
-        self.gru = nn.GRU(input_size=512, hidden_size=256, num_layers=1, bias=True, batch_first=True,
-                          bidirectional=True)
+        self.gru = _make_gru()
         self.att_block = AttBlock(n_in=512, n_out=25, activation='sigmoid')  # 25 is hard-coded (models.py:617)
-        self._init_gru()
-
-    def _init_gru(self):
-        # same distributions as reference init_gru (models.py:35-60)
-        for name, p in self.gru.named_parameters():
-            if "bias" in name:
-                nn.init.constant_(p, 0)
-            else:
-                fan_in = p.shape[1]
-                for g in range(3):
-                    blk = p.data[g * 256:(g + 1) * 256]
-                    if "weight_hh" in name and g == 2:
-                        nn.init.orthogonal_(blk)
-                    else:
-                        nn.init.uniform_(blk, -math.sqrt(3 / fan_in), math.sqrt(3 / fan_in))
 
 
 class Cnn_9layers_Transformer_FrameAtt(_Cnn9Base):
@@ -165,3 +174,54 @@ class Cnn_9layers_Transformer_FrameAtt(_Cnn9Base):
         super().__init__(sample_rate, window_size, hop_size, mel_bins, fmin, fmax, classes_num, feature_type)
         self.multihead = MultiHead(8, 512, 64, 64, 0.2)
         self.att_block = AttBlock(n_in=512, n_out=25, activation='sigmoid')
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Sibling heads on the same trunk.  Constructor signatures as in the reference: the three
+# heads without a temporal block take 7 arguments (no feature_type), the Gru / Transformer ones take 8.
+# ---------------------------------------------------------------------------------------------------------
+class Cnn_9layers_FrameMax(_Cnn9Base):
+    """pytorch/models.py:213-295: sigmoid(fc(x)) per frame, x8 interpolation, clipwise = max over frames."""
+    MODEL_TYPE = "Cnn_9layers_FrameMax"
+
+    def __init__(self, sample_rate, window_size, hop_size, mel_bins, fmin, fmax, classes_num):
+        super().__init__(sample_rate, window_size, hop_size, mel_bins, fmin, fmax, classes_num)
+        self.fc = _make_fc(classes_num)
+
+
+class Cnn_9layers_FrameAvg(_Cnn9Base):
+    """pytorch/models.py:298-380: as FrameMax with clipwise = mean over frames."""
+    MODEL_TYPE = "Cnn_9layers_FrameAvg"
+
+    def __init__(self, sample_rate, window_size, hop_size, mel_bins, fmin, fmax, classes_num):
+        super().__init__(sample_rate, window_size, hop_size, mel_bins, fmin, fmax, classes_num)
+        self.fc = _make_fc(classes_num)
+
+
+class Cnn_9layers_FrameAtt(_Cnn9Base):
+    """pytorch/models.py:383-463: AttBlock directly on the conv features; framewise is not padded."""
+    MODEL_TYPE = "Cnn_9layers_FrameAtt"
+
+    def __init__(self, sample_rate, window_size, hop_size, mel_bins, fmin, fmax, classes_num):
+        super().__init__(sample_rate, window_size, hop_size, mel_bins, fmin, fmax, classes_num)
+        self.att_block = AttBlock(n_in=512, n_out=25, activation='sigmoid')
+
+
+class Cnn_9layers_Gru_FrameAvg(_Cnn9Base):
+    """pytorch/models.py:466-561: bi-GRU then the FrameAvg head."""
+    MODEL_TYPE = "Cnn_9layers_Gru_FrameAvg"
+
+    def __init__(self, sample_rate, window_size, hop_size, mel_bins, fmin, fmax, classes_num, feature_type):
+        super().__init__(sample_rate, window_size, hop_size, mel_bins, fmin, fmax, classes_num, feature_type)
+        self.gru = _make_gru()
+        self.fc = _make_fc(classes_num)
+
+
+class Cnn_9layers_Transformer_FrameAvg(_Cnn9Base):
+    """pytorch/models.py:880-978: MultiHead then the FrameAvg head."""
+    MODEL_TYPE = "Cnn_9layers_Transformer_FrameAvg"
+
+    def __init__(self, sample_rate, window_size, hop_size, mel_bins, fmin, fmax, classes_num, feature_type):
+        super().__init__(sample_rate, window_size, hop_size, mel_bins, fmin, fmax, classes_num, feature_type)
+        self.multihead = MultiHead(8, 512, 64, 64, 0.2)
+        self.fc = _make_fc(classes_num)

@@ -25,6 +25,13 @@ PRESETS = {
 }
 
 MODEL_TYPES = ("Cnn_9layers_Gru_FrameAtt", "Cnn_9layers_Transformer_FrameAtt")
+# sibling heads on the same trunk (pytorch/models.py:213-561, 880-978): (temporal block, head)
+SIBLING_TYPES = {
+    "Cnn_9layers_FrameMax": (None, "fc"), "Cnn_9layers_FrameAvg": (None, "fc"), "Cnn_9layers_FrameAtt": (None, "att"),
+    "Cnn_9layers_Gru_FrameAvg": ("gru", "fc"), "Cnn_9layers_Transformer_FrameAvg": ("mha", "fc"),
+}
+_PLANS = dict({"Cnn_9layers_Gru_FrameAtt": ("gru", "att"), "Cnn_9layers_Transformer_FrameAtt": ("mha", "att")},
+              **SIBLING_TYPES)
 
 
 def synthetic_waveform(batch, samples, seed=1234, rank=0, kind="noise", sample_rate=16000):
@@ -71,10 +78,11 @@ def _bn_fold(sd, prefix):
     return scale, shift
 
 
-def synthetic_state_dict(model_type, sample_rate=16000, seed=0, calib_seconds=3.0, calib_clips=2):
+def synthetic_state_dict(model_type, sample_rate=16000, seed=0, calib_seconds=3.0, calib_clips=2, classes_num=25):
     """Reference-layout `state_dict` (float32 CPU tensors) with calibrated BN statistics."""
-    if model_type not in MODEL_TYPES:
+    if model_type not in _PLANS:
         raise ValueError("unsupported model_type %r" % (model_type,))
+    temporal, head = _PLANS[model_type]
     n_fft, hop, fmin, fmax = PRESETS[sample_rate]
     g = torch.Generator().manual_seed(1000003 * seed + 17)
     sd = {}
@@ -131,13 +139,13 @@ def synthetic_state_dict(model_type, sample_rate=16000, seed=0, calib_seconds=3.
             if i < 4:
                 x = F.avg_pool2d(x, 2)
 
-    if model_type == "Cnn_9layers_Gru_FrameAtt":
+    if temporal == "gru":
         for suffix in ("", "_reverse"):
             sd["gru.weight_ih_l0" + suffix] = (torch.rand(768, 512, generator=g) * 2 - 1) * math.sqrt(3.0 / 512)
             sd["gru.weight_hh_l0" + suffix] = (torch.rand(768, 256, generator=g) * 2 - 1) * math.sqrt(3.0 / 256)
             sd["gru.bias_ih_l0" + suffix] = 0.1 * torch.randn(768, generator=g)
             sd["gru.bias_hh_l0" + suffix] = 0.1 * torch.randn(768, generator=g)
-    else:
+    elif temporal == "mha":
         for name in ("w_qs", "w_ks", "w_vs"):
             sd["multihead.%s.weight" % name] = torch.randn(512, 512, generator=g) * math.sqrt(2.0 / (512 + 64))
             sd["multihead.%s.bias" % name] = 0.05 * torch.randn(512, generator=g)
@@ -147,7 +155,11 @@ def synthetic_state_dict(model_type, sample_rate=16000, seed=0, calib_seconds=3.
         sd["multihead.fc.bias"] = 0.05 * torch.randn(512, generator=g)
 
     # head gain chosen so framewise probabilities span roughly [0.02, 0.98] on the synthetic inputs
-    gain = 1.0 if model_type == "Cnn_9layers_Gru_FrameAtt" else 0.5
+    gain = 1.0 if temporal == "gru" else 0.5
+    if head == "fc":
+        sd["fc.weight"] = _xavier_uniform((classes_num, 512), g, gain=gain)
+        sd["fc.bias"] = 0.5 * torch.randn(classes_num, generator=g)
+        return {k: (v.float().contiguous() if v.is_floating_point() else v) for k, v in sd.items()}
     sd["att_block.att.weight"] = _xavier_uniform((25, 512, 1), g, gain=gain)
     sd["att_block.att.bias"] = 0.3 * torch.randn(25, generator=g)
     sd["att_block.cla.weight"] = _xavier_uniform((25, 512, 1), g, gain=gain)

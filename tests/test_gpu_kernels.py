@@ -34,7 +34,7 @@ def run_conv(x, w, scale, shift, mode, code, td, variant):
     oshape = {0: (NB, H, W, cout), 1: (NB, H // 2, W // 2, cout), 2: (NB, H, cout)}[mode]
     out = torch.full(oshape, float("nan"), dtype=td, device=DEV)
     rc = lib.sed_conv3x3_bn_relu(capi.ptr(xd), NB, H, W, cin, capi.ptr(wp), capi.ptr(sc), capi.ptr(sh), cout, mode,
-                                 capi.ptr(out), code, variant, capi.current_stream(DEV))
+                                 capi.ptr(out), None, code, variant, capi.current_stream(DEV))
     capi.check(rc, "sed_conv3x3_bn_relu")
     torch.cuda.synchronize()
     return out.float().cpu()
@@ -90,11 +90,11 @@ def test_conv_rejects_unsupported_layers():
     x = torch.zeros(1, 16, 8, 192, dtype=torch.float16, device=DEV)
     with pytest.raises(NotImplementedError):
         rc = lib.sed_conv3x3_bn_relu(capi.ptr(x), 1, 16, 8, 192, capi.ptr(x), capi.ptr(x), capi.ptr(x), 192, 0,
-                                     capi.ptr(x), 0, 0, capi.current_stream(DEV))
+                                     capi.ptr(x), None, 0, 0, capi.current_stream(DEV))
         capi.check(rc, "conv")
     with pytest.raises(ValueError):
         rc = lib.sed_conv3x3_bn_relu(capi.ptr(x), 1, 16, 7, 64, capi.ptr(x), capi.ptr(x), capi.ptr(x), 64, 1,
-                                     capi.ptr(x), 0, 0, capi.current_stream(DEV))
+                                     capi.ptr(x), None, 0, 0, capi.current_stream(DEV))
         capi.check(rc, "conv")
 
 

@@ -107,7 +107,7 @@ def run_stage(stage):
                 t0 = time.time()
                 xd, sc, sh = x.to(dev), scale.to(dev), shift.to(dev)
                 rc = lib.sed_conv3x3_bn_relu(capi.ptr(xd), NB, H, W, cin, capi.ptr(wp), capi.ptr(sc),
-                                             capi.ptr(sh), cout, mode, capi.ptr(out), code, variant, stream)
+                                             capi.ptr(sh), cout, mode, capi.ptr(out), None, code, variant, stream)
                 capi.check(rc, name)
                 torch.cuda.synchronize()
                 ref = conv_ref(x.float(), w.float(), scale, shift, mode)

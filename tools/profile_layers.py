@@ -55,7 +55,7 @@ def main():
         out = feat if dst is None else ws[dst]
         for variant in (0, 2):
             t = timeit(lambda: lib.sed_conv3x3_bn_relu(capi.ptr(x), mb, x.shape[1], x.shape[2], cin, capi.ptr(wp),
-                                                       capi.ptr(s), capi.ptr(b), cout, mode, capi.ptr(out),
+                                                       capi.ptr(s), capi.ptr(b), cout, mode, capi.ptr(out), None,
                                                        pm.dtype_code, variant, stream))
             flops = 2.0 * mb * x.shape[1] * x.shape[2] * 9 * cin * cout
             rows.append(("%s %d->%d %s" % (name, cin, cout, {0: "patch", 1: "tap", 2: "pair"}[variant]), t, flops,
