@@ -21,10 +21,14 @@ namespace sed {
 
 template <int NFFT>
 struct FrontCfg {
-  static constexpr int WARPS = 4;
-  static constexpr int FPB = 16;  // frames per block (even: frames are transformed in pairs); small blocks so
-                                  // that several are resident per SM and their load phases overlap
+  static constexpr int WARPS = 8;
+  // frames per work item (even: frames are transformed in pairs).  A persistent block loops over work items =
+  // (clip, chunk of FPB frames); the waveform segment of the next item is staged with cp.async while the current
+  // one is transformed.
+  static constexpr int FPB = (NFFT == 1024) ? 16 : 32;
   static constexpr int MELV = 1024;  // banded mel weights cached in shared memory (falls back to global beyond)
+  static constexpr bool WIN_REGS = (NFFT <= 512);  // window taps of the first pass live in registers
+  static constexpr int MIN_BLOCKS = (NFFT == 1024) ? 1 : 2;
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -79,14 +83,60 @@ __device__ __forceinline__ void butterfly<8>(float2 (&v)[8]) {
   }
 }
 
+// Per-lane twiddles of one Stockham pass (radix R, stride Ns) of an N-point transform.  They depend only on the
+// lane, not on the frame, so a persistent warp keeps them in registers; the widest case (N = 1024, Ns = 128) reads
+// the shared-memory table instead.
+template <int N, int R, int Ns>
+struct PassTw {
+  static constexpr int NB = N / R, BPL = NB / 32;
+  static constexpr int NK = (Ns > 32) ? BPL : 1;  // distinct k = (lane + 32 q) % Ns over the lane's butterflies
+  static constexpr bool IN_REGS = (Ns > 1) && (NK * (R - 1) <= 14);
+  static constexpr int TSTRIDE = N / (Ns * R);
+  float2 t[IN_REGS ? NK : 1][R - 1];
+  __device__ __forceinline__ void init(const float2* __restrict__ tw, int lane) {
+    if (IN_REGS) {
+#pragma unroll
+      for (int q = 0; q < NK; ++q) {
+        const int k = (lane + 32 * q) % Ns;
+#pragma unroll
+        for (int r = 1; r < R; ++r) t[q][r - 1] = tw[r * k * TSTRIDE];
+      }
+    }
+  }
+};
+
+// int16 PCM input follows the reference's HDF5 path: x = q / 32767 (utils/utilities.py:78-79).  The three-operation
+// sequence below (multiply by the rounded reciprocal, exact residual, correction) returns the correctly rounded
+// float32 quotient for every int16 q (checked exhaustively on the host) -- the value numpy's
+// (q / 32767.).astype(float32) produces.
+__device__ __forceinline__ float load_sample(const float* p) { return *p; }
+__device__ __forceinline__ float load_sample(const short* p) {
+  const float q = static_cast<float>(*p);
+  constexpr float kInv = 1.0f / 32767.0f;
+  const float r = q * kInv;
+  const float e = fmaf(-r, 32767.0f, q);
+  return fmaf(e, kInv, r);
+}
+__device__ __forceinline__ float load_sample_global(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float load_sample_global(const short* p) { return static_cast<float>(__ldg(p)); }
+__device__ __forceinline__ void store_raw(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_raw(short* p, float v) { *p = static_cast<short>(v); }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // One Stockham pass of radix R over N complex points, IN PLACE in (padded) shared memory, executed by one warp:
 // every lane first pulls the inputs of all its butterflies into registers, the warp synchronises, then the
-// autosorted outputs are written back.  first == true: inputs come from the windowed frame pair instead
-// (re = frame a, im = frame b).
-template <int N, int R>
-__device__ __forceinline__ void fft_pass(float2* __restrict__ buf, bool first, int Ns, const float2* __restrict__ tw,
-                                         const float* __restrict__ seg_a, const float* __restrict__ seg_b,
-                                         const float* __restrict__ win, int lane) {
+// autosorted outputs are written back.  FIRST: inputs come from the windowed frame pair instead (re = frame a,
+// im = frame b), staged as raw input samples.
+template <int N, int R, int Ns, bool FIRST, bool WINREG, typename TIn>
+__device__ __forceinline__ void fft_pass(float2* __restrict__ buf, const PassTw<N, R, Ns>& tws,
+                                         const float2* __restrict__ s_tw, const TIn* __restrict__ seg_a,
+                                         const TIn* __restrict__ seg_b, const float* __restrict__ s_win,
+                                         const float (&wreg)[N / 32], int lane) {
   constexpr int NB = N / R;
   constexpr int BPL = NB / 32;  // butterflies per lane
   float2 v[BPL][R];
@@ -96,9 +146,9 @@ __device__ __forceinline__ void fft_pass(float2* __restrict__ buf, bool first, i
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int idx = j + r * NB;
-      if (first) {
-        const float w = win[idx];
-        v[q][r] = make_float2(w * seg_a[idx], w * seg_b[idx]);
+      if (FIRST) {
+        const float w = WINREG ? wreg[q * R + r] : s_win[idx];
+        v[q][r] = make_float2(w * load_sample(seg_a + idx), w * load_sample(seg_b + idx));
       } else {
         v[q][r] = buf[pidx(idx)];
       }
@@ -110,9 +160,12 @@ __device__ __forceinline__ void fft_pass(float2* __restrict__ buf, bool first, i
     const int j = lane + 32 * q;
     const int k = j % Ns;
     if (Ns > 1) {
-      const int tstride = N / (Ns * R);
 #pragma unroll
-      for (int r = 1; r < R; ++r) v[q][r] = cmul(v[q][r], tw[r * k * tstride]);
+      for (int r = 1; r < R; ++r) {
+        const float2 w = PassTw<N, R, Ns>::IN_REGS ? tws.t[PassTw<N, R, Ns>::NK == 1 ? 0 : q][r - 1]
+                                                   : s_tw[r * k * PassTw<N, R, Ns>::TSTRIDE];
+        v[q][r] = cmul(v[q][r], w);
+      }
     }
     butterfly<R>(v[q]);
     const int j0 = (j / Ns) * Ns * R + k;
@@ -122,49 +175,79 @@ __device__ __forceinline__ void fft_pass(float2* __restrict__ buf, bool first, i
   __syncwarp();
 }
 
-// mode 0: out = log-mel (+ optional bn0 affine) [B, T, n_mels];  mode 1: out = power spectrogram [B, T, F]
-// int16 PCM input follows the reference's HDF5 path: x = q / 32767 (utils/utilities.py:78-79); the float32
-// division is correctly rounded and equals numpy's float64-then-float32 result for every int16 q.
-__device__ __forceinline__ float load_sample(const float* p) { return __ldg(p); }
-__device__ __forceinline__ float load_sample(const short* p) { return static_cast<float>(__ldg(p)) / 32767.0f; }
+// Radix schedule of the N-point transform: 256 = 4*8*8, 512 = 8*8*8, 1024 = 2*8*8*8.
+template <int N> struct Sched;
+template <> struct Sched<256> { static constexpr int R0 = 4; };
+template <> struct Sched<512> { static constexpr int R0 = 8; };
+template <> struct Sched<1024> { static constexpr int R0 = 2; };
 
-// Clip b starts at wave + b * clip_stride and is L samples long; samples at or beyond total_len (counted from
-// `wave`) read as zero (pad_truncate_sequence, utils/utilities.py:66-70).  clip_stride < L gives overlapping
-// windows of one long recording (predict.py:297-307) without materialising them.
+// Stage the raw waveform segment [q0, q0 + seg_len) of clip b (reflect padding at the clip ends, stft.py:236-237;
+// zero beyond total_len, pad_truncate_sequence utils/utilities.py:66-70) into shared memory.  Interior, 16-byte
+// aligned segments go through cp.async; edge segments through guarded loads.
 template <int NFFT, typename TIn>
-__global__ void __launch_bounds__(FrontCfg<NFFT>::WARPS * 32)
-frontend_kernel(const TIn* __restrict__ wave, long clip_stride, long total_len, int L, int T, int hop,
-                const float* __restrict__ window,
-                const float2* __restrict__ twiddle, const int* __restrict__ mel_lo, const int* __restrict__ mel_len,
-                const int* __restrict__ mel_off, const float* __restrict__ mel_val, int n_mels, float amin,
-                float db_offset, int is_log, const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
-                float* __restrict__ out, int mode, int dbg) {
+__device__ __forceinline__ void stage_segment(TIn* __restrict__ dst, const TIn* __restrict__ wave, long clip_stride,
+                                              long total_len, int L, int hop, int seg_len, int item, int chunks,
+                                              bool aligned) {
+  constexpr int FPB = FrontCfg<NFFT>::FPB;
+  const int b = item / chunks, c = item - b * chunks;
+  const long clip_base = static_cast<long>(b) * clip_stride;
+  const long q0 = static_cast<long>(c) * FPB * hop - NFFT / 2;
+  const TIn* w = wave + clip_base;
+  if (aligned && q0 >= 0 && q0 + seg_len <= L && clip_base + q0 + seg_len <= total_len) {
+    const char* src = reinterpret_cast<const char*>(w + q0);
+    char* d = reinterpret_cast<char*>(dst);
+    const int nvec = seg_len * static_cast<int>(sizeof(TIn)) / 16;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) cp_async16(d + 16 * i, src + 16 * i);
+  } else {
+    for (int s = threadIdx.x; s < seg_len; s += blockDim.x) {
+      long i = q0 + s;
+      if (i < 0) i = -i;
+      if (i >= L) i = 2L * (L - 1) - i;
+      const float v = (i >= 0 && i < L && clip_base + i < total_len) ? load_sample_global(w + i) : 0.0f;
+      store_raw(dst + s, v);
+    }
+  }
+  cp_async_commit();
+}
+
+// mode 0: out = log-mel (+ optional bn0 affine) [B, T, n_mels];  mode 1: out = power spectrogram [B, T, F]
+// Clip b starts at wave + b * clip_stride and is L samples long; samples at or beyond total_len (counted from
+// `wave`) read as zero.  clip_stride < L gives overlapping windows of one long recording (predict.py:297-307)
+// without materialising them.
+template <int NFFT, typename TIn>
+__global__ void __launch_bounds__(FrontCfg<NFFT>::WARPS * 32, FrontCfg<NFFT>::MIN_BLOCKS)
+frontend_kernel(const TIn* __restrict__ wave, long clip_stride, long total_len, int B, int L, int T, int hop,
+                const float* __restrict__ window, const float2* __restrict__ twiddle,
+                const int* __restrict__ mel_lo, const int* __restrict__ mel_len, const int* __restrict__ mel_off,
+                const float* __restrict__ mel_val, int n_mels, float amin, float db_offset, int is_log,
+                const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, float* __restrict__ out,
+                int mode, int aligned, int dbg) {
   constexpr int WARPS = FrontCfg<NFFT>::WARPS;
   constexpr int FPB = FrontCfg<NFFT>::FPB;
   constexpr int F = NFFT / 2 + 1;
-  extern __shared__ float smem_f[];
+  constexpr int BUF = NFFT + NFFT / 8;  // padded (see pidx)
+  constexpr bool WINREG = FrontCfg<NFFT>::WIN_REGS;
+  constexpr int R0 = Sched<NFFT>::R0;
+  constexpr int NS1 = R0, NS2 = R0 * 8, NS3 = R0 * 64;  // strides of the radix-8 passes after the first
+  extern __shared__ float4 smem_f4[];
   const int seg_len = (FPB - 1) * hop + NFFT;
-  float* s_seg = smem_f;                                            // [seg_len]
-  float* s_win = s_seg + ((seg_len + 3) & ~3);                      // [NFFT]
-  float2* s_tw = reinterpret_cast<float2*>(s_win + NFFT);           // [NFFT]
-  float2* s_buf = s_tw + NFFT;                                      // [WARPS][NFFT + NFFT/8]
-  constexpr int BUF = NFFT + NFFT / 8;                              // padded (see pidx)
-  float* s_melv = reinterpret_cast<float*>(s_buf + WARPS * BUF);    // [MELV] banded mel weights
+  const int seg_bytes = ((seg_len * static_cast<int>(sizeof(TIn)) + 15) & ~15);
+  uint8_t* sp = reinterpret_cast<uint8_t*>(smem_f4);
+  TIn* s_stage0 = reinterpret_cast<TIn*>(sp);
+  TIn* s_stage1 = reinterpret_cast<TIn*>(sp + seg_bytes);
+  float2* s_buf = reinterpret_cast<float2*>(sp + 2 * seg_bytes);     // [WARPS][BUF]
+  float2* s_tw = s_buf + WARPS * BUF;                                 // [NFFT]
+  float* s_win = reinterpret_cast<float*>(s_tw + NFFT);               // [NFFT]
+  float* s_melv = s_win + NFFT;                                       // [MELV] banded mel weights
   int* s_meli = reinterpret_cast<int*>(s_melv + FrontCfg<NFFT>::MELV);  // [3][n_mels] lo, len, off
 
-  const int b = blockIdx.y;
-  const int f_base = blockIdx.x * FPB;
-  const long clip_base = static_cast<long>(b) * clip_stride;
-  const TIn* w = wave + clip_base;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunks = (T + FPB - 1) / FPB;
+  const int items = B * chunks;
+  int item = blockIdx.x;
+  if (item < items)
+    stage_segment<NFFT, TIn>(s_stage0, wave, clip_stride, total_len, L, hop, seg_len, item, chunks, aligned != 0);
 
-  // stage the waveform segment with reflect padding (stft.py:236-237)
-  const long q0 = static_cast<long>(f_base) * hop - NFFT / 2;
-  for (int s = threadIdx.x; s < seg_len; s += blockDim.x) {
-    long i = q0 + s;
-    if (i < 0) i = -i;
-    if (i >= L) i = 2L * (L - 1) - i;
-    s_seg[s] = (i >= 0 && i < L && clip_base + i < total_len) ? load_sample(w + i) : 0.0f;
-  }
   for (int i = threadIdx.x; i < NFFT; i += blockDim.x) {
     s_win[i] = window[i];
     s_tw[i] = twiddle[i];
@@ -181,104 +264,140 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, long total_len, 
       for (int i = threadIdx.x; i < mel_total; i += blockDim.x) s_melv[i] = mel_val[i];
   }
   const bool mel_in_smem = mel_total <= FrontCfg<NFFT>::MELV;
-  __syncthreads();
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // per-lane constants of the transform, loaded once per persistent warp
+  PassTw<NFFT, R0, 1> tw0;  // first pass: no twiddles
+  PassTw<NFFT, 8, NS1> tw1;
+  PassTw<NFFT, 8, NS2> tw2;
+  PassTw<NFFT, 8, (NFFT == 1024) ? NS3 : 1> tw3;  // fourth pass exists for 1024 only
+  tw1.init(twiddle, lane);
+  tw2.init(twiddle, lane);
+  tw3.init(twiddle, lane);
+  float wreg[NFFT / 32];
+  if (WINREG) {
+    constexpr int NB0 = NFFT / R0, BPL0 = NB0 / 32;
+#pragma unroll
+    for (int q = 0; q < BPL0; ++q)
+#pragma unroll
+      for (int r = 0; r < R0; ++r) wreg[q * R0 + r] = __ldg(window + lane + 32 * q + r * NB0);
+  }
+
   float2* buf = s_buf + warp * BUF;
+  int sel = 0;
+  for (; item < items; item += gridDim.x, sel ^= 1) {
+    cp_async_wait_all();
+    __syncthreads();  // this item's segment is visible; every warp has finished the previous item
+    const int nxt = item + gridDim.x;
+    if (nxt < items)
+      stage_segment<NFFT, TIn>(sel ? s_stage0 : s_stage1, wave, clip_stride, total_len, L, hop, seg_len, nxt, chunks,
+                               aligned != 0);
+    const TIn* s_seg = sel ? s_stage1 : s_stage0;
+    const int b = item / chunks;
+    const int f_base = (item - b * chunks) * FPB;
 
-  for (int pair = warp; pair < FPB / 2; pair += WARPS) {
-    const int fa = f_base + 2 * pair;
-    if (fa >= T) break;
-    const float* seg_a = s_seg + (2 * pair) * hop;
-    const float* seg_b = seg_a + hop;
+    for (int pair = warp; pair < FPB / 2; pair += WARPS) {
+      const int fa = f_base + 2 * pair;
+      if (fa >= T) break;
+      const TIn* seg_a = s_seg + (2 * pair) * hop;
+      const TIn* seg_b = seg_a + hop;
 
-    // ---- 2 real frames -> 1 complex FFT of size NFFT (Stockham autosort, natural-order output) ----
-    // radix schedule: 256 = 4*8*8, 512 = 8*8*8, 1024 = 2*8*8*8
-    int Ns = 1;
-    bool first = true;
-    if (NFFT == 1024) {
-      fft_pass<NFFT, 2>(buf, first, Ns, s_tw, seg_a, seg_b, s_win, lane);
-      Ns = 2;
-      first = false;
-    } else if (NFFT == 256) {
-      fft_pass<NFFT, 4>(buf, first, Ns, s_tw, seg_a, seg_b, s_win, lane);
-      Ns = 4;
-      first = false;
-    }
-    while (Ns < NFFT) {
-      if ((dbg & 1) && Ns > 1) break;
-      fft_pass<NFFT, 8>(buf, first, Ns, s_tw, seg_a, seg_b, s_win, lane);
-      Ns *= 8;
-      first = false;
-    }
-    // ---- split the two real spectra and take the power (stft.py:663), in place: P[0..F) = |A|^2,
-    //      P[F..2F) = |B|^2 overwrite the spectrum after every lane has read its bins ----
-    constexpr int KPL = (F + 31) / 32;
-    float pa[KPL], pb[KPL];
-#pragma unroll
-    for (int i = 0; i < KPL; ++i) {
-      const int k = lane + 32 * i;
-      if (k < F) {
-        const float2 zk = buf[pidx(k & (NFFT - 1))];
-        const float2 zn = buf[pidx((NFFT - k) & (NFFT - 1))];
-        const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
-        const float br = 0.5f * (zk.y + zn.y), bi = 0.5f * (zn.x - zk.x);
-        pa[i] = ar * ar + ai * ai;
-        pb[i] = br * br + bi * bi;
+      // ---- 2 real frames -> 1 complex FFT of size NFFT (Stockham autosort, natural-order output) ----
+      fft_pass<NFFT, R0, 1, true, WINREG, TIn>(buf, tw0, s_tw, seg_a, seg_b, s_win, wreg, lane);
+      if (!(dbg & 1)) {
+        fft_pass<NFFT, 8, NS1, false, WINREG, TIn>(buf, tw1, s_tw, seg_a, seg_b, s_win, wreg, lane);
+        fft_pass<NFFT, 8, NS2, false, WINREG, TIn>(buf, tw2, s_tw, seg_a, seg_b, s_win, wreg, lane);
+        if (NFFT == 1024)
+          fft_pass<NFFT, 8, (NFFT == 1024) ? NS3 : 1, false, WINREG, TIn>(buf, tw3, s_tw, seg_a, seg_b, s_win, wreg,
+                                                                           lane);
       }
-    }
-    __syncwarp();
-    float* P = reinterpret_cast<float*>(buf);
+      // ---- split the two real spectra and take the power (stft.py:663), in place: P[0..F) = |A|^2,
+      //      P[F..2F) = |B|^2 overwrite the spectrum after every lane has read its bins ----
+      constexpr int KPL = (F + 31) / 32;
+      float pa[KPL], pb[KPL];
 #pragma unroll
-    for (int i = 0; i < KPL; ++i) {
-      const int k = lane + 32 * i;
-      if (k < F) {
-        P[k] = pa[i];
-        P[F + k] = pb[i];
+      for (int i = 0; i < KPL; ++i) {
+        const int k = lane + 32 * i;
+        if (k < F) {
+          const float2 zk = buf[pidx(k & (NFFT - 1))];
+          const float2 zn = buf[pidx((NFFT - k) & (NFFT - 1))];
+          const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
+          const float br = 0.5f * (zk.y + zn.y), bi = 0.5f * (zn.x - zk.x);
+          pa[i] = ar * ar + ai * ai;
+          pb[i] = br * br + bi * bi;
+        }
       }
-    }
-    __syncwarp();
-
+      __syncwarp();
+      float2* P2 = buf;  // P2[k] = (|A_k|^2, |B_k|^2): both frames of the pair side by side
 #pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      const int f = fa + which;
-      if (f >= T) break;
-      const float* Pf = P + which * F;
+      for (int i = 0; i < KPL; ++i) {
+        const int k = lane + 32 * i;
+        if (k < F) P2[k] = make_float2(pa[i], pb[i]);
+      }
+      __syncwarp();
+
+      const bool has_b = fa + 1 < T;
       if (dbg & 2) {
-        if (lane == 0) out[(static_cast<size_t>(b) * T + f) * n_mels] = Pf[3];
+        if (lane == 0) out[(static_cast<size_t>(b) * T + fa) * n_mels] = P2[3].x + P2[3].y;
       } else if (mode == 1) {
-        float* o = out + (static_cast<size_t>(b) * T + f) * F;
-        for (int k = lane; k < F; k += 32) o[k] = Pf[k];
+        float* o = out + (static_cast<size_t>(b) * T + fa) * F;
+        for (int k = lane; k < F; k += 32) {
+          const float2 p = P2[k];
+          o[k] = p.x;
+          if (has_b) o[F + k] = p.y;
+        }
       } else {
-        float* o = out + (static_cast<size_t>(b) * T + f) * n_mels;
-        // bins are visited as (lane, n_mels-1-lane, lane+32, ...): narrow low bands pair with wide high bands
+        float* o = out + (static_cast<size_t>(b) * T + fa) * n_mels;
+        // bins are visited as (lane, n_mels-1-lane, lane+32, ...): narrow low bands pair with wide high bands;
+        // both frames of the pair share every weight load
         for (int mi = lane; mi < n_mels; mi += 32) {
           const int pr = mi >> 5;
           const int m = (pr & 1) ? (n_mels - 1 - (mi - 32 * pr) - 32 * (pr >> 1)) : (lane + 32 * (pr >> 1));
           if (m < 0 || m >= n_mels) continue;
           const int lo = s_meli[m], len = s_meli[n_mels + m], off = s_meli[2 * n_mels + m];
-          float acc = 0.0f, acc2 = 0.0f;  // stft.py:709 restricted to the band of non-zero weights
+          const float2* Pm = P2 + lo;
+          float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;  // stft.py:709 restricted to the band of non-zero weights
           if (mel_in_smem) {
             const float* mv = s_melv + off;
             int i = 0;
             for (; i + 1 < len; i += 2) {
-              acc = fmaf(Pf[lo + i], mv[i], acc);
-              acc2 = fmaf(Pf[lo + i + 1], mv[i + 1], acc2);
+              const float2 p = Pm[i], q = Pm[i + 1];
+              const float w0 = mv[i], w1 = mv[i + 1];
+              a0 = fmaf(p.x, w0, a0);
+              b0 = fmaf(p.y, w0, b0);
+              a1 = fmaf(q.x, w1, a1);
+              b1 = fmaf(q.y, w1, b1);
             }
-            if (i < len) acc = fmaf(Pf[lo + i], mv[i], acc);
+            if (i < len) {
+              const float2 p = Pm[i];
+              const float w0 = mv[i];
+              a0 = fmaf(p.x, w0, a0);
+              b0 = fmaf(p.y, w0, b0);
+            }
           } else {
             const float* mv = mel_val + off;
-            for (int i = 0; i < len; ++i) acc = fmaf(Pf[lo + i], __ldg(mv + i), acc);
+            for (int i = 0; i < len; ++i) {
+              const float2 p = Pm[i];
+              const float w0 = __ldg(mv + i);
+              a0 = fmaf(p.x, w0, a0);
+              b0 = fmaf(p.y, w0, b0);
+            }
           }
-          acc += acc2;
-          float y = acc;
-          if (is_log) y = 10.0f * log10f(fmaxf(acc, amin)) - db_offset;  // stft.py:726-727
-          if (bn_scale != nullptr) y = fmaf(y, bn_scale[m], bn_shift[m]);  // models.py:642-644
-          o[m] = y;
+          float ya = a0 + a1, yb = b0 + b1;
+          if (is_log) {  // stft.py:726-727
+            ya = 10.0f * log10f(fmaxf(ya, amin)) - db_offset;
+            yb = 10.0f * log10f(fmaxf(yb, amin)) - db_offset;
+          }
+          if (bn_scale != nullptr) {  // models.py:642-644
+            const float sc = bn_scale[m], sh = bn_shift[m];
+            ya = fmaf(ya, sc, sh);
+            yb = fmaf(yb, sc, sh);
+          }
+          o[m] = ya;
+          if (has_b) o[n_mels + m] = yb;
         }
       }
+      __syncwarp();
     }
-    __syncwarp();
   }
 }
 
@@ -306,18 +425,38 @@ static int launch_frontend_t(const FrontendArgs& a, cudaStream_t stream) {
   constexpr int WARPS = FrontCfg<NFFT>::WARPS;
   constexpr int FPB = FrontCfg<NFFT>::FPB;
   const int seg_len = (FPB - 1) * a.hop + NFFT;
-  const size_t smem = sizeof(float) * (((seg_len + 3) & ~3) + NFFT + FrontCfg<NFFT>::MELV) +
-                      sizeof(float2) * (NFFT + WARPS * (NFFT + NFFT / 8)) + sizeof(int) * 3 * (a.n_mels > 0 ? a.n_mels : 1);
+  const int seg_bytes = (seg_len * static_cast<int>(sizeof(TIn)) + 15) & ~15;
+  const size_t smem = 2 * static_cast<size_t>(seg_bytes) + sizeof(float2) * (WARPS * (NFFT + NFFT / 8) + NFFT) +
+                      sizeof(float) * (NFFT + FrontCfg<NFFT>::MELV) + sizeof(int) * 3 * (a.n_mels > 0 ? a.n_mels : 1);
   if (smem > 227 * 1024) return SED_ERR_UNSUPPORTED;
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0)
+      sm_count = 148;
+  }
   cudaError_t e =
       cudaFuncSetAttribute(frontend_kernel<NFFT, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return SED_ERR_CUDA;
-  dim3 grid((a.T + FPB - 1) / FPB, a.B);
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frontend_kernel<NFFT, TIn>, WARPS * 32, smem) !=
+          cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  const long items = static_cast<long>(a.B) * ((a.T + FPB - 1) / FPB);
+  long blocks = static_cast<long>(sm_count) * per_sm;
+  if (blocks > items) blocks = items;
+  // cp.async staging needs 16-byte aligned interior segments
+  const size_t es = sizeof(TIn);
+  const int aligned = (reinterpret_cast<uintptr_t>(a.wave) % 16 == 0) && ((a.clip_stride * es) % 16 == 0) &&
+                      ((static_cast<size_t>(FPB) * a.hop * es) % 16 == 0) && ((NFFT / 2 * es) % 16 == 0) &&
+                      ((seg_len * es) % 16 == 0);
   const char* e_dbg = getenv("SED_FE_DBG");
   const int dbg = e_dbg ? atoi(e_dbg) : 0;
-  frontend_kernel<NFFT, TIn><<<grid, WARPS * 32, smem, stream>>>(
-      reinterpret_cast<const TIn*>(a.wave), a.clip_stride, a.total_len, a.L, a.T, a.hop, a.window, reinterpret_cast<const float2*>(a.twiddle), a.mel_lo, a.mel_len, a.mel_off,
-      a.mel_val, a.n_mels, a.amin, a.db_offset, a.is_log, a.bn_scale, a.bn_shift, a.out, a.mode, dbg);
+  frontend_kernel<NFFT, TIn><<<static_cast<unsigned>(blocks), WARPS * 32, smem, stream>>>(
+      reinterpret_cast<const TIn*>(a.wave), a.clip_stride, a.total_len, a.B, a.L, a.T, a.hop, a.window,
+      reinterpret_cast<const float2*>(a.twiddle), a.mel_lo, a.mel_len, a.mel_off, a.mel_val, a.n_mels, a.amin,
+      a.db_offset, a.is_log, a.bn_scale, a.bn_shift, a.out, a.mode, aligned, dbg);
   return cudaGetLastError() == cudaSuccess ? SED_OK : SED_ERR_CUDA;
 }
 

@@ -7,6 +7,9 @@
 //  * mha_core_kernel : softmax(q k^T / sqrt(64)) v per (clip, head)  (models.py:799-820, 863-875), float32,
 //                      one query row per thread, K/V of the head resident in shared memory.
 //  * attpool_kernel  : AttBlock + interpolate + pad_framewise_output (models.py:161-169, 84-95, 65-81).
+#include <cstdio>
+#include <cstdlib>
+
 #include "sed_common.cuh"
 #include "sed_kernels.h"
 
@@ -261,6 +264,15 @@ int gru_launch(const float* gi, const void* whh_packed, const float* bhh, int B,
   }
   dim3 grid(kGruCluster * (Bpad / 128), 2);
   cudaError_t e;
+  if (getenv("SED_GRU_DBG")) {  // developer aid: how many 8-CTA clusters can be resident at once
+    cudaFuncSetAttribute(gru_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGruSmem);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(kGruThreads); cfg.dynamicSmemBytes = kGruSmem; cfg.stream = stream;
+    int ncl = -1;
+    cudaError_t qe = cudaOccupancyMaxActiveClusters(&ncl, gru_kernel<__half>, &cfg);
+    fprintf(stderr, "[sed] gru: max active clusters = %d (%s), grid clusters = %d\n", ncl, cudaGetErrorString(qe),
+            (Bpad / 128) * 2);
+  }
   if (dtype == 0) {
     e = cudaFuncSetAttribute(gru_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGruSmem);
     if (e == cudaSuccess)
