@@ -77,31 +77,47 @@ int sed_conv_first_f32(const float* x, int NB, int H, int W, const float* w9, co
  *   x [NB, H, W, cin] NHWC 16-bit; wpacked [cout][9][cin] 16-bit (tap = 3*kh + kw);
  *   scale/shift [cout] f32; out NHWC 16-bit: [NB,H,W,cout] | [NB,H/2,W/2,cout] | [NB,H,cout];
  *   out_f32: optional float32 copy [NB,H,cout] of the FREQMEAN result (NULL otherwise).
+ *   out_stride_n / out_stride_h (FREQMEAN only; 0, 0 = default H, 1): output row of (image n, row h) is
+ *   n*out_stride_n + h*out_stride_h -- (1, batch) writes the features time-major for the GRU.
  *   Supported (cin,cout,mode): (64,64,POOL) (64,128,STORE) (128,128,POOL) (128,256,STORE)
  *   (256,256,POOL) (256,512,STORE) (512,512,FREQMEAN).
  *   variant 0 = single-CTA haloed-patch operand reuse, 1 = one TMA box per tap, 2 = CTA pairs (cta_group::2). */
 int sed_conv3x3_bn_relu(const void* x, int NB, int H, int W, int cin, const void* wpacked, const float* scale,
-                        const float* shift, int cout, int mode, void* out, void* out_f32, int dtype, int variant,
-                        void* stream);
+                        const float* shift, int cout, int mode, void* out, void* out_f32, long out_stride_n,
+                        long out_stride_h, int dtype, int variant, void* stream);
 
 /* out[M, N] = a[M, K] * w[N, K]^T + bias (optional ReLU) on the tensor cores; K in {256, 512},
  * N % 128 == 0.  Replaces the nn.Linear calls inside nn.GRU (input projection, models.py:670) and
  * MultiHead (w_qs/w_ks/w_vs/fc, models.py:863-865, 876).
- *   a16 [M,K], w16 [N,K] 16-bit; bias [N] f32 or NULL; out [M,N] f32; out16 [M,N] 16-bit or NULL. */
+ *   a16 [M,K], w16 [N,K] 16-bit; bias [N] f32 or NULL; out [M,N] f32; out16 [M,N] 16-bit or NULL.
+ *   out_layout 0: row-major.  1: 128-row transposed blocks (M % 128 == 0, out16 NULL): the float4 holding columns
+ *   4c..4c+3 of row r is float4 number ((r/128) * N/4 + c) * 128 + r%128 -- the layout sed_bigru streams. */
 int sed_linear(const void* a16, long M, int K, const void* w16, const float* bias, int N, int relu, float* out,
-               void* out16, int dtype, void* stream);
+               void* out16, int out_layout, int dtype, void* stream);
 
 /* Bytes of device scratch sed_bigru needs for a batch of B clips (16-bit hidden-state exchange buffer). */
 long sed_bigru_workspace_bytes(int B);
 
 /* Bidirectional GRU recurrence, hidden 256, gate order r,z,n, h0 = 0.
  * Replaces nn.GRU.forward pytorch/models.py:670 given the input projections.
- *   gi [B, T, 1536] f32 = x W_ih^T + b_ih, columns [dir][gate][256];
+ *   gi = x W_ih^T + b_ih (f32, columns [dir][gate][256]) for rows ordered time-major over the batch padded to
+ *   Bp = 128*ceil(B/128) clips (row r = t*Bp + clip), stored as 128-row transposed blocks (sed_linear out_layout 1,
+ *   M = T*Bp, N = 1536): rows of padding clips may hold anything;
  *   whh_packed [2*768, 256] 16-bit, row (dir*768 + 96*q + 32*g + jj) = W_hh[dir][g*256 + 32*q + jj];
- *   bhh [2][768] f32; out [B, T, 512] f32 = [forward | backward];
- *   workspace: sed_bigru_workspace_bytes(B) bytes, 128-byte aligned, contents irrelevant. */
+ *   bhh [2][768] f32; out = [forward | backward] f32 for the same padded time-major rows (r = t*Bp + clip,
+ *   512 columns), in the same 128-row transposed-block layout (T*Bp*512 floats; feed it to sed_attpool_blocks);
+ *   workspace: sed_bigru_workspace_bytes(B) bytes (kept for ABI stability; the hidden state is exchanged through
+ *   distributed shared memory). */
 int sed_bigru(const float* gi, const void* whh_packed, const float* bhh, int B, int T, float* out, void* workspace,
               int dtype, void* stream);
+
+/* sed_attpool for an input in 128-clip transposed blocks (the output layout of sed_bigru, or of sed_linear
+ * out_layout 1 over time-major rows r = t*Bp + clip, Bp = 128*ceil(B/128), 512 columns).  Same outputs as sed_attpool.
+ *   scratch: sed_attpool_blocks_scratch_bytes(B, T) bytes of device memory, contents irrelevant. */
+long sed_attpool_blocks_scratch_bytes(int B, int T);
+int sed_attpool_blocks(const float* x_blocks, int B, int T, const float* w_att, const float* b_att, const float* w_cla,
+                       const float* b_cla, int ratio, int frames_out, void* scratch, float* clip, float* frame,
+                       float* cla_t, float* norm_att_t, void* stream);
 
 /* Linear(512 -> classes) + sigmoid per frame, x`ratio` interpolation, clipwise mean (use_max = 0) or max (1)
  * over frames: the head of Cnn_9layers_FrameAvg / FrameMax / Gru_FrameAvg / Transformer_FrameAvg

@@ -32,13 +32,15 @@ SIGNATURES = {
     "sed_spectrogram_f32": ([_p, _i, _i, _i, _i, _p, _p, _p, _p], _i),
     "sed_logmel_rows_f32": ([_p, _l, _i, _p, _p, _p, _p, _i, _f, _f, _i, _p, _p], _i),
     "sed_conv_first_f32": ([_p, _i, _i, _i, _p, _p, _p, _p, _i, _p], _i),
-    "sed_conv3x3_bn_relu": ([_p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p, _i, _i, _p], _i),
+    "sed_conv3x3_bn_relu": ([_p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p, _l, _l, _i, _i, _p], _i),
     "sed_fcpool": ([_p, _i, _i, _p, _p, _i, _i, _i, _p, _p, _p], _i),
-    "sed_linear": ([_p, _l, _i, _p, _p, _i, _i, _p, _p, _i, _p], _i),
+    "sed_linear": ([_p, _l, _i, _p, _p, _i, _i, _p, _p, _i, _i, _p], _i),
     "sed_bigru_workspace_bytes": ([_i], _l),
     "sed_bigru": ([_p, _p, _p, _i, _i, _p, _p, _i, _p], _i),
     "sed_bigru_profile": ([_p, _p, _p, _i, _i, _p, _p, _i, _p, _p], _i),
     "sed_mha_core": ([_p, _i, _i, _p, _i, _p], _i),
+    "sed_attpool_blocks_scratch_bytes": ([_i, _i], _l),
+    "sed_attpool_blocks": ([_p, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p], _i),
     "sed_attpool": ([_p, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p], _i),
 }
 

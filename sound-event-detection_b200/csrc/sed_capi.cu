@@ -5,7 +5,7 @@
 
 #include "sed_kernels.h"
 
-#define SED_ABI_VERSION 5
+#define SED_ABI_VERSION 6
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -104,21 +104,21 @@ int sed_conv_first_f32(const float* x, int NB, int H, int W, const float* w9, co
 }
 
 int sed_conv3x3_bn_relu(const void* x, int NB, int H, int W, int cin, const void* wpacked, const float* scale,
-                        const float* shift, int cout, int mode, void* out, void* out_f32, int dtype, int variant,
-                        void* stream) {
+                        const float* shift, int cout, int mode, void* out, void* out_f32, long out_stride_n,
+                        long out_stride_h, int dtype, int variant, void* stream) {
   SED_REQUIRE(x); SED_REQUIRE(wpacked); SED_REQUIRE(scale); SED_REQUIRE(shift); SED_REQUIRE(out);
   if (variant < 0 || variant > 2) {
     sed::set_error("sed_conv3x3_bn_relu: variant must be 0 (patch), 1 (per-tap) or 2 (CTA pairs)");
     return SED_ERR_UNSUPPORTED;
   }
-  return sed::conv3x3_launch(x, NB, H, W, cin, wpacked, scale, shift, cout, mode, out, out_f32, dtype, variant,
-                             as_stream(stream));
+  return sed::conv3x3_launch(x, NB, H, W, cin, wpacked, scale, shift, cout, mode, out, out_f32, out_stride_n,
+                             out_stride_h, dtype, variant, as_stream(stream));
 }
 
 int sed_linear(const void* a16, long M, int K, const void* w16, const float* bias, int N, int relu, float* out,
-               void* out16, int dtype, void* stream) {
+               void* out16, int out_layout, int dtype, void* stream) {
   SED_REQUIRE(a16); SED_REQUIRE(w16); SED_REQUIRE(out);
-  return sed::linear_launch(a16, M, K, w16, bias, N, relu, out, out16, dtype, as_stream(stream));
+  return sed::linear_launch(a16, M, K, w16, bias, N, relu, out, out16, out_layout, dtype, as_stream(stream));
 }
 
 long sed_bigru_workspace_bytes(int B) { return B > 0 ? static_cast<long>(sed::gru_workspace_bytes(B)) : 0; }
@@ -133,6 +133,19 @@ int sed_bigru_profile(const float* gi, const void* whh_packed, const float* bhh,
                       void* workspace, int dtype, long long* stamps, void* stream) {
   SED_REQUIRE(gi); SED_REQUIRE(whh_packed); SED_REQUIRE(bhh); SED_REQUIRE(out); SED_REQUIRE(workspace); SED_REQUIRE(stamps);
   return sed::gru_launch(gi, whh_packed, bhh, B, T, out, workspace, dtype, as_stream(stream), stamps);
+}
+
+long sed_attpool_blocks_scratch_bytes(int B, int T) {
+  return (B > 0 && T > 0) ? static_cast<long>(sed::attpool_blocks_scratch_bytes(B, T)) : 0;
+}
+
+int sed_attpool_blocks(const float* x_blocks, int B, int T, const float* w_att, const float* b_att, const float* w_cla,
+                       const float* b_cla, int ratio, int frames_out, void* scratch, float* clip, float* frame,
+                       float* cla_t, float* norm_att_t, void* stream) {
+  SED_REQUIRE(x_blocks); SED_REQUIRE(w_att); SED_REQUIRE(b_att); SED_REQUIRE(w_cla); SED_REQUIRE(b_cla);
+  SED_REQUIRE(scratch); SED_REQUIRE(clip); SED_REQUIRE(frame);
+  return sed::attpool_blocks_launch(x_blocks, B, T, w_att, b_att, w_cla, b_cla, ratio, frames_out, scratch, clip, frame,
+                                    cla_t, norm_att_t, as_stream(stream));
 }
 
 int sed_fcpool(const float* x, int B, int T, const float* w, const float* b, int classes, int ratio, int use_max,

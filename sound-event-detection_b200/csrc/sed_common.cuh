@@ -71,6 +71,22 @@ SED_DEVICE_INLINE void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Wait with a hardware suspend-time hint: the warp sleeps inside try_wait (up to `ns`) instead of re-issuing the
+// poll, leaving the issue slots to the warps that feed the barrier.  For waits where many warps wait on one producer.
+SED_DEVICE_INLINE void mbar_wait_suspend(uint64_t* bar, uint32_t parity, uint32_t ns = 20000) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+  }
+}
 
 // ------------------------------------------------------------------ proxies / fences
 SED_DEVICE_INLINE void fence_proxy_async_smem() {

@@ -360,8 +360,8 @@ static int conv3x3_dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
 }
 
 int conv3x3_launch(const void* x, int NB, int H, int W, int cin, const void* wpacked, const float* scale,
-                   const float* shift, int cout, int mode, void* out, void* out_f32, int dtype, int variant,
-                   cudaStream_t stream) {
+                   const float* shift, int cout, int mode, void* out, void* out_f32, long out_sn, long out_sh,
+                   int dtype, int variant, cudaStream_t stream) {
   if (NB <= 0 || H <= 0 || W <= 0 || (W % 8) != 0 || (cin % 64) != 0) {
     set_error("conv3x3: bad shape NB=%d H=%d W=%d cin=%d", NB, H, W, cin);
     return SED_ERR_BAD_SHAPE;
@@ -412,7 +412,9 @@ int conv3x3_launch(const void* x, int NB, int H, int W, int cin, const void* wpa
   p.cout = cout;
   p.scale = scale; p.shift = shift;
   p.out = out; p.out2 = (mode == EPI_FREQMEAN) ? out_f32 : nullptr;
-  p.M = 0; p.ldc = 0; p.relu = 1;
+  p.M = 0; p.ldc = 0; p.relu = 1; p.tblock = 0;
+  p.out_sn = (mode == EPI_FREQMEAN && out_sn > 0) ? out_sn : H;
+  p.out_sh = (mode == EPI_FREQMEAN && out_sh > 0) ? out_sh : 1;
   {
     const char* e = getenv("SED_CONV_DBG");
     p.dbg = e ? atoi(e) : 0;
@@ -424,7 +426,11 @@ int conv3x3_launch(const void* x, int NB, int H, int W, int cin, const void* wpa
 }
 
 int linear_launch(const void* a16, long M, int K, const void* w16, const float* bias, int N, int relu, float* out,
-                  void* out16, int dtype, cudaStream_t stream) {
+                  void* out16, int out_layout, int dtype, cudaStream_t stream) {
+  if (out_layout != 0 && (out_layout != 1 || out16 != nullptr || (M % 128) != 0)) {
+    set_error("linear: out_layout must be 0 (row-major) or 1 (128-row transposed blocks: M %% 128 == 0, no 16-bit copy)");
+    return SED_ERR_UNSUPPORTED;
+  }
   if (M <= 0 || (N % 128) != 0 || N > 512 * 8) {
     set_error("linear: bad shape M=%ld N=%d K=%d", M, N, K);
     return SED_ERR_BAD_SHAPE;
@@ -466,9 +472,10 @@ int linear_launch(const void* a16, long M, int K, const void* w16, const float* 
     p.nslices = npanel / 128;
     p.scale = nullptr;
     p.shift = bias ? bias + n0 : nullptr;
-    p.out = out + n0;
+    p.out = out_layout ? out + (size_t)n0 * 128 : out + n0;  // transposed blocks: float4 column n0/4 = +n0/4*128*4 floats
     p.out2 = out16 ? (void*)((char*)out16 + (size_t)n0 * 2) : nullptr;
-    p.M = (int)M; p.ldc = N; p.relu = relu;
+    p.M = (int)M; p.ldc = N; p.relu = relu; p.tblock = out_layout;
+    p.out_sn = 0; p.out_sh = 0;
     if (K == 512) {
       rc = dtype == 0 ? launch_cfg<__half, 512, 128, 1, false, false, EPI_LINEAR, 4, 4>(tmA, tmBp, tmA, p, stream)
                       : launch_cfg<__nv_bfloat16, 512, 128, 1, false, false, EPI_LINEAR, 4, 4>(tmA, tmBp, tmA, p, stream);

@@ -34,6 +34,8 @@ struct ConvParams {
   void* out;               // EPI 0/1/2: 16-bit NHWC ; EPI 3: float [M, ldc]
   void* out2;              // EPI 3: optional 16-bit copy [M, ldc]; EPI 2: optional f32 copy [NB,H,cout] (may be null)
   int M, ldc, relu;        // linear only
+  int tblock;              // linear only: 1 = store float32 output as 128-row transposed blocks [tile][ldc/4][128][4]
+  long out_sn, out_sh;     // EPI 2: output row of (image n, row h) = n*out_sn + h*out_sh (default H, 1)
   int dbg;                 // profiling experiments only (SED_CONV_DBG): 1 = no stores, 2 = no drain, 4 = no MMA
 };
 
@@ -187,19 +189,30 @@ SED_DEVICE_INLINE void conv_epilogue_tile(const uint32_t taddr, const int chalf,
             }
             if (tile_ok && h < p.H) {
               const int ch = ch0 + cc * 16 + (b0 ? 8 : 0) + (b1 ? 4 : 0) + (b2 ? 2 : 0);
-              T* dst = out16 + (static_cast<size_t>(n) * p.H + h) * p.cout + ch;
+              const size_t orow = static_cast<size_t>(n) * p.out_sn + static_cast<size_t>(h) * p.out_sh;
+              T* dst = out16 + orow * p.cout + ch;
               *reinterpret_cast<uint32_t*>(dst) = Elem16<T>::pack2(k2[0], k2[1]);
               if (p.out2)  // optional float32 copy of the features (heads without a temporal block)
-                *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.out2) +
-                                           (static_cast<size_t>(n) * p.H + h) * p.cout + ch) = make_float2(k2[0], k2[1]);
+                *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.out2) + orow * p.cout + ch) =
+                    make_float2(k2[0], k2[1]);
             }
           } else {  // EPI_LINEAR
             const long row = static_cast<long>(tile) * 128 + m;
             if (tile_ok && row < p.M) {
+              if (p.tblock) {
+                // 128-row transposed blocks: float4 column c4 of row m of tile `tile` sits at
+                // ((tile * ldc/4 + c4) * 128 + m): a warp (32 consecutive rows) writes 512 contiguous bytes
+                float4* dst4 = reinterpret_cast<float4*>(p.out) +
+                               (static_cast<size_t>(tile) * (p.ldc >> 2) + ((ch0 + cc * 16) >> 2)) * 128 + m;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  dst4[j * 128] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              } else {
               float* dst = reinterpret_cast<float*>(p.out) + row * p.ldc + ch0 + cc * 16;
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              }
               if (p.out2) {
                 uint4 q0, q1;
                 q0.x = Elem16<T>::pack2(v[0], v[1]);   q0.y = Elem16<T>::pack2(v[2], v[3]);

@@ -37,11 +37,11 @@ int conv_first_launch(const float* x, int NB, int H, int W, const float* w9, con
 
 // mode: 0 = store NHWC, 1 = 2x2 avg-pool, 2 = freq-mean (W must be 8) ; variant: 0 = patch (halo reuse), 1 = per-tap
 int conv3x3_launch(const void* x, int NB, int H, int W, int cin, const void* wpacked, const float* scale,
-                   const float* shift, int cout, int mode, void* out, void* out_f32, int dtype, int variant,
-                   cudaStream_t stream);
+                   const float* shift, int cout, int mode, void* out, void* out_f32, long out_sn, long out_sh,
+                   int dtype, int variant, cudaStream_t stream);
 
 int linear_launch(const void* a16, long M, int K, const void* w16, const float* bias, int N, int relu, float* out,
-                  void* out16, int dtype, cudaStream_t stream);
+                  void* out16, int out_layout, int dtype, cudaStream_t stream);
 
 size_t gru_workspace_bytes(int B);
 int gru_launch(const float* gi, const void* whh_packed, const float* bhh, int B, int T, float* out, void* workspace,
@@ -59,6 +59,11 @@ int mha_core_launch(const float* qkv, int B, int T, void* out16, int dtype, cuda
 int attpool_launch(const float* x, int B, int T, const float* w_att, const float* b_att, const float* w_cla,
                    const float* b_cla, int ratio, int frames_out, float* clip, float* frame, float* cla_t,
                    float* norm_att_t, cudaStream_t stream);
+
+size_t attpool_blocks_scratch_bytes(int B, int T);
+int attpool_blocks_launch(const float* x_blocks, int B, int T, const float* w_att, const float* b_att,
+                          const float* w_cla, const float* b_cla, int ratio, int frames_out, void* scratch, float* clip,
+                          float* frame, float* cla_t, float* norm_att_t, cudaStream_t stream);
 
 int fcpool_launch(const float* x, int B, int T, const float* w, const float* b, int C, int ratio, int use_max,
                   float* clip, float* frame, cudaStream_t stream);

@@ -16,198 +16,274 @@
 namespace sed {
 
 // =================================================================================================
-// GRU recurrence: one 8-CTA cluster per (128-clip block, direction)
+// GRU recurrence: one 4-CTA cluster per (128-clip block, direction)
 // =================================================================================================
-// CTA `q` of the cluster owns hidden units 32q..32q+31 of all three gates: its 96x256 slice of W_hh stays
-// resident in shared memory for all T steps and its threads keep the float32 state of those units in
-// registers.  Per step every CTA (1) TMA-loads the full 16-bit h_{t-1} [128 x 256] (the UMMA A operand),
-// (2) issues 16 tcgen05.mma (M=128, N=96, K=256) into TMEM, (3) runs the gate math for its 32 units, writes
-// h_t (f32) to the output and the 16-bit copy to a double-buffered exchange tensor in global memory (L2),
-// and (4) signals the h_ready mbarrier of all 8 CTAs (remote arrive, release/acquire at cluster scope).
-constexpr int kGruCluster = 8;
-constexpr int kGruChunkRows = 96;                    // 32 hidden units x 3 gates
-constexpr int kGruWBytes = 4 * kGruChunkRows * 128;  // 4 k-chunks x 96 rows x 128 B
-constexpr int kGruABytes = 4 * 16384;                // 128 clips x 256 k x 2 B
-constexpr int kGruSmem = 1024 + kGruWBytes + kGruABytes + 512;
-constexpr int kGruThreads = 64 + 256;  // TMA warp, MMA warp, 8 gate-math warps (2 per TMEM lane quarter)
+// CTA `q` of the cluster owns hidden units 64q..64q+63 of all three gates: its 192x256 slice of W_hh (two packed
+// 96-row [r|z|n] x 32-unit blocks) stays resident in shared memory for all T steps and its 16 warps keep the
+// float32 state of those units in registers.  Per step every CTA
+//   (1) issues 2 x 16 tcgen05.mma (M = 128 clips, N = 96, K = 256) against the full 16-bit h_{t-1} [128 x 256] in
+//       its shared memory (UMMA A operand, SWIZZLE_128B, double buffered), one commit per 32-unit half so the warps
+//       of the first half start while the second half is still in the tensor pipe;
+//   (2) runs the gate math for its 64 units and writes h_t (f32) to the output;
+//   (3) every warp stores the 16-bit copy of its piece of h_t straight into the A buffer of all four CTAs
+//       (st.shared::cluster, swizzled layout) and release-arrives on each CTA's a_full mbarrier.
+// No global-memory round trip, no CTA-wide barrier and no generic->async proxy fence over global memory
+// (fence.proxy.async lowers to MEMBAR.GPU, several microseconds per step) are on the step's critical path.
+// Sixteen clusters (B = 1024, both directions) are resident at once; an 8-CTA cluster design fits only 15.
+constexpr int kGruCluster = 4;
+constexpr int kGruRows = 192;                        // 64 hidden units x 3 gates = two 96-row packed blocks
+constexpr int kGruWBytes = 4 * kGruRows * 128;       // 4 k-chunks x 192 rows x 128 B
+constexpr int kGruABytes = 4 * 16384;                // 128 clips x 256 k x 2 B (one buffer)
+constexpr int kGruSmem = 1024 + kGruWBytes + 2 * kGruABytes + 1024;
+constexpr int kGruWarps = 16;
+constexpr int kGruThreads = 32 * kGruWarps;          // every warp is a gate-math warp; warp kGruIssueWarp's lane 0
+constexpr int kGruIssueWarp = 8;                     // also issues the MMAs (a second-half warp: it has the slack)
 
-SED_DEVICE_INLINE float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-SED_DEVICE_INLINE float fast_tanh(float x) {
-  // 1 - 2 / (exp(2x) + 1); |error| ~1e-7 absolute, far below the 16-bit operand rounding of h W_hh^T
-  return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f);
+SED_DEVICE_INLINE float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+SED_DEVICE_INLINE float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// sigmoid of four pre-activations with ONE reciprocal (the gate phase is MUFU-bound): 1/(1+e^-x) for each, the
+// four denominators share rcp(d0 d1 d2 d3).  Inputs are clamped at -20 (sigmoid(-20) = 2e-9) so the product of
+// the denominators stays below 2^116.
+SED_DEVICE_INLINE void sigmoid4(float x0, float x1, float x2, float x3, float& s0, float& s1, float& s2, float& s3) {
+  constexpr float kNegLog2e = -1.4426950408889634f;
+  const float d0 = 1.0f + ex2_approx(fmaxf(x0, -20.0f) * kNegLog2e);
+  const float d1 = 1.0f + ex2_approx(fmaxf(x1, -20.0f) * kNegLog2e);
+  const float d2 = 1.0f + ex2_approx(fmaxf(x2, -20.0f) * kNegLog2e);
+  const float d3 = 1.0f + ex2_approx(fmaxf(x3, -20.0f) * kNegLog2e);
+  const float p01 = d0 * d1, p23 = d2 * d3;
+  const float inv = rcp_approx(p01 * p23);
+  const float i01 = inv * p23, i23 = inv * p01;
+  s0 = i01 * d1; s1 = i01 * d0; s2 = i23 * d3; s3 = i23 * d2;
+}
+// tanh of two pre-activations with one reciprocal: 1 - 2 / (e^{2x} + 1); |x| clamped at 20 (tanh(20) = 1 - 8e-18)
+SED_DEVICE_INLINE void tanh2(float x0, float x1, float& t0, float& t1) {
+  constexpr float k2Log2e = 2.8853900817779268f;
+  const float d0 = 1.0f + ex2_approx(fminf(x0, 20.0f) * k2Log2e);
+  const float d1 = 1.0f + ex2_approx(fminf(x1, 20.0f) * k2Log2e);
+  const float inv = rcp_approx(d0 * d1);
+  t0 = fmaf(-2.0f * inv, d1, 1.0f);
+  t1 = fmaf(-2.0f * inv, d0, 1.0f);
+}
+
+// 32 lanes x 8 consecutive 32-bit TMEM columns -> 8 registers per thread
+SED_DEVICE_INLINE void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+// TMA tile load delivered to the same shared-memory offset (and mbarrier) of every CTA in `cta_mask`
+SED_DEVICE_INLINE void tma_load_2d_mcast(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                         uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, "
+      "{%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+
+SED_DEVICE_INLINE void st_cluster_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+SED_DEVICE_INLINE void mbar_arrive_release_cluster_addr(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
 template <typename T>
 __global__ void __cluster_dims__(kGruCluster, 1, 1) __launch_bounds__(kGruThreads, 1)
-gru_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH,
-           const float* __restrict__ gi, const float* __restrict__ bhh, int B, int Bpad, int Tn,
-           float* __restrict__ out, T* __restrict__ hx, long long* __restrict__ stamps) {
+gru_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ gi, const float* __restrict__ bhh, int B,
+           int Tn, float* __restrict__ out, long long* __restrict__ stamps, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_w = smem;                 // [4][96 rows][128 B]   resident W_hh slice
-  // profiling hook (stamps != nullptr): CTA 0 records clock64() at 12 points of steps 8..15
+  uint8_t* smem_w = smem;                 // [4][192 rows][128 B]   resident W_hh slice
+  uint8_t* smem_a = smem + kGruWBytes;    // [2][4][128 rows][128 B]  h (double buffered)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + 2 * kGruABytes);
+  uint64_t* w_full = bars;
+  uint64_t* a_full = bars + 1;      // [2]  64 arrivals each: 16 warps x 4 CTAs
+  uint64_t* acc_full = bars + 3;    // [2]  one per 32-unit half
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  float* s_bias = reinterpret_cast<float*>(bars + 8);  // [3][64] b_hh of this CTA's units
+  // profiling hook (stamps != nullptr): CTA 0 records clock64() at a few points of steps 8..15
   const bool prof = stamps != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
 #define GRU_STAMP(step, slot)                                                       \
   do {                                                                               \
     if (prof && (step) >= 8 && (step) < 16) stamps[((step) - 8) * 12 + (slot)] = clock64(); \
   } while (0)
-  uint8_t* smem_a = smem + kGruWBytes;    // [4][128 rows][128 B]  h_{t-1}
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + kGruABytes);
-  uint64_t* w_full = bars;
-  uint64_t* a_full = bars + 1;
-  uint64_t* acc_full = bars + 2;
-  uint64_t* h_ready = bars + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-  float* s_bias = reinterpret_cast<float*>(bars + 5);  // [3][32] b_hh of this CTA's units
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = blockIdx.x % kGruCluster;  // == %cluster_ctarank for cluster dims (8,1,1)
-  const int clip0 = (blockIdx.x / kGruCluster) * 128;
+  const int q = blockIdx.x % kGruCluster;  // == %cluster_ctarank for cluster dims (4,1,1)
+  const int blk = blockIdx.x / kGruCluster, nblk = gridDim.x / kGruCluster;
   const int dir = blockIdx.y;
 
-  // h_{-1} = 0 (nn.GRU default h0)
+  // h_{-1} = 0 (nn.GRU default h0): step 0 reads buffer 1
   for (int i = threadIdx.x; i < kGruABytes / 16; i += blockDim.x)
-    reinterpret_cast<uint4*>(smem_a)[i] = make_uint4(0, 0, 0, 0);
+    reinterpret_cast<uint4*>(smem_a + kGruABytes)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
-  if (threadIdx.x < 96)
-    s_bias[threadIdx.x] = bhh[dir * 768 + (threadIdx.x >> 5) * 256 + q * 32 + (threadIdx.x & 31)];
+  if (threadIdx.x < 192)
+    s_bias[threadIdx.x] = bhh[dir * 768 + (threadIdx.x >> 6) * 256 + q * 64 + (threadIdx.x & 63)];
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmW);
-    tma_prefetch_desc(&tmH);
     mbar_init(w_full, 1);
-    mbar_init(a_full, 1);
+    mbar_init(a_full, kGruCluster * kGruWarps);
+    mbar_init(a_full + 1, kGruCluster * kGruWarps);
     mbar_init(acc_full, 1);
-    mbar_init(h_ready, kGruCluster);  // one arrival per source CTA
+    mbar_init(acc_full + 1, 1);
     fence_barrier_init();
+    mbar_expect_tx(w_full, kGruWBytes);
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc)
+      tma_load_2d(smem_w + kc * (kGruRows * 128), &tmW, w_full, kc * 64, dir * 768 + q * kGruRows);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 128);
+    tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();  // every CTA's barriers are initialised before anyone signals them remotely
+  cluster_sync_all();  // every CTA's barriers are initialised before any peer arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    if (elect_one()) {
-      mbar_expect_tx(w_full, kGruWBytes);
+  const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+  const int g = warp >> 2;                  // which 16 of the CTA's 64 hidden units this warp owns
+  const int half = g >> 1;                  // 32-unit half (accumulator columns half*96 ..)
+  const int m = quarter * 32 + lane;        // clip row of this thread
+  const int ul = g * 16;                    // first local unit of this thread
+  const int u0 = q * 64 + ul;               // first hidden unit of this thread
+  const bool issuer = warp == kGruIssueWarp;
+  const bool stamper = prof && warp == 0 && lane == 0;
+  float h[16];
 #pragma unroll
-      for (int kc = 0; kc < 4; ++kc)
-        tma_load_2d(smem_w + kc * (kGruChunkRows * 128), &tmW, w_full, kc * 64, dir * 768 + q * kGruChunkRows);
-      for (int s = 1; s < Tn; ++s) {
-        mbar_wait_cluster(h_ready, (s - 1) & 1);  // all 8 slices of h_{s-1} are in the exchange buffer
-        GRU_STAMP(s, 0);  // (the writers issued fence.proxy.async before their release-arrive)
-        GRU_STAMP(s, 1);
-        mbar_expect_tx(a_full, kGruABytes);
-        const int row = (((s - 1) & 1) * 2 + dir) * Bpad + clip0;
+  for (int j = 0; j < 16; ++j) h[j] = 0.0f;
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * 96 + (g & 1) * 16;
+  // exchange addresses: this thread's two 16-byte units of row m in chunk q of the A buffer (SWIZZLE_128B: unit u of
+  // row m sits at u ^ (m & 7)), in each of the four CTAs; lanes 0..3 signal CTA `lane`
+  const uint32_t xoff0 = q * 16384 + m * 128 + (((2 * g) ^ (m & 7)) << 4);
+  const uint32_t xoff1 = q * 16384 + m * 128 + (((2 * g + 1) ^ (m & 7)) << 4);
+  uint32_t a_remote[kGruCluster];
 #pragma unroll
-        for (int kc = 0; kc < 4; ++kc) tma_load_2d(smem_a + kc * 16384, &tmH, a_full, kc * 64, row);
+  for (int d = 0; d < kGruCluster; ++d) a_remote[d] = map_to_cta(smem_a, (q + d) & (kGruCluster - 1));
+  const uint32_t bar_remote = map_to_cta(a_full, lane & (kGruCluster - 1));
+
+  if (issuer && lane == 0) mbar_wait(w_full, 0);
+  __syncwarp();
+
+  for (int s = 0; s < Tn; ++s) {
+    const int t = dir ? (Tn - 1 - s) : s;
+    // output h_t (f32) in the same 128-clip transposed-block layout as gi: float4 column c4 (of 128) of clip row m of
+    // block (t, blk) at ((tile * 128 + c4) * 128 + m) -- coalesced 512-byte stores, consumed by sed_attpool_blocks
+    float4* out_t = reinterpret_cast<float4*>(out) +
+                    ((static_cast<size_t>(t) * nblk + blk) * 128 + ((dir * 256 + u0) >> 2)) * 128 + m;
+    // input projections of this step: gi is stored as 128-clip transposed blocks (float4 column c4 of clip row m of
+    // block (t, clip0/128) at ((tile * 384 + c4) * 128 + m)), so every warp-level load is 512 contiguous bytes.
+    // Issued before the waits so they overlap the exchange and the MMA.
+    const float4* gi_t = reinterpret_cast<const float4*>(gi) +
+                         ((static_cast<size_t>(t) * nblk + blk) * 384 + ((dir * 768 + u0) >> 2)) * 128 + m;
+    float4 gr[4], gz[4], gn[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      if (!(dbg & 1)) {
+        gr[v] = gi_t[v * 128];
+        gz[v] = gi_t[(64 + v) * 128];
+        gn[v] = gi_t[(128 + v) * 128];
+      } else {
+        gr[v] = gz[v] = gn[v] = make_float4(0, 0, 0, 0);
       }
     }
-  } else if (warp == 1) {
-    if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_f16(Elem16<T>::kFmt, 128, kGruChunkRows);
-      mbar_wait(w_full, 0);
-      const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_w);
-      for (int s = 0; s < Tn; ++s) {
-        if (s > 0) mbar_wait(a_full, (s - 1) & 1);
-        GRU_STAMP(s, 2);
+    if (issuer) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = umma_idesc_f16(Elem16<T>::kFmt, 128, 96);
+        const int buf = (s + 1) & 1;  // h_{s-1}
+        if (s > 0) {
+          mbar_wait_cluster(a_full + buf, ((s - 1) >> 1) & 1);  // all 64 pieces of h_{s-1} are in this CTA's buffer
+          fence_proxy_async_smem();  // peers' generic-proxy stores into this shared memory -> the UMMA operand reads
+        }
+        GRU_STAMP(s, 0);
         tc_fence_after();
+        const uint32_t a_base = smem_u32(smem_a + buf * kGruABytes), b_base = smem_u32(smem_w);
 #pragma unroll
-        for (int kc = 0; kc < 4; ++kc) {
+        for (int hf = 0; hf < 2; ++hf) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_f16(tmem_base, umma_desc_sw128(a_base + kc * 16384 + k * 32, 1024),
-                     umma_desc_sw128(b_base + kc * (kGruChunkRows * 128) + k * 32, 1024), idesc, (kc | k) ? 1u : 0u);
+          for (int kc = 0; kc < 4; ++kc) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_f16(tmem_base + hf * 96, umma_desc_sw128(a_base + kc * 16384 + k * 32, 1024),
+                       umma_desc_sw128(b_base + kc * (kGruRows * 128) + hf * (96 * 128) + k * 32, 1024), idesc,
+                       (kc | k) ? 1u : 0u);
+            }
           }
+          umma_commit(acc_full + hf);
+          GRU_STAMP(s, 1 + hf);
         }
-        umma_commit(acc_full);
-        GRU_STAMP(s, 3);
       }
+      __syncwarp();
     }
-  } else {
-    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;         // which 16 of the CTA's 32 hidden units this warp owns
-    const int m = quarter * 32 + lane;
-    const int clip = clip0 + m;
-    const bool valid = clip < B;
-    const int u0 = q * 32 + half * 16;        // first hidden unit of this thread
-    float h[16];
+    mbar_wait_suspend(acc_full + half, s & 1);
+    if (stamper) GRU_STAMP(s, 4);
+    tc_fence_after();
 #pragma unroll
-    for (int j = 0; j < 16; ++j) h[j] = 0.0f;
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * 16;
-    for (int s = 0; s < Tn; ++s) {
-      const int t = dir ? (Tn - 1 - s) : s;
-      const float* gi_row = gi + (static_cast<size_t>(clip) * Tn + t) * 1536 + dir * 768 + u0;
-      float* out_row = out + (static_cast<size_t>(clip) * Tn + t) * 512 + dir * 256 + u0;
-      // input projections for this step: issued before the accumulator wait so they overlap the MMA
-      float4 gr[4], gz[4], gn[4];
-#pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        if (valid) {
-          gr[v] = *reinterpret_cast<const float4*>(gi_row + v * 4);
-          gz[v] = *reinterpret_cast<const float4*>(gi_row + 256 + v * 4);
-          gn[v] = *reinterpret_cast<const float4*>(gi_row + 512 + v * 4);
-        } else {
-          gr[v] = gz[v] = gn[v] = make_float4(0, 0, 0, 0);
-        }
-      }
-      if (warp == 2 && lane == 0) GRU_STAMP(s, 4);
-      mbar_wait(acc_full, s & 1);
-      if (warp == 2 && lane == 0) GRU_STAMP(s, 5);
-      tc_fence_after();
-      uint32_t ar[16], az[16], an[16];
-      tmem_ld16(taddr, ar);
-      tmem_ld16(taddr + 32, az);
-      tmem_ld16(taddr + 64, an);
+    for (int c = 0; c < 2; ++c) {  // two chunks of 8 units
+      uint32_t ar[8], az[8], an[8];
+      tmem_ld8(taddr + c * 8, ar);
+      tmem_ld8(taddr + 32 + c * 8, az);
+      tmem_ld8(taddr + 64 + c * 8, an);
       tmem_ld_wait();
 #pragma unroll
-      for (int v4 = 0; v4 < 4; ++v4) {
-        const float grv[4] = {gr[v4].x, gr[v4].y, gr[v4].z, gr[v4].w};
-        const float gzv[4] = {gz[v4].x, gz[v4].y, gz[v4].z, gz[v4].w};
-        const float gnv[4] = {gn[v4].x, gn[v4].y, gn[v4].z, gn[v4].w};
+      for (int v = 0; v < 2; ++v) {
+        const float4 grv = gr[2 * c + v], gzv = gz[2 * c + v], gnv = gn[2 * c + v];
+        const float gre[4] = {grv.x, grv.y, grv.z, grv.w};
+        const float gze[4] = {gzv.x, gzv.y, gzv.z, gzv.w};
+        const float gne[4] = {gnv.x, gnv.y, gnv.z, gnv.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int jj = v4 * 4 + e;
-          const int j = half * 16 + jj;
-          const float r = fast_sigmoid(grv[e] + __uint_as_float(ar[jj]) + s_bias[j]);
-          const float z = fast_sigmoid(gzv[e] + __uint_as_float(az[jj]) + s_bias[32 + j]);
-          const float nn = fast_tanh(gnv[e] + r * (__uint_as_float(an[jj]) + s_bias[64 + j]));
-          h[jj] = (1.0f - z) * nn + z * h[jj];
+        for (int e = 0; e < 4; e += 2) {
+          const int jc = v * 4 + e;          // index within the chunk
+          const int jj = c * 8 + jc;         // index within the thread's 16 units
+          const int j = ul + jj;             // local unit (bias index)
+          float r0, z0, r1, z1, n0, n1;
+          sigmoid4(gre[e] + __uint_as_float(ar[jc]) + s_bias[j], gze[e] + __uint_as_float(az[jc]) + s_bias[64 + j],
+                   gre[e + 1] + __uint_as_float(ar[jc + 1]) + s_bias[j + 1],
+                   gze[e + 1] + __uint_as_float(az[jc + 1]) + s_bias[64 + j + 1], r0, z0, r1, z1);
+          tanh2(fmaf(r0, __uint_as_float(an[jc]) + s_bias[128 + j], gne[e]),
+                fmaf(r1, __uint_as_float(an[jc + 1]) + s_bias[128 + j + 1], gne[e + 1]), n0, n1);
+          h[jj] = fmaf(z0, h[jj] - n0, n0);              // (1 - z) n + z h
+          h[jj + 1] = fmaf(z1, h[jj + 1] - n1, n1);
         }
       }
-      if (warp == 2 && lane == 0) GRU_STAMP(s, 6);
-      if (valid) {
+    }
+    if (stamper) GRU_STAMP(s, 5);
+    if (s + 1 < Tn) {
+      // 16-bit copy of this thread's 16 units of h_t into buffer (s & 1) of all four CTAs (rows of padded clips
+      // >= B carry well-defined values too: their gi reads as zero)
+      uint4 p0, p1;
+      p0.x = Elem16<T>::pack2(h[0], h[1]);   p0.y = Elem16<T>::pack2(h[2], h[3]);
+      p0.z = Elem16<T>::pack2(h[4], h[5]);   p0.w = Elem16<T>::pack2(h[6], h[7]);
+      p1.x = Elem16<T>::pack2(h[8], h[9]);   p1.y = Elem16<T>::pack2(h[10], h[11]);
+      p1.z = Elem16<T>::pack2(h[12], h[13]); p1.w = Elem16<T>::pack2(h[14], h[15]);
+      const uint32_t boff = (s & 1) * kGruABytes;
 #pragma unroll
-        for (int v = 0; v < 4; ++v)
-          *reinterpret_cast<float4*>(out_row + v * 4) = make_float4(h[4 * v], h[4 * v + 1], h[4 * v + 2], h[4 * v + 3]);
+      for (int d = 0; d < kGruCluster; ++d) {
+        if ((dbg & 2) && d > 0) break;
+        st_cluster_v4(a_remote[d] + boff + xoff0, p0);
+        st_cluster_v4(a_remote[d] + boff + xoff1, p1);
       }
-      if (s + 1 < Tn) {
-        // 16-bit copy of this thread's slice of h_t into exchange buffer (s & 1)
-        T* hx_row = hx + (static_cast<size_t>((s & 1) * 2 + dir) * Bpad + clip) * 256 + u0;
+      tc_fence_before();
+      __syncwarp();
+      // release at cluster scope: the warp's piece of h_t is written everywhere and its TMEM loads have drained
+      if (lane < kGruCluster) mbar_arrive_release_cluster_addr(bar_remote + (s & 1) * 8);
+      if (stamper) GRU_STAMP(s, 8);
+    }
+    if (!(dbg & 4)) {
 #pragma unroll
-        for (int v = 0; v < 2; ++v) {
-          uint4 pk;
-          pk.x = Elem16<T>::pack2(h[8 * v], h[8 * v + 1]);
-          pk.y = Elem16<T>::pack2(h[8 * v + 2], h[8 * v + 3]);
-          pk.z = Elem16<T>::pack2(h[8 * v + 4], h[8 * v + 5]);
-          pk.w = Elem16<T>::pack2(h[8 * v + 6], h[8 * v + 7]);
-          reinterpret_cast<uint4*>(hx_row)[v] = pk;
-        }
-        if (warp == 2 && lane == 0) GRU_STAMP(s, 7);
-        tc_fence_before();
-        named_bar_sync(1, 256);  // all 8 gate warps have written their slice of h_t (and drained TMEM)
-        if (warp == 2 && lane == 0) GRU_STAMP(s, 8);
-        // warp (2 + r) publishes to CTA r: proxy fence (generic global writes -> the peers' TMA reads), then a
-        // release-arrive at cluster scope; the eight destinations are signalled in parallel
-        if (lane == 0) {
-          fence_proxy_async_all();
-          mbar_arrive_remote(h_ready, warp - 2);
-        }
-        if (warp == 2 && lane == 0) GRU_STAMP(s, 9);
-      }
+      for (int v = 0; v < 4; ++v) out_t[v * 128] = make_float4(h[4 * v], h[4 * v + 1], h[4 * v + 2], h[4 * v + 3]);
     }
   }
 
@@ -216,7 +292,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
   cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 128);
+    tmem_dealloc(tmem_base, 256);
   }
 }
 
@@ -256,14 +332,16 @@ int gru_launch(const float* gi, const void* whh_packed, const float* bhh, int B,
   }
   EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(fp);
   const int Bpad = (B + 127) / 128 * 128;
-  CUtensorMap tmW, tmH;
-  if (encode_2d(enc, &tmW, dtype, const_cast<void*>(whh_packed), 256, 2 * 768, kGruChunkRows) != SED_OK ||
-      encode_2d(enc, &tmH, dtype, workspace, 256, 4ull * Bpad, 128) != SED_OK) {
+  (void)workspace;  // h is exchanged through distributed shared memory; the workspace argument is kept for ABI stability
+  CUtensorMap tmW;
+  if (encode_2d(enc, &tmW, dtype, const_cast<void*>(whh_packed), 256, 2 * 768, kGruRows) != SED_OK) {
     set_error("gru: cuTensorMapEncodeTiled failed");
     return SED_ERR_DRIVER;
   }
   dim3 grid(kGruCluster * (Bpad / 128), 2);
   cudaError_t e;
+  const char* e_dbg2 = getenv("SED_GRU_DBG2");  // developer experiments: 1 = no gi loads, 2 = no remote stores, 4 = no out
+  const int dbg = e_dbg2 ? atoi(e_dbg2) : 0;
   if (getenv("SED_GRU_DBG")) {  // developer aid: how many 8-CTA clusters can be resident at once
     cudaFuncSetAttribute(gru_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGruSmem);
     cudaLaunchConfig_t cfg = {};
@@ -276,13 +354,11 @@ int gru_launch(const float* gi, const void* whh_packed, const float* bhh, int B,
   if (dtype == 0) {
     e = cudaFuncSetAttribute(gru_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGruSmem);
     if (e == cudaSuccess)
-      gru_kernel<__half><<<grid, kGruThreads, kGruSmem, stream>>>(tmW, tmH, gi, bhh, B, Bpad, Tn, out,
-                                                                  reinterpret_cast<__half*>(workspace), stamps);
+      gru_kernel<__half><<<grid, kGruThreads, kGruSmem, stream>>>(tmW, gi, bhh, B, Tn, out, stamps, dbg);
   } else {
     e = cudaFuncSetAttribute(gru_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGruSmem);
     if (e == cudaSuccess)
-      gru_kernel<__nv_bfloat16><<<grid, kGruThreads, kGruSmem, stream>>>(tmW, tmH, gi, bhh, B, Bpad, Tn, out,
-                                                                         reinterpret_cast<__nv_bfloat16*>(workspace), stamps);
+      gru_kernel<__nv_bfloat16><<<grid, kGruThreads, kGruSmem, stream>>>(tmW, gi, bhh, B, Tn, out, stamps, dbg);
   }
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -397,6 +473,49 @@ int mha_core_launch(const float* qkv, int B, int Tn, void* out16, int dtype, cud
 // =================================================================================================
 constexpr int kCls = 25;  // AttBlock(512, 25): hard-coded in the reference (models.py:617, 1022)
 
+// Shared tail of the pooling head for one clip: s_e[t][25] = exp(att)+1e-6 and s_c[t][25] = sigmoid(cla) are in shared
+// memory (all threads arrive here); computes the attention-weighted clip output and writes every output tensor.
+__device__ __forceinline__ void attpool_tail(const float* s_e, const float* s_c, float* s_sum, int b, int Tn, int ratio,
+                                             int frames_out, float* __restrict__ clip, float* __restrict__ frame,
+                                             float* __restrict__ cla_t, float* __restrict__ norm_att_t) {
+  __syncthreads();
+  if (threadIdx.x < kCls) {
+    float s = 0.0f;
+    for (int t = 0; t < Tn; ++t) s += s_e[t * kCls + threadIdx.x];
+    s_sum[threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < kCls) {
+    const int c = threadIdx.x;
+    const float s = s_sum[c];
+    float acc = 0.0f;
+    for (int t = 0; t < Tn; ++t) acc += (s_e[t * kCls + c] / s) * s_c[t * kCls + c];  // models.py:166, 168
+    clip[b * kCls + c] = acc;
+  }
+  // framewise: repeat each step `ratio` times, pad with the last frame (models.py:93-94, 74-78)
+  float* fr = frame + static_cast<size_t>(b) * frames_out * kCls;
+  for (int i = threadIdx.x; i < frames_out * kCls; i += blockDim.x) {
+    const int f = i / kCls, c = i - f * kCls;
+    int t = f / ratio;
+    if (t > Tn - 1) t = Tn - 1;
+    fr[i] = s_c[t * kCls + c];
+  }
+  if (cla_t != nullptr) {  // 'embedding' of the GRU model: cla [B, 25, T'] (models.py:686)
+    float* o = cla_t + static_cast<size_t>(b) * kCls * Tn;
+    for (int i = threadIdx.x; i < kCls * Tn; i += blockDim.x) {
+      const int c = i / Tn, t = i - c * Tn;
+      o[i] = s_c[t * kCls + c];
+    }
+  }
+  if (norm_att_t != nullptr) {
+    float* o = norm_att_t + static_cast<size_t>(b) * kCls * Tn;
+    for (int i = threadIdx.x; i < kCls * Tn; i += blockDim.x) {
+      const int c = i / Tn, t = i - c * Tn;
+      o[i] = s_e[t * kCls + c] / s_sum[c];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128)
 attpool_kernel(const float* __restrict__ x, int Tn, const float* __restrict__ w_att, const float* __restrict__ b_att,
                const float* __restrict__ w_cla, const float* __restrict__ b_cla, int ratio, int frames_out,
@@ -439,42 +558,7 @@ attpool_kernel(const float* __restrict__ x, int Tn, const float* __restrict__ w_
       s_c[t * kCls + c] = 1.0f / (1.0f + expf(-acc[kCls + c]));    // models.py:167 sigmoid
     }
   }
-  __syncthreads();
-  if (threadIdx.x < kCls) {
-    float s = 0.0f;
-    for (int t = 0; t < Tn; ++t) s += s_e[t * kCls + threadIdx.x];
-    s_sum[threadIdx.x] = s;
-  }
-  __syncthreads();
-  if (threadIdx.x < kCls) {
-    const int c = threadIdx.x;
-    const float s = s_sum[c];
-    float acc = 0.0f;
-    for (int t = 0; t < Tn; ++t) acc += (s_e[t * kCls + c] / s) * s_c[t * kCls + c];  // models.py:166, 168
-    clip[b * kCls + c] = acc;
-  }
-  // framewise: repeat each step `ratio` times, pad with the last frame (models.py:93-94, 74-78)
-  float* fr = frame + static_cast<size_t>(b) * frames_out * kCls;
-  for (int i = threadIdx.x; i < frames_out * kCls; i += blockDim.x) {
-    const int f = i / kCls, c = i - f * kCls;
-    int t = f / ratio;
-    if (t > Tn - 1) t = Tn - 1;
-    fr[i] = s_c[t * kCls + c];
-  }
-  if (cla_t != nullptr) {  // 'embedding' of the GRU model: cla [B, 25, T'] (models.py:686)
-    float* o = cla_t + static_cast<size_t>(b) * kCls * Tn;
-    for (int i = threadIdx.x; i < kCls * Tn; i += blockDim.x) {
-      const int c = i / Tn, t = i - c * Tn;
-      o[i] = s_c[t * kCls + c];
-    }
-  }
-  if (norm_att_t != nullptr) {
-    float* o = norm_att_t + static_cast<size_t>(b) * kCls * Tn;
-    for (int i = threadIdx.x; i < kCls * Tn; i += blockDim.x) {
-      const int c = i / Tn, t = i - c * Tn;
-      o[i] = s_e[t * kCls + c] / s_sum[c];
-    }
-  }
+  attpool_tail(s_e, s_c, s_sum, b, Tn, ratio, frames_out, clip, frame, cla_t, norm_att_t);
 }
 
 int attpool_launch(const float* x, int B, int Tn, const float* w_att, const float* b_att, const float* w_cla,
@@ -492,6 +576,141 @@ int attpool_launch(const float* x, int B, int Tn, const float* w_att, const floa
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("attpool launch: %s", cudaGetErrorString(e));
+    return SED_ERR_CUDA;
+  }
+  return SED_OK;
+}
+
+// ---- blocks variant: x arrives as 128-clip transposed blocks (what sed_bigru / sed_linear out_layout 1 write) ----
+// Kernel A: one warp per (32 consecutive clips, step t), lane = clip: every x load is 512 contiguous bytes and the
+// 50 weight rows are broadcast reads from shared memory.  e = exp(clamp(att)) + 1e-6 and c = sigmoid(cla) go to a
+// scratch tensor S[t][50][Bp] (clip fastest: coalesced).  Kernel B: one block per clip gathers its [T][50] slice and
+// runs the same tail as attpool_kernel.  The sums over t stay sequential per clip: results do not depend on how
+// the batch is split.
+constexpr int kApWarps = 8;
+constexpr int kApTM = 4;  // clips per lane: every broadcast weight load (the shared-memory pipe is the limiter)
+                          // feeds 4 x kApTM FMAs; a warp covers 32 * kApTM clips of one 128-clip block
+
+__global__ void __launch_bounds__(kApWarps * 32, 1)
+attproj_blocks_kernel(const float4* __restrict__ xb, int Bp, int Tn, const float* __restrict__ w_att,
+                      const float* __restrict__ b_att, const float* __restrict__ w_cla,
+                      const float* __restrict__ b_cla, float* __restrict__ S) {
+  extern __shared__ float smem_h[];
+  float* s_w = smem_h;  // [2*25][512]  att rows then cla rows
+  for (int i = threadIdx.x; i < kCls * 512; i += blockDim.x) {
+    s_w[i] = w_att[i];
+    s_w[kCls * 512 + i] = w_cla[i];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int GPB = 4 / kApTM;  // warp tasks per 128-clip block
+  const int groups = (Bp / 128) * GPB, nblk = Bp / 128;
+  const long tasks = static_cast<long>(groups) * Tn;
+  for (long task = static_cast<long>(blockIdx.x) * kApWarps + warp; task < tasks;
+       task += static_cast<long>(gridDim.x) * kApWarps) {
+    const int t = static_cast<int>(task / groups), cg = static_cast<int>(task - static_cast<long>(t) * groups);
+    const int blk = cg / GPB, m0 = (cg % GPB) * (32 * kApTM) + lane;  // this lane's clips: m0 + 32 i
+    const float4* xr = xb + (static_cast<size_t>(t) * nblk + blk) * 128 * 128 + m0;
+    float acc[kApTM][2 * kCls];
+#pragma unroll
+    for (int c = 0; c < kCls; ++c) {
+      const float ba = b_att[c], bc = b_cla[c];
+#pragma unroll
+      for (int i = 0; i < kApTM; ++i) {
+        acc[i][c] = ba;
+        acc[i][kCls + c] = bc;
+      }
+    }
+    float4 xv[kApTM];
+#pragma unroll
+    for (int i = 0; i < kApTM; ++i) xv[i] = xr[32 * i];
+    for (int k4 = 0; k4 < 128; ++k4) {
+      float4 xn[kApTM];
+#pragma unroll
+      for (int i = 0; i < kApTM; ++i)
+        xn[i] = (k4 + 1 < 128) ? xr[static_cast<size_t>(k4 + 1) * 128 + 32 * i] : make_float4(0, 0, 0, 0);
+#pragma unroll
+      for (int c = 0; c < 2 * kCls; ++c) {
+        const float4 wv = *reinterpret_cast<const float4*>(s_w + c * 512 + k4 * 4);
+#pragma unroll
+        for (int i = 0; i < kApTM; ++i) {
+          acc[i][c] = fmaf(xv[i].x, wv.x, acc[i][c]);
+          acc[i][c] = fmaf(xv[i].y, wv.y, acc[i][c]);
+          acc[i][c] = fmaf(xv[i].z, wv.z, acc[i][c]);
+          acc[i][c] = fmaf(xv[i].w, wv.w, acc[i][c]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kApTM; ++i) xv[i] = xn[i];
+    }
+    float* So = S + static_cast<size_t>(t) * 2 * kCls * Bp + blk * 128 + m0;
+#pragma unroll
+    for (int c = 0; c < kCls; ++c) {
+#pragma unroll
+      for (int i = 0; i < kApTM; ++i) {
+        const float a = fminf(fmaxf(acc[i][c], -10.0f), 10.0f);                                    // models.py:164
+        So[static_cast<size_t>(c) * Bp + 32 * i] = expf(a) + 1e-6f;                                  // models.py:165
+        So[static_cast<size_t>(kCls + c) * Bp + 32 * i] = 1.0f / (1.0f + expf(-acc[i][kCls + c]));   // models.py:167
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+attpool_tail_kernel(const float* __restrict__ S, int Bp, int Tn, int ratio, int frames_out, float* __restrict__ clip,
+                    float* __restrict__ frame, float* __restrict__ cla_t, float* __restrict__ norm_att_t) {
+  extern __shared__ float smem_h[];
+  float* s_e = smem_h;               // [Tn][25]
+  float* s_c = s_e + Tn * kCls;      // [Tn][25]
+  float* s_sum = s_c + Tn * kCls;    // [25]
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < Tn * 2 * kCls; i += blockDim.x) {
+    const int t = i / (2 * kCls), c = i - t * 2 * kCls;
+    const float v = S[(static_cast<size_t>(t) * 2 * kCls + c) * Bp + b];
+    if (c < kCls) s_e[t * kCls + c] = v; else s_c[t * kCls + c - kCls] = v;
+  }
+  attpool_tail(s_e, s_c, s_sum, b, Tn, ratio, frames_out, clip, frame, cla_t, norm_att_t);
+}
+
+size_t attpool_blocks_scratch_bytes(int B, int Tn) {
+  const size_t Bp = (static_cast<size_t>(B) + 127) / 128 * 128;
+  return sizeof(float) * static_cast<size_t>(Tn) * 2 * kCls * Bp;
+}
+
+int attpool_blocks_launch(const float* x_blocks, int B, int Tn, const float* w_att, const float* b_att,
+                          const float* w_cla, const float* b_cla, int ratio, int frames_out, void* scratch, float* clip,
+                          float* frame, float* cla_t, float* norm_att_t, cudaStream_t stream) {
+  const size_t smem_b = sizeof(float) * (2 * static_cast<size_t>(Tn) * kCls + 32);
+  if (B <= 0 || Tn <= 0 || ratio <= 0 || frames_out < Tn * ratio || smem_b > 220 * 1024) {
+    set_error("attpool_blocks: unsupported shape B=%d T=%d ratio=%d frames_out=%d", B, Tn, ratio, frames_out);
+    return SED_ERR_BAD_SHAPE;
+  }
+  const int Bp = (B + 127) / 128 * 128;
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0)
+      sm_count = 148;
+  }
+  const size_t smem_a = sizeof(float) * 2 * kCls * 512;
+  cudaError_t e = cudaFuncSetAttribute(attproj_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(attpool_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+  if (e == cudaSuccess) {
+    const long tasks = static_cast<long>(Bp / (32 * kApTM)) * Tn;
+    long blocks = (tasks + kApWarps - 1) / kApWarps;
+    if (blocks > static_cast<long>(sm_count)) blocks = sm_count;
+    attproj_blocks_kernel<<<static_cast<unsigned>(blocks), kApWarps * 32, smem_a, stream>>>(
+        reinterpret_cast<const float4*>(x_blocks), Bp, Tn, w_att, b_att, w_cla, b_cla, reinterpret_cast<float*>(scratch));
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) {
+    attpool_tail_kernel<<<B, 128, smem_b, stream>>>(reinterpret_cast<const float*>(scratch), Bp, Tn, ratio, frames_out,
+                                                    clip, frame, cla_t, norm_att_t);
+    e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) {
+    set_error("attpool_blocks launch: %s", cudaGetErrorString(e));
     return SED_ERR_CUDA;
   }
   return SED_OK;

@@ -240,6 +240,13 @@ def extract_events(frames, high, low, n_smooth, n_salt, max_events=64):
         max_events = most  # rare: more events than the buffer holds -> rerun once with the exact capacity
 
 
+def blocks_to_rows(xb, n, T):
+    """128-clip transposed blocks [T, nblk, C/4, 128, 4] (float4 column c4 of clip row m of block (t, blk) at
+    ((t*nblk + blk)*C/4 + c4)*128 + m) -> ordinary rows [n, T, C]."""
+    T_, nblk, c4, _, _ = xb.shape
+    return xb.permute(1, 3, 0, 2, 4).reshape(nblk * 128, T_, c4 * 4)[:n]
+
+
 class PackedModel:
     """Weights of one model repacked for the kernels, resident on one device."""
 
@@ -332,10 +339,12 @@ class PackedModel:
         return ws
 
     # ------------------------------------------------------------------ stages
-    def conv_stack(self, wave_mb, feat_out, variant=2, stages=None, windows=None, feat32=None):
+    def conv_stack(self, wave_mb, feat_out, variant=2, stages=None, windows=None, feat32=None, feat_strides=(0, 0)):
         """wave_mb [mb, L] (f32 / int16) -> feat_out [mb, T', 512] 16-bit (freq-mean of conv_block4).
         windows=(mb, L, stride): wave_mb is a 1-D recording read as overlapping windows.
-        feat32: optional [mb, T', 512] f32 copy of the features (models without a temporal block)."""
+        feat32: optional [mb, T', 512] f32 copy of the features (models without a temporal block).
+        feat_strides=(sn, sh): feature row of (clip n, step h) is n*sn + h*sh rows after feat_out's first element
+        ((0, 0) = clip-major [mb, T', 512]; (1, Bp) = time-major [T', Bp, 512] as the GRU wants it)."""
         lib = capi.load()
         if windows is None:
             mb, L = wave_mb.shape
@@ -360,7 +369,9 @@ class PackedModel:
             out = feat_out if dst is None else ws[dst]
             rc = lib.sed_conv3x3_bn_relu(capi.ptr(x), mb, x.shape[1], x.shape[2], cin, capi.ptr(wp), capi.ptr(s),
                                          capi.ptr(b), cout, mode, capi.ptr(out),
-                                         capi.ptr(feat32) if dst is None else None, self.dtype_code, variant, stream)
+                                         capi.ptr(feat32) if dst is None else None,
+                                         feat_strides[0] if dst is None else 0, feat_strides[1] if dst is None else 0,
+                                         self.dtype_code, variant, stream)
             capi.check(rc, "sed_conv3x3_bn_relu(%d->%d)" % (cin, cout))
             capi._count()
         if self.conv_events is not None:
@@ -372,14 +383,15 @@ class PackedModel:
             for k in ("a1", "p1", "a2", "p2", "a3", "p3", "a4"):
                 stages[k] = ws[k].clone()
 
-    def linear(self, a16, w16, bias, relu=False, out16=False):
+    def linear(self, a16, w16, bias, relu=False, out16=False, out_layout=0):
+        """out_layout 1: float32 output as 128-row transposed blocks (see sed_b200.h: sed_linear)."""
         lib = capi.load()
         M, K = a16.shape
         N = w16.shape[0]
         out = torch.empty((M, N), dtype=torch.float32, device=self.device)
         o16 = torch.empty((M, N), dtype=self.tdtype, device=self.device) if out16 else None
         rc = lib.sed_linear(capi.ptr(a16), M, K, capi.ptr(w16), capi.ptr(bias), N, 1 if relu else 0, capi.ptr(out),
-                            capi.ptr(o16), self.dtype_code, capi.current_stream(self.device))
+                            capi.ptr(o16), out_layout, self.dtype_code, capi.current_stream(self.device))
         capi.check(rc, "sed_linear")
         capi._count((N + 511) // 512)
         return (out, o16) if out16 else out
@@ -391,16 +403,10 @@ class PackedModel:
         stream = capi.current_stream(self.device)
         flat = feat16.view(B * Tp, 512)
         if self.temporal_kind == "gru":
-            gi = self.linear(flat, self.gru_wih, self.gru_bih)
-            out = torch.empty((B, Tp, 512), dtype=torch.float32, device=self.device)
-            ws = torch.empty((lib.sed_bigru_workspace_bytes(B),), dtype=torch.uint8, device=self.device)
-            rc = lib.sed_bigru(capi.ptr(gi), capi.ptr(self.gru_whh), capi.ptr(self.gru_bhh), B, Tp, capi.ptr(out),
-                               capi.ptr(ws), self.dtype_code, stream)
-            capi.check(rc, "sed_bigru")
-            capi._count()
-            if stages is not None:
-                stages["gi"] = gi
-            return out
+            # clip-major input (tests, tools): repack time-major over the padded batch, then the product path
+            feat_t = self.alloc_feat_tmajor(B, Tp)
+            feat_t[:, :B].copy_(feat16.transpose(0, 1))
+            return blocks_to_rows(self.gru_tmajor(feat_t, B, stages), B, Tp)
         if self.temporal_kind != "mha":
             raise RuntimeError("%s has no temporal block" % self.model_type)
         qkv = self.linear(flat, self.mha_wqkv, self.mha_bqkv)
@@ -414,6 +420,29 @@ class PackedModel:
             stages["ctx"] = ctx
         return out.view(B, Tp, 512)
 
+    def alloc_feat_tmajor(self, B, Tp):
+        """[T', Bp, 512] 16-bit feature buffer, Bp = B rounded up to 128 clips (padding rows zero)."""
+        Bp = (B + 127) // 128 * 128
+        make = torch.empty if Bp == B else torch.zeros
+        return make((Tp, Bp, 512), dtype=self.tdtype, device=self.device)
+
+    def gru_tmajor(self, feat_t, B, stages=None):
+        """feat_t [T', Bp, 512] 16-bit (time-major, batch padded to 128) -> bi-GRU output as 128-clip transposed
+        blocks (T'*Bp*512 f32, see blocks_to_rows).  The input projection writes gi in the same layout, which the
+        recurrence streams with fully coalesced loads (one contiguous 96 KB block per CTA and step)."""
+        lib = capi.load()
+        Tp, Bp, _ = feat_t.shape
+        gi = self.linear(feat_t.view(Tp * Bp, 512), self.gru_wih, self.gru_bih, out_layout=1)
+        out = torch.empty((Tp, Bp // 128, 128, 128, 4), dtype=torch.float32, device=self.device)
+        ws = torch.empty((max(16, lib.sed_bigru_workspace_bytes(B)),), dtype=torch.uint8, device=self.device)
+        rc = lib.sed_bigru(capi.ptr(gi), capi.ptr(self.gru_whh), capi.ptr(self.gru_bhh), B, Tp, capi.ptr(out),
+                           capi.ptr(ws), self.dtype_code, capi.current_stream(self.device))
+        capi.check(rc, "sed_bigru")
+        capi._count()
+        if stages is not None:
+            stages["gi_blocks"] = gi
+        return out
+
     def frames_for(self, Tp):
         """Number of framewise rows the model returns for T' pooled steps (x8 interpolation; only
         Cnn_9layers_Gru_FrameAtt pads to the next multiple of 100 when != 1000, models.py:62-63, 680-681)."""
@@ -422,11 +451,17 @@ class PackedModel:
             frames += 100 - frames % 100
         return frames
 
-    def head(self, x, frames_out, want_cla=True, want_norm_att=False, out=None):
-        """x [B, T', 512] f32 -> (clipwise [B,C], framewise [B,frames_out,C], cla | None, norm_att | None)."""
+    def head(self, x, frames_out, want_cla=True, want_norm_att=False, out=None, n=None, clip0=0):
+        """x [B, T', 512] f32 -> (clipwise [B,C], framewise [B,frames_out,C], cla | None, norm_att | None).
+        x may also be a 5-D transposed-block tensor (gru_tmajor output) covering n clips."""
         lib = capi.load()
-        B, Tp, _ = x.shape
         dev = self.device
+        if x.dim() == 5:
+            if self.head_kind != "att":
+                x = blocks_to_rows(x, n, x.shape[0])
+            else:
+                return self._head_blocks(x, n, frames_out, want_cla, want_norm_att, out)
+        B, Tp, _ = x.shape
         C = self.classes
         if out is not None:
             clip, frame = out  # preallocated [B,C] / [B,frames_out,C] (contiguous slices)
@@ -451,12 +486,34 @@ class PackedModel:
         capi._count()
         return clip, frame, None, None
 
+    def _head_blocks(self, xb, n, frames_out, want_cla, want_norm_att, out):
+        lib = capi.load()
+        dev = self.device
+        Tp = xb.shape[0]
+        if out is not None:
+            clip, frame = out
+        else:
+            clip = torch.empty((n, 25), dtype=torch.float32, device=dev)
+            frame = torch.empty((n, frames_out, 25), dtype=torch.float32, device=dev)
+        cla = torch.empty((n, 25, Tp), dtype=torch.float32, device=dev) if want_cla else None
+        natt = torch.empty((n, 25, Tp), dtype=torch.float32, device=dev) if want_norm_att else None
+        scratch = torch.empty((lib.sed_attpool_blocks_scratch_bytes(n, Tp),), dtype=torch.uint8, device=dev)
+        rc = lib.sed_attpool_blocks(capi.ptr(xb), n, Tp, capi.ptr(self.att_w), capi.ptr(self.att_b),
+                                    capi.ptr(self.cla_w), capi.ptr(self.cla_b), 8, frames_out, capi.ptr(scratch),
+                                    capi.ptr(clip), capi.ptr(frame), capi.ptr(cla), capi.ptr(natt),
+                                    capi.current_stream(dev))
+        capi.check(rc, "sed_attpool_blocks")
+        capi._count(2)
+        return clip, frame, cla, natt
+
     def _embedding(self, x, cla, feat32):
         """The reference's 'embedding' entry: cla for the two *_FrameAtt models that expose it (models.py:686, 460),
         else the [B, 512, T'] input of the head (models.py:1075, 288, 553, 970)."""
         if self.model_type in ("Cnn_9layers_Gru_FrameAtt", "Cnn_9layers_FrameAtt"):
             return cla
-        return (x if self.temporal_kind else feat32).transpose(1, 2)
+        if not self.temporal_kind:
+            return feat32.transpose(1, 2)
+        return x.transpose(1, 2)
 
     # ------------------------------------------------------------------ whole model
     def forward_host(self, wave_host, micro_batch=148, variant=2, head_chunk=256):
@@ -495,17 +552,18 @@ class PackedModel:
                 ev.record(cs)
                 events.append(ev)
         with self._lock:
-            feat16 = torch.empty((B, Tp, 512), dtype=self.tdtype, device=self.device)
-            feat32 = None if self.temporal_kind else torch.empty((B, Tp, 512), dtype=torch.float32, device=self.device)
+            feat16, feat32, slot = self._alloc_features(B, Tp)
             for (b0, b1), ev in zip(spans, events):
                 compute.wait_event(ev)
-                self.conv_stack(hb["dev"][b0:b1], feat16[b0:b1], variant=variant,
-                                feat32=None if feat32 is None else feat32[b0:b1])
-            x = self.temporal(feat16) if self.temporal_kind else feat32
+                self.conv_stack(hb["dev"][b0:b1], variant=variant, **slot(b0, b1))
+            x = self._temporal_or_features(feat16, feat32, B)
             # pooling head in chunks: the device->host copy of chunk i overlaps the head kernel of chunk i+1
+            if x.dim() == 5:
+                head_chunk = B  # transposed-block input: one call over the batch
             for c0 in range(0, B, head_chunk):
                 c1 = min(B, c0 + head_chunk)
-                self.head(x[c0:c1], frames, want_cla=False, out=(hb["clip_dev"][c0:c1], hb["frame_dev"][c0:c1]))
+                self.head(x if x.dim() == 5 else x[c0:c1], frames, want_cla=False,
+                          out=(hb["clip_dev"][c0:c1], hb["frame_dev"][c0:c1]), n=B)
                 done = torch.cuda.Event()
                 done.record(compute)
                 ds.wait_event(done)
@@ -515,15 +573,35 @@ class PackedModel:
         ds.synchronize()
         return {"clipwise_output": hb["clip"], "framewise_output": hb["frame"]}
 
+    def _alloc_features(self, n, Tp):
+        """Feature buffers of the conv stack and slot(b0, b1) -> conv_stack keyword arguments for one micro-batch.
+        GRU models get the features time-major ([T', Bp, 512]); the others clip-major ([n, T', 512])."""
+        if self.temporal_kind == "gru":
+            feat_t = self.alloc_feat_tmajor(n, Tp)
+            Bp = feat_t.shape[1]
+            return feat_t, None, (lambda b0, b1: {"feat_out": feat_t[0, b0:b1], "feat_strides": (1, Bp)})
+        feat16 = torch.empty((n, Tp, 512), dtype=self.tdtype, device=self.device)
+        feat32 = None if self.temporal_kind else torch.empty((n, Tp, 512), dtype=torch.float32, device=self.device)
+        return feat16, feat32, (lambda b0, b1: {"feat_out": feat16[b0:b1],
+                                                "feat32": None if feat32 is None else feat32[b0:b1]})
+
+    def _temporal_or_features(self, feat16, feat32, n, stages=None):
+        if self.temporal_kind == "gru":
+            return self.gru_tmajor(feat16, n, stages)
+        return self.temporal(feat16, stages) if self.temporal_kind else feat32
+
     def _run(self, n, Tp, conv_call, stages=None, want_norm_att=False):
         """Shared tail of forward / forward_windows: conv stack per micro-batch (conv_call(b0, b1, feat16, feat32,
         stages)), temporal block and head over the whole batch."""
-        feat16 = torch.empty((n, Tp, 512), dtype=self.tdtype, device=self.device)
-        feat32 = None if self.temporal_kind else torch.empty((n, Tp, 512), dtype=torch.float32, device=self.device)
-        conv_call(feat16, feat32)
-        x = self.temporal(feat16, stages) if self.temporal_kind else feat32
+        feat16, feat32, slot = self._alloc_features(n, Tp)
+        conv_call(slot)
+        x = self._temporal_or_features(feat16, feat32, n, stages)
+        if self.temporal_kind == "gru":
+            feat16 = feat16[:, :n].transpose(0, 1)  # clip-major view for the stage dump
         wants_cla = self.model_type in ("Cnn_9layers_Gru_FrameAtt", "Cnn_9layers_FrameAtt")
-        clip, frame, cla, natt = self.head(x, self.frames_for(Tp), want_cla=wants_cla, want_norm_att=want_norm_att)
+        clip, frame, cla, natt = self.head(x, self.frames_for(Tp), want_cla=wants_cla, want_norm_att=want_norm_att, n=n)
+        if x.dim() == 5 and (stages is not None or not wants_cla):
+            x = blocks_to_rows(x, n, Tp)  # clip-major view of the GRU output (stage dump / 'embedding' of *_FrameAvg)
         out = {"framewise_output": frame, "clipwise_output": clip, "embedding": self._embedding(x, cla, feat32)}
         return out, feat16, x, natt
 
@@ -538,12 +616,11 @@ class PackedModel:
         recording = recording.contiguous()
         T = window_samples // self.front.hop + 1
 
-        def conv_call(feat16, feat32):
+        def conv_call(slot):
             for b0 in range(0, n_windows, micro_batch):
                 b1 = min(n_windows, b0 + micro_batch)
-                self.conv_stack(recording[b0 * stride_samples:], feat16[b0:b1], variant=variant,
-                                windows=(b1 - b0, window_samples, stride_samples),
-                                feat32=None if feat32 is None else feat32[b0:b1])
+                self.conv_stack(recording[b0 * stride_samples:], variant=variant,
+                                windows=(b1 - b0, window_samples, stride_samples), **slot(b0, b1))
 
         with self._lock:
             return self._run(n_windows, T // 8, conv_call)[0]
@@ -561,12 +638,11 @@ class PackedModel:
         T = L // self.front.hop + 1
         stages = {} if return_stages else None
 
-        def conv_call(feat16, feat32):
+        def conv_call(slot):
             for b0 in range(0, B, micro_batch):
                 b1 = min(B, b0 + micro_batch)
-                self.conv_stack(wave[b0:b1], feat16[b0:b1], variant=variant,
-                                stages=stages if (return_stages and b0 == 0) else None,
-                                feat32=None if feat32 is None else feat32[b0:b1])
+                self.conv_stack(wave[b0:b1], variant=variant,
+                                stages=stages if (return_stages and b0 == 0) else None, **slot(b0, b1))
 
         with self._lock:
             out, feat16, x, natt = self._run(B, T // 8, conv_call, stages, want_norm_att=return_stages)

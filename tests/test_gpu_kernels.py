@@ -34,7 +34,7 @@ def run_conv(x, w, scale, shift, mode, code, td, variant):
     oshape = {0: (NB, H, W, cout), 1: (NB, H // 2, W // 2, cout), 2: (NB, H, cout)}[mode]
     out = torch.full(oshape, float("nan"), dtype=td, device=DEV)
     rc = lib.sed_conv3x3_bn_relu(capi.ptr(xd), NB, H, W, cin, capi.ptr(wp), capi.ptr(sc), capi.ptr(sh), cout, mode,
-                                 capi.ptr(out), None, code, variant, capi.current_stream(DEV))
+                                 capi.ptr(out), None, 0, 0, code, variant, capi.current_stream(DEV))
     capi.check(rc, "sed_conv3x3_bn_relu")
     torch.cuda.synchronize()
     return out.float().cpu()
@@ -90,11 +90,11 @@ def test_conv_rejects_unsupported_layers():
     x = torch.zeros(1, 16, 8, 192, dtype=torch.float16, device=DEV)
     with pytest.raises(NotImplementedError):
         rc = lib.sed_conv3x3_bn_relu(capi.ptr(x), 1, 16, 8, 192, capi.ptr(x), capi.ptr(x), capi.ptr(x), 192, 0,
-                                     capi.ptr(x), None, 0, 0, capi.current_stream(DEV))
+                                     capi.ptr(x), None, 0, 0, 0, 0, capi.current_stream(DEV))
         capi.check(rc, "conv")
     with pytest.raises(ValueError):
         rc = lib.sed_conv3x3_bn_relu(capi.ptr(x), 1, 16, 7, 64, capi.ptr(x), capi.ptr(x), capi.ptr(x), 64, 1,
-                                     capi.ptr(x), None, 0, 0, capi.current_stream(DEV))
+                                     capi.ptr(x), None, 0, 0, 0, 0, capi.current_stream(DEV))
         capi.check(rc, "conv")
 
 
@@ -121,7 +121,7 @@ def test_linear(M, K, N, relu):
     bias = torch.randn(N) * 0.1
     out = torch.full((M, N), float("nan"), dtype=torch.float32, device=DEV)
     ad, wd, bd = a.to(DEV), w.to(DEV), bias.to(DEV)
-    rc = lib.sed_linear(capi.ptr(ad), M, K, capi.ptr(wd), capi.ptr(bd), N, relu, capi.ptr(out), None, 0,
+    rc = lib.sed_linear(capi.ptr(ad), M, K, capi.ptr(wd), capi.ptr(bd), N, relu, capi.ptr(out), None, 0, 0,
                         capi.current_stream(DEV))
     capi.check(rc, "sed_linear")
     ref = a.float() @ w.float().t() + bias
@@ -168,3 +168,27 @@ def test_attpool_matches_oracle(B, T, frames):
     assert (frame.cpu() - rfw).abs().max() < 2e-6
     assert (cla.cpu() - rcla).abs().max() < 2e-6
     assert (natt.cpu() - rnatt).abs().max() < 2e-6
+
+
+def test_linear_transposed_block_layout_is_a_pure_permutation():
+    """sed_linear out_layout=1 (the layout sed_bigru streams): float4 c of row r at ((r/128)*N/4 + c)*128 + r%128."""
+    lib = capi.load()
+    M, K, N = 384, 512, 1536
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(M, K, generator=g).half().to(DEV)
+    w = (torch.randn(N, K, generator=g) * 0.05).half().to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    outs = []
+    for layout in (0, 1):
+        out = torch.full((M, N), float("nan"), device=DEV)
+        rc = lib.sed_linear(capi.ptr(a), M, K, capi.ptr(w), capi.ptr(b), N, 0, capi.ptr(out), None, layout, 0,
+                            capi.current_stream(DEV))
+        capi.check(rc, "sed_linear")
+        outs.append(out)
+    torch.cuda.synchronize()
+    blocks = outs[1].view(M // 128, N // 4, 128, 4).permute(0, 2, 1, 3).reshape(M, N)
+    assert torch.equal(blocks, outs[0])
+    with pytest.raises(NotImplementedError):
+        rc = lib.sed_linear(capi.ptr(a), 100, K, capi.ptr(w), capi.ptr(b), N, 0, capi.ptr(outs[0]), None, 1, 0,
+                            capi.current_stream(DEV))
+        capi.check(rc, "sed_linear")

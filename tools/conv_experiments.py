@@ -25,7 +25,7 @@ for (name, _, _, _), (cin, cout, mode, wp, s, b), (src, dst) in zip(engine.CONV_
     for flag in (0, 1, 2, 4, 6):
         os.environ["SED_CONV_DBG"] = str(flag)
         res.append(timeit(lambda: lib.sed_conv3x3_bn_relu(capi.ptr(x), mb, x.shape[1], x.shape[2], cin, capi.ptr(wp),
-                                                          capi.ptr(s), capi.ptr(b), cout, mode, capi.ptr(out), None,
+                                                          capi.ptr(s), capi.ptr(b), cout, mode, capi.ptr(out), None, 0, 0,
                                                           pm.dtype_code, 2, stream)))
     os.environ["SED_CONV_DBG"] = "0"
     flops = 2.0 * mb * x.shape[1] * x.shape[2] * 9 * cin * cout

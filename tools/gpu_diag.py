@@ -107,7 +107,7 @@ def run_stage(stage):
                 t0 = time.time()
                 xd, sc, sh = x.to(dev), scale.to(dev), shift.to(dev)
                 rc = lib.sed_conv3x3_bn_relu(capi.ptr(xd), NB, H, W, cin, capi.ptr(wp), capi.ptr(sc),
-                                             capi.ptr(sh), cout, mode, capi.ptr(out), None, code, variant, stream)
+                                             capi.ptr(sh), cout, mode, capi.ptr(out), None, 0, 0, code, variant, stream)
                 capi.check(rc, name)
                 torch.cuda.synchronize()
                 ref = conv_ref(x.float(), w.float(), scale, shift, mode)
@@ -125,7 +125,7 @@ def run_stage(stage):
             out = torch.full((M, N), float("nan"), dtype=torch.float32, device=dev)
             ad, wd, bd = a.to(dev), w.to(dev), bias.to(dev)
             rc = lib.sed_linear(capi.ptr(ad), M, K, capi.ptr(wd), capi.ptr(bd), N, relu,
-                                capi.ptr(out), None, code, stream)
+                                capi.ptr(out), None, 0, code, stream)
             capi.check(rc, "linear")
             torch.cuda.synchronize()
             ref = a.float() @ w.float().t() + bias

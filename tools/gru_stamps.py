@@ -10,7 +10,7 @@ mt = "Cnn_9layers_Gru_FrameAtt"
 pm = engine.PackedModel(synth.synthetic_state_dict(mt), mt, 512, 160, dev)
 B, T = 1024, 125
 feat = torch.randn(B, T, 512, device=dev).half()
-gi = pm.linear(feat.view(-1, 512), pm.gru_wih, pm.gru_bih)
+gi = pm.linear(feat.transpose(0, 1).contiguous().view(-1, 512), pm.gru_wih, pm.gru_bih, out_layout=1)
 out = torch.empty((B, T, 512), device=dev)
 ws = torch.empty((lib.sed_bigru_workspace_bytes(B),), dtype=torch.uint8, device=dev)
 stamps = torch.zeros(8 * 12, dtype=torch.int64, device=dev)
@@ -20,11 +20,10 @@ for _ in range(3):
     capi.check(rc, "profile")
 torch.cuda.synchronize()
 st = stamps.cpu().view(8, 12)
-names = ["prod: h_ready seen", "prod: after proxy fence", "mma: a_full seen", "mma: committed", "epi: before acc wait",
-         "epi: acc_full seen", "epi: gates done", "epi: stores issued", "epi: after proxy fence", "epi: arrives sent"]
-base = st[1, 0].item()
-for s in range(1, 5):
-    print("step", 8 + s, " ".join("%s=%d" % (n.split(":")[0] + str(i), st[s, i].item() - st[s, 0].item()) for i, n in enumerate(names)),
-          "| step period", st[s, 0].item() - st[s - 1, 0].item())
+names = ["issuer: a_full seen", "issuer: half 0 committed", "issuer: half 1 committed", "-", "warp0: acc seen",
+         "warp0: gates done", "-", "-", "warp0: stores + arrive sent"]
+for s_ in range(1, 5):
+    print("step", 8 + s_, " ".join("s%d=%d" % (i, st[s_, i].item() - st[s_, 0].item()) for i in (0, 1, 2, 4, 5, 8)),
+          "| step period", st[s_, 0].item() - st[s_ - 1, 0].item())
 for i, n in enumerate(names):
     print(i, n)

@@ -55,7 +55,7 @@ def main():
         out = feat if dst is None else ws[dst]
         for variant in (0, 2):
             t = timeit(lambda: lib.sed_conv3x3_bn_relu(capi.ptr(x), mb, x.shape[1], x.shape[2], cin, capi.ptr(wp),
-                                                       capi.ptr(s), capi.ptr(b), cout, mode, capi.ptr(out), None,
+                                                       capi.ptr(s), capi.ptr(b), cout, mode, capi.ptr(out), None, 0, 0,
                                                        pm.dtype_code, variant, stream))
             flops = 2.0 * mb * x.shape[1] * x.shape[2] * 9 * cin * cout
             rows.append(("%s %d->%d %s" % (name, cin, cout, {0: "patch", 1: "tap", 2: "pair"}[variant]), t, flops,
@@ -65,8 +65,8 @@ def main():
     if args.model.endswith("Gru_FrameAtt"):
         t = timeit(lambda: pm.linear(featB.view(-1, 512), pm.gru_wih, pm.gru_bih))
         rows.append(("gru input projection (B=%d)" % B, t * mb / B, 2.0 * mb * 125 * 1536 * 512, 0))
-        gi = pm.linear(featB.view(-1, 512), pm.gru_wih, pm.gru_bih)
-        out = torch.empty((B, 125, 512), dtype=torch.float32, device=dev)
+        gi = pm.linear(featB.transpose(0, 1).contiguous().view(-1, 512), pm.gru_wih, pm.gru_bih, out_layout=1)
+        out = torch.empty((125, (B + 127) // 128, 128, 128, 4), dtype=torch.float32, device=dev)
         gws = torch.empty((lib.sed_bigru_workspace_bytes(B),), dtype=torch.uint8, device=dev)
         t = timeit(lambda: lib.sed_bigru(capi.ptr(gi), capi.ptr(pm.gru_whh), capi.ptr(pm.gru_bhh), B, 125, capi.ptr(out),
                                          capi.ptr(gws), pm.dtype_code, stream))
@@ -76,7 +76,7 @@ def main():
         t = timeit(lambda: pm.temporal(featB))
         rows.append(("multihead (B=%d)" % B, t * mb / B, 2.0 * mb * 147e6, 0))
         x = pm.temporal(featB)
-    t = timeit(lambda: pm.head(x, 1000))
+    t = timeit(lambda: pm.head(x, 1000, n=B))
     rows.append(("attpool head (B=%d)" % B, t * mb / B, 2.0 * mb * 3.2e6, 0))
     tot = 0.0
     print("per micro-batch of %d clips (temporal/head rows scaled from B=%d)" % (mb, B))
