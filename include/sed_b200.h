@@ -151,8 +151,11 @@ int sed_bigru_profile(const float* gi, const void* whh_packed, const float* bhh,
 
 /* softmax(q k^T / 8) v for 8 heads of 64.  Replaces ScaledDotProductAttention.forward
  * pytorch/models.py:808-820 and the head split/merge :863-875.
- *   qkv [B, T, 1536] f32 = [q | k | v], head h = columns h*64..h*64+63; out16 [B, T, 512] 16-bit. */
-int sed_mha_core(const float* qkv, int B, int T, void* out16, int dtype, void* stream);
+ *   qkv rows of 1536 f32 = [q | k | v], head h = columns h*64..h*64+63; out16 rows of 512 16-bit values.
+ *   Row of (clip b, step t) = b*row_stride_b + t*row_stride_t in both tensors: (0, 0) selects the clip-major
+ *   default (1, T); (Bp, 1) is time-major over a batch padded to Bp clips. */
+int sed_mha_core(const float* qkv, int B, int T, long row_stride_t, long row_stride_b, void* out16, int dtype,
+                 void* stream);
 
 /* Frame-attention pooling + framewise interpolation/padding.
  * Replaces AttBlock.forward pytorch/models.py:161-169, interpolate :84-95, pad_framewise_output :65-81.

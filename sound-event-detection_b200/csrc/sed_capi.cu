@@ -154,9 +154,10 @@ int sed_fcpool(const float* x, int B, int T, const float* w, const float* b, int
   return sed::fcpool_launch(x, B, T, w, b, classes, ratio, use_max, clip, frame, as_stream(stream));
 }
 
-int sed_mha_core(const float* qkv, int B, int T, void* out16, int dtype, void* stream) {
+int sed_mha_core(const float* qkv, int B, int T, long row_stride_t, long row_stride_b, void* out16, int dtype,
+                 void* stream) {
   SED_REQUIRE(qkv); SED_REQUIRE(out16);
-  return sed::mha_core_launch(qkv, B, T, out16, dtype, as_stream(stream));
+  return sed::mha_core_launch(qkv, B, T, row_stride_t, row_stride_b, out16, dtype, as_stream(stream));
 }
 
 int sed_attpool(const float* x, int B, int T, const float* w_att, const float* b_att, const float* w_cla,

@@ -54,7 +54,7 @@ int events_launch(const float* frames, int n_clips, int n_frames, int classes, c
                   const int* n_smooth, const int* n_salt, int max_events, int* events, int* counts,
                   cudaStream_t stream);
 
-int mha_core_launch(const float* qkv, int B, int T, void* out16, int dtype, cudaStream_t stream);
+int mha_core_launch(const float* qkv, int B, int T, long rs_t, long rs_b, void* out16, int dtype, cudaStream_t stream);
 
 int attpool_launch(const float* x, int B, int T, const float* w_att, const float* b_att, const float* w_cla,
                    const float* b_cla, int ratio, int frames_out, float* clip, float* frame, float* cla_t,

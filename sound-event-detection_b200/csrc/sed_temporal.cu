@@ -21,14 +21,17 @@ namespace sed {
 // CTA `q` of the cluster owns hidden units 64q..64q+63 of all three gates: its 192x256 slice of W_hh (two packed
 // 96-row [r|z|n] x 32-unit blocks) stays resident in shared memory for all T steps and its 16 warps keep the
 // float32 state of those units in registers.  Per step every CTA
-//   (1) issues 2 x 16 tcgen05.mma (M = 128 clips, N = 96, K = 256) against the full 16-bit h_{t-1} [128 x 256] in
-//       its shared memory (UMMA A operand, SWIZZLE_128B, double buffered), one commit per 32-unit half so the warps
-//       of the first half start while the second half is still in the tensor pipe;
-//   (2) runs the gate math for its 64 units and writes h_t (f32) to the output;
-//   (3) every warp stores the 16-bit copy of its piece of h_t straight into the A buffer of all four CTAs
-//       (st.shared::cluster, swizzled layout) and release-arrives on each CTA's a_full mbarrier.
-// No global-memory round trip, no CTA-wide barrier and no generic->async proxy fence over global memory
-// (fence.proxy.async lowers to MEMBAR.GPU, several microseconds per step) are on the step's critical path.
+//   (1) issues 16 tcgen05.mma (M = 128 clips, N = 192, K = 256) against the full 16-bit h_{t-1} [128 x 256] in its
+//       shared memory (UMMA A operand, SWIZZLE_128B, double buffered).  K-chunk kc of that operand is exactly the
+//       slice produced by CTA kc, so the four MMAs of a chunk go out as soon as that slice has landed;
+//   (2) runs the gate math for its 64 units (one reciprocal shared by four sigmoids / two tanh: the phase is
+//       MUFU-bound) and writes h_t (f32) to the output in coalesced 128-clip blocks;
+//   (3) stores the 16-bit copy of its slice of h_t into its own A buffer; the last warp to finish ships the
+//       contiguous 16 KB slice to the three peers with bulk shared->distributed-shared copies that complete bytes
+//       on the peers' per-slice mbarriers.
+// No global-memory round trip and no generic->async proxy fence over global memory (fence.proxy.async lowers to
+// MEMBAR.GPU, several microseconds per step) sit on the step's critical path; the exchange itself runs at the
+// ~12-17 B/clk per SM that distributed shared memory delivers.
 // Sixteen clusters (B = 1024, both directions) are resident at once; an 8-CTA cluster design fits only 15.
 constexpr int kGruCluster = 4;
 constexpr int kGruRows = 192;                        // 64 hidden units x 3 gates = two 96-row packed blocks
@@ -36,8 +39,8 @@ constexpr int kGruWBytes = 4 * kGruRows * 128;       // 4 k-chunks x 192 rows x 
 constexpr int kGruABytes = 4 * 16384;                // 128 clips x 256 k x 2 B (one buffer)
 constexpr int kGruSmem = 1024 + kGruWBytes + 2 * kGruABytes + 1024;
 constexpr int kGruWarps = 16;
-constexpr int kGruThreads = 32 * kGruWarps;          // every warp is a gate-math warp; warp kGruIssueWarp's lane 0
-constexpr int kGruIssueWarp = 8;                     // also issues the MMAs (a second-half warp: it has the slack)
+constexpr int kGruThreads = 32 * kGruWarps;          // 16 gate-math warps (a 17th warp would cap registers at 96)
+constexpr int kGruIssueWarp = 8;                     // lane 0 of this warp also issues the MMAs
 
 SED_DEVICE_INLINE float ex2_approx(float x) {
   float y;
@@ -90,12 +93,26 @@ SED_DEVICE_INLINE void tma_load_2d_mcast(void* dst, const CUtensorMap* m, uint64
       : "memory");
 }
 
+// bulk copy own shared memory -> a peer CTA's shared memory, completing `bytes` on the peer's mbarrier
+SED_DEVICE_INLINE void bulk_copy_to_peer(uint32_t dst_cluster_addr, const void* src_smem, uint32_t bytes,
+                                         uint32_t mbar_cluster_addr) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   dst_cluster_addr),
+               "r"(smem_u32(src_smem)), "r"(bytes), "r"(mbar_cluster_addr)
+               : "memory");
+}
+SED_DEVICE_INLINE void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 SED_DEVICE_INLINE void st_cluster_v4(uint32_t addr, const uint4& v) {
   asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
 }
-SED_DEVICE_INLINE void mbar_arrive_release_cluster_addr(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+// 16-byte store into a peer CTA's shared memory that also completes 16 bytes on that CTA's mbarrier: the data is
+// visible to whoever observes the barrier phase complete -- no separate release fence / arrive on the producer side
+SED_DEVICE_INLINE void st_async_v4(uint32_t cluster_addr, const uint4& v, uint32_t cluster_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                   cluster_addr),
+               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(cluster_mbar)
+               : "memory");
 }
 
 template <typename T>
@@ -108,10 +125,11 @@ gru_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ gi
   uint8_t* smem_a = smem + kGruWBytes;    // [2][4][128 rows][128 B]  h (double buffered)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + 2 * kGruABytes);
   uint64_t* w_full = bars;
-  uint64_t* a_full = bars + 1;      // [2]  64 arrivals each: 16 warps x 4 CTAs
-  uint64_t* acc_full = bars + 3;    // [2]  one per 32-unit half
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
-  float* s_bias = reinterpret_cast<float*>(bars + 8);  // [3][64] b_hh of this CTA's units
+  uint64_t* a_full = bars + 1;      // [2 buffers][4 source CTAs]: the 16 KB slice of h from CTA kc has landed
+  uint64_t* acc_full = bars + 9;    // all 16 MMAs of the step have completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  unsigned int* s_done = reinterpret_cast<unsigned int*>(bars + 11);  // warps that finished their piece of h_t
+  float* s_bias = reinterpret_cast<float*>(bars + 12);  // [3][64] b_hh of this CTA's units
   // profiling hook (stamps != nullptr): CTA 0 records clock64() at a few points of steps 8..15
   const bool prof = stamps != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
 #define GRU_STAMP(step, slot)                                                       \
@@ -131,13 +149,18 @@ gru_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ gi
   if (threadIdx.x < 192)
     s_bias[threadIdx.x] = bhh[dir * 768 + (threadIdx.x >> 6) * 256 + q * 64 + (threadIdx.x & 63)];
   if (warp == 0 && lane == 0) {
+    *s_done = 0;
     tma_prefetch_desc(&tmW);
     mbar_init(w_full, 1);
-    mbar_init(a_full, kGruCluster * kGruWarps);
-    mbar_init(a_full + 1, kGruCluster * kGruWarps);
+    for (int i = 0; i < 8; ++i) mbar_init(a_full + i, 1);  // own slice: the shipping thread's arrive; peers: arming
     mbar_init(acc_full, 1);
-    mbar_init(acc_full + 1, 1);
     fence_barrier_init();
+    // arm the peer slices of both h buffers: h_0 -> buffer 0 (read at step 1), h_1 -> buffer 1 (read at step 2)
+    for (int kc = 0; kc < kGruCluster; ++kc) {
+      if (kc == q) continue;
+      if (Tn > 1) mbar_expect_tx(a_full + kc, 16384);
+      if (Tn > 2) mbar_expect_tx(a_full + 4 + kc, 16384);
+    }
     mbar_expect_tx(w_full, kGruWBytes);
 #pragma unroll
     for (int kc = 0; kc < 4; ++kc)
@@ -153,137 +176,177 @@ gru_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ gi
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int quarter = warp & 3;             // TMEM lane quarter this warp may access
-  const int g = warp >> 2;                  // which 16 of the CTA's 64 hidden units this warp owns
-  const int half = g >> 1;                  // 32-unit half (accumulator columns half*96 ..)
-  const int m = quarter * 32 + lane;        // clip row of this thread
-  const int ul = g * 16;                    // first local unit of this thread
-  const int u0 = q * 64 + ul;               // first hidden unit of this thread
-  const bool issuer = warp == kGruIssueWarp;
-  const bool stamper = prof && warp == 0 && lane == 0;
-  float h[16];
+  {
+    // ---------------- 16 gate-math warps; lane 0 of warp kGruIssueWarp also issues the MMAs ----------------
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+    const int g = warp >> 2;                  // which 16 of the CTA's 64 hidden units this warp owns
+    const int m = quarter * 32 + lane;        // clip row of this thread
+    const int ul = g * 16;                    // first local unit of this thread
+    const int u0 = q * 64 + ul;               // first hidden unit of this thread
+    const bool stamper = prof && warp == 0 && lane == 0;
+    float h[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) h[j] = 0.0f;
-  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * 96 + (g & 1) * 16;
-  // exchange addresses: this thread's two 16-byte units of row m in chunk q of the A buffer (SWIZZLE_128B: unit u of
-  // row m sits at u ^ (m & 7)), in each of the four CTAs; lanes 0..3 signal CTA `lane`
-  const uint32_t xoff0 = q * 16384 + m * 128 + (((2 * g) ^ (m & 7)) << 4);
-  const uint32_t xoff1 = q * 16384 + m * 128 + (((2 * g + 1) ^ (m & 7)) << 4);
-  uint32_t a_remote[kGruCluster];
+    for (int j = 0; j < 16; ++j) h[j] = 0.0f;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + ul + (g >> 1) * 64;
+    // exchange addresses: this thread's two 16-byte units of row m in chunk q of the A buffer (SWIZZLE_128B: unit u
+    // of row m sits at u ^ (m & 7))
+    const uint32_t xoff0 = q * 16384 + m * 128 + (((2 * g) ^ (m & 7)) << 4);
+    const uint32_t xoff1 = q * 16384 + m * 128 + (((2 * g + 1) ^ (m & 7)) << 4);
+    uint32_t a_remote[kGruCluster - 1], bar_remote[kGruCluster - 1];  // the three peers, starting at rank q + 1
 #pragma unroll
-  for (int d = 0; d < kGruCluster; ++d) a_remote[d] = map_to_cta(smem_a, (q + d) & (kGruCluster - 1));
-  const uint32_t bar_remote = map_to_cta(a_full, lane & (kGruCluster - 1));
+    for (int d = 1; d < kGruCluster; ++d) {
+      a_remote[d - 1] = map_to_cta(smem_a, (q + d) & (kGruCluster - 1));
+      bar_remote[d - 1] = map_to_cta(a_full + q, (q + d) & (kGruCluster - 1));  // the peer's barrier for OUR slice
+    }
+    // gi / out are stored as 128-clip transposed blocks: float4 column c4 of clip row m of block (t, blk) sits at
+    // ((tile * ncol4 + c4) * 128 + m), tile = t * nblk + blk, so every warp-level access is 512 contiguous bytes
+    // (ncol4 = 384 for gi [dir][gate][256], 128 for the output [fwd | bwd]).
+    const size_t gi_col = static_cast<size_t>((dir * 768 + u0) >> 2) * 128 + m;
+    const size_t out_col = static_cast<size_t>((dir * 256 + u0) >> 2) * 128 + m;
+    const float4* gi4 = reinterpret_cast<const float4*>(gi);
+    float4* out4 = reinterpret_cast<float4*>(out);
+    const long tstep = dir ? -1 : 1;
+    long tile = (dir ? static_cast<long>(Tn - 1) : 0L) * nblk + blk;  // tile of the current step
+    const long dtile = tstep * nblk;
 
-  if (issuer && lane == 0) mbar_wait(w_full, 0);
-  __syncwarp();
-
-  for (int s = 0; s < Tn; ++s) {
-    const int t = dir ? (Tn - 1 - s) : s;
-    // output h_t (f32) in the same 128-clip transposed-block layout as gi: float4 column c4 (of 128) of clip row m of
-    // block (t, blk) at ((tile * 128 + c4) * 128 + m) -- coalesced 512-byte stores, consumed by sed_attpool_blocks
-    float4* out_t = reinterpret_cast<float4*>(out) +
-                    ((static_cast<size_t>(t) * nblk + blk) * 128 + ((dir * 256 + u0) >> 2)) * 128 + m;
-    // input projections of this step: gi is stored as 128-clip transposed blocks (float4 column c4 of clip row m of
-    // block (t, clip0/128) at ((tile * 384 + c4) * 128 + m)), so every warp-level load is 512 contiguous bytes.
-    // Issued before the waits so they overlap the exchange and the MMA.
-    const float4* gi_t = reinterpret_cast<const float4*>(gi) +
-                         ((static_cast<size_t>(t) * nblk + blk) * 384 + ((dir * 768 + u0) >> 2)) * 128 + m;
+    // input projections are software-pipelined through the same registers: the values of step s + 1 are loaded as
+    // soon as the gate math of step s has consumed a chunk, so the loads spread over the whole gate phase instead
+    // of bursting into the memory pipe right when the slice has to be shipped
     float4 gr[4], gz[4], gn[4];
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
-      if (!(dbg & 1)) {
-        gr[v] = gi_t[v * 128];
-        gz[v] = gi_t[(64 + v) * 128];
-        gn[v] = gi_t[(128 + v) * 128];
-      } else {
-        gr[v] = gz[v] = gn[v] = make_float4(0, 0, 0, 0);
-      }
+      const float4* p0 = gi4 + static_cast<size_t>(tile) * 384 * 128 + gi_col;
+      gr[v] = p0[v * 128];
+      gz[v] = p0[(64 + v) * 128];
+      gn[v] = p0[(128 + v) * 128];
     }
-    if (issuer) {
-      if (lane == 0) {
-        constexpr uint32_t idesc = umma_idesc_f16(Elem16<T>::kFmt, 128, 96);
-        const int buf = (s + 1) & 1;  // h_{s-1}
-        if (s > 0) {
-          mbar_wait_cluster(a_full + buf, ((s - 1) >> 1) & 1);  // all 64 pieces of h_{s-1} are in this CTA's buffer
-          fence_proxy_async_smem();  // peers' generic-proxy stores into this shared memory -> the UMMA operand reads
+
+    for (int s = 0; s < Tn; ++s) {
+      const bool xchg = s + 1 < Tn;
+      const uint32_t boff = (s & 1) * kGruABytes;
+      const float4* gi_next = gi4 + static_cast<size_t>(tile + dtile) * 384 * 128 + gi_col;  // step s + 1 (if any)
+      float4* out_t = out4 + static_cast<size_t>(tile) * 128 * 128 + out_col;
+      if (s + 3 < Tn && (lane & 7) == 0 && !(dbg & 8)) {
+        // pull the blocks of step s + 3 into L2 (one 128-byte line per 8 lanes)
+        const float4* pf = gi4 + static_cast<size_t>(tile + 3 * dtile) * 384 * 128 + gi_col;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          prefetch_l2(pf + v * 128);
+          prefetch_l2(pf + (64 + v) * 128);
+          prefetch_l2(pf + (128 + v) * 128);
         }
-        GRU_STAMP(s, 0);
-        tc_fence_after();
-        const uint32_t a_base = smem_u32(smem_a + buf * kGruABytes), b_base = smem_u32(smem_w);
+      }
+      if (warp == kGruIssueWarp) {
+        if (lane == 0) {
+          // K-chunk kc of the A operand is exactly the slice of h_{s-1} produced by CTA kc: the MMAs of a chunk are
+          // issued as soon as that slice has landed (own slice first), so only the last slice's quarter of the
+          // tensor work is exposed after the exchange.  (The gi loads of this warp were issued during the previous
+          // gate phase, so nothing of its own delays this thread on its way here.)
+          constexpr uint32_t idesc = umma_idesc_f16(Elem16<T>::kFmt, 128, kGruRows);
+          const int buf = (s + 1) & 1;  // h_{s-1}
+          const uint32_t a_base = smem_u32(smem_a + buf * kGruABytes), b_base = smem_u32(smem_w);
+          if (s == 0) mbar_wait(w_full, 0);
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
+          for (int i = 0; i < kGruCluster; ++i) {
+            const int kc = (q + i) & (kGruCluster - 1);
+            if (s > 0) {
+              if (i == 0) GRU_STAMP(s, 3);
+              mbar_wait_cluster(a_full + buf * 4 + kc, ((s - 1) >> 1) & 1);
+              if (kc != q && s + 2 < Tn) mbar_expect_tx(a_full + buf * 4 + kc, 16384);  // re-arm for h_{s+1}
+              // no proxy fence needed: peer slices are written by the async proxy (bulk copies) and the local
+              // warps fenced their generic stores before arriving
+            }
+            if (i == 0) GRU_STAMP(s, 0);
+            tc_fence_after();
 #pragma unroll
-          for (int kc = 0; kc < 4; ++kc) {
+            for (int k = 0; k < 4; ++k)
+              umma_f16(tmem_base, umma_desc_sw128(a_base + kc * 16384 + k * 32, 1024),
+                       umma_desc_sw128(b_base + kc * (kGruRows * 128) + k * 32, 1024), idesc, (i | k) ? 1u : 0u);
+            if (i == 0) GRU_STAMP(s, 1);
+          }
+          umma_commit(acc_full);
+          GRU_STAMP(s, 2);
+        }
+        __syncwarp();
+      }
+      if (prof && s == 12 && lane == 0) stamps[(warp & 7) * 12 + 6 + (warp >> 3)] = clock64();  // per-warp top
+      mbar_wait(acc_full, s & 1);
+      if (stamper) GRU_STAMP(s, 4);
+      tc_fence_after();
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_f16(tmem_base + hf * 96, umma_desc_sw128(a_base + kc * 16384 + k * 32, 1024),
-                       umma_desc_sw128(b_base + kc * (kGruRows * 128) + hf * (96 * 128) + k * 32, 1024), idesc,
-                       (kc | k) ? 1u : 0u);
+      for (int c = 0; c < 2; ++c) {  // two chunks of 8 units
+        uint32_t ar[8], az[8], an[8];
+        tmem_ld8(taddr + c * 8, ar);
+        tmem_ld8(taddr + 32 + c * 8, az);
+        tmem_ld8(taddr + 64 + c * 8, an);
+        tmem_ld_wait();
+        if (c == 1) tc_fence_before();  // this thread's TMEM loads of step s are done before its arrive below
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const float4 grv = gr[2 * c + v], gzv = gz[2 * c + v], gnv = gn[2 * c + v];
+          const float gre[4] = {grv.x, grv.y, grv.z, grv.w};
+          const float gze[4] = {gzv.x, gzv.y, gzv.z, gzv.w};
+          const float gne[4] = {gnv.x, gnv.y, gnv.z, gnv.w};
+#pragma unroll
+          for (int e = 0; e < 4; e += 2) {
+            const int jc = v * 4 + e;          // index within the chunk
+            const int jj = c * 8 + jc;         // index within the thread's 16 units
+            const int j = ul + jj;             // local unit (bias index)
+            float r0, z0, r1, z1, n0, n1;
+            sigmoid4(gre[e] + __uint_as_float(ar[jc]) + s_bias[j], gze[e] + __uint_as_float(az[jc]) + s_bias[64 + j],
+                     gre[e + 1] + __uint_as_float(ar[jc + 1]) + s_bias[j + 1],
+                     gze[e + 1] + __uint_as_float(az[jc + 1]) + s_bias[64 + j + 1], r0, z0, r1, z1);
+            tanh2(fmaf(r0, __uint_as_float(an[jc]) + s_bias[128 + j], gne[e]),
+                  fmaf(r1, __uint_as_float(an[jc + 1]) + s_bias[128 + j + 1], gne[e + 1]), n0, n1);
+            h[jj] = fmaf(z0, h[jj] - n0, n0);              // (1 - z) n + z h
+            h[jj + 1] = fmaf(z1, h[jj + 1] - n1, n1);
+          }
+        }
+        if (xchg) {
+          // 16-bit copy of these 8 units of h_t into this CTA's own buffer (s & 1), chunk q (swizzled layout); rows
+          // of padded clips >= B carry well-defined values too
+          uint4 pk;
+          pk.x = Elem16<T>::pack2(h[8 * c], h[8 * c + 1]);     pk.y = Elem16<T>::pack2(h[8 * c + 2], h[8 * c + 3]);
+          pk.z = Elem16<T>::pack2(h[8 * c + 4], h[8 * c + 5]); pk.w = Elem16<T>::pack2(h[8 * c + 6], h[8 * c + 7]);
+          *reinterpret_cast<uint4*>(smem_a + boff + (c ? xoff1 : xoff0)) = pk;
+          if (!(dbg & 1)) {  // this chunk's gi registers are free: fetch the values of step s + 1
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+              gr[2 * c + v] = gi_next[(2 * c + v) * 128];
+              gz[2 * c + v] = gi_next[(64 + 2 * c + v) * 128];
+              gn[2 * c + v] = gi_next[(128 + 2 * c + v) * 128];
             }
           }
-          umma_commit(acc_full + hf);
-          GRU_STAMP(s, 1 + hf);
+        }
+        if (!(dbg & 4)) {  // h_t (f32) of these 8 units
+          out_t[(2 * c) * 128] = make_float4(h[8 * c], h[8 * c + 1], h[8 * c + 2], h[8 * c + 3]);
+          out_t[(2 * c + 1) * 128] = make_float4(h[8 * c + 4], h[8 * c + 5], h[8 * c + 6], h[8 * c + 7]);
         }
       }
-      __syncwarp();
-    }
-    mbar_wait_suspend(acc_full + half, s & 1);
-    if (stamper) GRU_STAMP(s, 4);
-    tc_fence_after();
+      if (stamper) GRU_STAMP(s, 5);
+      if (xchg) {
+        // the last warp to finish ships the CTA's complete 16 KB slice (chunk q is contiguous) to the three peers
+        // with bulk shared->distributed-shared copies that complete bytes on the peers' per-slice barriers
+        fence_proxy_async_smem();  // this thread's generic stores -> the bulk copy's (async proxy) reads
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence_block();
+          const unsigned int prev = atomicAdd(s_done, 1u);
+          if (prev == static_cast<unsigned int>(kGruWarps * (s + 1) - 1)) {
+            __threadfence_block();
+            fence_proxy_async_smem();
+            const uint8_t* src = smem_a + boff + q * 16384;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {  // two chunks of 8 units
-      uint32_t ar[8], az[8], an[8];
-      tmem_ld8(taddr + c * 8, ar);
-      tmem_ld8(taddr + 32 + c * 8, az);
-      tmem_ld8(taddr + 64 + c * 8, an);
-      tmem_ld_wait();
-#pragma unroll
-      for (int v = 0; v < 2; ++v) {
-        const float4 grv = gr[2 * c + v], gzv = gz[2 * c + v], gnv = gn[2 * c + v];
-        const float gre[4] = {grv.x, grv.y, grv.z, grv.w};
-        const float gze[4] = {gzv.x, gzv.y, gzv.z, gzv.w};
-        const float gne[4] = {gnv.x, gnv.y, gnv.z, gnv.w};
-#pragma unroll
-        for (int e = 0; e < 4; e += 2) {
-          const int jc = v * 4 + e;          // index within the chunk
-          const int jj = c * 8 + jc;         // index within the thread's 16 units
-          const int j = ul + jj;             // local unit (bias index)
-          float r0, z0, r1, z1, n0, n1;
-          sigmoid4(gre[e] + __uint_as_float(ar[jc]) + s_bias[j], gze[e] + __uint_as_float(az[jc]) + s_bias[64 + j],
-                   gre[e + 1] + __uint_as_float(ar[jc + 1]) + s_bias[j + 1],
-                   gze[e + 1] + __uint_as_float(az[jc + 1]) + s_bias[64 + j + 1], r0, z0, r1, z1);
-          tanh2(fmaf(r0, __uint_as_float(an[jc]) + s_bias[128 + j], gne[e]),
-                fmaf(r1, __uint_as_float(an[jc + 1]) + s_bias[128 + j + 1], gne[e + 1]), n0, n1);
-          h[jj] = fmaf(z0, h[jj] - n0, n0);              // (1 - z) n + z h
-          h[jj + 1] = fmaf(z1, h[jj + 1] - n1, n1);
+            for (int d = 0; d < kGruCluster - 1; ++d)
+              bulk_copy_to_peer(a_remote[d] + boff + q * 16384, src, 16384, bar_remote[d] + (s & 1) * 32);
+            mbar_arrive(a_full + (s & 1) * 4 + q);  // own slice in place (every local warp drained its TMEM loads)
+            GRU_STAMP(s, 9);
+          }
         }
+        if (stamper) GRU_STAMP(s, 8);
+        if (prof && s == 12 && lane == 0) stamps[(warp & 7) * 12 + 10 + (warp >> 3)] = clock64();  // per-warp finish
       }
-    }
-    if (stamper) GRU_STAMP(s, 5);
-    if (s + 1 < Tn) {
-      // 16-bit copy of this thread's 16 units of h_t into buffer (s & 1) of all four CTAs (rows of padded clips
-      // >= B carry well-defined values too: their gi reads as zero)
-      uint4 p0, p1;
-      p0.x = Elem16<T>::pack2(h[0], h[1]);   p0.y = Elem16<T>::pack2(h[2], h[3]);
-      p0.z = Elem16<T>::pack2(h[4], h[5]);   p0.w = Elem16<T>::pack2(h[6], h[7]);
-      p1.x = Elem16<T>::pack2(h[8], h[9]);   p1.y = Elem16<T>::pack2(h[10], h[11]);
-      p1.z = Elem16<T>::pack2(h[12], h[13]); p1.w = Elem16<T>::pack2(h[14], h[15]);
-      const uint32_t boff = (s & 1) * kGruABytes;
-#pragma unroll
-      for (int d = 0; d < kGruCluster; ++d) {
-        if ((dbg & 2) && d > 0) break;
-        st_cluster_v4(a_remote[d] + boff + xoff0, p0);
-        st_cluster_v4(a_remote[d] + boff + xoff1, p1);
-      }
-      tc_fence_before();
-      __syncwarp();
-      // release at cluster scope: the warp's piece of h_t is written everywhere and its TMEM loads have drained
-      if (lane < kGruCluster) mbar_arrive_release_cluster_addr(bar_remote + (s & 1) * 8);
-      if (stamper) GRU_STAMP(s, 8);
-    }
-    if (!(dbg & 4)) {
-#pragma unroll
-      for (int v = 0; v < 4; ++v) out_t[v * 128] = make_float4(h[4 * v], h[4 * v + 1], h[4 * v + 2], h[4 * v + 3]);
+      tile += dtile;
     }
   }
 
@@ -373,23 +436,25 @@ int gru_launch(const float* gi, const void* whh_packed, const float* bhh, int B,
 // =================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(128)
-mha_core_kernel(const float* __restrict__ qkv, int Tn, T* __restrict__ out16) {
+mha_core_kernel(const float* __restrict__ qkv, int Tn, long rs_t, long rs_b, T* __restrict__ out16) {
   extern __shared__ float smem_kv[];
   float* Ks = smem_kv;            // [Tn][64]
   float* Vs = smem_kv + Tn * 64;  // [Tn][64]
   const int head = blockIdx.x, b = blockIdx.y;
-  const float* base = qkv + static_cast<size_t>(b) * Tn * 1536;
+  // row of (clip b, step t) = b*rs_b + t*rs_t: (Tn, 1) clip-major, (1, Bp) time-major over the padded batch
+  const float* base = qkv + static_cast<size_t>(b) * rs_b * 1536;
+  const size_t rstep = static_cast<size_t>(rs_t) * 1536;
   for (int i = threadIdx.x; i < Tn * 16; i += blockDim.x) {
     const int row = i >> 4, c4 = i & 15;
     reinterpret_cast<float4*>(Ks)[i] =
-        *reinterpret_cast<const float4*>(base + static_cast<size_t>(row) * 1536 + 512 + head * 64 + c4 * 4);
+        *reinterpret_cast<const float4*>(base + row * rstep + 512 + head * 64 + c4 * 4);
     reinterpret_cast<float4*>(Vs)[i] =
-        *reinterpret_cast<const float4*>(base + static_cast<size_t>(row) * 1536 + 1024 + head * 64 + c4 * 4);
+        *reinterpret_cast<const float4*>(base + row * rstep + 1024 + head * 64 + c4 * 4);
   }
   __syncthreads();
   for (int qi = threadIdx.x; qi < Tn; qi += blockDim.x) {
     float q[64], o[64];
-    const float* qp = base + static_cast<size_t>(qi) * 1536 + head * 64;
+    const float* qp = base + qi * rstep + head * 64;
 #pragma unroll
     for (int d = 0; d < 64; d += 4) {
       const float4 v = *reinterpret_cast<const float4*>(qp + d);
@@ -430,7 +495,7 @@ mha_core_kernel(const float* __restrict__ qkv, int Tn, T* __restrict__ out16) {
       }
     }
     const float inv = 1.0f / l;
-    T* op = out16 + (static_cast<size_t>(b) * Tn + qi) * 512 + head * 64;
+    T* op = out16 + (static_cast<size_t>(b) * rs_b + static_cast<size_t>(qi) * rs_t) * 512 + head * 64;
 #pragma unroll
     for (int d = 0; d < 64; d += 8) {
       uint4 pk;
@@ -443,7 +508,12 @@ mha_core_kernel(const float* __restrict__ qkv, int Tn, T* __restrict__ out16) {
   }
 }
 
-int mha_core_launch(const float* qkv, int B, int Tn, void* out16, int dtype, cudaStream_t stream) {
+int mha_core_launch(const float* qkv, int B, int Tn, long rs_t, long rs_b, void* out16, int dtype,
+                    cudaStream_t stream) {
+  if (rs_t <= 0 || rs_b <= 0) {
+    rs_t = 1;
+    rs_b = Tn;
+  }
   const size_t smem = static_cast<size_t>(Tn) * 64 * 2 * sizeof(float);
   if (B <= 0 || Tn <= 0 || smem > 200 * 1024) {
     set_error("mha_core: unsupported shape B=%d T=%d", B, Tn);
@@ -454,11 +524,12 @@ int mha_core_launch(const float* qkv, int B, int Tn, void* out16, int dtype, cud
   if (dtype == 0) {
     e = cudaFuncSetAttribute(mha_core_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
-      mha_core_kernel<__half><<<grid, 128, smem, stream>>>(qkv, Tn, reinterpret_cast<__half*>(out16));
+      mha_core_kernel<__half><<<grid, 128, smem, stream>>>(qkv, Tn, rs_t, rs_b, reinterpret_cast<__half*>(out16));
   } else {
     e = cudaFuncSetAttribute(mha_core_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
-      mha_core_kernel<__nv_bfloat16><<<grid, 128, smem, stream>>>(qkv, Tn, reinterpret_cast<__nv_bfloat16*>(out16));
+      mha_core_kernel<__nv_bfloat16><<<grid, 128, smem, stream>>>(qkv, Tn, rs_t, rs_b,
+                                                                   reinterpret_cast<__nv_bfloat16*>(out16));
   }
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {

@@ -411,7 +411,7 @@ class PackedModel:
             raise RuntimeError("%s has no temporal block" % self.model_type)
         qkv = self.linear(flat, self.mha_wqkv, self.mha_bqkv)
         ctx = torch.empty((B * Tp, 512), dtype=self.tdtype, device=self.device)
-        rc = lib.sed_mha_core(capi.ptr(qkv), B, Tp, capi.ptr(ctx), self.dtype_code, stream)
+        rc = lib.sed_mha_core(capi.ptr(qkv), B, Tp, 0, 0, capi.ptr(ctx), self.dtype_code, stream)
         capi.check(rc, "sed_mha_core")
         capi._count()
         out = self.linear(ctx, self.mha_wfc, self.mha_bfc, relu=True)
@@ -442,6 +442,25 @@ class PackedModel:
         if stages is not None:
             stages["gi_blocks"] = gi
         return out
+
+    def mha_tmajor(self, feat_t, B, stages=None):
+        """feat_t [T', Bp, 512] 16-bit (time-major, batch padded to 128) -> relu(fc(attention)) as 128-clip transposed
+        blocks (the layout sed_attpool_blocks consumes)."""
+        lib = capi.load()
+        Tp, Bp, _ = feat_t.shape
+        qkv = self.linear(feat_t.view(Tp * Bp, 512), self.mha_wqkv, self.mha_bqkv)
+        ctx = torch.empty((Tp * Bp, 512), dtype=self.tdtype, device=self.device)
+        if Bp != B:
+            ctx.zero_()  # rows of padding clips are not produced by the attention kernel
+        rc = lib.sed_mha_core(capi.ptr(qkv), B, Tp, Bp, 1, capi.ptr(ctx), self.dtype_code,
+                              capi.current_stream(self.device))
+        capi.check(rc, "sed_mha_core")
+        capi._count()
+        out = self.linear(ctx, self.mha_wfc, self.mha_bfc, relu=True, out_layout=1)
+        if stages is not None:
+            stages["qkv_tmajor"] = qkv
+            stages["ctx_tmajor"] = ctx
+        return out.view(Tp, Bp // 128, 128, 128, 4)
 
     def frames_for(self, Tp):
         """Number of framewise rows the model returns for T' pooled steps (x8 interpolation; only
@@ -575,8 +594,9 @@ class PackedModel:
 
     def _alloc_features(self, n, Tp):
         """Feature buffers of the conv stack and slot(b0, b1) -> conv_stack keyword arguments for one micro-batch.
-        GRU models get the features time-major ([T', Bp, 512]); the others clip-major ([n, T', 512])."""
-        if self.temporal_kind == "gru":
+        Models with a temporal block get the features time-major ([T', Bp, 512]: the GRU / MultiHead kernels then
+        read and write 128-clip blocks), the others clip-major ([n, T', 512])."""
+        if self.temporal_kind is not None:
             feat_t = self.alloc_feat_tmajor(n, Tp)
             Bp = feat_t.shape[1]
             return feat_t, None, (lambda b0, b1: {"feat_out": feat_t[0, b0:b1], "feat_strides": (1, Bp)})
@@ -586,9 +606,9 @@ class PackedModel:
                                                 "feat32": None if feat32 is None else feat32[b0:b1]})
 
     def _temporal_or_features(self, feat16, feat32, n, stages=None):
-        if self.temporal_kind == "gru":
-            return self.gru_tmajor(feat16, n, stages)
-        return self.temporal(feat16, stages) if self.temporal_kind else feat32
+        if self.temporal_kind is None:
+            return feat32
+        return (self.gru_tmajor if self.temporal_kind == "gru" else self.mha_tmajor)(feat16, n, stages)
 
     def _run(self, n, Tp, conv_call, stages=None, want_norm_att=False):
         """Shared tail of forward / forward_windows: conv stack per micro-batch (conv_call(b0, b1, feat16, feat32,
@@ -596,7 +616,7 @@ class PackedModel:
         feat16, feat32, slot = self._alloc_features(n, Tp)
         conv_call(slot)
         x = self._temporal_or_features(feat16, feat32, n, stages)
-        if self.temporal_kind == "gru":
+        if x.dim() == 5:
             feat16 = feat16[:, :n].transpose(0, 1)  # clip-major view for the stage dump
         wants_cla = self.model_type in ("Cnn_9layers_Gru_FrameAtt", "Cnn_9layers_FrameAtt")
         clip, frame, cla, natt = self.head(x, self.frames_for(Tp), want_cla=wants_cla, want_norm_att=want_norm_att, n=n)

@@ -41,7 +41,7 @@ def test_binding_matches_header():
 
 def test_null_pointer_is_rejected_without_a_gpu():
     lib = capi.load()
-    rc = lib.sed_mha_core(None, 1, 1, None, 0, None)
+    rc = lib.sed_mha_core(None, 1, 1, 0, 0, None, 0, None)
     assert rc == 4  # SED_ERR_NULL
     assert b"null pointer" in lib.sed_last_error_string()
 

@@ -20,10 +20,16 @@ for _ in range(3):
     capi.check(rc, "profile")
 torch.cuda.synchronize()
 st = stamps.cpu().view(8, 12)
-names = ["issuer: a_full seen", "issuer: half 0 committed", "issuer: half 1 committed", "-", "warp0: acc seen",
-         "warp0: gates done", "-", "-", "warp0: stores + arrive sent"]
+names = ["issuer: own slice of h seen", "issuer: own-chunk MMAs issued", "issuer: all MMAs committed",
+         "issuer: starts waiting", "warp0: acc seen", "warp0: gates done", "(step 12: per-warp top, warps 0-7)",
+         "(step 12: per-warp top, warps 8-15)", "warp0: arrive sent", "last warp: slice shipped"]
 for s_ in range(1, 5):
-    print("step", 8 + s_, " ".join("s%d=%d" % (i, st[s_, i].item() - st[s_, 0].item()) for i in (0, 1, 2, 4, 5, 8)),
+    print("step", 8 + s_, " ".join("s%d=%d" % (i, st[s_, i].item() - st[s_, 0].item()) for i in (3, 0, 1, 2, 4, 5, 8, 9)),
           "| step period", st[s_, 0].item() - st[s_ - 1, 0].item())
 for i, n in enumerate(names):
     print(i, n)
+
+base12 = st[4, 0].item()
+print("step 12 per-warp (relative to own-slice-seen): gi loads issued / finish")
+for w in range(16):
+    print("  warp %2d: top %6d  finish %6d" % (w, st[w % 8, 6 + w // 8].item() - base12, st[w % 8, 10 + w // 8].item() - base12))
