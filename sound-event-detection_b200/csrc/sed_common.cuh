@@ -28,6 +28,15 @@ SED_DEVICE_INLINE uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// 1024-byte aligned start of the dynamic shared memory window, computed as pointer + offset so that the compiler keeps
+// the shared address space (an integer round trip turns every later access into a generic LD/ST)
+SED_DEVICE_INLINE uint8_t* align_smem_1024(uint8_t* p) { return p + ((1024u - (smem_u32(p) & 1023u)) & 1023u); }
+
+// x / d for a launch-invariant divisor: magic = ceil(2^32 / d) (0 encodes d == 1); exact while x * d < 2^32
+SED_DEVICE_INLINE int fast_div(int x, uint32_t magic) {
+  return magic ? static_cast<int>(__umulhi(static_cast<uint32_t>(x), magic)) : x;
+}
+
 SED_DEVICE_INLINE bool elect_one() {
   uint32_t pred = 0;
   asm volatile(

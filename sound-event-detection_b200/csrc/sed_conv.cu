@@ -409,6 +409,15 @@ int conv3x3_launch(const void* x, int NB, int H, int W, int cin, const void* wpa
   p.tiles_h = (H + 15) / 16;
   p.tiles_w = W / 8;
   p.num_tiles = NB * p.tiles_h * p.tiles_w;
+  {
+    const unsigned long long per_img = static_cast<unsigned long long>(p.tiles_h) * p.tiles_w;
+    if (per_img * (static_cast<unsigned long long>(p.num_tiles) + 4096) >= (1ull << 32)) {
+      set_error("conv3x3: too many tiles for the index arithmetic (NB=%d H=%d W=%d)", NB, H, W);
+      return SED_ERR_BAD_SHAPE;
+    }
+    p.magic_img = per_img > 1 ? static_cast<uint32_t>(((1ull << 32) + per_img - 1) / per_img) : 0u;
+    p.magic_w = p.tiles_w > 1 ? static_cast<uint32_t>(((1ull << 32) + p.tiles_w - 1) / p.tiles_w) : 0u;
+  }
   p.cout = cout;
   p.scale = scale; p.shift = shift;
   p.out = out; p.out2 = (mode == EPI_FREQMEAN) ? out_f32 : nullptr;

@@ -26,6 +26,7 @@ enum : int { EPI_STORE = 0, EPI_POOL = 1, EPI_FREQMEAN = 2, EPI_LINEAR = 3 };
 struct ConvParams {
   int NB, H, W;            // images, rows, cols of the (same-size) convolution; W % 8 == 0
   int tiles_h, tiles_w;    // ceil(H/16), W/8
+  uint32_t magic_img, magic_w;  // fast_div magics for tiles_h*tiles_w and tiles_w
   int num_tiles;           // conv: NB*tiles_h*tiles_w ; linear: ceil(M/128)
   int cout;                // total output channels (row stride of the output)
   int nslices;             // cout / BN
@@ -253,7 +254,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int ACC_STAGES = Cfg::ACC_STAGES;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::SMEM_A;
   uint8_t* smem_stg = smem_b + Cfg::B_BYTES;  // [NSTG][128 px][128 B] SWIZZLE_128B staging for TMA stores
@@ -313,9 +314,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   auto tile_coords = [&](int tile, int& n, int& h0, int& w0) {
     const int per_img = p.tiles_h * p.tiles_w;
-    n = tile / per_img;
+    n = fast_div(tile, p.magic_img);
     const int rem = tile - n * per_img;
-    const int th = rem / p.tiles_w;
+    const int th = fast_div(rem, p.magic_w);
     h0 = th * 16;
     w0 = (rem - th * p.tiles_w) * 8;
   };
@@ -531,7 +532,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   constexpr int NCHUNK = Cfg::NCHUNK;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::SMEM_A;
   uint8_t* smem_stg = smem_b + Cfg::B_BYTES;
@@ -592,9 +593,9 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   auto tile_coords = [&](int tile, int& n, int& h0, int& w0) {
     const int per_img = p.tiles_h * p.tiles_w;
-    n = tile / per_img;
+    n = fast_div(tile, p.magic_img);
     const int rem = tile - n * per_img;
-    const int th = rem / p.tiles_w;
+    const int th = fast_div(rem, p.magic_w);
     h0 = th * 16;
     w0 = (rem - th * p.tiles_w) * 8;
   };

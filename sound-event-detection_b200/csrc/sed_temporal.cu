@@ -120,7 +120,7 @@ __global__ void __cluster_dims__(kGruCluster, 1, 1) __launch_bounds__(kGruThread
 gru_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ gi, const float* __restrict__ bhh, int B,
            int Tn, float* __restrict__ out, long long* __restrict__ stamps, int dbg) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* smem_w = smem;                 // [4][192 rows][128 B]   resident W_hh slice
   uint8_t* smem_a = smem + kGruWBytes;    // [2][4][128 rows][128 B]  h (double buffered)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + 2 * kGruABytes);
