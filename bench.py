@@ -159,7 +159,7 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (one JSON line only)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL banners / warnings never reach stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     capi.load()
 
