@@ -499,7 +499,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // warp1 = TMEM allocation (+ MMA issue on the leader only, commits multicast to both CTAs),
 // warps2-9 = epilogue of the CTA's own 128 accumulator rows.
 // =================================================================================================
-template <int CIN, int BN, int EPI, int SA, int ACC, bool BRES, int NT, int SB>
+template <int CIN, int BN, int EPI, int SA, int ACC, bool BRES, int NT, int SB, int EG = 1>
 struct Conv2Cfg {
   static constexpr int NCHUNK = CIN / 64;
   static constexpr int TAPS = 9;
@@ -516,18 +516,21 @@ struct Conv2Cfg {
   static constexpr int ACC_COLS = NT * BN;
   static constexpr int TMEM_COLS = (ACC * ACC_COLS <= 32) ? 32 : (ACC * ACC_COLS <= 64) ? 64
                                    : (ACC * ACC_COLS <= 128) ? 128 : (ACC * ACC_COLS <= 256) ? 256 : 512;
-  static constexpr int THREADS = 64 + 32 * 8;
+  // EG epilogue groups of 8 warps drain alternate accumulator stages.  Measured on conv_block1.conv2 (N = 64): no
+  // gain from EG = 2 -- that layer is bound by the shared-memory pipe (operand reads + TMA writes), not the epilogue
+  static constexpr int THREADS = 64 + 32 * 8 * EG;
+  static_assert(EG == 1 || EPI != EPI_STORE, "the TMA-store staging tiles belong to one epilogue group");
   static_assert(ACC * ACC_COLS <= 512, "TMEM columns");
   static_assert(BN % 32 == 0 && BN <= 256, "pair MMA: N multiple of 16 per CTA half");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-template <typename T, int CIN, int BN, int EPI, int SA, int ACC, bool BRES, int NT, int SB>
+template <typename T, int CIN, int BN, int EPI, int SA, int ACC, bool BRES, int NT, int SB, int EG = 1>
 __global__ void __cluster_dims__(2, 1, 1)
-__launch_bounds__(Conv2Cfg<CIN, BN, EPI, SA, ACC, BRES, NT, SB>::THREADS, 1)
+__launch_bounds__(Conv2Cfg<CIN, BN, EPI, SA, ACC, BRES, NT, SB, EG>::THREADS, 1)
 conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmO, const ConvParams p) {
-  using Cfg = Conv2Cfg<CIN, BN, EPI, SA, ACC, BRES, NT, SB>;
+  using Cfg = Conv2Cfg<CIN, BN, EPI, SA, ACC, BRES, NT, SB, EG>;
   constexpr int TAPS = Cfg::TAPS;
   constexpr int NCHUNK = Cfg::NCHUNK;
 
@@ -693,13 +696,17 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // =============================== epilogue (8 warps, both CTAs) ==========================
+    // =============================== epilogue (EG groups of 8 warps, both CTAs) =============
+    const int ew = warp - 2;
+    const int grp = ew >> 3;            // epilogue group: drains the work items with (index % EG) == grp
     const int quarter = warp & 3;
-    const int chalf = (warp - 2) >> 2;
+    const int chalf = (ew & 7) >> 2;
     constexpr int CPW = Cfg::CPW;
     const bool stg_leader = (lane == 0) && (warp == ((CPW >= 64) ? 2 + 4 * chalf : 2));
-    uint32_t acc = 0, pacc = 0;
-    for (int w = work_begin; w < work_end; w += work_stride) {
+    uint32_t it = 0;
+    for (int w = work_begin; w < work_end; w += work_stride, ++it) {
+      if (EG > 1 && static_cast<int>(it % EG) != grp) continue;
+      const uint32_t acc = it % ACC, pacc = (it / ACC) & 1;
       const int item = BRES ? w : w / p.nslices;
       const int slice = BRES ? fixed_slice : w - item * p.nslices;
       const int ch0 = slice * BN;
@@ -720,7 +727,6 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote_light(&t_empty[acc], 0);
-      if (++acc == ACC) { acc = 0; pacc ^= 1; }
     }
     if (EPI == EPI_STORE && stg_leader) bulk_wait_all0();
   }
