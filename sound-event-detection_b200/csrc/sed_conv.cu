@@ -292,11 +292,12 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   return SED_OK;
 }
 
-template <typename T, int CIN, int BN, int EPI, int SA, int ACC, bool BRES, int NT, int SB, int EG = 1>
+template <typename T, int CIN, int BN, int EPI, int SA, int ACC, bool BRES, int NT, int SB, int EG = 1,
+          bool FUSE1 = false>
 static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvParams& p,
                        cudaStream_t stream) {
-  using Cfg = Conv2Cfg<CIN, BN, EPI, SA, ACC, BRES, NT, SB, EG>;
-  auto kern = conv_umma2_kernel<T, CIN, BN, EPI, SA, ACC, BRES, NT, SB, EG>;
+  using Cfg = Conv2Cfg<CIN, BN, EPI, SA, ACC, BRES, NT, SB, EG, FUSE1>;
+  auto kern = conv_umma2_kernel<T, CIN, BN, EPI, SA, ACC, BRES, NT, SB, EG, FUSE1>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(pair, smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
@@ -431,6 +432,53 @@ int conv3x3_launch(const void* x, int NB, int H, int W, int cin, const void* wpa
   if (dtype == 0) return conv3x3_dispatch<__half>(tmA, tmB, tmO, p, cin, cout, mode, variant, stream);
   if (dtype == 1) return conv3x3_dispatch<__nv_bfloat16>(tmA, tmB, tmO, p, cin, cout, mode, variant, stream);
   set_error("conv3x3: dtype must be 0 (fp16) or 1 (bf16)");
+  return SED_ERR_UNSUPPORTED;
+}
+
+// conv_block1 as one kernel: conv1 (1 -> 64, CUDA cores, float32) feeds conv2's tensor-core operand through shared
+// memory; the [NB, H, 64, 64] intermediate never exists in HBM.
+int conv_block1_launch(const float* x, int NB, int H, int W, const float* w1s, const float* shift1, const void* w2packed,
+                       const float* scale2, const float* shift2, void* out, int dtype, cudaStream_t stream) {
+  if (NB <= 0 || H <= 0 || W <= 0 || (W % 16) != 0) {
+    set_error("conv_block1: bad shape NB=%d H=%d W=%d (W %% 16 == 0)", NB, H, W);
+    return SED_ERR_BAD_SHAPE;
+  }
+  CUtensorMap tmB;
+  {
+    const uint64_t dims[2] = {(uint64_t)9 * 64, (uint64_t)64};
+    const uint64_t str[1] = {(uint64_t)9 * 64 * 2};
+    const uint32_t box[2] = {64, 32};  // each CTA of a pair loads half of the 64 weight rows
+    int rc = make_map(&tmB, dtype, 2, const_cast<void*>(w2packed), dims, str, box);
+    if (rc) return rc;
+  }
+  ConvParams p{};
+  p.NB = NB; p.H = H; p.W = W;
+  p.tiles_h = (H + 15) / 16;
+  p.tiles_w = W / 8;
+  p.num_tiles = NB * p.tiles_h * p.tiles_w;
+  {
+    const unsigned long long per_img = static_cast<unsigned long long>(p.tiles_h) * p.tiles_w;
+    if (per_img * (static_cast<unsigned long long>(p.num_tiles) + 4096) >= (1ull << 32)) {
+      set_error("conv_block1: too many tiles for the index arithmetic (NB=%d H=%d W=%d)", NB, H, W);
+      return SED_ERR_BAD_SHAPE;
+    }
+    p.magic_img = per_img > 1 ? static_cast<uint32_t>(((1ull << 32) + per_img - 1) / per_img) : 0u;
+    p.magic_w = p.tiles_w > 1 ? static_cast<uint32_t>(((1ull << 32) + p.tiles_w - 1) / p.tiles_w) : 0u;
+  }
+  p.cout = 64; p.nslices = 1;
+  p.scale = scale2; p.shift = shift2;
+  p.out = out; p.out2 = nullptr;
+  p.relu = 1;
+  p.out_sn = H; p.out_sh = 1;
+  p.x1 = x; p.w1 = w1s; p.shift1 = shift1;
+  {
+    const char* e = getenv("SED_CONV_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
+  if (dtype == 0) return launch_pair<__half, 64, 64, EPI_POOL, 6, 4, true, 1, 1, 1, true>(tmB, tmB, tmB, p, stream);
+  if (dtype == 1)
+    return launch_pair<__nv_bfloat16, 64, 64, EPI_POOL, 6, 4, true, 1, 1, 1, true>(tmB, tmB, tmB, p, stream);
+  set_error("conv_block1: dtype must be 0 (fp16) or 1 (bf16)");
   return SED_ERR_UNSUPPORTED;
 }
 

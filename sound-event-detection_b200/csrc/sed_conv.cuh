@@ -37,6 +37,10 @@ struct ConvParams {
   int M, ldc, relu;        // linear only
   int tblock;              // linear only: 1 = store float32 output as 128-row transposed blocks [tile][ldc/4][128][4]
   long out_sn, out_sh;     // EPI 2: output row of (image n, row h) = n*out_sn + h*out_sh (default H, 1)
+  // fused conv_block1 (FUSE1): the A operand is computed in the kernel from the 1-channel input
+  const float* x1;         // [NB, H, W] f32 (log-mel after bn0)
+  const float* w1;         // [64][9] f32 conv_block1.conv1 weights with the bn1 scale folded in
+  const float* shift1;     // [64] f32 folded bn1 shift
   int dbg;                 // profiling experiments only (SED_CONV_DBG): 1 = no stores, 2 = no drain, 4 = no MMA
 };
 
@@ -499,7 +503,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // warp1 = TMEM allocation (+ MMA issue on the leader only, commits multicast to both CTAs),
 // warps2-9 = epilogue of the CTA's own 128 accumulator rows.
 // =================================================================================================
-template <int CIN, int BN, int EPI, int SA, int ACC, bool BRES, int NT, int SB, int EG = 1>
+template <int CIN, int BN, int EPI, int SA, int ACC, bool BRES, int NT, int SB, int EG = 1, bool FUSE1 = false>
 struct Conv2Cfg {
   static constexpr int NCHUNK = CIN / 64;
   static constexpr int TAPS = 9;
@@ -511,26 +515,30 @@ struct Conv2Cfg {
   static constexpr int NSTG = (EPI == EPI_STORE) ? (CPW >= 64 ? 2 : 1) : 0;
   static constexpr int SMEM_STG = NSTG * kTileBytes;
   static constexpr int SS = BRES ? BN : 512;
-  static constexpr int SMEM_MISC = 2 * SS * 4 + 256;
+  static constexpr int PW = FUSE1 ? 6 : 0;                            // operand-producer warps (fused conv_block1)
+  static constexpr int SMEM_IN = PW * 5 * 12 * 4;                     // per producer warp: 5 x 12 input window (f32)
+  static constexpr int SMEM_MISC = 2 * SS * 4 + 256 + SMEM_IN;
   static constexpr int SMEM_BYTES = 1024 + SMEM_A + B_BYTES + SMEM_STG + SMEM_MISC;
   static constexpr int ACC_COLS = NT * BN;
   static constexpr int TMEM_COLS = (ACC * ACC_COLS <= 32) ? 32 : (ACC * ACC_COLS <= 64) ? 64
                                    : (ACC * ACC_COLS <= 128) ? 128 : (ACC * ACC_COLS <= 256) ? 256 : 512;
+  static_assert(!FUSE1 || (CIN == 64 && NT == 1 && BRES), "fused conv_block1: 64 input channels, one tile per CTA");
   // EG epilogue groups of 8 warps drain alternate accumulator stages.  Measured on conv_block1.conv2 (N = 64): no
   // gain from EG = 2 -- that layer is bound by the shared-memory pipe (operand reads + TMA writes), not the epilogue
-  static constexpr int THREADS = 64 + 32 * 8 * EG;
+  static constexpr int THREADS = 64 + 32 * 8 * EG + 32 * PW;
   static_assert(EG == 1 || EPI != EPI_STORE, "the TMA-store staging tiles belong to one epilogue group");
   static_assert(ACC * ACC_COLS <= 512, "TMEM columns");
   static_assert(BN % 32 == 0 && BN <= 256, "pair MMA: N multiple of 16 per CTA half");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-template <typename T, int CIN, int BN, int EPI, int SA, int ACC, bool BRES, int NT, int SB, int EG = 1>
+template <typename T, int CIN, int BN, int EPI, int SA, int ACC, bool BRES, int NT, int SB, int EG = 1,
+          bool FUSE1 = false>
 __global__ void __cluster_dims__(2, 1, 1)
-__launch_bounds__(Conv2Cfg<CIN, BN, EPI, SA, ACC, BRES, NT, SB, EG>::THREADS, 1)
+__launch_bounds__(Conv2Cfg<CIN, BN, EPI, SA, ACC, BRES, NT, SB, EG, FUSE1>::THREADS, 1)
 conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmO, const ConvParams p) {
-  using Cfg = Conv2Cfg<CIN, BN, EPI, SA, ACC, BRES, NT, SB, EG>;
+  using Cfg = Conv2Cfg<CIN, BN, EPI, SA, ACC, BRES, NT, SB, EG, FUSE1>;
   constexpr int TAPS = Cfg::TAPS;
   constexpr int NCHUNK = Cfg::NCHUNK;
 
@@ -549,6 +557,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* t_full = b_empty + SB;    // [ACC] per CTA (multicast commit)
   uint64_t* t_empty = t_full + ACC;   // [ACC] leader's copy, 16 arrivals (8 warps x 2 CTAs)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + ACC);
+  float* s_in = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_shift + Cfg::SS) + 256);  // [PW][5][12] (FUSE1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -579,7 +588,8 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (EPI == EPI_STORE) tma_prefetch_desc(&tmO);
-    for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    // a_full: one TMA transaction (armed by the leader) or, fused, one arrive per producer warp of both CTAs
+    for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], FUSE1 ? 2 * Cfg::PW : 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < ACC; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 16); }
     fence_barrier_init();
@@ -615,7 +625,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             fixed_slice * BN + rank * (BN / 2));
       }
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
-      for (int w = work_begin; w < work_end; w += work_stride) {
+      for (int w = work_begin; w < work_end && !FUSE1; w += work_stride) {
         const int item = BRES ? w : w / p.nslices;
         const int slice = BRES ? fixed_slice : w - item * p.nslices;
         for (int c = 0; c < NCHUNK; ++c) {
@@ -660,7 +670,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_after();
         const uint32_t d_base = tmem_base + acc * Cfg::ACC_COLS;
         for (int c = 0; c < NCHUNK; ++c) {
-          mbar_wait(&a_full[sa], pa);
+          if (FUSE1) mbar_wait_cluster(&a_full[sa], pa); else mbar_wait(&a_full[sa], pa);
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + sa * (Cfg::A_STAGE >> 4);
 #pragma unroll
@@ -695,7 +705,102 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (++acc == ACC) { acc = 0; pacc ^= 1; }
       }
     }
-  } else {
+  } else if (FUSE1 && warp >= 2 + 8 * EG) {
+    // =============================== fused conv_block1.conv1 operand producer ===============
+    // EXPERIMENTAL (engine variant 3, not the default).  Measured on B200: 1.07 ms per 148 clips against 0.28 + 0.53 ms
+    // for the split-fp16 tensor-core conv1 kernel + this kernel fed by TMA.  The 104 k float32 FMAs per tile occupy the
+    // FMA pipe for >= 810 clk and six producer warps execute them as latency-exposed serial streams (~4000 clk per
+    // tile); more producer warps would cap registers below what the epilogue needs.  Kept as the record of that
+    // experiment and as a second implementation the parity tests can cross-check.
+    // conv_block1.conv2's A operand -- the haloed 18 x 10 pixel x 64 channel patch of relu(bn1(conv1(x))) -- is computed
+    // here from the one-channel input instead of being read back from HBM (pytorch/models.py:128 feeding :129).
+    // Warp pw owns patch rows 3pw..3pw+2; lane l owns channels 2l, 2l+1 (packed f32x2 FMAs); pixels outside the image
+    // are the ZERO padding of conv2, inputs outside the image the zero padding of conv1.
+    const int pw = warp - (2 + 8 * EG);
+    float* win = s_in + pw * 60;  // 5 input rows x 12 columns
+    unsigned long long wreg[9];   // {w[2l][tap], w[2l+1][tap]}
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wreg[t] = pack_f32x2(p.w1[(2 * lane) * 9 + t], p.w1[(2 * lane + 1) * 9 + t]);
+    const unsigned long long shreg = pack_f32x2(p.shift1[2 * lane], p.shift1[2 * lane + 1]);
+    // input element e (0..59) of a tile's window for this warp: row e / 12, column e % 12
+    auto load_inputs = [&](int tile, float& v0, float& v1) {
+      int n, h0, w0;
+      tile_coords(tile, n, h0, w0);
+      const bool tv = tile < p.num_tiles;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int e = lane + 32 * k;
+        const int hh = h0 - 2 + 3 * pw + e / 12, ww = w0 - 2 + e % 12;
+        float v = 0.0f;
+        if (tv && e < 60 && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W)
+          v = __ldg(p.x1 + (static_cast<size_t>(n) * p.H + hh) * p.W + ww);
+        if (k == 0) v0 = v; else v1 = v;
+      }
+    };
+    uint32_t sa = 0, pa = 0;
+    // two tiles of input prefetch in registers; the loads are issued right AFTER a tile's release-arrive (which waits
+    // for every outstanding memory operation of the thread) and consumed two tiles later
+    float c0 = 0.0f, c1 = 0.0f, d0 = 0.0f, d1 = 0.0f;
+    if (work_begin < work_end) load_inputs((work_begin * 2 + static_cast<int>(rank)) * NT, c0, c1);
+    if (work_begin + work_stride < work_end)
+      load_inputs(((work_begin + work_stride) * 2 + static_cast<int>(rank)) * NT, d0, d1);
+    for (int w = work_begin; w < work_end; w += work_stride) {
+      const int tile = (w * 2 + static_cast<int>(rank)) * NT;
+      int n, h0, w0;
+      tile_coords(tile, n, h0, w0);
+      const bool tv = tile < p.num_tiles;
+      win[lane] = c0;
+      if (lane < 28) win[32 + lane] = c1;
+      __syncwarp();
+      mbar_wait(&a_empty[sa], pa ^ 1);
+      uint8_t* patch = smem_a + sa * Cfg::A_STAGE;
+#pragma unroll
+      for (int rr = 0; rr < 3; ++rr) {
+        const int r = 3 * pw + rr;       // patch row; image row h0 - 1 + r
+        const int hh = h0 - 1 + r;
+        const bool rv = tv && hh >= 0 && hh < p.H;
+        float x[3][12];
+#pragma unroll
+        for (int dr = 0; dr < 3; ++dr)
+#pragma unroll
+          for (int q4 = 0; q4 < 3; ++q4) {
+            const float4 v = *reinterpret_cast<const float4*>(win + (rr + dr) * 12 + q4 * 4);
+            x[dr][q4 * 4] = v.x; x[dr][q4 * 4 + 1] = v.y; x[dr][q4 * 4 + 2] = v.z; x[dr][q4 * 4 + 3] = v.w;
+          }
+        // ten independent accumulator chains (one per pixel of the row), taps outermost: full FMA-pipe ILP
+        unsigned long long acc[10];
+#pragma unroll
+        for (int c = 0; c < 10; ++c) acc[c] = shreg;
+#pragma unroll
+        for (int dr = 0; dr < 3; ++dr)
+#pragma unroll
+          for (int dc = 0; dc < 3; ++dc)
+#pragma unroll
+            for (int c = 0; c < 10; ++c)
+              acc[c] = ffma2(pack_f32x2(x[dr][c + dc], x[dr][c + dc]), wreg[dr * 3 + dc], acc[c]);
+#pragma unroll
+        for (int c = 0; c < 10; ++c) {
+          const int ww = w0 - 1 + c;
+          float y0, y1;
+          unpack_f32x2(acc[c], y0, y1);
+          const bool valid = rv && ww >= 0 && ww < p.W;
+          const uint32_t packed = valid ? Elem16<T>::pack2(fmaxf(y0, 0.0f), fmaxf(y1, 0.0f)) : 0u;
+          const int pr = r * 10 + c;
+          *reinterpret_cast<uint32_t*>(patch + pr * 128 + (((lane >> 2) ^ (pr & 7)) << 4) + (lane & 3) * 4) = packed;
+        }
+      }
+      fence_proxy_async_smem();  // generic stores -> the tensor core's (async proxy) operand reads
+      __syncwarp();
+      // the patch lives in THIS SM's shared memory and is read by THIS SM's tensor-core datapath: after the proxy fence
+      // a default (.release.cta) arrive on the leader's barrier is enough; a cluster-scope release costs ~1.5 us
+      if (lane == 0) mbar_arrive_remote_light(&a_full[sa], 0);
+      if (++sa == SA) { sa = 0; pa ^= 1; }
+      c0 = d0;
+      c1 = d1;
+      if (w + 2 * work_stride < work_end)
+        load_inputs(((w + 2 * work_stride) * 2 + static_cast<int>(rank)) * NT, d0, d1);
+    }
+  } else if (warp >= 2 && warp < 2 + 8 * EG) {
     // =============================== epilogue (EG groups of 8 warps, both CTAs) =============
     const int ew = warp - 2;
     const int grp = ew >> 3;            // epilogue group: drains the work items with (index % EG) == grp

@@ -275,6 +275,8 @@ class PackedModel:
         self.c11_w = sd["conv_block1.conv1.weight"].float().reshape(64, 9).contiguous().to(dev)
         s, b = fold_bn(sd, "conv_block1.bn1")
         self.c11_scale, self.c11_shift = s.to(dev), b.to(dev)
+        # fused conv_block1 (variant 3): bn1 scale folded into the nine taps (float64 fold, float32 result)
+        self.c11_ws = (sd["conv_block1.conv1.weight"].double().reshape(64, 9) * s.double()[:, None]).float().contiguous().to(dev)
         self.convs = []
         for name, cin, cout, mode in CONV_LAYERS:
             w = sd[name + ".weight"].float()
@@ -356,15 +358,27 @@ class PackedModel:
         ws = self._workspace(mb, T)
         stream = capi.current_stream(self.device)
         logmel_forward(self.front, wave_mb, self.bn0_scale, self.bn0_shift, out=ws["logmel"], windows=windows)
-        rc = lib.sed_conv_first_f32(capi.ptr(ws["logmel"]), mb, T, 64, capi.ptr(self.c11_w), capi.ptr(self.c11_scale),
-                                    capi.ptr(self.c11_shift), capi.ptr(ws["a1"]), self.dtype_code, stream)
-        capi.check(rc, "sed_conv_first_f32")
-        capi._count()
+        fused1 = variant == 3  # conv_block1 as one kernel (its 64-channel intermediate stays on chip)
+        if fused1:
+            variant = 2
+        else:
+            rc = lib.sed_conv_first_f32(capi.ptr(ws["logmel"]), mb, T, 64, capi.ptr(self.c11_w),
+                                        capi.ptr(self.c11_scale), capi.ptr(self.c11_shift), capi.ptr(ws["a1"]),
+                                        self.dtype_code, stream)
+            capi.check(rc, "sed_conv_first_f32")
+            capi._count()
         chain = [("a1", "p1"), ("p1", "a2"), ("a2", "p2"), ("p2", "a3"), ("a3", "p3"), ("p3", "a4"), ("a4", None)]
         if self.conv_events is not None:
             ev0 = torch.cuda.Event(enable_timing=True)
             ev0.record(torch.cuda.current_stream(self.device))
-        for (cin, cout, mode, wp, s, b), (src, dst) in zip(self.convs, chain):
+        for li, ((cin, cout, mode, wp, s, b), (src, dst)) in enumerate(zip(self.convs, chain)):
+            if fused1 and li == 0:
+                rc = lib.sed_conv_block1(capi.ptr(ws["logmel"]), mb, T, 64, capi.ptr(self.c11_ws),
+                                         capi.ptr(self.c11_shift), capi.ptr(wp), capi.ptr(s), capi.ptr(b),
+                                         capi.ptr(ws["p1"]), self.dtype_code, stream)
+                capi.check(rc, "sed_conv_block1")
+                capi._count()
+                continue
             x = ws[src]
             out = feat_out if dst is None else ws[dst]
             rc = lib.sed_conv3x3_bn_relu(capi.ptr(x), mb, x.shape[1], x.shape[2], cin, capi.ptr(wp), capi.ptr(s),
@@ -381,7 +395,8 @@ class PackedModel:
         if stages is not None:
             stages["bn0"] = ws["logmel"].clone()
             for k in ("a1", "p1", "a2", "p2", "a3", "p3", "a4"):
-                stages[k] = ws[k].clone()
+                if not (fused1 and k == "a1"):  # the fused block never materialises a1
+                    stages[k] = ws[k].clone()
 
     def linear(self, a16, w16, bias, relu=False, out16=False, out_layout=0):
         """out_layout 1: float32 output as 128-row transposed blocks (see sed_b200.h: sed_linear)."""

@@ -96,7 +96,7 @@ class _Cnn9Base(nn.Module):
         self._generation = [0]
         self.precision = "fp16"   # 16-bit operand type of the tensor-core layers: 'fp16' or 'bf16'
         self.micro_batch = 148
-        self.conv_variant = 2   # 2 = CTA-pair kernels where weights are resident, 0 = single-CTA patch, 1 = per-tap
+        self.conv_variant = 2   # 2 = CTA-pair kernels (default), 0 = single-CTA patch, 1 = per-tap, 3 = 2 + fused conv_block1 (slower)
 
     # any parameter movement / reload invalidates the packed copies
     def _invalidate(self):
