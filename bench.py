@@ -48,7 +48,9 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled while the timed region runs."""
+    """nvidia-smi clocks/throttle reasons sampled while the timed regions run.  The sampler is started before the
+    warm-up (nvidia-smi needs a few hundred ms to come up); only samples taken between mark_begin() and mark_end()
+    -- i.e. under the benchmark's load -- are reported."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -56,7 +58,9 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.lines = []   # (monotonic time, text)
+        self.t_begin = None
+        self.t_end = None
 
     def start(self):
         try:
@@ -70,20 +74,30 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.monotonic(), line.strip()))
+
+    def mark_begin(self):
+        self.t_begin = time.monotonic()
+
+    def mark_end(self):
+        self.t_end = time.monotonic()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        t1 = (self.t_end if self.t_end is not None else time.monotonic()) + 0.06  # a sample reports the interval before it
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if ts < t0 or ts > t1:
+                continue
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -97,7 +111,7 @@ class ClockSampler:
                     reasons.add(nm)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": "device-resident + end-to-end timed regions"}
 
 
 def cpu_reference_throughput(steps, warmup, batch=32):
@@ -181,14 +195,16 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(warmup):
         step_device()
     barrier()
 
     # ---------------- timed region 1: inputs resident in HBM ----------------
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.mark_begin()
     capi.reset_launches()
     pm.conv_events = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -203,7 +219,6 @@ def run_b200(args):
     conv_ms = sum(a.elapsed_time(b) for a, b, _ in pm.conv_events)
     conv_clips = sum(n for _, _, n in pm.conv_events)
     pm.conv_events = None
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -245,6 +260,10 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_i16_ms = t.item()
+    clocks = None
+    if rank == 0:
+        sampler.mark_end()
+        clocks = sampler.stop()
 
     if rank == 0:
         peaks = load_peaks()

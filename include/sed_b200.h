@@ -122,11 +122,15 @@ int sed_bigru(const float* gi, const void* whh_packed, const float* bhh, int B, 
 
 /* sed_attpool for an input in 128-clip transposed blocks (the output layout of sed_bigru, or of sed_linear
  * out_layout 1 over time-major rows r = t*Bp + clip, Bp = 128*ceil(B/128), 512 columns).  Same outputs as sed_attpool.
- *   scratch: sed_attpool_blocks_scratch_bytes(B, T) bytes of device memory, contents irrelevant. */
+ *   scratch: sed_attpool_blocks_scratch_bytes(B, T) bytes of device memory, contents irrelevant.
+ *   stage 0: everything for clips [clip_begin, clip_begin + n_clips) (pass 0, B for the whole batch);
+ *   stage 1: only the projections of ALL clips into `scratch`; stage 2: only the per-clip pooling / output pass of clips
+ *   [clip_begin, clip_begin + n_clips) from a `scratch` filled by stage 1 -- lets a caller overlap the device->host copy of
+ *   one range with the pooling of the next.  Output tensors are always indexed by the absolute clip. */
 long sed_attpool_blocks_scratch_bytes(int B, int T);
 int sed_attpool_blocks(const float* x_blocks, int B, int T, const float* w_att, const float* b_att, const float* w_cla,
                        const float* b_cla, int ratio, int frames_out, void* scratch, float* clip, float* frame,
-                       float* cla_t, float* norm_att_t, void* stream);
+                       float* cla_t, float* norm_att_t, int stage, int clip_begin, int n_clips, void* stream);
 
 /* Linear(512 -> classes) + sigmoid per frame, x`ratio` interpolation, clipwise mean (use_max = 0) or max (1)
  * over frames: the head of Cnn_9layers_FrameAvg / FrameMax / Gru_FrameAvg / Transformer_FrameAvg

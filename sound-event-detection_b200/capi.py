@@ -41,7 +41,7 @@ SIGNATURES = {
     "sed_bigru_profile": ([_p, _p, _p, _i, _i, _p, _p, _i, _p, _p], _i),
     "sed_mha_core": ([_p, _i, _i, _l, _l, _p, _i, _p], _i),
     "sed_attpool_blocks_scratch_bytes": ([_i, _i], _l),
-    "sed_attpool_blocks": ([_p, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p], _i),
+    "sed_attpool_blocks": ([_p, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p], _i),
     "sed_attpool": ([_p, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p], _i),
 }
 

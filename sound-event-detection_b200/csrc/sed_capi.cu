@@ -5,7 +5,7 @@
 
 #include "sed_kernels.h"
 
-#define SED_ABI_VERSION 7
+#define SED_ABI_VERSION 8
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -149,11 +149,11 @@ long sed_attpool_blocks_scratch_bytes(int B, int T) {
 
 int sed_attpool_blocks(const float* x_blocks, int B, int T, const float* w_att, const float* b_att, const float* w_cla,
                        const float* b_cla, int ratio, int frames_out, void* scratch, float* clip, float* frame,
-                       float* cla_t, float* norm_att_t, void* stream) {
+                       float* cla_t, float* norm_att_t, int stage, int clip_begin, int n_clips, void* stream) {
   SED_REQUIRE(x_blocks); SED_REQUIRE(w_att); SED_REQUIRE(b_att); SED_REQUIRE(w_cla); SED_REQUIRE(b_cla);
   SED_REQUIRE(scratch); SED_REQUIRE(clip); SED_REQUIRE(frame);
   return sed::attpool_blocks_launch(x_blocks, B, T, w_att, b_att, w_cla, b_cla, ratio, frames_out, scratch, clip, frame,
-                                    cla_t, norm_att_t, as_stream(stream));
+                                    cla_t, norm_att_t, stage, clip_begin, n_clips, as_stream(stream));
 }
 
 int sed_fcpool(const float* x, int B, int T, const float* w, const float* b, int classes, int ratio, int use_max,

@@ -66,7 +66,8 @@ int attpool_launch(const float* x, int B, int T, const float* w_att, const float
 size_t attpool_blocks_scratch_bytes(int B, int T);
 int attpool_blocks_launch(const float* x_blocks, int B, int T, const float* w_att, const float* b_att,
                           const float* w_cla, const float* b_cla, int ratio, int frames_out, void* scratch, float* clip,
-                          float* frame, float* cla_t, float* norm_att_t, cudaStream_t stream);
+                          float* frame, float* cla_t, float* norm_att_t, int stage, int clip0, int n,
+                          cudaStream_t stream);
 
 int fcpool_launch(const float* x, int B, int T, const float* w, const float* b, int C, int ratio, int use_max,
                   float* clip, float* frame, cudaStream_t stream);

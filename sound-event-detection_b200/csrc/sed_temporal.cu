@@ -728,13 +728,14 @@ attproj_blocks_kernel(const float4* __restrict__ xb, int Bp, int Tn, const float
 }
 
 __global__ void __launch_bounds__(128)
-attpool_tail_kernel(const float* __restrict__ S, int Bp, int Tn, int ratio, int frames_out, float* __restrict__ clip,
-                    float* __restrict__ frame, float* __restrict__ cla_t, float* __restrict__ norm_att_t) {
+attpool_tail_kernel(const float* __restrict__ S, int Bp, int Tn, int ratio, int frames_out, int clip0,
+                    float* __restrict__ clip, float* __restrict__ frame, float* __restrict__ cla_t,
+                    float* __restrict__ norm_att_t) {
   extern __shared__ float smem_h[];
   float* s_e = smem_h;               // [Tn][25]
   float* s_c = s_e + Tn * kCls;      // [Tn][25]
   float* s_sum = s_c + Tn * kCls;    // [25]
-  const int b = blockIdx.x;
+  const int b = clip0 + blockIdx.x;  // outputs are indexed by the absolute clip
   for (int i = threadIdx.x; i < Tn * 2 * kCls; i += blockDim.x) {
     const int t = i / (2 * kCls), c = i - t * 2 * kCls;
     const float v = S[(static_cast<size_t>(t) * 2 * kCls + c) * Bp + b];
@@ -748,12 +749,17 @@ size_t attpool_blocks_scratch_bytes(int B, int Tn) {
   return sizeof(float) * static_cast<size_t>(Tn) * 2 * kCls * Bp;
 }
 
+// stage 1 (all clips) and stage 2 (clips [clip0, clip0 + n)) can be launched separately so that a caller can overlap
+// the device->host copy of one range of clips with the tail kernel of the next
 int attpool_blocks_launch(const float* x_blocks, int B, int Tn, const float* w_att, const float* b_att,
                           const float* w_cla, const float* b_cla, int ratio, int frames_out, void* scratch, float* clip,
-                          float* frame, float* cla_t, float* norm_att_t, cudaStream_t stream) {
+                          float* frame, float* cla_t, float* norm_att_t, int stage, int clip0, int n,
+                          cudaStream_t stream) {
   const size_t smem_b = sizeof(float) * (2 * static_cast<size_t>(Tn) * kCls + 32);
-  if (B <= 0 || Tn <= 0 || ratio <= 0 || frames_out < Tn * ratio || smem_b > 220 * 1024) {
-    set_error("attpool_blocks: unsupported shape B=%d T=%d ratio=%d frames_out=%d", B, Tn, ratio, frames_out);
+  if (B <= 0 || Tn <= 0 || ratio <= 0 || frames_out < Tn * ratio || smem_b > 220 * 1024 || stage < 0 || stage > 2 ||
+      clip0 < 0 || n < 0 || clip0 + n > B) {
+    set_error("attpool_blocks: unsupported shape B=%d T=%d ratio=%d frames_out=%d stage=%d clips [%d, %d)", B, Tn, ratio,
+              frames_out, stage, clip0, clip0 + n);
     return SED_ERR_BAD_SHAPE;
   }
   const int Bp = (B + 127) / 128 * 128;
@@ -764,21 +770,27 @@ int attpool_blocks_launch(const float* x_blocks, int B, int Tn, const float* w_a
     if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0)
       sm_count = 148;
   }
-  const size_t smem_a = sizeof(float) * 2 * kCls * 512;
-  cudaError_t e = cudaFuncSetAttribute(attproj_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(attpool_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
-  if (e == cudaSuccess) {
-    const long tasks = static_cast<long>(Bp / (32 * kApTM)) * Tn;
-    long blocks = (tasks + kApWarps - 1) / kApWarps;
-    if (blocks > static_cast<long>(sm_count)) blocks = sm_count;
-    attproj_blocks_kernel<<<static_cast<unsigned>(blocks), kApWarps * 32, smem_a, stream>>>(
-        reinterpret_cast<const float4*>(x_blocks), Bp, Tn, w_att, b_att, w_cla, b_cla, reinterpret_cast<float*>(scratch));
-    e = cudaGetLastError();
+  cudaError_t e = cudaSuccess;
+  if (stage == 0 || stage == 1) {
+    const size_t smem_a = sizeof(float) * 2 * kCls * 512;
+    e = cudaFuncSetAttribute(attproj_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+    if (e == cudaSuccess) {
+      const long tasks = static_cast<long>(Bp / (32 * kApTM)) * Tn;
+      long blocks = (tasks + kApWarps - 1) / kApWarps;
+      if (blocks > static_cast<long>(sm_count)) blocks = sm_count;
+      attproj_blocks_kernel<<<static_cast<unsigned>(blocks), kApWarps * 32, smem_a, stream>>>(
+          reinterpret_cast<const float4*>(x_blocks), Bp, Tn, w_att, b_att, w_cla, b_cla,
+          reinterpret_cast<float*>(scratch));
+      e = cudaGetLastError();
+    }
   }
-  if (e == cudaSuccess) {
-    attpool_tail_kernel<<<B, 128, smem_b, stream>>>(reinterpret_cast<const float*>(scratch), Bp, Tn, ratio, frames_out,
-                                                    clip, frame, cla_t, norm_att_t);
-    e = cudaGetLastError();
+  if (e == cudaSuccess && (stage == 0 || stage == 2) && n > 0) {
+    e = cudaFuncSetAttribute(attpool_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+    if (e == cudaSuccess) {
+      attpool_tail_kernel<<<n, 128, smem_b, stream>>>(reinterpret_cast<const float*>(scratch), Bp, Tn, ratio,
+                                                      frames_out, clip0, clip, frame, cla_t, norm_att_t);
+      e = cudaGetLastError();
+    }
   }
   if (e != cudaSuccess) {
     set_error("attpool_blocks launch: %s", cudaGetErrorString(e));

@@ -520,7 +520,10 @@ class PackedModel:
         capi._count()
         return clip, frame, None, None
 
-    def _head_blocks(self, xb, n, frames_out, want_cla, want_norm_att, out):
+    def _head_blocks(self, xb, n, frames_out, want_cla, want_norm_att, out, stage=0, clips=None, scratch=None):
+        """Pooling head on a transposed-block input.  stage / clips=(begin, count) / scratch expose the two launches
+        of sed_attpool_blocks separately (forward_host overlaps result copies with the per-clip pass); `out` tensors
+        always cover all n clips."""
         lib = capi.load()
         dev = self.device
         Tp = xb.shape[0]
@@ -531,13 +534,15 @@ class PackedModel:
             frame = torch.empty((n, frames_out, 25), dtype=torch.float32, device=dev)
         cla = torch.empty((n, 25, Tp), dtype=torch.float32, device=dev) if want_cla else None
         natt = torch.empty((n, 25, Tp), dtype=torch.float32, device=dev) if want_norm_att else None
-        scratch = torch.empty((lib.sed_attpool_blocks_scratch_bytes(n, Tp),), dtype=torch.uint8, device=dev)
+        if scratch is None:
+            scratch = torch.empty((lib.sed_attpool_blocks_scratch_bytes(n, Tp),), dtype=torch.uint8, device=dev)
+        c0, cn = (0, n) if clips is None else clips
         rc = lib.sed_attpool_blocks(capi.ptr(xb), n, Tp, capi.ptr(self.att_w), capi.ptr(self.att_b),
                                     capi.ptr(self.cla_w), capi.ptr(self.cla_b), 8, frames_out, capi.ptr(scratch),
-                                    capi.ptr(clip), capi.ptr(frame), capi.ptr(cla), capi.ptr(natt),
+                                    capi.ptr(clip), capi.ptr(frame), capi.ptr(cla), capi.ptr(natt), stage, c0, cn,
                                     capi.current_stream(dev))
         capi.check(rc, "sed_attpool_blocks")
-        capi._count(2)
+        capi._count(2 if stage == 0 else 1)
         return clip, frame, cla, natt
 
     def _embedding(self, x, cla, feat32):
@@ -592,12 +597,21 @@ class PackedModel:
                 self.conv_stack(hb["dev"][b0:b1], variant=variant, **slot(b0, b1))
             x = self._temporal_or_features(feat16, feat32, B)
             # pooling head in chunks: the device->host copy of chunk i overlaps the head kernel of chunk i+1
-            if x.dim() == 5:
-                head_chunk = B  # transposed-block input: one call over the batch
+            blocks = x.dim() == 5 and self.head_kind == "att"
+            if blocks:  # projections of the whole batch once, then the per-clip pass chunk by chunk
+                scratch = torch.empty((capi.load().sed_attpool_blocks_scratch_bytes(B, Tp),), dtype=torch.uint8,
+                                      device=self.device)
+                self._head_blocks(x, B, frames, False, False, (hb["clip_dev"], hb["frame_dev"]), stage=1,
+                                  scratch=scratch)
+            elif x.dim() == 5:
+                x = blocks_to_rows(x, B, Tp)
             for c0 in range(0, B, head_chunk):
                 c1 = min(B, c0 + head_chunk)
-                self.head(x if x.dim() == 5 else x[c0:c1], frames, want_cla=False,
-                          out=(hb["clip_dev"][c0:c1], hb["frame_dev"][c0:c1]), n=B)
+                if blocks:
+                    self._head_blocks(x, B, frames, False, False, (hb["clip_dev"], hb["frame_dev"]), stage=2,
+                                      clips=(c0, c1 - c0), scratch=scratch)
+                else:
+                    self.head(x[c0:c1], frames, want_cla=False, out=(hb["clip_dev"][c0:c1], hb["frame_dev"][c0:c1]))
                 done = torch.cuda.Event()
                 done.record(compute)
                 ds.wait_event(done)
