@@ -4,4 +4,4 @@ Cnn_9layers_Gru_FrameAtt / Cnn_9layers_Transformer_FrameAtt).
 
 The directory name carries a hyphen (repo layout contract); import it as `sed_b200`.
 """
-__all__ = ["stft", "models", "synth", "engine", "capi", "dist"]
+__all__ = ["stft", "models", "synth", "engine", "capi", "dist", "streaming", "pytorch_utils"]
