@@ -44,12 +44,14 @@ const char* sed_last_error_string(void);
  * pad_truncate_sequence of the streaming loop pytorch/predict.py:302-305.
  *   wave: clip b = wave + b*clip_stride, L samples, f32 (wave_dtype 0) or int16 PCM (wave_dtype 1); samples at
  *   index >= total_len (counted from `wave`) read as zero.  Dense batch: clip_stride = L, total_len = B*L.
+ *   clip_offset: optional device table [B] of clip starts in samples (overrides b*clip_stride) -- the windows of
+ *   many padded clips as one batch, pytorch/main_strong.py:786-805.
  *   window [n_fft] f32 (row 0 of the loaded conv_real kernel); twiddle [n_fft][2] f32 = exp(-2 pi i k / n_fft);
  *   banded mel matrix: for mel bin m the non-zero weights melW[mel_lo[m] .. mel_lo[m]+mel_len[m]) are stored at
  *   mel_val[mel_off[m] ..]; db_offset = 10*log10(max(amin, ref)); bn_scale/bn_shift [n_mels] or NULL;
  *   out [B, T, n_mels] f32 with T = L / hop + 1.  n_fft in {256, 512, 1024}. */
-int sed_frontend_logmel(const void* wave, int wave_dtype, int B, int L, long clip_stride, long total_len, int n_fft,
-                        int hop, const float* window, const float* twiddle, const int* mel_lo, const int* mel_len,
+int sed_frontend_logmel(const void* wave, int wave_dtype, int B, int L, long clip_stride, const long* clip_offset,
+                        long total_len, int n_fft, int hop, const float* window, const float* twiddle, const int* mel_lo, const int* mel_len,
                         const int* mel_off, const float* mel_val, int n_mels, float amin, float db_offset, int is_log,
                         const float* bn_scale, const float* bn_shift, float* out, void* stream);
 
@@ -142,10 +144,11 @@ int sed_fcpool(const float* x, int B, int T, const float* w, const float* b, int
 /* Overlap-add of per-window framewise outputs followed by the reference's block-wise averaging.
  * Replaces merge + avg_merge utils/utilities.py:405-446 as driven by pytorch/predict.py:323-349 (bug-compatible:
  * the first and last overlap_interval frames are never divided, inner blocks use the reference's divisor rule).
- *   frames [n_windows, frames_per_window, classes] f32; window k starts at frame k*overlap_interval;
- *   merged [(n_windows-1)*overlap_interval + frames_per_window, classes] f32. */
+ *   frames [n_recordings, n_windows, frames_per_window, classes] f32; window k starts at frame k*overlap_interval;
+ *   merged [n_recordings, (n_windows-1)*overlap_interval + frames_per_window, classes] f32 (recordings independent:
+ *   the per-file loops of pytorch/predict.py:264 and pytorch/main_strong.py:768 as one launch). */
 int sed_window_merge_avg(const float* frames, int n_windows, int frames_per_window, int classes, int overlap_interval,
-                         int sample_duration, float* merged, void* stream);
+                         int sample_duration, int n_recordings, float* merged, void* stream);
 
 /* Frame-wise probabilities -> sound events per (clip, class): double-threshold hysteresis, smoothing, salt removal.
  * Replaces activity_detection utils/vad.py:11-45 (+ helpers :108-199) as called per clip and class by

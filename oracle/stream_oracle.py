@@ -93,6 +93,36 @@ def streaming_predict(sd, audio_full, model_type, sample_rate, n_fft, hop, sampl
 # ----------------------------------------------------------------------------------------------
 # Event extraction: utils/vad.py:11-45 activity_detection and helpers :108-199
 # ----------------------------------------------------------------------------------------------
+def overlap_eval_predict(sd, audio_full, audio_duration, model_type, sample_rate, n_fft, hop, sample_duration,
+                         overlap_value):
+    """The per-file loop of pytorch/main_strong.py:768-835: `audio_full` is already padded / truncated to 10 s (:785);
+    windows advance by `overlap_value` seconds (:826), are sliced without padding (:790-792) and run with batch size 1;
+    merge from the second window on (:813-818), avg_merge at the end (:835).  Returns (merged, list of window frames)."""
+    import torch
+    import sed_oracle
+    num_segment, start, end = 1, 0, 0
+    merged = prev = None
+    frames = []
+    while end <= audio_duration:
+        start_index = int(start * sample_rate)
+        end_index = int((sample_duration * sample_rate) + start_index)
+        audio = torch.from_numpy(np.asarray(audio_full[start_index:end_index], dtype=np.float32))[None]
+        curr = sed_oracle.model_forward(sd, audio, model_type, n_fft, hop)["framewise_output"].numpy()
+        frames.append(curr)
+        if num_segment == 2:
+            merged = merge(prev, curr, sample_duration, num_segment, overlap_value)
+        elif num_segment > 2:
+            merged = merge(merged, curr, sample_duration, num_segment, overlap_value)
+        else:
+            merged = curr
+        prev = curr
+        start += overlap_value
+        end = start + sample_duration
+        num_segment += 1
+    merged = avg_merge(merged.copy(), sample_duration, overlap_value)
+    return merged, frames
+
+
 def find_bgn_fin_pairs(locts):
     """vad.py:108-130.  Gap handling adds +1 to the closing fin AND to the next bgn; the last fin has no +1."""
     if len(locts) == 0:

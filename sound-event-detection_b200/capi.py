@@ -26,9 +26,9 @@ _f = ctypes.c_float
 SIGNATURES = {
     "sed_abi_version": ([], _i),
     "sed_last_error_string": ([], ctypes.c_char_p),
-    "sed_frontend_logmel": ([_p, _i, _i, _i, _l, _l, _i, _i, _p, _p, _p, _p, _p, _p, _i, _f, _f, _i, _p, _p, _p, _p], _i),
+    "sed_frontend_logmel": ([_p, _i, _i, _i, _l, _p, _l, _i, _i, _p, _p, _p, _p, _p, _p, _i, _f, _f, _i, _p, _p, _p, _p], _i),
     "sed_events": ([_p, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p], _i),
-    "sed_window_merge_avg": ([_p, _i, _i, _i, _i, _i, _p, _p], _i),
+    "sed_window_merge_avg": ([_p, _i, _i, _i, _i, _i, _i, _p, _p], _i),
     "sed_spectrogram_f32": ([_p, _i, _i, _i, _i, _p, _p, _p, _p], _i),
     "sed_logmel_rows_f32": ([_p, _l, _i, _p, _p, _p, _p, _i, _f, _f, _i, _p, _p], _i),
     "sed_conv_first_f32": ([_p, _i, _i, _i, _p, _p, _p, _p, _i, _p], _i),

@@ -5,7 +5,7 @@
 
 #include "sed_kernels.h"
 
-#define SED_ABI_VERSION 8
+#define SED_ABI_VERSION 9
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -23,8 +23,8 @@ int sed_abi_version(void) { return SED_ABI_VERSION; }
 
 const char* sed_last_error_string(void) { return sed::last_error(); }
 
-int sed_frontend_logmel(const void* wave, int wave_dtype, int B, int L, long clip_stride, long total_len, int n_fft,
-                        int hop, const float* window, const float* twiddle, const int* mel_lo, const int* mel_len,
+int sed_frontend_logmel(const void* wave, int wave_dtype, int B, int L, long clip_stride, const long* clip_offset,
+                        long total_len, int n_fft, int hop, const float* window, const float* twiddle, const int* mel_lo, const int* mel_len,
                         const int* mel_off, const float* mel_val, int n_mels, float amin, float db_offset, int is_log,
                         const float* bn_scale, const float* bn_shift, float* out, void* stream) {
   SED_REQUIRE(wave); SED_REQUIRE(window); SED_REQUIRE(twiddle); SED_REQUIRE(mel_lo); SED_REQUIRE(mel_len);
@@ -34,7 +34,8 @@ int sed_frontend_logmel(const void* wave, int wave_dtype, int B, int L, long cli
     return SED_ERR_NULL;
   }
   sed::FrontendArgs a{};
-  a.wave = wave; a.wave_dtype = wave_dtype; a.clip_stride = clip_stride; a.total_len = total_len;
+  a.wave = wave; a.wave_dtype = wave_dtype; a.clip_stride = clip_stride; a.clip_offset = clip_offset;
+  a.total_len = total_len;
   a.B = B; a.L = L; a.n_fft = n_fft; a.hop = hop;
   a.T = (hop > 0) ? L / hop + 1 : 0;
   a.window = window; a.twiddle = twiddle;
@@ -68,10 +69,10 @@ int sed_spectrogram_f32(const float* wave, int B, int L, int n_fft, int hop, con
 }
 
 int sed_window_merge_avg(const float* frames, int n_windows, int frames_per_window, int classes, int overlap_interval,
-                         int sample_duration, float* merged, void* stream) {
+                         int sample_duration, int n_recordings, float* merged, void* stream) {
   SED_REQUIRE(frames); SED_REQUIRE(merged);
   return sed::window_merge_launch(frames, n_windows, frames_per_window, classes, overlap_interval, sample_duration,
-                                  merged, as_stream(stream));
+                                  n_recordings, merged, as_stream(stream));
 }
 
 int sed_events(const float* frames, int n_clips, int n_frames, int classes, const double* high, const double* low,

@@ -187,11 +187,12 @@ template <> struct Sched<1024> { static constexpr int R0 = 2; };
 // aligned segments go through cp.async; edge segments through guarded loads.
 template <int NFFT, typename TIn>
 __device__ __forceinline__ void stage_segment(TIn* __restrict__ dst, const TIn* __restrict__ wave, long clip_stride,
-                                              long total_len, int L, int hop, int seg_len, int item, int chunks,
-                                              bool aligned) {
+                                              const long* __restrict__ clip_offset, long total_len, int L, int hop,
+                                              int seg_len, int item, int chunks, bool aligned) {
   constexpr int FPB = FrontCfg<NFFT>::FPB;
   const int b = item / chunks, c = item - b * chunks;
-  const long clip_base = static_cast<long>(b) * clip_stride;
+  const long clip_base = clip_offset ? clip_offset[b] : static_cast<long>(b) * clip_stride;
+  aligned = aligned && ((clip_base * static_cast<long>(sizeof(TIn))) & 15) == 0;
   const long q0 = static_cast<long>(c) * FPB * hop - NFFT / 2;
   const TIn* w = wave + clip_base;
   if (aligned && q0 >= 0 && q0 + seg_len <= L && clip_base + q0 + seg_len <= total_len) {
@@ -212,12 +213,13 @@ __device__ __forceinline__ void stage_segment(TIn* __restrict__ dst, const TIn* 
 }
 
 // mode 0: out = log-mel (+ optional bn0 affine) [B, T, n_mels];  mode 1: out = power spectrogram [B, T, F]
-// Clip b starts at wave + b * clip_stride and is L samples long; samples at or beyond total_len (counted from
+// Clip b starts at wave + b * clip_stride (or wave + clip_offset[b] when a table is given) and is L samples long; samples at or beyond total_len (counted from
 // `wave`) read as zero.  clip_stride < L gives overlapping windows of one long recording (predict.py:297-307)
 // without materialising them.
 template <int NFFT, typename TIn>
 __global__ void __launch_bounds__(FrontCfg<NFFT>::WARPS * 32, FrontCfg<NFFT>::MIN_BLOCKS)
-frontend_kernel(const TIn* __restrict__ wave, long clip_stride, long total_len, int B, int L, int T, int hop,
+frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __restrict__ clip_offset, long total_len,
+                int B, int L, int T, int hop,
                 const float* __restrict__ window, const float2* __restrict__ twiddle,
                 const int* __restrict__ mel_lo, const int* __restrict__ mel_len, const int* __restrict__ mel_off,
                 const float* __restrict__ mel_val, int n_mels, float amin, float db_offset, int is_log,
@@ -247,7 +249,8 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, long total_len, 
   const int items = B * chunks;
   int item = blockIdx.x;
   if (item < items)
-    stage_segment<NFFT, TIn>(s_stage0, wave, clip_stride, total_len, L, hop, seg_len, item, chunks, aligned != 0);
+    stage_segment<NFFT, TIn>(s_stage0, wave, clip_stride, clip_offset, total_len, L, hop, seg_len, item, chunks,
+                             aligned != 0);
 
   for (int i = threadIdx.x; i < NFFT; i += blockDim.x) {
     s_win[i] = window[i];
@@ -290,8 +293,8 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, long total_len, 
     __syncthreads();  // this item's segment is visible; every warp has finished the previous item
     const int nxt = item + gridDim.x;
     if (nxt < items)
-      stage_segment<NFFT, TIn>(sel ? s_stage0 : s_stage1, wave, clip_stride, total_len, L, hop, seg_len, nxt, chunks,
-                               aligned != 0);
+      stage_segment<NFFT, TIn>(sel ? s_stage0 : s_stage1, wave, clip_stride, clip_offset, total_len, L, hop, seg_len,
+                               nxt, chunks, aligned != 0);
     const TIn* s_seg = sel ? s_stage1 : s_stage0;
     const int b = item / chunks;
     const int f_base = (item - b * chunks) * FPB;
@@ -449,13 +452,14 @@ static int launch_frontend_t(const FrontendArgs& a, cudaStream_t stream) {
   if (blocks > items) blocks = items;
   // cp.async staging needs 16-byte aligned interior segments
   const size_t es = sizeof(TIn);
-  const int aligned = (reinterpret_cast<uintptr_t>(a.wave) % 16 == 0) && ((a.clip_stride * es) % 16 == 0) &&
+  const int aligned = (reinterpret_cast<uintptr_t>(a.wave) % 16 == 0) &&
+                      (a.clip_offset != nullptr || (a.clip_stride * es) % 16 == 0) &&
                       ((static_cast<size_t>(FPB) * a.hop * es) % 16 == 0) && ((NFFT / 2 * es) % 16 == 0) &&
                       ((seg_len * es) % 16 == 0);
   const char* e_dbg = getenv("SED_FE_DBG");
   const int dbg = e_dbg ? atoi(e_dbg) : 0;
   frontend_kernel<NFFT, TIn><<<static_cast<unsigned>(blocks), WARPS * 32, smem, stream>>>(
-      reinterpret_cast<const TIn*>(a.wave), a.clip_stride, a.total_len, a.B, a.L, a.T, a.hop, a.window,
+      reinterpret_cast<const TIn*>(a.wave), a.clip_stride, a.clip_offset, a.total_len, a.B, a.L, a.T, a.hop, a.window,
       reinterpret_cast<const float2*>(a.twiddle), a.mel_lo, a.mel_len, a.mel_off, a.mel_val, a.n_mels, a.amin,
       a.db_offset, a.is_log, a.bn_scale, a.bn_shift, a.out, a.mode, aligned, dbg);
   return cudaGetLastError() == cudaSuccess ? SED_OK : SED_ERR_CUDA;

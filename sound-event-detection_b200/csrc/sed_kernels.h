@@ -10,6 +10,7 @@ struct FrontendArgs {
   const void* wave;   // clip b = wave + b*clip_stride, L samples (f32 or i16)
   int wave_dtype;     // 0 = float32, 1 = int16 PCM (x = q / 32767)
   long clip_stride;   // samples between clip starts (== L for a dense batch)
+  const long* clip_offset;  // optional [B] device table of clip starts (samples from `wave`); overrides clip_stride
   long total_len;     // samples readable from `wave`; beyond -> 0
   int B, L, T, n_fft, hop;
   const float* window;   // [n_fft]
@@ -51,7 +52,7 @@ int gru_launch(const float* gi, const void* whh_packed, const float* bhh, int B,
                int dtype, cudaStream_t stream, long long* stamps = nullptr);
 
 int window_merge_launch(const float* frames, int n_windows, int frames_per_window, int classes, int overlap_interval,
-                        int sample_duration, float* merged, cudaStream_t stream);
+                        int sample_duration, int n_recordings, float* merged, cudaStream_t stream);
 
 int events_launch(const float* frames, int n_clips, int n_frames, int classes, const double* high, const double* low,
                   const int* n_smooth, const int* n_salt, int max_events, int* events, int* counts,

@@ -11,6 +11,8 @@ __global__ void window_merge_kernel(const float* __restrict__ frames, int n_wind
                                     int sample_duration, int total_frames, float* __restrict__ merged) {
   const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long>(total_frames) * classes) return;
+  frames += static_cast<size_t>(blockIdx.y) * n_windows * fpw * classes;   // recording blockIdx.y
+  merged += static_cast<size_t>(blockIdx.y) * total_frames * classes;
   const int f = static_cast<int>(idx / classes);
   const int c = static_cast<int>(idx - static_cast<long>(f) * classes);
   // merge(): window k (0-based) occupies frames [k*oi, k*oi + fpw); later windows are added to the running sum
@@ -41,8 +43,8 @@ __global__ void window_merge_kernel(const float* __restrict__ frames, int n_wind
 }
 
 int window_merge_launch(const float* frames, int n_windows, int frames_per_window, int classes, int overlap_interval,
-                        int sample_duration, float* merged, cudaStream_t stream) {
-  if (n_windows <= 0 || frames_per_window <= 0 || classes <= 0 || overlap_interval <= 0 || sample_duration <= 0 ||
+                        int sample_duration, int n_recordings, float* merged, cudaStream_t stream) {
+  if (n_recordings <= 0 || n_recordings > 65535 || n_windows <= 0 || frames_per_window <= 0 || classes <= 0 || overlap_interval <= 0 || sample_duration <= 0 ||
       overlap_interval > frames_per_window) {
     set_error("window_merge: bad shape n_windows=%d frames=%d classes=%d overlap_interval=%d duration=%d", n_windows,
               frames_per_window, classes, overlap_interval, sample_duration);
@@ -50,7 +52,7 @@ int window_merge_launch(const float* frames, int n_windows, int frames_per_windo
   }
   const int total = (n_windows - 1) * overlap_interval + frames_per_window;
   const long n = static_cast<long>(total) * classes;
-  window_merge_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+  window_merge_kernel<<<dim3(static_cast<unsigned>((n + 255) / 256), n_recordings), 256, 0, stream>>>(
       frames, n_windows, frames_per_window, classes, overlap_interval, sample_duration, total, merged);
   return cudaGetLastError() == cudaSuccess ? SED_OK : SED_ERR_CUDA;
 }

@@ -136,7 +136,9 @@ def logmel_forward(plan, wave, bn_scale=None, bn_shift=None, out=None, windows=N
     """wave [B, L] (f32 or int16 PCM) cuda -> [B, T, n_mels] f32.
 
     windows=(n_windows, L, stride): `wave` is one 1-D recording; window k = wave[k*stride : k*stride + L], zero
-    padded past the end (the slicing of predict.py:302-305) -- read in place, never materialised."""
+    padded past the end (the slicing of predict.py:302-305) -- read in place, never materialised.
+    windows=(n_windows, L, offsets): offsets = int64 CUDA tensor [n_windows] of window starts in samples (the windows
+    of many padded clips as one batch, main_strong.py:786-805)."""
     lib = capi.load()
     code = _wave_dtype_code(wave)
     if windows is None:
@@ -144,15 +146,24 @@ def logmel_forward(plan, wave, bn_scale=None, bn_shift=None, out=None, windows=N
             raise ValueError("waveform batch must be a contiguous (batch_size, data_length) tensor")
         B, L = wave.shape
         stride, total = L, B * L
+        offsets = None
     else:
         if wave.dim() != 1 or not wave.is_contiguous():
             raise ValueError("windowed input must be a contiguous 1-D recording")
-        B, L, stride = (int(v) for v in windows)
+        offsets = None
+        if torch.is_tensor(windows[2]):
+            B, L, stride = int(windows[0]), int(windows[1]), 0
+            offsets = windows[2]
+            if offsets.dtype != torch.int64 or offsets.numel() != B or offsets.device != wave.device:
+                raise ValueError("window offsets must be an int64 tensor [n_windows] on the waveform's device")
+        else:
+            B, L, stride = (int(v) for v in windows)
         total = wave.numel()
     T = L // plan.hop + 1
     if out is None:
         out = torch.empty((B, T, plan.n_mels), dtype=torch.float32, device=wave.device)
-    rc = lib.sed_frontend_logmel(capi.ptr(wave), code, B, L, stride, total, plan.n_fft, plan.hop,
+    rc = lib.sed_frontend_logmel(capi.ptr(wave), code, B, L, max(stride, 1),
+                                 capi.ptr(offsets), total, plan.n_fft, plan.hop,
                                  capi.ptr(plan.window), capi.ptr(plan.twiddle), capi.ptr(plan.mel_lo),
                                  capi.ptr(plan.mel_len), capi.ptr(plan.mel_off), capi.ptr(plan.mel_val), plan.n_mels,
                                  plan.amin, plan.db_offset, plan.is_log, capi.ptr(bn_scale), capi.ptr(bn_shift),
@@ -164,14 +175,16 @@ def logmel_forward(plan, wave, bn_scale=None, bn_shift=None, out=None, windows=N
 
 def window_merge_avg(frames, overlap_interval, sample_duration):
     """frames [n_windows, frames_per_window, classes] f32 cuda -> merged [1, total_frames, classes]
-    (merge + avg_merge, utils/utilities.py:405-446)."""
+    (merge + avg_merge, utils/utilities.py:405-446); a 4-D input [n_recordings, n_windows, fpw, classes] merges every
+    recording independently -> [n_recordings, total_frames, classes]."""
     lib = capi.load()
     frames = frames.contiguous()
-    nw, fpw, ncls = frames.shape
+    nrec = 1 if frames.dim() == 3 else frames.shape[0]
+    nw, fpw, ncls = frames.shape[-3:]
     total = (nw - 1) * overlap_interval + fpw
-    merged = torch.empty((1, total, ncls), dtype=torch.float32, device=frames.device)
+    merged = torch.empty((nrec, total, ncls), dtype=torch.float32, device=frames.device)
     rc = lib.sed_window_merge_avg(capi.ptr(frames), nw, fpw, ncls, int(overlap_interval), int(sample_duration),
-                                  capi.ptr(merged), capi.current_stream(frames.device))
+                                  nrec, capi.ptr(merged), capi.current_stream(frames.device))
     capi.check(rc, "sed_window_merge_avg")
     capi._count()
     return merged
@@ -654,10 +667,12 @@ class PackedModel:
         out = {"framewise_output": frame, "clipwise_output": clip, "embedding": self._embedding(x, cla, feat32)}
         return out, feat16, x, natt
 
-    def forward_windows(self, recording, window_samples, stride_samples, n_windows, micro_batch=148, variant=2):
+    def forward_windows(self, recording, window_samples, stride_samples, n_windows, micro_batch=148, variant=2,
+                        offsets=None):
         """Run the model on `n_windows` overlapping windows of one 1-D recording (f32 or int16, on device):
         window k = recording[k*stride : k*stride + window_samples], zero padded past the end.  Returns the same
-        dict as forward() with batch dimension = windows (the per-window calls of predict.py:311-313 as one batch)."""
+        dict as forward() with batch dimension = windows (the per-window calls of predict.py:311-313 as one batch).
+        offsets: int64 CUDA tensor [n_windows] of window starts (overrides the constant stride)."""
         if recording.dim() != 1 or recording.device != self.device:
             raise ValueError("recording must be a 1-D tensor on %s" % (self.device,))
         if recording.dtype != torch.int16:
@@ -668,8 +683,12 @@ class PackedModel:
         def conv_call(slot):
             for b0 in range(0, n_windows, micro_batch):
                 b1 = min(n_windows, b0 + micro_batch)
-                self.conv_stack(recording[b0 * stride_samples:], variant=variant,
-                                windows=(b1 - b0, window_samples, stride_samples), **slot(b0, b1))
+                if offsets is not None:
+                    self.conv_stack(recording, variant=variant, windows=(b1 - b0, window_samples, offsets[b0:b1]),
+                                    **slot(b0, b1))
+                else:
+                    self.conv_stack(recording[b0 * stride_samples:], variant=variant,
+                                    windows=(b1 - b0, window_samples, stride_samples), **slot(b0, b1))
 
         with self._lock:
             return self._run(n_windows, T // 8, conv_call)[0]

@@ -49,6 +49,76 @@ def predict_framewise(model, recording, sample_rate, sample_duration=5, overlap_
     return merged
 
 
+def overlap_window_counts(audio_durations, sample_duration, overlap_value):
+    """Windows the loop of main_strong.py:786-834 runs per file: start k*overlap_value for k = 0 and every k with
+    k*overlap_value + sample_duration <= audio_duration (the `while end <= audio_duration` rule, end updated after
+    each window)."""
+    counts = []
+    for d in audio_durations:
+        n, start, end = 0, 0.0, 0.0
+        while end <= d:
+            n += 1
+            start += overlap_value
+            end = start + sample_duration
+        counts.append(n)
+    return counts
+
+
+def predict_framewise_overlap(model, clips, sample_rate, sample_duration, overlap_value, audio_durations=None):
+    """The overlap evaluation loop of pytorch/main_strong.py:768-834 for a batch of files at once.
+
+    clips: (n_files, 10 * sample_rate) float32 / int16 CUDA tensor, every file already padded / truncated to 10 s
+    (`pad_truncate_sequence`, main_strong.py:785); audio_durations: the files' real durations in seconds (default
+    10.0 each) -- they decide how many windows a file gets.  All windows of all files run as ONE batch (the front-end
+    reads them in place through an offset table), each file's windows are overlap-added and block-averaged on the
+    device.  Returns a list of per-file tensors [1, total_frames, classes] (what `merged` holds after :835)."""
+    if isinstance(model, engine.PackedModel):
+        packed, micro_batch, variant = model, 148, 2
+    else:
+        if model.training:
+            raise RuntimeError("inference only -- call .eval()")
+        if not clips.is_cuda:
+            raise RuntimeError("clips are on %s; the B200 path has no CPU fallback" % (clips.device,))
+        packed = model._packed_for(clips.device)
+        micro_batch, variant = model.micro_batch, model.conv_variant
+    if clips.dim() != 2:
+        raise ValueError("clips must be (n_files, samples)")
+    n_files, L = clips.shape
+    if audio_durations is None:
+        audio_durations = [L / float(sample_rate)] * n_files
+    counts = overlap_window_counts(audio_durations, sample_duration, overlap_value)
+    window_samples = int(sample_duration * sample_rate)
+    starts = []
+    for f, nw in enumerate(counts):
+        for k in range(nw):
+            s0 = int(k * overlap_value * sample_rate)  # int(start * sample_rate), main_strong.py:790
+            if s0 + window_samples > L:
+                raise ValueError("file %d: window %d runs past the padded clip (the reference would feed a short "
+                                 "window to the model)" % (f, k))
+            starts.append(f * L + s0)
+    offsets = torch.tensor(starts, dtype=torch.int64, device=clips.device)
+    flat = clips.contiguous().view(-1)
+    with torch.no_grad():
+        out = packed.forward_windows(flat, window_samples, 0, len(starts), micro_batch=micro_batch, variant=variant,
+                                     offsets=offsets)
+        frames = out["framewise_output"]
+        merged = [None] * n_files
+        oi = int(100 * overlap_value)
+        first = 0
+        firsts = []
+        for nw in counts:
+            firsts.append(first)
+            first += nw
+        for nw in sorted(set(counts)):  # files with the same number of windows are merged by one launch
+            idx = [f for f in range(n_files) if counts[f] == nw]
+            rows = torch.tensor([firsts[f] + k for f in idx for k in range(nw)], dtype=torch.int64, device=clips.device)
+            group = frames.index_select(0, rows).view(len(idx), nw, frames.shape[1], frames.shape[2])
+            m = engine.window_merge_avg(group, oi, int(sample_duration))
+            for j, f in enumerate(idx):
+                merged[f] = m[j:j + 1]
+    return merged
+
+
 # Class names of the 25-class strong-label task (utils/config.py:26)
 LABELS = ['Applause', 'Breathing', 'Chatter', 'Cheering', 'Child_speech_kid_speaking', 'Clapping', 'Conversation',
           'Cough', 'Crowd', 'Crying_sobbing', 'Female_speech_woman_speaking', 'Laughter',

@@ -91,3 +91,33 @@ def test_windowed_frontend_reads_in_place():
     a = pm.forward(batch)
     b = pm.forward_windows(rec, L, stride, n)
     assert torch.equal(a["framewise_output"], b["framewise_output"])
+
+
+@pytest.mark.parametrize("ov,dur", [(1, 5), (0.5, 6)])
+def test_overlap_evaluation_loop_batched_over_files(ov, dur):
+    """main_strong.py:768-835: per-file window loop with stride = overlap_value on clips padded to 10 s; here all
+    windows of all files form one batch.  Files of different real durations get different numbers of windows."""
+    mt = "Cnn_9layers_Gru_FrameAtt"
+    sr = 16000
+    sd = synthetic_sd(mt, sr)
+    durations = [10.0, 7.3, 9.99]
+    clips = torch.zeros(3, 10 * sr)
+    for i, d in enumerate(durations):
+        n = int(d * sr)
+        clips[i, :n] = synth.synthetic_waveform(1, n, seed=60 + i, kind="events")[0]   # pad_truncate_sequence to 10 s
+    merged = streaming.predict_framewise_overlap(build(mt), clips.to(DEV), sr, dur, ov, audio_durations=durations)
+    assert streaming.overlap_window_counts(durations, dur, ov) == [len(stream_oracle.overlap_eval_predict(
+        sd, clips[i].numpy(), durations[i], mt, sr, 512, 160, dur, ov)[1]) for i in range(3)]
+    for i, d in enumerate(durations):
+        ref, _ = stream_oracle.overlap_eval_predict(sd, clips[i].numpy(), d, mt, sr, 512, 160, dur, ov)
+        got = merged[i].cpu().numpy()
+        assert got.shape == ref.shape, (i, got.shape, ref.shape)
+        assert np.abs(got - ref).max() <= 2e-3, (i, np.abs(got - ref).max())
+
+
+def test_batched_merge_equals_per_recording_merge():
+    g = torch.Generator().manual_seed(3)
+    frames = torch.rand(4, 6, 500, 25, generator=g).to(DEV)
+    both = engine.window_merge_avg(frames, 100, 5)
+    for r in range(4):
+        assert torch.equal(both[r:r + 1], engine.window_merge_avg(frames[r], 100, 5))

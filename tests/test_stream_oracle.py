@@ -77,3 +77,12 @@ def test_oracle_matches_live_reference_utilities():
     assert np.array_equal(so.pad_truncate_sequence(x, 1500), ref_util.pad_truncate_sequence(x, 1500))
     q = (rng.rand(100) * 65535 - 32768).astype(np.int16)
     assert np.array_equal(ref_util.int16_to_float32(q), (q / 32767.).astype(np.float32))
+
+
+def test_overlap_window_rule_matches_main_strong_loop():
+    """`while end <= audio_duration` with end updated after each window (main_strong.py:789, 826-828)."""
+    from sed_b200 import streaming
+    assert streaming.overlap_window_counts([10.0], 5, 1) == [6]        # starts 0..5
+    assert streaming.overlap_window_counts([10.0], 6, 0.5) == [9]      # starts 0, 0.5, ..., 4
+    assert streaming.overlap_window_counts([10.0], 7, 1) == [4]
+    assert streaming.overlap_window_counts([7.3, 4.0, 9.99], 5, 1) == [3, 1, 5]
