@@ -8,6 +8,7 @@ the reference forward (SpecAugment / mixup / timeshift, models.py:647-661) are n
 `forward` refuses to run in training mode.  Inputs must be CUDA tensors; there is no CPU fallback.
 """
 import math
+import threading
 
 import torch
 import torch.nn as nn
@@ -94,6 +95,7 @@ class _Cnn9Base(nn.Module):
         # engine state shared (by reference) with DataParallel replicas
         self._packed = {}
         self._generation = [0]
+        self._pack_lock = threading.RLock()
         self.precision = "fp16"   # 16-bit operand type of the tensor-core layers: 'fp16' or 'bf16'
         self.micro_batch = 148
         self.conv_variant = 2   # 2 = CTA-pair kernels (default), 0 = single-CTA patch, 1 = per-tap, 3 = 2 + fused conv_block1 (slower)
@@ -112,14 +114,40 @@ class _Cnn9Base(nn.Module):
         self._invalidate()
         return out
 
+    # the engine state (device copies, lock) is not part of the module's value: copy / pickle rebuild it lazily
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_packed"] = {}
+        state["_generation"] = [0]
+        state.pop("_pack_lock", None)
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._pack_lock = threading.RLock()
+
+    def _full_state(self):
+        """state_dict()-like view that also works on DataParallel replicas, whose parameters are plain attributes
+        (torch.nn.parallel.replicate keeps them in `_former_parameters`, so `state_dict()` there returns buffers only)."""
+        sd = {}
+        for prefix, mod in self.named_modules():
+            params = dict(mod._parameters)
+            params.update(getattr(mod, "_former_parameters", {}))
+            for k, v in list(params.items()) + list(mod._buffers.items()):
+                if v is not None and k not in mod._non_persistent_buffers_set:
+                    sd[(prefix + "." if prefix else "") + k] = v
+        return sd
+
     def _packed_for(self, device):
         key = (device.type, device.index, self.precision)
         hit = self._packed.get(key)
         if hit is None or hit[0] != self._generation[0]:
-            sd = {k: v for k, v in self.state_dict().items()}
-            hit = (self._generation[0],
-                   engine.PackedModel(sd, self.MODEL_TYPE, self.window_size, self.hop_size, device, self.precision))
-            self._packed[key] = hit
+            with self._pack_lock:  # DataParallel runs one thread per replica; they share _packed by reference
+                hit = self._packed.get(key)
+                if hit is None or hit[0] != self._generation[0]:
+                    hit = (self._generation[0], engine.PackedModel(self._full_state(), self.MODEL_TYPE, self.window_size,
+                                                                   self.hop_size, device, self.precision))
+                    self._packed[key] = hit
         return hit[1]
 
     def forward(self, input, mixup_lambda=None, timeshift=False, spec_augment=True):

@@ -78,3 +78,26 @@ def test_module_names_resolve_like_reference():
     exec("from sed_b200.models import *", ns)
     for name in synth.MODEL_TYPES:
         assert name in ns
+
+
+def test_model_can_be_deep_copied_and_pickled():
+    import copy
+    import pickle
+    model = models.Cnn_9layers_Gru_FrameAtt(16000, 512, 160, 64, 25, 7000, 25, "logmel")
+    clone = copy.deepcopy(model)
+    assert clone._packed == {} and clone._packed is not model._packed
+    again = pickle.loads(pickle.dumps(model))
+    assert list(again.state_dict().keys()) == list(model.state_dict().keys())
+
+
+def test_full_state_matches_state_dict_and_survives_replication():
+    """DataParallel replicas keep their parameters as plain attributes (state_dict() there has buffers only)."""
+    model = models.Cnn_9layers_Transformer_FrameAtt(16000, 512, 160, 64, 25, 7000, 25, "logmel")
+    full = model._full_state()
+    sd = model.state_dict()
+    assert list(full.keys()) == list(sd.keys())
+    replica = model._replicate_for_data_parallel()
+    replica._former_parameters = dict(replica._parameters)
+    replica._parameters = {}
+    assert "bn0.weight" in replica._full_state()
+    assert replica._packed is model._packed and replica._pack_lock is model._pack_lock

@@ -162,3 +162,33 @@ def test_fused_conv_block1_matches_the_two_kernel_path():
     a = pm.forward(wave5, variant=2)["framewise_output"]
     b = pm.forward(wave5, variant=3)["framewise_output"]
     assert (a - b).abs().max().item() <= 1e-3
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_data_parallel_two_gpus_matches_single_gpu():
+    """torch.nn.DataParallel (main_strong.py:541, predict.py:239): one Python thread per GPU, module re-replicated
+    every call; packed weights / workspaces are cached per device and the kernels run on each device's stream."""
+    mt = "Cnn_9layers_Gru_FrameAtt"
+    single = build(mt)
+    wave = synth.synthetic_waveform(6, 48000, seed=17, kind="events")
+    ref = single(wave.to(DEV))
+    dp = torch.nn.DataParallel(build(mt), device_ids=[0, 1])
+    for _ in range(2):  # second call re-uses the per-device packed weights
+        out = dp(wave.to(DEV))
+        for k in ("framewise_output", "clipwise_output"):
+            assert out[k].device == torch.device(DEV)
+            assert torch.equal(out[k], ref[k]), k
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_second_device_direct():
+    mt = "Cnn_9layers_Transformer_FrameAtt"
+    a = build(mt)
+    wave = synth.synthetic_waveform(2, 32000, seed=23)
+    ref = a(wave.to(DEV))["clipwise_output"].cpu()
+    b = getattr(models, mt)(*ARGS[16000])
+    b.load_state_dict(synthetic_sd(mt))
+    b = b.to("cuda:1").eval()
+    with torch.cuda.device(1):
+        got = b(wave.to("cuda:1"))["clipwise_output"].cpu()
+    assert torch.equal(got, ref)
