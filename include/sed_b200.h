@@ -90,12 +90,15 @@ int sed_conv3x3_bn_relu(const void* x, int NB, int H, int W, int cin, const void
 
 /* conv_block1 in one kernel: conv1 (1 -> 64) + bn1 + ReLU computed on the fly as the tensor-core operand of
  * conv2 (64 -> 64) + bn2 + ReLU + 2x2 avg-pool.  Replaces ConvBlock.forward pytorch/models.py:125-141 for
- * conv_block1 (models.py:663); the [NB, H, W, 64] intermediate never reaches HBM.  Experimental: measured slower
- * (1.07 ms per 148 clips) than sed_conv_first_f32 + sed_conv3x3_bn_relu (0.28 + 0.53 ms); not used by default.
+ * conv_block1 (models.py:663); the [NB, H, W, 64] intermediate never reaches HBM.
+ *   producer 0: conv1 on the CUDA cores (packed f32x2 FMAs) -- measured slower (1.07 ms per 148 clips) than
+ *   sed_conv_first_f32 + sed_conv3x3_bn_relu (0.28 + 0.53 ms); producer 1: conv1 as a split-fp16 tensor-core GEMM
+ *   whose accumulators are drained from TMEM into conv2's shared-memory operand.
  *   x [NB, H, W] f32 (log-mel after bn0, W % 16 == 0); w1_scaled [64][9] f32 = conv1 weights x folded bn1 scale;
  *   shift1 [64] folded bn1 shift; w2packed [64][9][64] 16-bit; scale2/shift2 [64]; out [NB, H/2, W/2, 64] 16-bit. */
 int sed_conv_block1(const float* x, int NB, int H, int W, const float* w1_scaled, const float* shift1,
-                    const void* w2packed, const float* scale2, const float* shift2, void* out, int dtype, void* stream);
+                    const void* w2packed, const float* scale2, const float* shift2, void* out, int producer, int dtype,
+                    void* stream);
 
 /* out[M, N] = a[M, K] * w[N, K]^T + bias (optional ReLU) on the tensor cores; K in {256, 512},
  * N % 128 == 0.  Replaces the nn.Linear calls inside nn.GRU (input projection, models.py:670) and

@@ -33,7 +33,7 @@ SIGNATURES = {
     "sed_logmel_rows_f32": ([_p, _l, _i, _p, _p, _p, _p, _i, _f, _f, _i, _p, _p], _i),
     "sed_conv_first_f32": ([_p, _i, _i, _i, _p, _p, _p, _p, _i, _p], _i),
     "sed_conv3x3_bn_relu": ([_p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p, _l, _l, _i, _i, _p], _i),
-    "sed_conv_block1": ([_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p], _i),
+    "sed_conv_block1": ([_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p], _i),
     "sed_fcpool": ([_p, _i, _i, _p, _p, _i, _i, _i, _p, _p, _p], _i),
     "sed_linear": ([_p, _l, _i, _p, _p, _i, _i, _p, _p, _i, _i, _p], _i),
     "sed_bigru_workspace_bytes": ([_i], _l),

@@ -5,7 +5,7 @@
 
 #include "sed_kernels.h"
 
-#define SED_ABI_VERSION 9
+#define SED_ABI_VERSION 10
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -117,10 +117,11 @@ int sed_conv3x3_bn_relu(const void* x, int NB, int H, int W, int cin, const void
 }
 
 int sed_conv_block1(const float* x, int NB, int H, int W, const float* w1_scaled, const float* shift1,
-                    const void* w2packed, const float* scale2, const float* shift2, void* out, int dtype, void* stream) {
+                    const void* w2packed, const float* scale2, const float* shift2, void* out, int producer, int dtype,
+                    void* stream) {
   SED_REQUIRE(x); SED_REQUIRE(w1_scaled); SED_REQUIRE(shift1); SED_REQUIRE(w2packed); SED_REQUIRE(scale2);
   SED_REQUIRE(shift2); SED_REQUIRE(out);
-  return sed::conv_block1_launch(x, NB, H, W, w1_scaled, shift1, w2packed, scale2, shift2, out, dtype,
+  return sed::conv_block1_launch(x, NB, H, W, w1_scaled, shift1, w2packed, scale2, shift2, out, producer, dtype,
                                  as_stream(stream));
 }
 

@@ -331,6 +331,10 @@ struct Elem16<__half> {
     return r;
   }
   SED_DEVICE_INLINE static float to_float(uint16_t v) { return __half2float(__ushort_as_half(v)); }
+  SED_DEVICE_INLINE static uint32_t relu2(uint32_t v) {  // max(x, 0) on both halves (exact: commutes with rounding)
+    const __half2 h = __hmax2(*reinterpret_cast<const __half2*>(&v), __float2half2_rn(0.0f));
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
 };
 template <>
 struct Elem16<__nv_bfloat16> {
@@ -341,6 +345,10 @@ struct Elem16<__nv_bfloat16> {
     return r;
   }
   SED_DEVICE_INLINE static float to_float(uint16_t v) { return __uint_as_float(static_cast<uint32_t>(v) << 16); }
+  SED_DEVICE_INLINE static uint32_t relu2(uint32_t v) {
+    const __nv_bfloat162 h = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&v), __float2bfloat162_rn(0.0f));
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
 };
 
 }  // namespace sed

@@ -262,6 +262,342 @@ int conv_first_launch(const float* x, int NB, int H, int W, const float* w9, con
 // ---------------------------------------------------------------------------------------------
 // tcgen05 conv / linear launch
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// conv_block1 as ONE tensor-core kernel (engine variant 4): conv1 (1 -> 64 channels) runs as a split-fp16 tcgen05 GEMM
+// (K = 9 taps padded to 16, hi*hi + lo*hi + hi*lo, float32-grade like conv_first_umma_kernel) on the 18 x 10 pixel halo
+// patch of every conv2 tile; its accumulators are drained from TMEM through bn1 + ReLU straight into the swizzled
+// shared-memory patch that conv2's implicit-GEMM MMAs read -- the [NB, H, 64, 64] intermediate never exists in HBM.
+// CTA pairs (cta_group::2) as in conv_umma2_kernel: M = 256 = one tile per CTA, each CTA holds half of the weight
+// rows of both layers.  Warp roles: 0 weight TMA, 1 MMA issuer (leader CTA: conv1 of tile i+1, then conv2 of tile i),
+// 2-9 conv2 pooling epilogue, 10-17 two groups of conv1 operand builders (im2col of the one-channel input, hi/lo
+// split) + TMEM drainers working on alternate tiles.
+// ---------------------------------------------------------------------------------------------
+namespace c1tc {
+constexpr int SA = 5;                       // conv2 patch stages
+constexpr int ACC = 4;                      // conv2 accumulator stages (64 columns each)
+constexpr int A_BYTES = SA * kPatchStride;  // 117,760
+constexpr int B2_HALF = 32 * 128;           // one tap block of this CTA's 32 conv2 weight rows
+constexpr int B2_BYTES = 9 * B2_HALF;       // 36,864
+constexpr int OP_STAGE = 2 * 256 * 32;      // conv1 A operand, hi + lo, 256 rows x 32 B
+constexpr int OP_BYTES = 2 * OP_STAGE;      // two stages
+constexpr int B1_BYTES = 2 * 32 * 32;       // conv1 weights of this CTA's 32 channels, hi + lo
+constexpr int MISC = 4096;
+constexpr int SMEM_BYTES = 1024 + A_BYTES + B2_BYTES + OP_BYTES + 2048 + MISC;
+constexpr int PG = 1;                       // producer groups (4 warps each): group g builds / drains tiles j = g mod 2
+constexpr int THREADS = 64 + 256 + 128 * PG;
+constexpr int C1_COL0 = ACC * 64;           // conv1 accumulators: columns 256 + stage*128 + mtile*64
+}  // namespace c1tc
+
+template <typename T>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(c1tc::THREADS, 1)
+conv_block1_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+  using namespace c1tc;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem_1024(smem_raw);
+  uint8_t* smem_a = smem;                          // [SA] conv2 patches (SWIZZLE_128B, 180 pixel rows x 128 B)
+  uint8_t* smem_b = smem_a + A_BYTES;              // conv2 weights, 9 taps x 32 rows x 128 B
+  uint8_t* s_op = smem_b + B2_BYTES;               // [2 stages][hi | lo][256 rows x 32 B] (SWIZZLE_32B)
+  uint8_t* s_b1 = s_op + OP_BYTES;                 // [hi | lo][32 rows x 32 B]
+  float* s_scale = reinterpret_cast<float*>(s_b1 + 2048);
+  float* s_shift = s_scale + 64;
+  float* s_shift1 = s_shift + 64;
+  float* s_win = s_shift1 + 64;                    // [2 stages][256] one-channel input windows (20 x 12 used)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_win + 512);
+  uint64_t* a_full = bars;              // [SA]  leader: 8 producer-warp arrivals (both CTAs)
+  uint64_t* a_empty = a_full + SA;      // [SA]  per CTA (multicast commit)
+  uint64_t* b_full = a_empty + SA;      // leader: conv2 weights landed
+  uint64_t* t_full = b_full + 1;        // [ACC] per CTA (multicast commit)
+  uint64_t* t_empty = t_full + ACC;     // [ACC] leader: 16 epilogue-warp arrivals
+  uint64_t* op_full = t_empty + ACC;    // [2]   leader: 8 producer-warp arrivals
+  uint64_t* op_empty = op_full + 2;     // [2]   per CTA (multicast commit)
+  uint64_t* c1_full = op_empty + 2;     // [2]   per CTA (multicast commit)
+  uint64_t* c1_empty = c1_full + 2;     // [2]   leader: 8 producer-warp arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c1_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pr_cta = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int items = (p.num_tiles + 1) / 2;
+
+  if (threadIdx.x < 64) {
+    s_scale[threadIdx.x] = p.scale[threadIdx.x];
+    s_shift[threadIdx.x] = p.shift[threadIdx.x];
+    s_shift1[threadIdx.x] = p.shift1[threadIdx.x];
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 96) {
+    // conv1 weights (bn1 scale folded in) of channel rank*32 + r -> split fp16 operand row r (SWIZZLE_32B)
+    const int r = threadIdx.x - 64, ch = static_cast<int>(rank) * 32 + r;
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      // K slot 9 carries the folded bn1 shift (the operand rows hold a constant 1 there): the bias rides the GEMM
+      const float v0 = (2 * t < 9) ? p.w1[ch * 9 + 2 * t] : 0.0f;
+      const float v1 = (2 * t + 1 < 9) ? p.w1[ch * 9 + 2 * t + 1] : (2 * t + 1 == 9 ? p.shift1[ch] : 0.0f);
+      const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+      const __half l0 = __float2half_rn(v0 - __half2float(h0)), l1 = __float2half_rn(v1 - __half2float(h1));
+      hi[t] = static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
+      lo[t] = static_cast<uint32_t>(__half_as_ushort(l0)) | (static_cast<uint32_t>(__half_as_ushort(l1)) << 16);
+    }
+    const int sw = (r >> 2) & 1;
+    *reinterpret_cast<uint4*>(s_b1 + r * 32 + ((0 ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(s_b1 + r * 32 + ((1 ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    *reinterpret_cast<uint4*>(s_b1 + 1024 + r * 32 + ((0 ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(s_b1 + 1024 + r * 32 + ((1 ^ sw) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 8); mbar_init(&a_empty[i], 1); }
+    mbar_init(b_full, 1);
+    for (int i = 0; i < ACC; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 16); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&op_full[i], 8); mbar_init(&op_empty[i], 1);
+      mbar_init(&c1_full[i], 1); mbar_init(&c1_empty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc2(tmem_slot, 512);
+    tmem_relinquish2();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_coords = [&](int tile, int& n, int& h0, int& w0) {
+    const int per_img = p.tiles_h * p.tiles_w;
+    n = fast_div(tile, p.magic_img);
+    const int rem = tile - n * per_img;
+    const int th = fast_div(rem, p.magic_w);
+    h0 = th * 16;
+    w0 = (rem - th * p.tiles_w) * 8;
+  };
+
+  if (warp == 0) {
+    // =============================== conv2 weights (resident) ================================
+    if (elect_one()) {
+      const uint32_t bfull_leader = map_to_cta(b_full, 0);
+      if (leader) mbar_expect_tx(b_full, 2 * B2_BYTES);
+      for (int tap = 0; tap < 9; ++tap)
+        tma_load_2d_2sm(smem_b + tap * B2_HALF, &tmB, bfull_leader, tap * 64, static_cast<int>(rank) * 32);
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer (leader CTA only) ============================
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc2 = umma_idesc_f16(Elem16<T>::kFmt, 256, 64);
+      constexpr uint32_t idesc1 = umma_idesc_f16(0, 256, 64);  // conv1 operands are fp16 whatever T is
+      constexpr uint32_t a_hi = desc_hi_sw128(1280), b_hi = desc_hi_sw128(1024), d32 = desc_hi_sw32(256);
+      const uint32_t a_lo0 = desc_lo(smem_u32(smem_a)), b_lo0 = desc_lo(smem_u32(smem_b));
+      const uint32_t op_lo0 = desc_lo(smem_u32(s_op)), b1_hi_lo = desc_lo(smem_u32(s_b1)),
+                     b1_lo_lo = desc_lo(smem_u32(s_b1 + 1024));
+      mbar_wait(b_full, 0);
+      tc_fence_after();
+      const int n_local = (items - pr_cta + npairs - 1) / npairs;  // work items of this pair
+      auto conv1 = [&](int j) {
+        const int st = j & 1, ph = (j >> 1) & 1;
+        mbar_wait_cluster(&op_full[st], ph);
+        mbar_wait_cluster(&c1_empty[st], ph ^ 1);
+        tc_fence_after();
+        const uint32_t a_h = op_lo0 + st * (OP_STAGE >> 4), a_l = a_h + (8192 >> 4);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const uint32_t d = tmem_base + C1_COL0 + st * 128 + mt * 64;
+          const uint32_t mo = mt * (4096 >> 4);
+          umma_f16_2sm(d, desc_join(a_h + mo, d32), desc_join(b1_hi_lo, d32), idesc1, 0u);
+          umma_f16_2sm(d, desc_join(a_l + mo, d32), desc_join(b1_hi_lo, d32), idesc1, 1u);
+          umma_f16_2sm(d, desc_join(a_h + mo, d32), desc_join(b1_lo_lo, d32), idesc1, 1u);
+        }
+        umma_commit_2sm(&c1_full[st], 3);
+        umma_commit_2sm(&op_empty[st], 3);
+      };
+      uint32_t sa = 0, pa = 0, acc = 0, pacc = 0;
+      if (n_local > 0) conv1(0);
+      for (int i = 0; i < n_local; ++i) {
+        if (i + 1 < n_local) conv1(i + 1);
+        mbar_wait(&t_empty[acc], pacc ^ 1);
+        mbar_wait_cluster(&a_full[sa], pa);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + acc * 64;
+        const uint32_t a_lo = a_lo0 + sa * (kPatchStride >> 4);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t b_lo = b_lo0 + tap * (B2_HALF >> 4);
+          const uint32_t tap_off = ((tap / 3) * 10 + (tap % 3)) * 8;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_2sm(d_base, desc_join(a_lo + tap_off + k * 2, a_hi), desc_join(b_lo + k * 2, b_hi), idesc2,
+                         (tap | k) ? 1u : 0u);
+        }
+        umma_commit_2sm(&a_empty[sa], 3);
+        umma_commit_2sm(&t_full[acc], 3);
+        if (++sa == SA) { sa = 0; pa ^= 1; }
+        if (++acc == ACC) { acc = 0; pacc ^= 1; }
+      }
+    }
+  } else if (warp < 10) {
+    // =============================== conv2 epilogue (8 warps, both CTAs) ====================
+    const int quarter = warp & 3;
+    const int chalf = (warp - 2) >> 2;
+    uint32_t acc = 0, pacc = 0;
+    for (int w = pr_cta; w < items; w += npairs) {
+      mbar_wait(&t_full[acc], pacc);
+      tc_fence_after();
+      const int tile = w * 2 + static_cast<int>(rank);
+      const bool tile_ok = tile < p.num_tiles;
+      int n, h0, w0;
+      tile_coords(tile, n, h0, w0);
+      const uint32_t taddr = tmem_base + acc * 64 + chalf * 32 + (static_cast<uint32_t>(quarter * 32) << 16);
+      conv_epilogue_tile<T, 64, true, EPI_POOL>(taddr, chalf, warp, lane, s_scale, s_shift, 0, tile, tile_ok, n, h0, w0,
+                                                p, nullptr, nullptr);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote_light(&t_empty[acc], 0);
+      if (++acc == ACC) { acc = 0; pacc ^= 1; }
+    }
+  } else {
+    // =============================== conv1 operand build + TMEM drain (4 warps) ==============
+    const int m_tm = (warp & 3) * 32 + lane;  // TMEM lane this thread may read = its patch row within an M-tile
+    // patch rows of this thread: pr = mt*128 + m_tm (mt = 0, 1; rows >= 180 do not exist)
+    int prr[2], prc[2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int pr = mt * 128 + m_tm;
+      prr[mt] = pr / 10;
+      prc[mt] = pr - prr[mt] * 10;
+    }
+    const int grp = (warp - 10) >> 2;                  // producer group: owns operand / accumulator stage `grp`
+    const int ptid = ((warp - 10) & 3) * 32 + lane;    // 0..127 within the producer group
+    // the tile's 20 x 12 one-channel input window (zero outside the image = conv1's padding): two values per thread
+    auto gather = [&](int tile, float (&g)[2]) {
+      int n, h0, w0;
+      tile_coords(tile, n, h0, w0);
+      const bool tv = tile < p.num_tiles;
+      const float* xn = p.x1 + static_cast<size_t>(n) * p.H * p.W;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int e = ptid + 128 * k;
+        const int er = e / 12, ec = e - er * 12;
+        const int hh = h0 - 2 + er, ww = w0 - 2 + ec;
+        g[k] = (tv && e < 240 && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W) ? __ldg(xn + hh * p.W + ww) : 0.0f;
+      }
+    };
+    auto build = [&](int j, int tile, const float (&g)[2]) {
+      const int st = j & 1, ph = (j >> 1) & 1;
+      float* win = s_win + st * 256;
+      win[ptid] = g[0];
+      if (ptid < 112) win[128 + ptid] = g[1];
+      int n, h0, w0;
+      tile_coords(tile, n, h0, w0);
+      const bool tv = tile < p.num_tiles;
+      named_bar_sync(2 + grp, 128);  // the window is complete (the producer group's own barrier)
+      mbar_wait(&op_empty[st], ph ^ 1);
+      uint8_t* hi_base = s_op + st * OP_STAGE;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int row = mt * 128 + m_tm;
+        // a patch pixel outside the image is conv2's ZERO padding: its whole operand row (bias slot included) is zero
+        const int ph_ = h0 - 1 + prr[mt], pw_ = w0 - 1 + prc[mt];
+        const bool rowv = tv && row < 180 && ph_ >= 0 && ph_ < p.H && pw_ >= 0 && pw_ < p.W;
+        float in[10];
+#pragma unroll
+        for (int dr = 0; dr < 3; ++dr)
+#pragma unroll
+          for (int dc = 0; dc < 3; ++dc)
+            in[dr * 3 + dc] = (rowv) ? win[(prr[mt] + dr) * 12 + prc[mt] + dc] : 0.0f;
+        in[9] = rowv ? 1.0f : 0.0f;
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int t = 0; t < 5; ++t) {  // packed conversions: hi = rn16(v), lo = rn16(v - hi)
+          const __half2 h = __floats2half2_rn(in[2 * t], in[2 * t + 1]);
+          const float2 hf = __half22float2(h);
+          const __half2 l = __floats2half2_rn(in[2 * t] - hf.x, in[2 * t + 1] - hf.y);
+          hi[t] = *reinterpret_cast<const uint32_t*>(&h);
+          lo[t] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+#pragma unroll
+        for (int t = 5; t < 8; ++t) hi[t] = lo[t] = 0u;
+        const int sw = (row >> 2) & 1;
+        uint8_t* rp = hi_base + row * 32;
+        *reinterpret_cast<uint4*>(rp + ((0 ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(rp + ((1 ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+        *reinterpret_cast<uint4*>(rp + 8192 + ((0 ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(rp + 8192 + ((1 ^ sw) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote_light(&op_full[st], 0);
+    };
+    auto drain = [&](int j, int tile) {
+      const uint32_t sa = static_cast<uint32_t>(j) % SA, pa = (static_cast<uint32_t>(j) / SA) & 1;
+      const int st = j & 1, ph = (j >> 1) & 1;
+      (void)tile;
+      mbar_wait(&c1_full[st], ph);
+      mbar_wait(&a_empty[sa], pa ^ 1);
+      tc_fence_after();
+      uint8_t* patch = smem_a + sa * kPatchStride;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        uint32_t r[4][16];
+        const uint32_t taddr = tmem_base + C1_COL0 + st * 128 + mt * 64 + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) tmem_ld16(taddr + u * 16, r[u]);
+        tmem_ld_wait();
+        const int pr = mt * 128 + m_tm;
+        if (pr < 180) {
+          // accumulators already hold conv1 + folded bn1 shift (zero for padding pixels): ReLU on the packed 16-bit pairs
+          uint8_t* rowp = patch + pr * 128;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              pk[q] = Elem16<T>::relu2(Elem16<T>::pack2(__uint_as_float(r[u][2 * q]), __uint_as_float(r[u][2 * q + 1])));
+            *reinterpret_cast<uint4*>(rowp + (((2 * u) ^ (pr & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(rowp + (((2 * u + 1) ^ (pr & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_remote_light(&a_full[sa], 0);
+        mbar_arrive_remote_light(&c1_empty[st], 0);
+      }
+    };
+    // software pipeline per group (tiles j = grp, grp + PG, ...): the one-channel inputs of the group's tile after next
+    // are in flight while its next tile is built and its current tile drained
+    float nin[2];
+    auto tile_of = [&](int jj) { return (pr_cta + jj * npairs) * 2 + static_cast<int>(rank); };
+    auto has = [&](int jj) { return pr_cta + jj * npairs < items; };
+    int j = grp;
+    if (has(j)) {
+      gather(tile_of(j), nin);
+      build(j, tile_of(j), nin);
+      if (has(j + PG)) gather(tile_of(j + PG), nin);
+    }
+    for (; has(j); j += PG) {
+      if (has(j + PG)) {
+        build(j + PG, tile_of(j + PG), nin);
+        if (has(j + 2 * PG)) gather(tile_of(j + 2 * PG), nin);
+      }
+      drain(j, tile_of(j));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+
 template <typename T, int CIN, int BN, int NT, bool BRES, bool PATCH, int EPI, int SA, int SB>
 static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvParams& p,
                       cudaStream_t stream) {
@@ -438,7 +774,12 @@ int conv3x3_launch(const void* x, int NB, int H, int W, int cin, const void* wpa
 // conv_block1 as one kernel: conv1 (1 -> 64, CUDA cores, float32) feeds conv2's tensor-core operand through shared
 // memory; the [NB, H, 64, 64] intermediate never exists in HBM.
 int conv_block1_launch(const float* x, int NB, int H, int W, const float* w1s, const float* shift1, const void* w2packed,
-                       const float* scale2, const float* shift2, void* out, int dtype, cudaStream_t stream) {
+                       const float* scale2, const float* shift2, void* out, int producer, int dtype,
+                       cudaStream_t stream) {
+  if (producer != 0 && producer != 1) {
+    set_error("conv_block1: producer must be 0 (CUDA-core FMAs) or 1 (split-fp16 tensor cores)");
+    return SED_ERR_UNSUPPORTED;
+  }
   if (NB <= 0 || H <= 0 || W <= 0 || (W % 16) != 0) {
     set_error("conv_block1: bad shape NB=%d H=%d W=%d (W %% 16 == 0)", NB, H, W);
     return SED_ERR_BAD_SHAPE;
@@ -474,6 +815,33 @@ int conv_block1_launch(const float* x, int NB, int H, int W, const float* w1s, c
   {
     const char* e = getenv("SED_CONV_DBG");
     p.dbg = e ? atoi(e) : 0;
+  }
+  if (producer == 1) {
+    if (dtype != 0 && dtype != 1) {
+      set_error("conv_block1: dtype must be 0 (fp16) or 1 (bf16)");
+      return SED_ERR_UNSUPPORTED;
+    }
+    int pairs = num_sms() / 2;
+    const int items = (p.num_tiles + 1) / 2;
+    if (pairs > items) pairs = items;
+    cudaError_t e;
+    if (dtype == 0) {
+      e = cudaFuncSetAttribute(conv_block1_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               c1tc::SMEM_BYTES);
+      if (e == cudaSuccess)
+        conv_block1_tc_kernel<__half><<<2 * pairs, c1tc::THREADS, c1tc::SMEM_BYTES, stream>>>(tmB, p);
+    } else {
+      e = cudaFuncSetAttribute(conv_block1_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               c1tc::SMEM_BYTES);
+      if (e == cudaSuccess)
+        conv_block1_tc_kernel<__nv_bfloat16><<<2 * pairs, c1tc::THREADS, c1tc::SMEM_BYTES, stream>>>(tmB, p);
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_error("conv_block1 (tensor-core producer) launch: %s", cudaGetErrorString(e));
+      return SED_ERR_CUDA;
+    }
+    return SED_OK;
   }
   if (dtype == 0) return launch_pair<__half, 64, 64, EPI_POOL, 6, 4, true, 1, 1, 1, true>(tmB, tmB, tmB, p, stream);
   if (dtype == 1)

@@ -42,7 +42,8 @@ int conv3x3_launch(const void* x, int NB, int H, int W, int cin, const void* wpa
                    int dtype, int variant, cudaStream_t stream);
 
 int conv_block1_launch(const float* x, int NB, int H, int W, const float* w1s, const float* shift1, const void* w2packed,
-                       const float* scale2, const float* shift2, void* out, int dtype, cudaStream_t stream);
+                       const float* scale2, const float* shift2, void* out, int producer, int dtype,
+                       cudaStream_t stream);
 
 int linear_launch(const void* a16, long M, int K, const void* w16, const float* bias, int N, int relu, float* out,
                   void* out16, int out_layout, int dtype, cudaStream_t stream);

@@ -354,7 +354,7 @@ class PackedModel:
         return ws
 
     # ------------------------------------------------------------------ stages
-    def conv_stack(self, wave_mb, feat_out, variant=2, stages=None, windows=None, feat32=None, feat_strides=(0, 0)):
+    def conv_stack(self, wave_mb, feat_out, variant=4, stages=None, windows=None, feat32=None, feat_strides=(0, 0)):
         """wave_mb [mb, L] (f32 / int16) -> feat_out [mb, T', 512] 16-bit (freq-mean of conv_block4).
         windows=(mb, L, stride): wave_mb is a 1-D recording read as overlapping windows.
         feat32: optional [mb, T', 512] f32 copy of the features (models without a temporal block).
@@ -371,7 +371,8 @@ class PackedModel:
         ws = self._workspace(mb, T)
         stream = capi.current_stream(self.device)
         logmel_forward(self.front, wave_mb, self.bn0_scale, self.bn0_shift, out=ws["logmel"], windows=windows)
-        fused1 = variant == 3  # conv_block1 as one kernel (its 64-channel intermediate stays on chip)
+        fused1 = variant in (3, 4)  # conv_block1 as one kernel (its 64-channel intermediate stays on chip)
+        producer = 1 if variant == 4 else 0  # conv1 on the tensor cores (split fp16) / on the CUDA cores
         if fused1:
             variant = 2
         else:
@@ -388,7 +389,7 @@ class PackedModel:
             if fused1 and li == 0:
                 rc = lib.sed_conv_block1(capi.ptr(ws["logmel"]), mb, T, 64, capi.ptr(self.c11_ws),
                                          capi.ptr(self.c11_shift), capi.ptr(wp), capi.ptr(s), capi.ptr(b),
-                                         capi.ptr(ws["p1"]), self.dtype_code, stream)
+                                         capi.ptr(ws["p1"]), producer, self.dtype_code, stream)
                 capi.check(rc, "sed_conv_block1")
                 capi._count()
                 continue
@@ -568,7 +569,7 @@ class PackedModel:
         return x.transpose(1, 2)
 
     # ------------------------------------------------------------------ whole model
-    def forward_host(self, wave_host, micro_batch=148, variant=2, head_chunk=256):
+    def forward_host(self, wave_host, micro_batch=148, variant=4, head_chunk=256):
         """End-to-end call with HOST buffers: `wave_host` [B, L] f32 (pinned for full speed) is copied to
         the device micro-batch by micro-batch on a copy stream that runs ahead of the compute stream, and
         `clipwise_output` / `framewise_output` come back as host tensors (the reference callers do
@@ -667,7 +668,7 @@ class PackedModel:
         out = {"framewise_output": frame, "clipwise_output": clip, "embedding": self._embedding(x, cla, feat32)}
         return out, feat16, x, natt
 
-    def forward_windows(self, recording, window_samples, stride_samples, n_windows, micro_batch=148, variant=2,
+    def forward_windows(self, recording, window_samples, stride_samples, n_windows, micro_batch=148, variant=4,
                         offsets=None):
         """Run the model on `n_windows` overlapping windows of one 1-D recording (f32 or int16, on device):
         window k = recording[k*stride : k*stride + window_samples], zero padded past the end.  Returns the same
@@ -693,7 +694,7 @@ class PackedModel:
         with self._lock:
             return self._run(n_windows, T // 8, conv_call)[0]
 
-    def forward(self, wave, micro_batch=148, variant=2, return_stages=False):
+    def forward(self, wave, micro_batch=148, variant=4, return_stages=False):
         """wave [B, L] f32 on self.device -> reference output dict (models.py:683-686 / :1072-1075)."""
         if wave.dim() != 2:
             raise ValueError("input must be (batch_size, data_length)")

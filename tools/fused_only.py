@@ -8,6 +8,6 @@ pm = engine.PackedModel(synth.synthetic_state_dict(mt, 16000), mt, 512, 160, dev
 wave = synth.synthetic_waveform(148, 160000).to(dev)
 feat = torch.empty((148, 125, 512), dtype=pm.tdtype, device=dev)
 for _ in range(2):
-    pm.conv_stack(wave, feat, variant=3)
+    pm.conv_stack(wave, feat, variant=int(os.environ.get("SED_VARIANT", "4")))
 torch.cuda.synchronize()
 print("ok")
