@@ -243,6 +243,7 @@ SED_DEVICE_INLINE void mbar_arrive_remote_light(uint64_t* bar, uint32_t cta_rank
       "r"(cta_rank)
       : "memory");
 }
+SED_DEVICE_INLINE void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 SED_DEVICE_INLINE void mbar_arrive_release_cluster_at(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
