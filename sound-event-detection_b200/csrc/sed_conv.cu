@@ -280,7 +280,6 @@ constexpr int B2_HALF = 32 * 128;           // one tap block of this CTA's 32 co
 constexpr int B2_BYTES = 9 * B2_HALF;       // 36,864
 constexpr int OP_STAGE = 2 * 256 * 32;      // conv1 A operand, hi + lo, 256 rows x 32 B
 constexpr int OP_BYTES = 2 * OP_STAGE;      // two stages
-constexpr int B1_BYTES = 2 * 32 * 32;       // conv1 weights of this CTA's 32 channels, hi + lo
 constexpr int MISC = 4096;
 constexpr int SMEM_BYTES = 1024 + A_BYTES + B2_BYTES + OP_BYTES + 2048 + MISC;
 constexpr int PG = 1;                       // producer groups (4 warps each): group g builds / drains tiles j = g mod 2
