@@ -546,14 +546,14 @@ conv_block1_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ConvParams 
         tmem_ld_wait();
         const int pr = mt * 128 + m_tm;
         if (pr < 180) {
-          // accumulators already hold conv1 + folded bn1 shift (zero for padding pixels): ReLU on the packed 16-bit pairs
+          // accumulators already hold conv1 + folded bn1 shift (zero for padding pixels): cvt.rn.relu packs + clamps
           uint8_t* rowp = patch + pr * 128;
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             uint32_t pk[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-              pk[q] = Elem16<T>::relu2(Elem16<T>::pack2(__uint_as_float(r[u][2 * q]), __uint_as_float(r[u][2 * q + 1])));
+              pk[q] = Elem16<T>::pack2_relu(__uint_as_float(r[u][2 * q]), __uint_as_float(r[u][2 * q + 1]));
             *reinterpret_cast<uint4*>(rowp + (((2 * u) ^ (pr & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             *reinterpret_cast<uint4*>(rowp + (((2 * u + 1) ^ (pr & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
