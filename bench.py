@@ -137,6 +137,10 @@ def cpu_reference_throughput(steps, warmup, batch=32):
             "ms_per_step": 1e3 * total / steps, "batch": batch}
 
 
+def pm_spans(B, micro_batch):
+    return list(range(0, B, micro_batch))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -272,7 +276,7 @@ def run_b200(args):
         # variant 4 runs conv_block1.conv1 inside the first timed launch: the timed group is the whole conv stack
         conv_gflop = 26.031 if args.variant == 4 else CONV_GFLOP_TC
         conv_tflops = conv_gflop * 1e9 * conv_clips / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
-        n_conv_launch = 7 * len([1 for _ in range(0, B, args.micro_batch)]) * steps
+        n_conv_launch = 7 * len(pm_spans(B, args.micro_batch)) * steps
         line = {
             "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": elapsed_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -281,7 +285,7 @@ def run_b200(args):
                                    "10 s clips, seeded synthetic checkpoint" % B,
                        "batch_per_gpu": B, "micro_batch": args.micro_batch, "parallelism": "dp%d (batch shards, "
                        "NCCL gather of outputs to rank 0)" % world,
-                       "l2": "inputs (%.0f MB/step) and activations (>2 GB/micro-batch) exceed the 126 MB L2" %
+                       "l2": "inputs (%.0f MB/step) and activations (>6 GB/micro-batch) exceed the 126 MB L2" %
                              (B * CLIP_SAMPLES * 4 / 1e6)},
             "e2e": {"value": world * B * steps / (e2e_ms / 1e3), "unit": "clips/s",
                     "h2d_bytes_per_step": B * CLIP_SAMPLES * 4, "d2h_bytes_per_step": d2h,
@@ -293,11 +297,13 @@ def run_b200(args):
             "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": peaks["tflops_sustained"],
                          "unit": "TFLOP/s", "frac": conv_tflops / peaks["tflops_sustained"],
                          "traffic": traffic["dram_bytes_total"] if traffic else None,
-                         "traffic_note": "dram__bytes_read+write summed over the 7 conv launches of one 148-clip "
-                                         "micro-batch (profiles/r01_ncu_full_conv_umma2_raw.csv, r01_ncu_full_conv_block1_tc_raw.csv); algorithmic "
+                         "traffic_note": "dram__bytes_read+write summed over the 7 conv launches for 148 clips (ncu "
+                                         "--set full at micro-batch 148: profiles/r01_ncu_full_conv_umma2_raw.csv, "
+                                         "r01_ncu_full_conv_block1_tc_raw.csv; the default 444-clip launches move 3x "
+                                         "this); algorithmic "
                                          "activation bytes (each layer input read once + output written once) for the same group: %.3e" % (148 * 21888256.0),
                          "kernel": "conv_block1_tc_kernel + 6 x conv_umma2_kernel (7 tcgen05 cta_group::2 implicit-GEMM "
-                                   "launches per 148-clip micro-batch, %.3f GFLOP/clip algorithmic)" % conv_gflop,
+                                   "launches per micro-batch, %.3f GFLOP/clip algorithmic)" % conv_gflop,
                          "peak_source": peaks["source"] + ", sustained bf16; burst %.1f" % peaks["tflops_burst"],
                          "launches_timed": n_conv_launch, "conv_ms_per_step": conv_ms / steps},
         }
@@ -317,7 +323,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="clips per GPU per step")
-    ap.add_argument("--micro-batch", type=int, default=148)
+    ap.add_argument("--micro-batch", type=int, default=444)
     ap.add_argument("--variant", type=int, default=4)
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--ref-batch", type=int, default=32)

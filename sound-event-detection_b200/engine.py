@@ -5,8 +5,9 @@ Data layout in HBM (all allocations are torch tensors; the C ABI only sees raw p
   ([mb,T,64,64] -> [mb,T/2,32,64] -> ... -> [mb,T/8,8,512]) -> freq-mean features [B, T', 512] 16-bit
   -> GRU: gi [B,T',1536] f32 -> h [B,T',512] f32 | MHA: qkv [B,T',1536] f32 -> ctx 16-bit -> fc [B,T',512] f32
   -> clipwise [B,25], framewise [B,frames,25], embedding.
-The conv stack runs over micro-batches (default 148 clips = one per SM, which makes every layer's tile
-count a multiple of the persistent grid); the temporal block and the head run once over the batch.
+The conv stack runs over micro-batches (default 444 clips = three per SM: every layer's tile count is then a
+multiple of the persistent grid, and fewer launches mean fewer drain / fill gaps between the persistent kernels);
+the temporal block and the head run once over the batch.
 """
 import math
 import threading
@@ -334,24 +335,31 @@ class PackedModel:
         self.conv_events = None  # set to [] to collect (start, end) CUDA events around the tensor-core conv launches
 
     # ------------------------------------------------------------------ workspaces
-    def _workspace(self, mb, T):
-        key = (mb, T)
-        ws = self._ws.get(key)
-        if ws is None:
+    def _workspace(self, mb, T, need_a1=False):
+        """Activation buffers of the conv stack for a micro-batch of `mb` clips: views into one allocation per T sized
+        for the largest micro-batch seen (micro-batch sizes vary inside forward_host).  a1, the 8.2 MB/clip output of
+        conv_block1.conv1, only exists for the two-kernel variants of block 1."""
+        ent = self._ws.get(T)
+        if ent is None or ent["cap"] < mb or (need_a1 and "a1" not in ent["buf"]):
+            cap = mb if ent is None else max(mb, ent["cap"])
+            need_a1 = need_a1 or (ent is not None and "a1" in ent["buf"])
             dev, td = self.device, self.tdtype
             H1, H2, H3 = T // 2, T // 4, T // 8
-            ws = {
-                "logmel": torch.empty((mb, T, 64), dtype=torch.float32, device=dev),
-                "a1": torch.empty((mb, T, 64, 64), dtype=td, device=dev),
-                "p1": torch.empty((mb, H1, 32, 64), dtype=td, device=dev),
-                "a2": torch.empty((mb, H1, 32, 128), dtype=td, device=dev),
-                "p2": torch.empty((mb, H2, 16, 128), dtype=td, device=dev),
-                "a3": torch.empty((mb, H2, 16, 256), dtype=td, device=dev),
-                "p3": torch.empty((mb, H3, 8, 256), dtype=td, device=dev),
-                "a4": torch.empty((mb, H3, 8, 512), dtype=td, device=dev),
+            self._ws = {}  # drop the old allocation first (keep only the most recent T)
+            buf = {
+                "logmel": torch.empty((cap, T, 64), dtype=torch.float32, device=dev),
+                "p1": torch.empty((cap, H1, 32, 64), dtype=td, device=dev),
+                "a2": torch.empty((cap, H1, 32, 128), dtype=td, device=dev),
+                "p2": torch.empty((cap, H2, 16, 128), dtype=td, device=dev),
+                "a3": torch.empty((cap, H2, 16, 256), dtype=td, device=dev),
+                "p3": torch.empty((cap, H3, 8, 256), dtype=td, device=dev),
+                "a4": torch.empty((cap, H3, 8, 512), dtype=td, device=dev),
             }
-            self._ws = {key: ws}  # keep only the most recent shape
-        return ws
+            if need_a1:
+                buf["a1"] = torch.empty((cap, T, 64, 64), dtype=td, device=dev)
+            ent = {"cap": cap, "buf": buf}
+            self._ws = {T: ent}
+        return {k: v[:mb] for k, v in ent["buf"].items()}
 
     # ------------------------------------------------------------------ stages
     def conv_stack(self, wave_mb, feat_out, variant=4, stages=None, windows=None, feat32=None, feat_strides=(0, 0)):
@@ -368,10 +376,10 @@ class PackedModel:
         T = L // self.front.hop + 1
         if T // 8 < 1:
             raise ValueError("clip too short: %d frames" % T)
-        ws = self._workspace(mb, T)
+        fused1 = variant in (3, 4)  # conv_block1 as one kernel (its 64-channel intermediate stays on chip)
+        ws = self._workspace(mb, T, need_a1=not fused1)
         stream = capi.current_stream(self.device)
         logmel_forward(self.front, wave_mb, self.bn0_scale, self.bn0_shift, out=ws["logmel"], windows=windows)
-        fused1 = variant in (3, 4)  # conv_block1 as one kernel (its 64-channel intermediate stays on chip)
         producer = 1 if variant == 4 else 0  # conv1 on the tensor cores (split fp16) / on the CUDA cores
         if fused1:
             variant = 2
@@ -409,7 +417,7 @@ class PackedModel:
         if stages is not None:
             stages["bn0"] = ws["logmel"].clone()
             for k in ("a1", "p1", "a2", "p2", "a3", "p3", "a4"):
-                if not (fused1 and k == "a1"):  # the fused block never materialises a1
+                if k in ws and not (fused1 and k == "a1"):  # the fused block never materialises a1
                     stages[k] = ws[k].clone()
 
     def linear(self, a16, w16, bias, relu=False, out16=False, out_layout=0):
@@ -569,7 +577,7 @@ class PackedModel:
         return x.transpose(1, 2)
 
     # ------------------------------------------------------------------ whole model
-    def forward_host(self, wave_host, micro_batch=148, variant=4, head_chunk=256):
+    def forward_host(self, wave_host, micro_batch=444, variant=4, head_chunk=256):
         """End-to-end call with HOST buffers: `wave_host` [B, L] f32 (pinned for full speed) is copied to
         the device micro-batch by micro-batch on a copy stream that runs ahead of the compute stream, and
         `clipwise_output` / `framewise_output` come back as host tensors (the reference callers do
@@ -594,9 +602,20 @@ class PackedModel:
         cs, ds = hb["copy_stream"], hb["d2h_stream"]
         compute = torch.cuda.current_stream(self.device)
         cs.wait_stream(compute)  # the previous call may still be reading the staging buffer
-        # a short first micro-batch lets the conv stack start after ~0.4 ms of PCIe traffic instead of ~1.7 ms
-        first = min(B, max(1, micro_batch // 4))
-        spans = [(0, first)] + [(b0, min(B, b0 + micro_batch)) for b0 in range(first, B, micro_batch)]
+        # a short first micro-batch lets the conv stack start after ~0.4 ms of PCIe traffic instead of ~1.7 ms; the
+        # copies run ~1.8x faster than the conv stack, so later micro-batches can grow (fewer launches, fewer
+        # drain / fill gaps between the persistent kernels): 37, 148, 296, then `micro_batch` clips
+        spans, b0 = [], 0
+        for size in (37, 148, 296):
+            if b0 >= B or size >= micro_batch:
+                break
+            spans.append((b0, min(B, b0 + size)))
+            b0 = spans[-1][1]
+        while b0 < B:
+            spans.append((b0, min(B, b0 + micro_batch)))
+            b0 = spans[-1][1]
+        T = L // self.front.hop + 1
+        self._workspace(max(b1 - b0 for b0, b1 in spans), T, need_a1=variant not in (3, 4))  # size once for the call
         events = []
         with torch.cuda.stream(cs):
             for (b0, b1) in spans:
@@ -668,7 +687,7 @@ class PackedModel:
         out = {"framewise_output": frame, "clipwise_output": clip, "embedding": self._embedding(x, cla, feat32)}
         return out, feat16, x, natt
 
-    def forward_windows(self, recording, window_samples, stride_samples, n_windows, micro_batch=148, variant=4,
+    def forward_windows(self, recording, window_samples, stride_samples, n_windows, micro_batch=444, variant=4,
                         offsets=None):
         """Run the model on `n_windows` overlapping windows of one 1-D recording (f32 or int16, on device):
         window k = recording[k*stride : k*stride + window_samples], zero padded past the end.  Returns the same
@@ -694,7 +713,7 @@ class PackedModel:
         with self._lock:
             return self._run(n_windows, T // 8, conv_call)[0]
 
-    def forward(self, wave, micro_batch=148, variant=4, return_stages=False):
+    def forward(self, wave, micro_batch=444, variant=4, return_stages=False):
         """wave [B, L] f32 on self.device -> reference output dict (models.py:683-686 / :1072-1075)."""
         if wave.dim() != 2:
             raise ValueError("input must be (batch_size, data_length)")

@@ -28,7 +28,7 @@ def predict_framewise(model, recording, sample_rate, sample_duration=5, overlap_
     (what `merged` holds after predict.py:349)."""
     if isinstance(model, engine.PackedModel):
         packed = model
-        micro_batch, variant = 148, 4
+        micro_batch, variant = 444, 4
     else:
         if model.training:
             raise RuntimeError("inference only -- call .eval()")
@@ -73,7 +73,7 @@ def predict_framewise_overlap(model, clips, sample_rate, sample_duration, overla
     reads them in place through an offset table), each file's windows are overlap-added and block-averaged on the
     device.  Returns a list of per-file tensors [1, total_frames, classes] (what `merged` holds after :835)."""
     if isinstance(model, engine.PackedModel):
-        packed, micro_batch, variant = model, 148, 4
+        packed, micro_batch, variant = model, 444, 4
     else:
         if model.training:
             raise RuntimeError("inference only -- call .eval()")
