@@ -171,6 +171,11 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: everything any library prints to fd 1 (NCCL's version banner, ...) is sent
+    # to stderr, the result line is written to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the B200 arm)")
     torch.cuda.set_device(local_rank)
@@ -310,7 +315,8 @@ def run_b200(args):
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_throughput(steps=3, warmup=1, batch=args.ref_batch)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
