@@ -80,22 +80,6 @@ SED_DEVICE_INLINE void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
-// Wait with a hardware suspend-time hint: the warp sleeps inside try_wait (up to `ns`) instead of re-issuing the
-// poll, leaving the issue slots to the warps that feed the barrier.  For waits where many warps wait on one producer.
-SED_DEVICE_INLINE void mbar_wait_suspend(uint64_t* bar, uint32_t parity, uint32_t ns = 20000) {
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
-        : "memory");
-  }
-}
 
 // ------------------------------------------------------------------ proxies / fences
 SED_DEVICE_INLINE void fence_proxy_async_smem() {
@@ -243,10 +227,6 @@ SED_DEVICE_INLINE void mbar_arrive_remote_light(uint64_t* bar, uint32_t cta_rank
       "r"(cta_rank)
       : "memory");
 }
-SED_DEVICE_INLINE void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
-SED_DEVICE_INLINE void mbar_arrive_release_cluster_at(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
 // packed f32x2 arithmetic (sm_100): two float32 FMAs per instruction on a 64-bit register pair
 SED_DEVICE_INLINE unsigned long long pack_f32x2(float lo, float hi) {
   unsigned long long r;
@@ -332,10 +312,6 @@ struct Elem16<__half> {
     return r;
   }
   SED_DEVICE_INLINE static float to_float(uint16_t v) { return __half2float(__ushort_as_half(v)); }
-  SED_DEVICE_INLINE static uint32_t relu2(uint32_t v) {  // max(x, 0) on both halves (exact: commutes with rounding)
-    const __half2 h = __hmax2(*reinterpret_cast<const __half2*>(&v), __float2half2_rn(0.0f));
-    return *reinterpret_cast<const uint32_t*>(&h);
-  }
   // {max(a,0), max(b,0)} rounded to 16 bits in ONE instruction (a in the low half)
   SED_DEVICE_INLINE static uint32_t pack2_relu(float a, float b) {
     uint32_t r;
@@ -352,10 +328,6 @@ struct Elem16<__nv_bfloat16> {
     return r;
   }
   SED_DEVICE_INLINE static float to_float(uint16_t v) { return __uint_as_float(static_cast<uint32_t>(v) << 16); }
-  SED_DEVICE_INLINE static uint32_t relu2(uint32_t v) {
-    const __nv_bfloat162 h = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&v), __float2bfloat162_rn(0.0f));
-    return *reinterpret_cast<const uint32_t*>(&h);
-  }
   SED_DEVICE_INLINE static uint32_t pack2_relu(float a, float b) {
     uint32_t r;
     asm("cvt.rn.relu.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));

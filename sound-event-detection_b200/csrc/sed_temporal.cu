@@ -83,15 +83,6 @@ SED_DEVICE_INLINE void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                : "r"(taddr)
                : "memory");
 }
-// TMA tile load delivered to the same shared-memory offset (and mbarrier) of every CTA in `cta_mask`
-SED_DEVICE_INLINE void tma_load_2d_mcast(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
-                                         uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, "
-      "{%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
-      : "memory");
-}
 
 // bulk copy own shared memory -> a peer CTA's shared memory, completing `bytes` on the peer's mbarrier
 SED_DEVICE_INLINE void bulk_copy_to_peer(uint32_t dst_cluster_addr, const void* src_smem, uint32_t bytes,
@@ -102,18 +93,6 @@ SED_DEVICE_INLINE void bulk_copy_to_peer(uint32_t dst_cluster_addr, const void* 
                : "memory");
 }
 SED_DEVICE_INLINE void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-SED_DEVICE_INLINE void st_cluster_v4(uint32_t addr, const uint4& v) {
-  asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-               : "memory");
-}
-// 16-byte store into a peer CTA's shared memory that also completes 16 bytes on that CTA's mbarrier: the data is
-// visible to whoever observes the barrier phase complete -- no separate release fence / arrive on the producer side
-SED_DEVICE_INLINE void st_async_v4(uint32_t cluster_addr, const uint4& v, uint32_t cluster_mbar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
-                   cluster_addr),
-               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(cluster_mbar)
-               : "memory");
-}
 
 template <typename T>
 __global__ void __cluster_dims__(kGruCluster, 1, 1) __launch_bounds__(kGruThreads, 1)
