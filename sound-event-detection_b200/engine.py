@@ -588,6 +588,7 @@ class PackedModel:
         key = (B, L, wave_host.dtype)
         hb = self._host.get(key)
         T = L // self.front.hop + 1
+        self._check_frames(T)
         Tp = T // 8
         frames = self.frames_for(Tp)
         C = self.classes
@@ -654,6 +655,10 @@ class PackedModel:
         ds.synchronize()
         return {"clipwise_output": hb["clip"], "framewise_output": hb["frame"]}
 
+    def _check_frames(self, T):
+        if T // 8 < 1:
+            raise ValueError("clip too short: %d STFT frames give no pooled time step (need >= 8)" % T)
+
     def _alloc_features(self, n, Tp):
         """Feature buffers of the conv stack and slot(b0, b1) -> conv_stack keyword arguments for one micro-batch.
         Models with a temporal block get the features time-major ([T', Bp, 512]: the GRU / MultiHead kernels then
@@ -699,6 +704,7 @@ class PackedModel:
             recording = recording.float()
         recording = recording.contiguous()
         T = window_samples // self.front.hop + 1
+        self._check_frames(T)
 
         def conv_call(slot):
             for b0 in range(0, n_windows, micro_batch):
@@ -724,6 +730,7 @@ class PackedModel:
         wave = wave.contiguous()
         B, L = wave.shape
         T = L // self.front.hop + 1
+        self._check_frames(T)
         stages = {} if return_stages else None
 
         def conv_call(slot):

@@ -64,3 +64,20 @@ def test_full_batch_spot_check_against_oracle(full_run, thresholds):
     thr = np.asarray(thresholds["%s/best_logmel_16k.sed.valid.pkl" % MT]["sed_high_threshold"])
     agree = ((fw > thr[None, None, :]) == (ref["framewise_output"].numpy() > thr[None, None, :])).mean()
     assert agree >= 0.999, agree
+
+
+def test_long_clips_60s():
+    """60 s clips (T = 6001, T' = 750 GRU steps, 6000 framewise rows): nothing on the path is specialised to 10 s."""
+    pm = engine.PackedModel(synthetic_sd(MT), MT, 512, 160, torch.device(DEV))
+    wave = synth.synthetic_waveform(2, 960000, seed=71, kind="events")
+    out = pm.forward(wave.to(DEV))
+    assert out["framewise_output"].shape == (2, 6000, 25)
+    ref = so.model_forward(synthetic_sd(MT), wave, MT, 512, 160)
+    assert np.abs(out["framewise_output"].cpu().numpy() - ref["framewise_output"].numpy()).max() <= 2e-3
+    assert np.abs(out["clipwise_output"].cpu().numpy() - ref["clipwise_output"].numpy()).max() <= 2e-3
+
+
+def test_too_short_clip_is_rejected():
+    pm = engine.PackedModel(synthetic_sd(MT), MT, 512, 160, torch.device(DEV))
+    with pytest.raises(ValueError):
+        pm.forward(torch.zeros(1, 800, device=DEV))  # T = 6 frames < one pooled step
