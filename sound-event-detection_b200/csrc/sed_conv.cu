@@ -320,8 +320,8 @@ conv_block1_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ConvParams 
   const int items = (p.num_tiles + 1) / 2;
 
   if (threadIdx.x < 64) {
-    s_scale[threadIdx.x] = p.scale[threadIdx.x];
-    s_shift[threadIdx.x] = p.shift[threadIdx.x];
+    s_scale[threadIdx.x] = 0.25f * p.scale[threadIdx.x];  // the 1/4 of the 2x2 average rides the bn2 affine (exact)
+    s_shift[threadIdx.x] = 0.25f * p.shift[threadIdx.x];
     s_shift1[threadIdx.x] = p.shift1[threadIdx.x];
   }
   if (threadIdx.x >= 64 && threadIdx.x < 96) {

@@ -154,7 +154,7 @@ SED_DEVICE_INLINE void conv_epilogue_tile(const uint32_t taddr, const int chalf,
             for (int j = 0; j < 4; ++j) {
               const float send = hodd ? k8[j] : k8[4 + j];
               const float keep = hodd ? k8[4 + j] : k8[j];
-              k4[j] = 0.25f * (keep + __shfl_xor_sync(0xffffffffu, send, 8));
+              k4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);  // the 1/4 of the average is folded into scale/shift
             }
             const int Hp = p.H >> 1, Wp = p.W >> 1;
             const int hp = h >> 1, wp = w >> 1;
@@ -190,7 +190,7 @@ SED_DEVICE_INLINE void conv_epilogue_tile(const uint32_t taddr, const int chalf,
             for (int j = 0; j < 2; ++j) {
               const float send = b2 ? k4[j] : k4[2 + j];
               const float keep = b2 ? k4[2 + j] : k4[j];
-              k2[j] = 0.125f * (keep + __shfl_xor_sync(0xffffffffu, send, 4));
+              k2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);  // the 1/8 of the mean is folded into scale/shift
             }
             if (tile_ok && h < p.H) {
               const int ch = ch0 + cc * 16 + (b0 ? 8 : 0) + (b1 ? 4 : 0) + (b2 ? 2 : 0);
@@ -295,8 +295,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // folded BatchNorm scale / shift (linear: 1 / bias); resident-weight CTAs only cache their own slice
   const int ss_base = BRES ? fixed_slice * BN : 0;
   for (int i = threadIdx.x; i < Cfg::SS && ss_base + i < p.cout; i += blockDim.x) {
-    s_scale[i] = (EPI == EPI_LINEAR) ? 1.0f : p.scale[ss_base + i];
-    s_shift[i] = p.shift ? p.shift[ss_base + i] : 0.0f;
+    // the averaging factor of the pooling epilogues rides the BN affine: relu(k x) = k relu(x) for k > 0, and scaling
+    // by a power of two is exact, so the result is bit-identical to averaging afterwards
+    constexpr float kAvg = (EPI == EPI_POOL) ? 0.25f : (EPI == EPI_FREQMEAN) ? 0.125f : 1.0f;
+    s_scale[i] = (EPI == EPI_LINEAR) ? 1.0f : kAvg * p.scale[ss_base + i];
+    s_shift[i] = p.shift ? kAvg * p.shift[ss_base + i] : 0.0f;
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -581,8 +584,9 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int ss_base = BRES ? fixed_slice * BN : 0;
   for (int i = threadIdx.x; i < Cfg::SS && ss_base + i < p.cout; i += blockDim.x) {
-    s_scale[i] = p.scale[ss_base + i];
-    s_shift[i] = p.shift[ss_base + i];
+    constexpr float kAvg = (EPI == EPI_POOL) ? 0.25f : (EPI == EPI_FREQMEAN) ? 0.125f : 1.0f;  // see conv_umma_kernel
+    s_scale[i] = kAvg * p.scale[ss_base + i];
+    s_shift[i] = kAvg * p.shift[ss_base + i];
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
