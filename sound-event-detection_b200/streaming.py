@@ -49,6 +49,57 @@ def predict_framewise(model, recording, sample_rate, sample_duration=5, overlap_
     return merged
 
 
+def predict_framewise_many(model, recordings, sample_rate, sample_duration=5, overlap_value=1):
+    """predict_framewise for several recordings in ONE batch (the per-file loop of pytorch/predict.py:264 folded into the
+    batch dimension): `recordings` is a list of 1-D float32 / int16 CUDA tensors of one dtype.  Every recording is laid
+    out in one buffer, zero padded up to the end of its last window (the reference zero-pads the last window,
+    predict.py:302-305), the windows of all recordings are read in place through an offset table, and recordings with
+    the same number of windows are merged by one launch.  Returns a list of [1, total_frames, classes] tensors equal,
+    bit for bit, to calling predict_framewise per recording."""
+    if isinstance(model, engine.PackedModel):
+        packed, micro_batch, variant = model, 444, 4
+    else:
+        if model.training:
+            raise RuntimeError("inference only -- call .eval()")
+        packed = model._packed_for(recordings[0].device)
+        micro_batch, variant = model.micro_batch, model.conv_variant
+    dev, dtype = recordings[0].device, recordings[0].dtype
+    if any(r.dim() != 1 or r.device != dev or r.dtype != dtype for r in recordings):
+        raise ValueError("recordings must be 1-D tensors of one dtype on one CUDA device")
+    window_samples = int(sample_rate * sample_duration)
+    counts, seg_len = [], []
+    for r in recordings:
+        starts = window_starts(r.numel() / float(sample_rate), sample_duration, overlap=True)
+        counts.append(len(starts))
+        need = max(r.numel(), starts[-1] * int(sample_rate) + window_samples)
+        seg_len.append((need + 7) // 8 * 8)  # keep every segment 16-byte aligned for the cp.async staging
+    flat = torch.zeros(sum(seg_len), dtype=dtype, device=dev)
+    offsets, base = [], 0
+    for r, nw, sl in zip(recordings, counts, seg_len):
+        flat[base:base + r.numel()].copy_(r)
+        offsets.extend(base + k * int(sample_rate) for k in range(nw))
+        base += sl
+    offsets = torch.tensor(offsets, dtype=torch.int64, device=dev)
+    with torch.no_grad():
+        out = packed.forward_windows(flat, window_samples, 0, int(offsets.numel()), micro_batch=micro_batch,
+                                     variant=variant, offsets=offsets)
+        frames = out["framewise_output"]
+        merged = [None] * len(recordings)
+        firsts, first = [], 0
+        for nw in counts:
+            firsts.append(first)
+            first += nw
+        oi = int(100 * overlap_value)
+        for nw in sorted(set(counts)):
+            idx = [f for f in range(len(recordings)) if counts[f] == nw]
+            rows = torch.tensor([firsts[f] + k for f in idx for k in range(nw)], dtype=torch.int64, device=dev)
+            group = frames.index_select(0, rows).view(len(idx), nw, frames.shape[1], frames.shape[2])
+            m = engine.window_merge_avg(group, oi, int(sample_duration))
+            for j, f in enumerate(idx):
+                merged[f] = m[j:j + 1]
+    return merged
+
+
 def overlap_window_counts(audio_durations, sample_duration, overlap_value):
     """Windows the loop of main_strong.py:786-834 runs per file: start k*overlap_value for k = 0 and every k with
     k*overlap_value + sample_duration <= audio_duration (the `while end <= audio_duration` rule, end updated after

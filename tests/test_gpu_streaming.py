@@ -125,3 +125,16 @@ def test_batched_merge_equals_per_recording_merge():
     both = engine.window_merge_avg(frames, 100, 5)
     for r in range(4):
         assert torch.equal(both[r:r + 1], engine.window_merge_avg(frames[r], 100, 5))
+
+
+def test_many_recordings_in_one_batch_equal_per_recording_calls():
+    mt = "Cnn_9layers_Gru_FrameAtt"
+    sr = 16000
+    model = build(mt)
+    recs = [synth.synthetic_waveform(1, int(d * sr), seed=80 + i, kind="events")[0].to(DEV)
+            for i, d in enumerate((13.4, 7.0, 13.0, 3.3))]
+    many = streaming.predict_framewise_many(model, recs, sr, 5, 1)
+    for r, m in zip(recs, many):
+        one = streaming.predict_framewise(model, r, sr, 5, 1)
+        assert m.shape == one.shape
+        assert torch.equal(m, one)

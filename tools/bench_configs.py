@@ -29,6 +29,11 @@ rec = synth.synthetic_waveform(1, 60 * 32000, seed=3, kind="events", sample_rate
 t = timeit(lambda: streaming.predict_framewise(pm32, rec, 32000, 5, 1), n=10, warm=3)
 res["config4_streaming_32k_60s_file"] = {"ms_per_file": t, "windows_per_s": 56 / t * 1e3, "audio_seconds_per_s": 60 / t * 1e3,
                                          "note": "one file per call (56 windows = a partial wave of the persistent grids)"}
+recs = [rec] * 16
+t = timeit(lambda: streaming.predict_framewise_many(pm32, recs, 32000, 5, 1), n=10, warm=3)
+res["config4_streaming_32k_16_files_per_call"] = {"ms_per_call": t, "windows_per_s": 16 * 56 / t * 1e3,
+                                                  "audio_seconds_per_s": 16 * 60 / t * 1e3,
+                                                  "note": "896 windows per call through the offset table"}
 recq = torch.round(rec * 32767).to(torch.int16)
 t = timeit(lambda: streaming.predict_framewise(pm32, recq, 32000, 5, 1), n=10, warm=3)
 res["config4_streaming_32k_60s_file_int16"] = {"ms_per_file": t, "windows_per_s": 56 / t * 1e3}
