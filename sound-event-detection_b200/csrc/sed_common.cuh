@@ -81,6 +81,12 @@ SED_DEVICE_INLINE void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Register re-balancing between warpgroups (all four warps of a warpgroup execute the same one).
+template <int R>
+SED_DEVICE_INLINE void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R>
+SED_DEVICE_INLINE void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+
 // ------------------------------------------------------------------ proxies / fences
 SED_DEVICE_INLINE void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

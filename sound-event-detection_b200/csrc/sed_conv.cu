@@ -282,10 +282,29 @@ constexpr int OP_STAGE = 2 * 256 * 32;      // conv1 A operand, hi + lo, 256 row
 constexpr int OP_BYTES = 2 * OP_STAGE;      // two stages
 constexpr int MISC = 4096;
 constexpr int SMEM_BYTES = 1024 + A_BYTES + B2_BYTES + OP_BYTES + 2048 + MISC;
-constexpr int PG = 1;                       // producer groups (4 warps each): group g builds / drains tiles j = g mod 2
-constexpr int THREADS = 64 + 256 + 128 * PG;
+constexpr int PG = 2;                       // producer groups (4 warps each): group g builds / drains tiles j = g mod 2
+// Warpgroup 0 = control (warp 0 weights TMA, warp 1 MMA issue, warps 2-3 idle), warpgroups 1-2 = pooling epilogue,
+// warpgroups 3-4 = producers.  20 warps launch at 96 registers per thread; the control group hands most of its
+// registers to the producer groups (setmaxnreg), which need ~118.
+constexpr int EPI_WARP0 = 4, PROD_WARP0 = 12;
+constexpr int THREADS = 128 + 256 + 128 * PG;
+constexpr int REG_CTRL = 40, REG_PROD = 120;
 constexpr int C1_COL0 = ACC * 64;           // conv1 accumulators: columns 256 + stage*128 + mtile*64
 }  // namespace c1tc
+
+#ifdef SED_C1_STAMPS
+// Debug build only (make NVFLAGS+=-DSED_C1_STAMPS; tools/c1_stamps.py): clock64 of each role of CTA 0 at the pipeline's
+// hand-over points, for local work items [kStampFirst, kStampFirst + 32).
+__device__ long long g_c1_stamps[3][32][8];
+constexpr int kStampFirst = 200;
+#define C1_STAMP(role, item, k)                                                               \
+  do {                                                                                        \
+    if (blockIdx.x == 0 && (item) >= kStampFirst && (item) < kStampFirst + 32)                \
+      g_c1_stamps[role][(item) - kStampFirst][k] = clock64();                                 \
+  } while (0)
+#else
+#define C1_STAMP(role, item, k) do {} while (0)
+#endif
 
 template <typename T>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(c1tc::THREADS, 1)
@@ -375,6 +394,9 @@ conv_block1_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ConvParams 
     w0 = (rem - th * p.tiles_w) * 8;
   };
 
+  if (warp < EPI_WARP0) setmaxnreg_dec<REG_CTRL>();
+  if (warp >= PROD_WARP0) setmaxnreg_inc<REG_PROD>();
+
   if (warp == 0) {
     // =============================== conv2 weights (resident) ================================
     if (elect_one()) {
@@ -398,7 +420,9 @@ conv_block1_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ConvParams 
       auto conv1 = [&](int j) {
         const int st = j & 1, ph = (j >> 1) & 1;
         mbar_wait_cluster(&op_full[st], ph);  // (CTA-scope polling + one fence.acq_rel.cluster per wait measured 1.8x slower)
+        C1_STAMP(0, j, 0);
         mbar_wait_cluster(&c1_empty[st], ph ^ 1);
+        C1_STAMP(0, j, 1);
         tc_fence_after();
         const uint32_t a_h = op_lo0 + st * (OP_STAGE >> 4), a_l = a_h + (8192 >> 4);
 #pragma unroll
@@ -417,32 +441,45 @@ conv_block1_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ConvParams 
       for (int i = 0; i < n_local; ++i) {
         if (i + 1 < n_local) conv1(i + 1);
         mbar_wait(&t_empty[acc], pacc ^ 1);
+        C1_STAMP(0, i, 2);
         mbar_wait_cluster(&a_full[sa], pa);
+        C1_STAMP(0, i, 3);
         tc_fence_after();
         const uint32_t d_base = tmem_base + acc * 64;
         const uint32_t a_lo = a_lo0 + sa * (kPatchStride >> 4);
+        // rolled over the taps on purpose: unrolled, the 36 descriptor pairs get hoisted out of the item loop and do
+        // not fit the control group's register budget
+#pragma unroll 1
+        for (int tr = 0; tr < 3; ++tr) {
+#pragma unroll 1
+          for (int tc = 0; tc < 3; ++tc) {
+            const uint32_t b_lo = b_lo0 + (tr * 3 + tc) * (B2_HALF >> 4);
+            const uint32_t tap_off = (tr * 10 + tc) * 8;
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const uint32_t b_lo = b_lo0 + tap * (B2_HALF >> 4);
-          const uint32_t tap_off = ((tap / 3) * 10 + (tap % 3)) * 8;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16_2sm(d_base, desc_join(a_lo + tap_off + k * 2, a_hi), desc_join(b_lo + k * 2, b_hi), idesc2,
-                         (tap | k) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              umma_f16_2sm(d_base, desc_join(a_lo + tap_off + k * 2, a_hi), desc_join(b_lo + k * 2, b_hi), idesc2,
+                           (tr | tc | k) ? 1u : 0u);
+          }
         }
         umma_commit_2sm(&a_empty[sa], 3);
         umma_commit_2sm(&t_full[acc], 3);
+        C1_STAMP(0, i, 4);
         if (++sa == SA) { sa = 0; pa ^= 1; }
         if (++acc == ACC) { acc = 0; pacc ^= 1; }
       }
     }
-  } else if (warp < 10) {
+  } else if (warp < EPI_WARP0) {
+    // idle warps of the control group
+  } else if (warp < PROD_WARP0) {
     // =============================== conv2 epilogue (8 warps, both CTAs) ====================
     const int quarter = warp & 3;
-    const int chalf = (warp - 2) >> 2;
+    const int chalf = (warp - EPI_WARP0) >> 2;
     uint32_t acc = 0, pacc = 0;
-    for (int w = pr_cta; w < items; w += npairs) {
+    int li = 0;
+    (void)li;
+    for (int w = pr_cta; w < items; w += npairs, ++li) {
       mbar_wait(&t_full[acc], pacc);
+      if (warp == EPI_WARP0 && lane == 0) C1_STAMP(1, li, 0);
       tc_fence_after();
       const int tile = w * 2 + static_cast<int>(rank);
       const bool tile_ok = tile < p.num_tiles;
@@ -454,6 +491,7 @@ conv_block1_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ConvParams 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote_light(&t_empty[acc], 0);
+      if (warp == EPI_WARP0 && lane == 0) C1_STAMP(1, li, 1);
       if (++acc == ACC) { acc = 0; pacc ^= 1; }
     }
   } else {
@@ -467,8 +505,8 @@ conv_block1_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ConvParams 
       prr[mt] = pr / 10;
       prc[mt] = pr - prr[mt] * 10;
     }
-    const int grp = (warp - 10) >> 2;                  // producer group: owns operand / accumulator stage `grp`
-    const int ptid = ((warp - 10) & 3) * 32 + lane;    // 0..127 within the producer group
+    const int grp = (warp - PROD_WARP0) >> 2;                  // producer group: owns operand / accumulator stage `grp`
+    const int ptid = ((warp - PROD_WARP0) & 3) * 32 + lane;    // 0..127 within the producer group
     // the tile's 20 x 12 one-channel input window (zero outside the image = conv1's padding): two values per thread
     auto gather = [&](int tile, float (&g)[2]) {
       int n, h0, w0;
@@ -486,13 +524,16 @@ conv_block1_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ConvParams 
     auto build = [&](int j, int tile, const float (&g)[2]) {
       const int st = j & 1, ph = (j >> 1) & 1;
       float* win = s_win + st * 256;
+      if (ptid == 0) C1_STAMP(2, j, 0);
       win[ptid] = g[0];
       if (ptid < 112) win[128 + ptid] = g[1];
       int n, h0, w0;
       tile_coords(tile, n, h0, w0);
       const bool tv = tile < p.num_tiles;
       if (grp == 0) named_bar_sync(2, 128); else named_bar_sync(3, 128);  // window complete (the group's own barrier)
+      if (ptid == 0) C1_STAMP(2, j, 1);
       mbar_wait(&op_empty[st], ph ^ 1);
+      if (ptid == 0) C1_STAMP(2, j, 2);
       uint8_t* hi_base = s_op + st * OP_STAGE;
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
@@ -528,13 +569,17 @@ conv_block1_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ConvParams 
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote_light(&op_full[st], 0);
+      if (ptid == 0) C1_STAMP(2, j, 3);
     };
     auto drain = [&](int j, int tile) {
       const uint32_t sa = static_cast<uint32_t>(j) % SA, pa = (static_cast<uint32_t>(j) / SA) & 1;
       const int st = j & 1, ph = (j >> 1) & 1;
       (void)tile;
+      if (ptid == 0) C1_STAMP(2, j, 4);
       mbar_wait(&c1_full[st], ph);
+      if (ptid == 0) C1_STAMP(2, j, 5);
       mbar_wait(&a_empty[sa], pa ^ 1);
+      if (ptid == 0) C1_STAMP(2, j, 6);
       tc_fence_after();
       uint8_t* patch = smem_a + sa * kPatchStride;
 #pragma unroll
@@ -566,6 +611,7 @@ conv_block1_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ConvParams 
         mbar_arrive_remote_light(&a_full[sa], 0);
         mbar_arrive_remote_light(&c1_empty[st], 0);
       }
+      if (ptid == 0) C1_STAMP(2, j, 7);
     };
     // software pipeline per group (tiles j = grp, grp + PG, ...): the one-channel inputs of the group's tile after next
     // are in flight while its next tile is built and its current tile drained
@@ -579,11 +625,13 @@ conv_block1_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ConvParams 
       if (has(j + PG)) gather(tile_of(j + PG), nin);
     }
     for (; has(j); j += PG) {
+      // drain first: conv2(j) waits for it, while the group's next operand (conv1(j + PG), queued behind conv2(j - 1) in
+      // the tensor pipe) has a whole conv2 of slack
+      drain(j, tile_of(j));
       if (has(j + PG)) {
         build(j + PG, tile_of(j + PG), nin);
         if (has(j + 2 * PG)) gather(tile_of(j + 2 * PG), nin);
       }
-      drain(j, tile_of(j));
     }
   }
 
@@ -848,6 +896,12 @@ int conv_block1_launch(const float* x, int NB, int H, int W, const float* w1s, c
   set_error("conv_block1: dtype must be 0 (fp16) or 1 (bf16)");
   return SED_ERR_UNSUPPORTED;
 }
+
+#ifdef SED_C1_STAMPS
+extern "C" int sed_debug_c1_stamps(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, g_c1_stamps, sizeof(g_c1_stamps)) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 int linear_launch(const void* a16, long M, int K, const void* w16, const float* bias, int N, int relu, float* out,
                   void* out16, int out_layout, int dtype, cudaStream_t stream) {
