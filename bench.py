@@ -150,11 +150,14 @@ def run_reference(args):
     batch = args.ref_batch
     cb = cpu_reference_throughput(steps, warmup, batch)
     line = {
-        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "clips/s", "n_gpus": 0, "steps": steps,
-        "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "clips/s", "n_gpus": args.gpus,
+        "gpus_used": 0, "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "Cnn_9layers_Gru_FrameAtt logmel 16k, synthetic 10 s clips, batch %d per step "
-                               "(bounded sample of the batch-1024 workload), host CPU" % batch},
+        "config": {"workload": "Cnn_9layers_Gru_FrameAtt logmel 16k batch %d per GPU (BASELINE.json configs[1]), "
+                               "10 s clips, seeded synthetic checkpoint" % args.batch,
+                   "batch_per_gpu": args.batch,
+                   "sample": "each step is %d clips of that workload on the host CPU (same clips, same checkpoint)"
+                             % batch},
         "cpu_baseline": {"value": cb["value"], "unit": "clips/s", "cores": cb["cores"], "kind": "port",
                          "sample": cb["sample"]},
         "e2e": {"value": cb["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
