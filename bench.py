@@ -27,6 +27,11 @@ CONV_GFLOP_TC = 26.031 - 0.0738  # tensor-core conv layers per clip (SURVEY.md 8
 METRIC = "clips/sec (10 s, 16 kHz) logmel+CRNN inference"
 
 
+def config_index():
+    """BASELINE.json configs[1] = the GRU model (the headline); configs[2] = the Transformer model, 512 clips per GPU."""
+    return 1 if MODEL_TYPE == "Cnn_9layers_Gru_FrameAtt" else 2
+
+
 def load_conv_traffic():
     """DRAM bytes of the seven conv launches of one 148-clip micro-batch, from the committed ncu --set full capture."""
     path = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
@@ -114,8 +119,10 @@ class ClockSampler:
                 "samples": len(sm), "window": "device-resident + end-to-end timed regions"}
 
 
-def cpu_reference_throughput(steps, warmup, batch=32):
-    """The reference algorithm (oracle port of pytorch/models.py forward) on the host CPU, all cores."""
+def cpu_reference_throughput(steps, warmup, batch=32, device="cpu"):
+    """The reference algorithm (oracle port of pytorch/models.py forward) on the host CPU, all cores.  With
+    device="cuda" (`--ref-device cuda`, an extra row, never the reference arm the driver runs) the same float32 torch
+    ops run eagerly on the GPU: the incumbent a user of the reference has today."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch
     import sed_oracle
@@ -124,16 +131,32 @@ def cpu_reference_throughput(steps, warmup, batch=32):
     torch.set_num_threads(cores)
     sd = synth.synthetic_state_dict(MODEL_TYPE, SR)
     wave = synth.synthetic_waveform(batch, CLIP_SAMPLES, seed=1234)
+    on_gpu = device != "cpu"
+    if on_gpu:
+        sd = {k: v.to(device) for k, v in sd.items()}
+        wave = wave.to(device)
+
+    def sync():
+        if on_gpu:
+            torch.cuda.synchronize()
+
     for _ in range(warmup):
         sed_oracle.model_forward(sd, wave, MODEL_TYPE, N_FFT, HOP)
+    sync()
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        sed_oracle.model_forward(sd, wave, MODEL_TYPE, N_FFT, HOP)
+        out = sed_oracle.model_forward(sd, wave, MODEL_TYPE, N_FFT, HOP)
+        if on_gpu:
+            out["framewise_output"].cpu()
+        sync()
         times.append(time.perf_counter() - t0)
     total = sum(times)
+    where = ("float32 torch eager ops on %s (cudnn tf32 %s)" % (torch.cuda.get_device_name(0),
+                                                                 torch.backends.cudnn.allow_tf32)) if on_gpu else \
+        "float32 torch CPU ops, %d threads" % cores
     return {"value": batch * steps / total, "unit": "clips/s", "cores": cores, "kind": "port",
-            "sample": "%d steps of batch %d x 10 s clips, float32 torch CPU ops, %d threads" % (steps, batch, cores),
+            "sample": "%d steps of batch %d x 10 s clips, %s" % (steps, batch, where),
             "ms_per_step": 1e3 * total / steps, "batch": batch}
 
 
@@ -148,13 +171,13 @@ def run_reference(args):
     steps = max(1, args.steps)
     warmup = max(0, args.warmup)
     batch = args.ref_batch
-    cb = cpu_reference_throughput(steps, warmup, batch)
+    cb = cpu_reference_throughput(steps, warmup, batch, args.ref_device)
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "clips/s", "n_gpus": args.gpus,
-        "gpus_used": 0, "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "gpus_used": 0 if args.ref_device == "cpu" else 1, "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "Cnn_9layers_Gru_FrameAtt logmel 16k batch %d per GPU (BASELINE.json configs[1]), "
-                               "10 s clips, seeded synthetic checkpoint" % args.batch,
+        "config": {"workload": "%s logmel 16k batch %d per GPU (BASELINE.json configs[%d]), "
+                               "10 s clips, seeded synthetic checkpoint" % (MODEL_TYPE, args.batch, config_index()),
                    "batch_per_gpu": args.batch,
                    "sample": "each step is %d clips of that workload on the host CPU (same clips, same checkpoint)"
                              % batch},
@@ -289,8 +312,8 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": elapsed_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": "Cnn_9layers_Gru_FrameAtt logmel 16k batch %d per GPU (BASELINE.json configs[1]), "
-                                   "10 s clips, seeded synthetic checkpoint" % B,
+            "config": {"workload": "%s logmel 16k batch %d per GPU (BASELINE.json configs[%d]), "
+                                   "10 s clips, seeded synthetic checkpoint" % (MODEL_TYPE, B, config_index()),
                        "batch_per_gpu": B, "micro_batch": args.micro_batch, "parallelism": "dp%d (batch shards, "
                        "NCCL gather of outputs to rank 0)" % world,
                        "l2": "inputs (%.0f MB/step) and activations (>6 GB/micro-batch) exceed the 126 MB L2" %
@@ -335,9 +358,15 @@ def main():
     ap.add_argument("--micro-batch", type=int, default=444)
     ap.add_argument("--variant", type=int, default=4)
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--model-type", default=MODEL_TYPE,
+                    choices=["Cnn_9layers_Gru_FrameAtt", "Cnn_9layers_Transformer_FrameAtt"],
+                    help="default = the headline config; the Transformer model is BASELINE config 3 (use --batch 512)")
     ap.add_argument("--ref-batch", type=int, default=32)
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="cpu = the reference arm (default); cuda = extra row: the same torch ops eagerly on the GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    globals()["MODEL_TYPE"] = args.model_type
     if args.impl == "reference":
         run_reference(args)
     else:
