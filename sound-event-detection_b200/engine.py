@@ -577,7 +577,7 @@ class PackedModel:
         return x.transpose(1, 2)
 
     # ------------------------------------------------------------------ whole model
-    def forward_host(self, wave_host, micro_batch=444, variant=4, head_chunk=256):
+    def forward_host(self, wave_host, micro_batch=444, variant=4, head_chunk=256, result_parts=1, trace=None):
         """End-to-end call with HOST buffers: `wave_host` [B, L] f32 (pinned for full speed) is copied to
         the device micro-batch by micro-batch on a copy stream that runs ahead of the compute stream, and
         `clipwise_output` / `framewise_output` come back as host tensors (the reference callers do
@@ -603,55 +603,81 @@ class PackedModel:
         cs, ds = hb["copy_stream"], hb["d2h_stream"]
         compute = torch.cuda.current_stream(self.device)
         cs.wait_stream(compute)  # the previous call may still be reading the staging buffer
-        # a short first micro-batch lets the conv stack start after ~0.4 ms of PCIe traffic instead of ~1.7 ms; the
-        # copies run ~1.8x faster than the conv stack, so later micro-batches can grow (fewer launches, fewer
-        # drain / fill gaps between the persistent kernels): 37, 148, 296, then `micro_batch` clips
-        spans, b0 = [], 0
-        for size in (37, 148, 296):
-            if b0 >= B or size >= micro_batch:
-                break
-            spans.append((b0, min(B, b0 + size)))
-            b0 = spans[-1][1]
-        while b0 < B:
-            spans.append((b0, min(B, b0 + micro_batch)))
-            b0 = spans[-1][1]
+
+        def mark(label, stream):  # optional timeline for tools/e2e_ab.py: (label, event) pairs on the stream's order
+            if trace is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream)
+                trace.append((label, ev))
+
+        mark("start", compute)
+        # result_parts=2 cuts the batch in two PARTS (the last one 185 clips) that each run conv stack -> temporal block
+        # -> head on their own, so that the 100 KB/clip result copy of part 0 hides behind the conv stack of part 1.
+        # Measured on one box (tools/e2e_ab.py, batch 1024): 23.6 ms either way -- the second launch of the latency-bound
+        # temporal block + head (1.4 ms) costs what the hidden copy saves (1.7 ms) -- so the default is one part.
+        # Inside a part: a short first micro-batch lets the conv stack start after ~0.4 ms of PCIe traffic; after that a
+        # micro-batch may only grow as fast as its copy hides behind the previous one's conv stack (~21 us per clip
+        # against ~12 us of PCIe for float32, ~6 us for int16); sizes are multiples of 37 clips = whole waves of the
+        # persistent grids, and a short remainder of a part is folded into its last micro-batch.
+        last = 185  # 5 x 37 clips
+        parts = [(0, B - last), (B - last, B)] if (result_parts == 2 and B >= 640) else [(0, B)]
+        growth = iter((37, 37, 74, 111, 185, 296) if wave_host.dtype == torch.float32 else (37, 111, 296))
+        plan = []
+        for (p0, p1) in parts:
+            spans, b0 = [], p0
+            while b0 < p1:
+                size = min(next(growth, micro_batch), micro_batch)
+                if p1 - b0 <= min(size + size // 2, micro_batch):
+                    size = p1 - b0
+                spans.append((b0, min(p1, b0 + size)))
+                b0 = spans[-1][1]
+            plan.append(spans)
         T = L // self.front.hop + 1
-        self._workspace(max(b1 - b0 for b0, b1 in spans), T, need_a1=variant not in (3, 4))  # size once for the call
+        self._workspace(max(b1 - b0 for spans in plan for b0, b1 in spans), T, need_a1=variant not in (3, 4))
         events = []
         with torch.cuda.stream(cs):
-            for (b0, b1) in spans:
-                hb["dev"][b0:b1].copy_(wave_host[b0:b1], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(cs)
-                events.append(ev)
+            for spans in plan:
+                for (b0, b1) in spans:
+                    hb["dev"][b0:b1].copy_(wave_host[b0:b1], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                    events.append(ev)
+        events = iter(events)
         with self._lock:
-            feat16, feat32, slot = self._alloc_features(B, Tp)
-            for (b0, b1), ev in zip(spans, events):
-                compute.wait_event(ev)
-                self.conv_stack(hb["dev"][b0:b1], variant=variant, **slot(b0, b1))
-            x = self._temporal_or_features(feat16, feat32, B)
-            # pooling head in chunks: the device->host copy of chunk i overlaps the head kernel of chunk i+1
-            blocks = x.dim() == 5 and self.head_kind == "att"
-            if blocks:  # projections of the whole batch once, then the per-clip pass chunk by chunk
-                scratch = torch.empty((capi.load().sed_attpool_blocks_scratch_bytes(B, Tp),), dtype=torch.uint8,
-                                      device=self.device)
-                self._head_blocks(x, B, frames, False, False, (hb["clip_dev"], hb["frame_dev"]), stage=1,
-                                  scratch=scratch)
-            elif x.dim() == 5:
-                x = blocks_to_rows(x, B, Tp)
-            for c0 in range(0, B, head_chunk):
-                c1 = min(B, c0 + head_chunk)
-                if blocks:
-                    self._head_blocks(x, B, frames, False, False, (hb["clip_dev"], hb["frame_dev"]), stage=2,
-                                      clips=(c0, c1 - c0), scratch=scratch)
-                else:
-                    self.head(x[c0:c1], frames, want_cla=False, out=(hb["clip_dev"][c0:c1], hb["frame_dev"][c0:c1]))
-                done = torch.cuda.Event()
-                done.record(compute)
-                ds.wait_event(done)
-                with torch.cuda.stream(ds):
-                    hb["clip"][c0:c1].copy_(hb["clip_dev"][c0:c1], non_blocking=True)
-                    hb["frame"][c0:c1].copy_(hb["frame_dev"][c0:c1], non_blocking=True)
+            for (p0, p1), spans in zip(parts, plan):
+                n = p1 - p0
+                feat16, feat32, slot = self._alloc_features(n, Tp)
+                for (b0, b1) in spans:
+                    compute.wait_event(next(events))
+                    mark("conv %d:%d begin" % (b0, b1), compute)
+                    self.conv_stack(hb["dev"][b0:b1], variant=variant, **slot(b0 - p0, b1 - p0))
+                    mark("conv %d:%d end" % (b0, b1), compute)
+                x = self._temporal_or_features(feat16, feat32, n)
+                mark("temporal %d:%d end" % (p0, p1), compute)
+                out = (hb["clip_dev"][p0:p1], hb["frame_dev"][p0:p1])
+                # pooling head in chunks: the device->host copy of chunk i overlaps the head kernel of chunk i+1
+                blocks = x.dim() == 5 and self.head_kind == "att"
+                if blocks:  # projections of the whole part once, then the per-clip pass chunk by chunk
+                    scratch = torch.empty((capi.load().sed_attpool_blocks_scratch_bytes(n, Tp),), dtype=torch.uint8,
+                                          device=self.device)
+                    self._head_blocks(x, n, frames, False, False, out, stage=1, scratch=scratch)
+                elif x.dim() == 5:
+                    x = blocks_to_rows(x, n, Tp)
+                for c0 in range(0, n, head_chunk):
+                    c1 = min(n, c0 + head_chunk)
+                    if blocks:
+                        self._head_blocks(x, n, frames, False, False, out, stage=2, clips=(c0, c1 - c0),
+                                          scratch=scratch)
+                    else:
+                        self.head(x[c0:c1], frames, want_cla=False, out=(out[0][c0:c1], out[1][c0:c1]))
+                    done = torch.cuda.Event()
+                    done.record(compute)
+                    ds.wait_event(done)
+                    with torch.cuda.stream(ds):
+                        hb["clip"][p0 + c0:p0 + c1].copy_(out[0][c0:c1], non_blocking=True)
+                        hb["frame"][p0 + c0:p0 + c1].copy_(out[1][c0:c1], non_blocking=True)
+                    mark("head %d:%d end" % (p0 + c0, p0 + c1), compute)
+                    mark("d2h %d:%d end" % (p0 + c0, p0 + c1), ds)
         ds.synchronize()
         return {"clipwise_output": hb["clip"], "framewise_output": hb["frame"]}
 

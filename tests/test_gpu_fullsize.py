@@ -52,6 +52,10 @@ def test_full_batch_host_entry_matches(full_run):
     q = torch.round(wave * 32767.0).to(torch.int16)
     host16 = pm.forward_host(q.pin_memory())  # int16 PCM in: x = q / 32767 reproduces the float input exactly
     assert torch.equal(host16["framewise_output"], host["framewise_output"])
+    ref_frames = host["framewise_output"].clone()
+    two = pm.forward_host(wave.pin_memory(), result_parts=2)  # temporal block + head per part of the batch
+    assert torch.equal(two["framewise_output"], ref_frames)
+    assert torch.equal(two["clipwise_output"], out["clipwise_output"].cpu())
 
 
 def test_full_batch_spot_check_against_oracle(full_run, thresholds):
