@@ -185,6 +185,38 @@ int sed_attpool(const float* x, int B, int T, const float* w_att, const float* b
                 const float* b_cla, int ratio, int frames_out, float* clip, float* frame, float* cla_t,
                 float* norm_att_t, void* stream);
 
+/* ---- Weight preparation: what the reference gets for free by keeping nn.Module parameters.  One-time work per
+ * checkpoint; with these a caller needs no tensor library to go from a reference-layout state_dict (raw float32
+ * arrays) to the packed operands the entries above take (examples/sed_infer.c does exactly that). ---- */
+
+/* Eval-mode BatchNorm as y = x*scale + shift: scale = weight / sqrt(running_var + eps), shift = bias - running_mean*scale,
+ * folded in float64, results float32.  Replaces nn.BatchNorm2d.forward in eval mode (bn0 pytorch/models.py:642-644,
+ * bn1/bn2 of ConvBlock :128-129; eps = 1e-5).  All arrays [channels] f32 on the device. */
+int sed_fold_bn(const float* weight, const float* bias, const float* running_mean, const float* running_var,
+                int channels, double eps, float* scale, float* shift, void* stream);
+
+/* nn.Conv2d weight [cout, cin, 3, 3] f32 (pytorch/models.py:103-111) -> wpacked [cout][3*kh+kw][cin] 16-bit (round to
+ * nearest even), the operand layout of sed_conv3x3_bn_relu / sed_conv_block1. */
+int sed_pack_conv3x3(const float* w_oihw, int cout, int cin, void* wpacked, int dtype, void* stream);
+
+/* conv_block1.conv1 weight [64, 1, 3, 3] f32 times the folded bn1 scale [64] (float64 product, float32 result)
+ * -> w1_scaled [64][9] for sed_conv_block1. */
+int sed_pack_conv_first(const float* w1, const float* scale1, float* w1_scaled, void* stream);
+
+/* nn.GRU weight_hh_l0 / weight_hh_l0_reverse [768, 256] f32 (rows [r | z | n]) -> whh_packed [2*768, 256] 16-bit in the
+ * row order sed_bigru documents. */
+int sed_pack_gru_whh(const float* whh_fwd, const float* whh_bwd, void* whh_packed, int dtype, void* stream);
+
+/* float32 -> 16-bit (round to nearest even) for the nn.Linear / weight_ih operands of sed_linear. */
+int sed_cast_16(const float* src, long n, void* dst, int dtype, void* stream);
+
+/* Front-end constants, HOST pointers: twiddle_host [n_fft][2] f32 = (cos, sin)(-2 pi k / n_fft) computed in float64;
+ * the banded form of the loaded mel matrix melW_host [F, n_mels] f32 (LogmelFilterBank.melW, pytorch/stft.py:688-693):
+ * mel_lo/mel_len/mel_off [n_mels], mel_val [val_capacity] (F*n_mels always suffices), *n_val = values written. */
+int sed_frontend_twiddle(int n_fft, float* twiddle_host);
+int sed_band_mel(const float* melW_host, int F, int n_mels, int* mel_lo, int* mel_len, int* mel_off, float* mel_val,
+                 int val_capacity, int* n_val);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,7 @@ _p = ctypes.c_void_p
 _i = ctypes.c_int
 _l = ctypes.c_long
 _f = ctypes.c_float
+_d = ctypes.c_double
 
 # name -> argtypes; mirrors include/sed_b200.h one to one (checked by tests/test_capi_symbols.py)
 SIGNATURES = {
@@ -34,6 +35,13 @@ SIGNATURES = {
     "sed_conv_first_f32": ([_p, _i, _i, _i, _p, _p, _p, _p, _i, _p], _i),
     "sed_conv3x3_bn_relu": ([_p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p, _l, _l, _i, _i, _p], _i),
     "sed_conv_block1": ([_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p], _i),
+    "sed_fold_bn": ([_p, _p, _p, _p, _i, _d, _p, _p, _p], _i),
+    "sed_pack_conv3x3": ([_p, _i, _i, _p, _i, _p], _i),
+    "sed_pack_conv_first": ([_p, _p, _p, _p], _i),
+    "sed_pack_gru_whh": ([_p, _p, _p, _i, _p], _i),
+    "sed_cast_16": ([_p, _l, _p, _i, _p], _i),
+    "sed_frontend_twiddle": ([_i, _p], _i),
+    "sed_band_mel": ([_p, _i, _i, _p, _p, _p, _p, _i, _p], _i),
     "sed_fcpool": ([_p, _i, _i, _p, _p, _i, _i, _i, _p, _p, _p], _i),
     "sed_linear": ([_p, _l, _i, _p, _p, _i, _i, _p, _p, _i, _i, _p], _i),
     "sed_bigru_workspace_bytes": ([_i], _l),

@@ -5,7 +5,7 @@
 
 #include "sed_kernels.h"
 
-#define SED_ABI_VERSION 10
+#define SED_ABI_VERSION 11
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -177,6 +177,45 @@ int sed_attpool(const float* x, int B, int T, const float* w_att, const float* b
   SED_REQUIRE(clip); SED_REQUIRE(frame);
   return sed::attpool_launch(x, B, T, w_att, b_att, w_cla, b_cla, ratio, frames_out, clip, frame, cla_t, norm_att_t,
                              as_stream(stream));
+}
+
+int sed_fold_bn(const float* weight, const float* bias, const float* running_mean, const float* running_var,
+                int channels, double eps, float* scale, float* shift, void* stream) {
+  SED_REQUIRE(weight); SED_REQUIRE(bias); SED_REQUIRE(running_mean); SED_REQUIRE(running_var);
+  SED_REQUIRE(scale); SED_REQUIRE(shift);
+  return sed::fold_bn_launch(weight, bias, running_mean, running_var, channels, eps, scale, shift, as_stream(stream));
+}
+
+int sed_pack_conv3x3(const float* w_oihw, int cout, int cin, void* wpacked, int dtype, void* stream) {
+  SED_REQUIRE(w_oihw); SED_REQUIRE(wpacked);
+  return sed::pack_conv3x3_launch(w_oihw, cout, cin, wpacked, dtype, as_stream(stream));
+}
+
+int sed_pack_conv_first(const float* w1, const float* scale1, float* w1_scaled, void* stream) {
+  SED_REQUIRE(w1); SED_REQUIRE(scale1); SED_REQUIRE(w1_scaled);
+  return sed::pack_conv_first_launch(w1, scale1, w1_scaled, as_stream(stream));
+}
+
+int sed_pack_gru_whh(const float* whh_fwd, const float* whh_bwd, void* whh_packed, int dtype, void* stream) {
+  SED_REQUIRE(whh_fwd); SED_REQUIRE(whh_bwd); SED_REQUIRE(whh_packed);
+  return sed::pack_gru_whh_launch(whh_fwd, whh_bwd, whh_packed, dtype, as_stream(stream));
+}
+
+int sed_cast_16(const float* src, long n, void* dst, int dtype, void* stream) {
+  SED_REQUIRE(src); SED_REQUIRE(dst);
+  return sed::cast16_launch(src, n, dst, dtype, as_stream(stream));
+}
+
+int sed_frontend_twiddle(int n_fft, float* twiddle_host) {
+  SED_REQUIRE(twiddle_host);
+  return sed::frontend_twiddle_host(n_fft, twiddle_host);
+}
+
+int sed_band_mel(const float* melW_host, int F, int n_mels, int* mel_lo, int* mel_len, int* mel_off, float* mel_val,
+                 int val_capacity, int* n_val) {
+  SED_REQUIRE(melW_host); SED_REQUIRE(mel_lo); SED_REQUIRE(mel_len); SED_REQUIRE(mel_off); SED_REQUIRE(mel_val);
+  SED_REQUIRE(n_val);
+  return sed::band_mel_host(melW_host, F, n_mels, mel_lo, mel_len, mel_off, mel_val, val_capacity, n_val);
 }
 
 }  // extern "C"

@@ -71,6 +71,15 @@ int attpool_blocks_launch(const float* x_blocks, int B, int T, const float* w_at
                           float* frame, float* cla_t, float* norm_att_t, int stage, int clip0, int n,
                           cudaStream_t stream);
 
+// sed_pack.cu: weight preparation
+int fold_bn_launch(const float* w, const float* b, const float* mean, const float* var, int n, double eps, float* scale,
+                   float* shift, cudaStream_t stream);
+int pack_conv3x3_launch(const float* w, int cout, int cin, void* out, int dtype, cudaStream_t stream);
+int pack_conv_first_launch(const float* w, const float* scale, float* out, cudaStream_t stream);
+int pack_gru_whh_launch(const float* fwd, const float* bwd, void* out, int dtype, cudaStream_t stream);
+int cast16_launch(const float* src, long n, void* dst, int dtype, cudaStream_t stream);
+int frontend_twiddle_host(int n_fft, float* out);
+int band_mel_host(const float* melW, int F, int M, int* lo, int* len, int* off, float* val, int cap, int* n_val);
 int fcpool_launch(const float* x, int B, int T, const float* w, const float* b, int C, int ratio, int use_max,
                   float* clip, float* frame, cudaStream_t stream);
 

@@ -55,6 +55,30 @@ def fold_bn(sd, prefix, eps=1e-5):
     return scale.float().contiguous(), shift.float().contiguous()
 
 
+def _call(name, *args):
+    capi.check(getattr(capi.load(), name)(*args), name)
+
+
+def fold_bn_device(sd, prefix, device, eps=1e-5):
+    """fold_bn through the C ABI (sed_fold_bn): raw BatchNorm buffers up, float32 scale / shift on the device."""
+    raw = [sd[prefix + k].detach().float().contiguous().to(device)
+           for k in (".weight", ".bias", ".running_mean", ".running_var")]
+    n = raw[0].numel()
+    scale = torch.empty(n, dtype=torch.float32, device=device)
+    shift = torch.empty(n, dtype=torch.float32, device=device)
+    _call("sed_fold_bn", *[capi.ptr(t) for t in raw], n, float(eps), capi.ptr(scale), capi.ptr(shift),
+          capi.current_stream(device))
+    return scale, shift
+
+
+def cast16_device(w, tdtype, dtype_code, device):
+    """float32 parameter -> 16-bit operand on the device (sed_cast_16, round to nearest even)."""
+    src = w.detach().float().contiguous().to(device)
+    dst = torch.empty(src.shape, dtype=tdtype, device=device)
+    _call("sed_cast_16", capi.ptr(src), src.numel(), capi.ptr(dst), dtype_code, capi.current_stream(device))
+    return dst
+
+
 def twiddle_table(n_fft):
     k = np.arange(n_fft, dtype=np.float64)
     ang = -2.0 * np.pi * k / n_fft
@@ -85,6 +109,18 @@ def band_mel(melW):
             torch.from_numpy(np.ascontiguousarray(val, dtype=np.float32)))
 
 
+def band_mel_c(melW):
+    """band_mel through the C ABI's host helper (sed_band_mel)."""
+    W = melW.detach().cpu().float().contiguous()
+    F, M = W.shape
+    lo, ln, off = (torch.zeros(M, dtype=torch.int32) for _ in range(3))
+    val = torch.zeros(max(1, F * M), dtype=torch.float32)
+    n = np.zeros(1, np.int32)
+    _call("sed_band_mel", capi.ptr(W), F, M, capi.ptr(lo), capi.ptr(ln), capi.ptr(off), capi.ptr(val), val.numel(),
+          n.ctypes.data)
+    return lo, ln, off, val[:max(1, int(n[0]))].clone()
+
+
 def check_windowed_dft(conv_real, conv_imag, n_fft, tol=2e-5):
     """The fused front-end evaluates the loaded Conv1d kernels as window x DFT.  Verify that the
     loaded kernels have that structure (stft.py:207-212) and return the window (row 0 of conv_real)."""
@@ -113,13 +149,15 @@ class FrontendPlan:
         if self.n_fft not in (256, 512, 1024):
             raise NotImplementedError("n_fft=%d: only the reference presets 256/512/1024 are built" % n_fft)
         self.window = check_windowed_dft(conv_real, conv_imag, self.n_fft).to(device)
-        self.twiddle = twiddle_table(self.n_fft).to(device)
+        tw = torch.empty((self.n_fft, 2), dtype=torch.float32)
+        _call("sed_frontend_twiddle", self.n_fft, capi.ptr(tw))
+        self.twiddle = tw.to(device)
         self.amin = float(amin)
         self.db_offset = float(10.0 * np.log10(np.maximum(amin, ref)))
         self.is_log = 1 if is_log else 0
         self.n_mels = 0
         if melW is not None:
-            lo, ln, off, val = band_mel(melW)
+            lo, ln, off, val = band_mel_c(melW)
             self.mel_lo, self.mel_len, self.mel_off, self.mel_val = (t.to(device) for t in (lo, ln, off, val))
             self.n_mels = int(melW.shape[1])
             self.F = int(melW.shape[0])
@@ -283,39 +321,41 @@ class PackedModel:
                                   sd["logmel_extractor.melW"], dev)
         if self.front.n_mels != 64:
             raise NotImplementedError("Cnn_9layers needs mel_bins == 64 (bn0 is BatchNorm2d(64), models.py:607)")
-        s, b = fold_bn(sd, "bn0")
-        self.bn0_scale, self.bn0_shift = s.to(dev), b.to(dev)
-        # conv_block1.conv1 (Cin = 1): float32 CUDA-core layer
+        # weight preparation goes through the C ABI's helpers (sed_fold_bn / sed_pack_* / sed_cast_16), the same calls
+        # a torch-free caller makes (examples/sed_infer.c)
+        stream = capi.current_stream(dev)
+        self.bn0_scale, self.bn0_shift = fold_bn_device(sd, "bn0", dev)
+        # conv_block1.conv1 (Cin = 1): float32 weights; bn1 folded
         self.c11_w = sd["conv_block1.conv1.weight"].float().reshape(64, 9).contiguous().to(dev)
-        s, b = fold_bn(sd, "conv_block1.bn1")
-        self.c11_scale, self.c11_shift = s.to(dev), b.to(dev)
-        # fused conv_block1 (variant 3): bn1 scale folded into the nine taps (float64 fold, float32 result)
-        self.c11_ws = (sd["conv_block1.conv1.weight"].double().reshape(64, 9) * s.double()[:, None]).float().contiguous().to(dev)
+        self.c11_scale, self.c11_shift = fold_bn_device(sd, "conv_block1.bn1", dev)
+        # fused conv_block1: bn1 scale folded into the nine taps (float64 product, float32 result)
+        self.c11_ws = torch.empty((64, 9), dtype=torch.float32, device=dev)
+        _call("sed_pack_conv_first", capi.ptr(self.c11_w), capi.ptr(self.c11_scale), capi.ptr(self.c11_ws), stream)
         self.convs = []
         for name, cin, cout, mode in CONV_LAYERS:
             w = sd[name + ".weight"].float()
             if tuple(w.shape) != (cout, cin, 3, 3):
                 raise ValueError("%s.weight has shape %s" % (name, tuple(w.shape)))
-            wp = w.permute(0, 2, 3, 1).reshape(cout, 9 * cin).to(td).contiguous().to(dev)  # [Cout][tap][Cin]
-            s, b = fold_bn(sd, name.replace(".conv", ".bn"))
-            self.convs.append((cin, cout, mode, wp, s.to(dev), b.to(dev)))
+            w_dev = w.contiguous().to(dev)
+            wp = torch.empty((cout, 9 * cin), dtype=td, device=dev)  # [Cout][tap][Cin]
+            _call("sed_pack_conv3x3", capi.ptr(w_dev), cout, cin, capi.ptr(wp), self.dtype_code, stream)
+            s, b = fold_bn_device(sd, name.replace(".conv", ".bn"), dev)
+            self.convs.append((cin, cout, mode, wp, s, b))
         if self.temporal_kind == "gru":
-            wih = torch.cat([sd["gru.weight_ih_l0"], sd["gru.weight_ih_l0_reverse"]], 0).float()
-            self.gru_wih = wih.to(td).contiguous().to(dev)  # [1536, 512]
+            wih = torch.cat([sd["gru.weight_ih_l0"], sd["gru.weight_ih_l0_reverse"]], 0)
+            self.gru_wih = cast16_device(wih, td, self.dtype_code, dev)  # [1536, 512]
             self.gru_bih = torch.cat([sd["gru.bias_ih_l0"], sd["gru.bias_ih_l0_reverse"]], 0).float().contiguous().to(dev)
-            packed = []
-            for suffix in ("", "_reverse"):
-                whh = sd["gru.weight_hh_l0" + suffix].float()  # [768, 256] rows = [r | z | n]
-                # block q holds hidden units 32q..32q+31 of all three gates (see sed_b200.h: sed_bigru)
-                packed.append(whh.view(3, 8, 32, 256).permute(1, 0, 2, 3).reshape(768, 256))
-            self.gru_whh = torch.cat(packed, 0).to(td).contiguous().to(dev)  # [1536, 256]
+            # block q of a direction holds hidden units 32q..32q+31 of all three gates (see sed_b200.h: sed_bigru)
+            whh = [sd["gru.weight_hh_l0" + suffix].float().contiguous().to(dev) for suffix in ("", "_reverse")]
+            self.gru_whh = torch.empty((1536, 256), dtype=td, device=dev)
+            _call("sed_pack_gru_whh", capi.ptr(whh[0]), capi.ptr(whh[1]), capi.ptr(self.gru_whh), self.dtype_code, stream)
             self.gru_bhh = torch.stack([sd["gru.bias_hh_l0"], sd["gru.bias_hh_l0_reverse"]], 0).float().contiguous().to(dev)
         elif self.temporal_kind == "mha":
             wqkv = torch.cat([sd["multihead.w_qs.weight"], sd["multihead.w_ks.weight"], sd["multihead.w_vs.weight"]], 0)
-            self.mha_wqkv = wqkv.float().to(td).contiguous().to(dev)
+            self.mha_wqkv = cast16_device(wqkv, td, self.dtype_code, dev)
             self.mha_bqkv = torch.cat([sd["multihead.w_qs.bias"], sd["multihead.w_ks.bias"],
                                        sd["multihead.w_vs.bias"]], 0).float().contiguous().to(dev)
-            self.mha_wfc = sd["multihead.fc.weight"].float().to(td).contiguous().to(dev)
+            self.mha_wfc = cast16_device(sd["multihead.fc.weight"], td, self.dtype_code, dev)
             self.mha_bfc = sd["multihead.fc.bias"].float().contiguous().to(dev)
         if self.head_kind == "att":
             self.classes = 25  # hard-coded in the reference (models.py:617)

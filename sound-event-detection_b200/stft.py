@@ -110,7 +110,7 @@ class LogmelFilterBank(nn.Module):
 def _mel_only_plan(melW, device, amin, ref, is_log):
     plan = engine.FrontendPlan.__new__(engine.FrontendPlan)
     import numpy as np
-    lo, ln, off, val = engine.band_mel(melW)
+    lo, ln, off, val = engine.band_mel_c(melW)
     plan.mel_lo, plan.mel_len, plan.mel_off, plan.mel_val = (t.to(device) for t in (lo, ln, off, val))
     plan.n_mels = int(melW.shape[1])
     plan.F = int(melW.shape[0])

@@ -192,3 +192,41 @@ def test_linear_transposed_block_layout_is_a_pure_permutation():
         rc = lib.sed_linear(capi.ptr(a), 100, K, capi.ptr(w), capi.ptr(b), N, 0, capi.ptr(outs[0]), None, 1, 0,
                             capi.current_stream(DEV))
         capi.check(rc, "sed_linear")
+
+
+def test_weight_preparation_helpers_match_the_host_statements():
+    """sed_fold_bn / sed_pack_conv3x3 / sed_pack_conv_first / sed_pack_gru_whh / sed_cast_16 against the torch
+    expressions they replace, bit for bit, for both 16-bit types."""
+    from sed_b200 import synth
+    sd = synth.synthetic_state_dict("Cnn_9layers_Gru_FrameAtt", 16000)
+    for prefix in ("bn0", "conv_block1.bn1", "conv_block4.bn2"):
+        s_ref, b_ref = engine.fold_bn(sd, prefix)
+        s, b = engine.fold_bn_device(sd, prefix, DEV)
+        assert torch.equal(s.cpu(), s_ref) and torch.equal(b.cpu(), b_ref)
+    lib = capi.load()
+    stream = capi.current_stream(DEV)
+    for code, td in ((capi.SED_DTYPE_F16, torch.float16), (capi.SED_DTYPE_BF16, torch.bfloat16)):
+        w = sd["conv_block3.conv1.weight"].float()
+        ref = w.permute(0, 2, 3, 1).reshape(256, 9 * 128).to(td)
+        got = torch.empty((256, 9 * 128), dtype=td, device=DEV)
+        wd = w.contiguous().to(DEV)
+        assert lib.sed_pack_conv3x3(capi.ptr(wd), 256, 128, capi.ptr(got), code, stream) == 0
+        assert torch.equal(got.cpu(), ref)
+        packed = []
+        for suffix in ("", "_reverse"):
+            whh = sd["gru.weight_hh_l0" + suffix].float()
+            packed.append(whh.view(3, 8, 32, 256).permute(1, 0, 2, 3).reshape(768, 256))
+        ref = torch.cat(packed, 0).to(td)
+        got = torch.empty((1536, 256), dtype=td, device=DEV)
+        f, r = (sd["gru.weight_hh_l0" + x].float().contiguous().to(DEV) for x in ("", "_reverse"))
+        assert lib.sed_pack_gru_whh(capi.ptr(f), capi.ptr(r), capi.ptr(got), code, stream) == 0
+        assert torch.equal(got.cpu(), ref)
+        x = torch.randn(100003, generator=torch.Generator().manual_seed(1)) * 3
+        assert torch.equal(engine.cast16_device(x, td, code, DEV).cpu(), x.to(td))
+    s1, _ = engine.fold_bn(sd, "conv_block1.bn1")
+    ref = (sd["conv_block1.conv1.weight"].double().reshape(64, 9) * s1.double()[:, None]).float()
+    w1 = sd["conv_block1.conv1.weight"].float().reshape(64, 9).contiguous().to(DEV)
+    got = torch.empty((64, 9), dtype=torch.float32, device=DEV)
+    assert lib.sed_pack_conv_first(capi.ptr(w1), capi.ptr(s1.to(DEV)), capi.ptr(got), stream) == 0
+    assert torch.equal(got.cpu(), ref)
+    assert lib.sed_pack_conv3x3(capi.ptr(w1), 64, 1, capi.ptr(got), 7, stream) != 0

@@ -81,3 +81,28 @@ def test_synthetic_waveform_is_int16_quantised_and_seeded():
 def test_flops_per_clip_match_survey():
     f = so.flops_per_clip(1001, 512)
     assert abs(f["conv"] - 26.031) < 0.01 and abs(f["total"] - 26.892) < 0.02
+
+
+def test_c_abi_host_helpers_match_the_python_statements():
+    """sed_frontend_twiddle / sed_band_mel (host entries of the C ABI, no GPU needed) against engine.twiddle_table /
+    engine.band_mel."""
+    import ctypes
+    from sed_b200 import capi
+    lib = capi.load()
+    for n_fft in (256, 512, 1024):
+        tw = torch.empty((n_fft, 2), dtype=torch.float32)
+        assert lib.sed_frontend_twiddle(n_fft, capi.ptr(tw)) == 0
+        assert torch.equal(tw, engine.twiddle_table(n_fft))
+    assert lib.sed_frontend_twiddle(500, capi.ptr(torch.empty((500, 2)))) != 0
+    assert b"n_fft" in lib.sed_last_error_string()
+    g = torch.Generator().manual_seed(3)
+    W = torch.zeros((257, 64))
+    for m in range(64):  # banded columns with a gap inside one band and an empty column
+        a = int(torch.randint(0, 200, (1,), generator=g))
+        W[a:a + 9, m] = torch.rand(9, generator=g) + 0.1
+    W[5, 3] = 0.0
+    W[:, 7] = 0.0
+    ref = engine.band_mel(W)
+    got = engine.band_mel_c(W)
+    for a, b in zip(ref, got):
+        assert torch.equal(a, b)
