@@ -204,6 +204,8 @@ def run_b200(args):
     os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the B200 arm)")
+    full_affinity = os.sched_getaffinity(0)
+    numa = "off" if os.environ.get("SED_NO_NUMA_BIND") else sdist.bind_host_to_gpu(local_rank)  # before pinned buffers
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -321,6 +323,7 @@ def run_b200(args):
             "e2e": {"value": world * B * steps / (e2e_ms / 1e3), "unit": "clips/s",
                     "h2d_bytes_per_step": B * CLIP_SAMPLES * 4, "d2h_bytes_per_step": d2h,
                     "api": "PackedModel.forward_host (pinned host f32 waveform in, host clipwise/framewise out)",
+                    "host_affinity": numa,
                     "int16_input_value": world * B * steps / (e2e_i16_ms / 1e3),
                     "int16_h2d_bytes_per_step": B * CLIP_SAMPLES * 2},
             "gpu_launches": launches,
@@ -339,6 +342,7 @@ def run_b200(args):
                          "launches_timed": n_conv_launch, "conv_ms_per_step": conv_ms / steps},
         }
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, full_affinity)  # the CPU baseline gets every host core again
             cb = cpu_reference_throughput(steps=3, warmup=1, batch=args.ref_batch)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         sys.stdout.flush()
