@@ -16,7 +16,6 @@ oracle is pinned against OUTPUTS OF THE REFERENCE ITSELF, imported unchanged in 
 All functions take the reference's `state_dict` layout so the same checkpoint feeds
 the reference, this oracle and the CUDA path.
 """
-import math
 
 import numpy as np
 import torch

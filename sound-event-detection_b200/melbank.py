@@ -5,7 +5,6 @@ windowed DFT matrix as two Conv1d weights) and `pytorch/stft.py:688` (`librosa.f
 scale, area-normalised).  They are ordinary parameters in the reference `state_dict`, so a loaded
 checkpoint overrides them and the CUDA path always consumes the loaded tensors.
 """
-import math
 
 import numpy as np
 import torch

@@ -1,6 +1,5 @@
 """Drop-in boundary: constructors, state_dict layout, checkpoint format, error behaviour (CPU-only checks)."""
 import inspect
-import io
 
 import pytest
 import torch

@@ -86,7 +86,6 @@ def test_flops_per_clip_match_survey():
 def test_c_abi_host_helpers_match_the_python_statements():
     """sed_frontend_twiddle / sed_band_mel (host entries of the C ABI, no GPU needed) against engine.twiddle_table /
     engine.band_mel."""
-    import ctypes
     from sed_b200 import capi
     lib = capi.load()
     for n_fft in (256, 512, 1024):
