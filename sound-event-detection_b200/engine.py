@@ -299,6 +299,34 @@ def blocks_to_rows(xb, n, T):
     return xb.permute(1, 3, 0, 2, 4).reshape(nblk * 128, T_, c4 * 4)[:n]
 
 
+def plan_host_micro_batches(B, int16_input, micro_batch=444, result_parts=1):
+    """Micro-batch schedule of forward_host: (parts, plan) with parts = [(begin, end)] clip ranges that each run conv
+    stack -> temporal block -> head on their own and plan[i] = the conv micro-batches [(b0, b1)] of part i.
+
+    result_parts=2 cuts the batch in two parts (the last one 185 clips), so that the 100 KB/clip result copy of part 0
+    hides behind the conv stack of part 1.  Measured on one box (tools/e2e_ab.py, batch 1024): 23.6 ms either way -- the
+    second launch of the latency-bound temporal block + head (1.4 ms) costs what the hidden copy saves (1.7 ms) -- so the
+    default is one part.
+    Inside a part: a short first micro-batch lets the conv stack start after ~0.4 ms of PCIe traffic; after that a
+    micro-batch may only grow as fast as its copy hides behind the previous one's conv stack (~21 us per clip against
+    ~12 us of PCIe for float32, ~6 us for int16); sizes are multiples of 37 clips = whole waves of the persistent grids,
+    and a short remainder of a part is folded into its last micro-batch."""
+    last = 185  # 5 x 37 clips
+    parts = [(0, B - last), (B - last, B)] if (result_parts == 2 and B >= 640) else [(0, B)]
+    growth = iter((37, 111, 296) if int16_input else (37, 37, 74, 111, 185, 296))
+    plan = []
+    for (p0, p1) in parts:
+        spans, b0 = [], p0
+        while b0 < p1:
+            size = min(next(growth, micro_batch), micro_batch)
+            if p1 - b0 <= min(size + size // 2, micro_batch):
+                size = p1 - b0
+            spans.append((b0, min(p1, b0 + size)))
+            b0 = spans[-1][1]
+        plan.append(spans)
+    return parts, plan
+
+
 class PackedModel:
     """Weights of one model repacked for the kernels, resident on one device."""
 
@@ -651,27 +679,7 @@ class PackedModel:
                 trace.append((label, ev))
 
         mark("start", compute)
-        # result_parts=2 cuts the batch in two PARTS (the last one 185 clips) that each run conv stack -> temporal block
-        # -> head on their own, so that the 100 KB/clip result copy of part 0 hides behind the conv stack of part 1.
-        # Measured on one box (tools/e2e_ab.py, batch 1024): 23.6 ms either way -- the second launch of the latency-bound
-        # temporal block + head (1.4 ms) costs what the hidden copy saves (1.7 ms) -- so the default is one part.
-        # Inside a part: a short first micro-batch lets the conv stack start after ~0.4 ms of PCIe traffic; after that a
-        # micro-batch may only grow as fast as its copy hides behind the previous one's conv stack (~21 us per clip
-        # against ~12 us of PCIe for float32, ~6 us for int16); sizes are multiples of 37 clips = whole waves of the
-        # persistent grids, and a short remainder of a part is folded into its last micro-batch.
-        last = 185  # 5 x 37 clips
-        parts = [(0, B - last), (B - last, B)] if (result_parts == 2 and B >= 640) else [(0, B)]
-        growth = iter((37, 37, 74, 111, 185, 296) if wave_host.dtype == torch.float32 else (37, 111, 296))
-        plan = []
-        for (p0, p1) in parts:
-            spans, b0 = [], p0
-            while b0 < p1:
-                size = min(next(growth, micro_batch), micro_batch)
-                if p1 - b0 <= min(size + size // 2, micro_batch):
-                    size = p1 - b0
-                spans.append((b0, min(p1, b0 + size)))
-                b0 = spans[-1][1]
-            plan.append(spans)
+        parts, plan = plan_host_micro_batches(B, wave_host.dtype == torch.int16, micro_batch, result_parts)
         T = L // self.front.hop + 1
         self._workspace(max(b1 - b0 for spans in plan for b0, b1 in spans), T, need_a1=variant not in (3, 4))
         events = []

@@ -105,3 +105,30 @@ def test_c_abi_host_helpers_match_the_python_statements():
     got = engine.band_mel_c(W)
     for a, b in zip(ref, got):
         assert torch.equal(a, b)
+
+
+def test_host_micro_batch_plan_tiles_the_batch():
+    """forward_host's schedule: contiguous cover of [0, B), no micro-batch above the cap, parts respected, and the
+    copy of a micro-batch never more than ~1.8x (float32) / ~3.6x (int16) the clips of the one before it."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(B=st.integers(1, 5000), i16=st.booleans(), mb=st.integers(1, 600), parts=st.sampled_from([1, 2]))
+    def check(B, i16, mb, parts):
+        ranges, plan = engine.plan_host_micro_batches(B, i16, mb, parts)
+        assert len(ranges) == len(plan) and ranges[0][0] == 0 and ranges[-1][1] == B
+        pos = 0
+        for (p0, p1), spans in zip(ranges, plan):
+            assert p0 == pos and spans[0][0] == p0 and spans[-1][1] == p1
+            for (b0, b1) in spans:
+                assert b0 == pos and b0 < b1 <= p1 and b1 - b0 <= mb
+                pos = b1
+        assert pos == B
+
+    check()
+    _, plan = engine.plan_host_micro_batches(1024, False)
+    assert [b1 - b0 for b0, b1 in plan[0]] == [37, 37, 74, 111, 185, 296, 284]
+    _, plan = engine.plan_host_micro_batches(1024, True)
+    assert [b1 - b0 for b0, b1 in plan[0]] == [37, 111, 296, 444, 136]
+    ranges, plan = engine.plan_host_micro_batches(1024, False, result_parts=2)
+    assert ranges == [(0, 839), (839, 1024)] and plan[1] == [(839, 1024)]
