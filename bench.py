@@ -330,12 +330,13 @@ def run_b200(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": peaks["tflops_sustained"],
                          "unit": "TFLOP/s", "frac": conv_tflops / peaks["tflops_sustained"],
-                         "traffic": traffic["dram_bytes_total"] if traffic else None,
-                         "traffic_note": "dram__bytes_read+write summed over the 7 conv launches for 148 clips (ncu "
-                                         "--set full at micro-batch 148: profiles/r01_ncu_full_conv_umma2_raw.csv, "
-                                         "r01_ncu_full_conv_block1_tc_raw.csv; the default 444-clip launches move 3x "
-                                         "this); algorithmic "
-                                         "activation bytes (each layer input read once + output written once) for the same group: %.3e" % (148 * 21888256.0),
+                         "traffic": traffic["dram_bytes_total"] * B / traffic["clips"] if traffic else None,
+                         "traffic_note": "DRAM bytes of the 7 conv launches of one step (%d clips): dram__bytes_read+write "
+                                         "from ncu --set full of a 148-clip launch group (profiles/r01_ncu_full_conv_umma2"
+                                         "_raw.csv, r01_ncu_full_conv_block1_tc_raw.csv: %.3e B), scaled by clips; "
+                                         "algorithmic activation bytes (each layer input read once + output written "
+                                         "once) for the same launches: %.3e" % (B, traffic["dram_bytes_total"] if traffic
+                                                                                else 0.0, B * 21888256.0),
                          "kernel": "conv_block1_tc_kernel + 6 x conv_umma2_kernel (7 tcgen05 cta_group::2 implicit-GEMM "
                                    "launches per micro-batch, %.3f GFLOP/clip algorithmic)" % conv_gflop,
                          "peak_source": peaks["source"] + ", sustained bf16; burst %.1f" % peaks["tflops_burst"],
@@ -359,7 +360,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="clips per GPU per step")
-    ap.add_argument("--micro-batch", type=int, default=444)
+    ap.add_argument("--micro-batch", type=int, default=1036, help="cap of a conv-stack launch group (engine default)")
     ap.add_argument("--variant", type=int, default=4)
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--model-type", default=MODEL_TYPE,

@@ -5,9 +5,10 @@ Data layout in HBM (all allocations are torch tensors; the C ABI only sees raw p
   ([mb,T,64,64] -> [mb,T/2,32,64] -> ... -> [mb,T/8,8,512]) -> freq-mean features [B, T', 512] 16-bit
   -> GRU: gi [B,T',1536] f32 -> h [B,T',512] f32 | MHA: qkv [B,T',1536] f32 -> ctx 16-bit -> fc [B,T',512] f32
   -> clipwise [B,25], framewise [B,frames,25], embedding.
-The conv stack runs over micro-batches (default 444 clips = three per SM: every layer's tile count is then a
-multiple of the persistent grid, and fewer launches mean fewer drain / fill gaps between the persistent kernels);
-the temporal block and the head run once over the batch.
+The conv stack runs over micro-batches (default cap 1036 clips = seven per SM: every layer's tile count is then a
+multiple of the persistent grid, and fewer launches mean fewer drain / fill gaps between the persistent kernels; a
+batch of 1024 is one launch group with a 14.5 GB activation workspace); the temporal block and the head run once over
+the batch.
 """
 import math
 import threading
@@ -27,6 +28,9 @@ CONV_LAYERS = (
     ("conv_block4.conv1", 256, 512, capi.CONV_STORE),
     ("conv_block4.conv2", 512, 512, capi.CONV_FREQMEAN),
 )
+
+# clips per conv-stack launch group: 28 x 37 = seven whole waves of 148 persistent CTAs for every layer
+DEFAULT_MICRO_BATCH = 1036
 
 _DTYPES = {"fp16": (capi.SED_DTYPE_F16, torch.float16), "bf16": (capi.SED_DTYPE_BF16, torch.bfloat16)}
 
@@ -299,7 +303,7 @@ def blocks_to_rows(xb, n, T):
     return xb.permute(1, 3, 0, 2, 4).reshape(nblk * 128, T_, c4 * 4)[:n]
 
 
-def plan_host_micro_batches(B, int16_input, micro_batch=444, result_parts=1):
+def plan_host_micro_batches(B, int16_input, micro_batch=DEFAULT_MICRO_BATCH, result_parts=1):
     """Micro-batch schedule of forward_host: (parts, plan) with parts = [(begin, end)] clip ranges that each run conv
     stack -> temporal block -> head on their own and plan[i] = the conv micro-batches [(b0, b1)] of part i.
 
@@ -645,7 +649,7 @@ class PackedModel:
         return x.transpose(1, 2)
 
     # ------------------------------------------------------------------ whole model
-    def forward_host(self, wave_host, micro_batch=444, variant=4, head_chunk=256, result_parts=1, trace=None):
+    def forward_host(self, wave_host, micro_batch=DEFAULT_MICRO_BATCH, variant=4, head_chunk=256, result_parts=1, trace=None):
         """End-to-end call with HOST buffers: `wave_host` [B, L] f32 (pinned for full speed) is copied to
         the device micro-batch by micro-batch on a copy stream that runs ahead of the compute stream, and
         `clipwise_output` / `framewise_output` come back as host tensors (the reference callers do
@@ -766,7 +770,7 @@ class PackedModel:
         out = {"framewise_output": frame, "clipwise_output": clip, "embedding": self._embedding(x, cla, feat32)}
         return out, feat16, x, natt
 
-    def forward_windows(self, recording, window_samples, stride_samples, n_windows, micro_batch=444, variant=4,
+    def forward_windows(self, recording, window_samples, stride_samples, n_windows, micro_batch=DEFAULT_MICRO_BATCH, variant=4,
                         offsets=None):
         """Run the model on `n_windows` overlapping windows of one 1-D recording (f32 or int16, on device):
         window k = recording[k*stride : k*stride + window_samples], zero padded past the end.  Returns the same
@@ -793,7 +797,7 @@ class PackedModel:
         with self._lock:
             return self._run(n_windows, T // 8, conv_call)[0]
 
-    def forward(self, wave, micro_batch=444, variant=4, return_stages=False):
+    def forward(self, wave, micro_batch=DEFAULT_MICRO_BATCH, variant=4, return_stages=False):
         """wave [B, L] f32 on self.device -> reference output dict (models.py:683-686 / :1072-1075)."""
         if wave.dim() != 2:
             raise ValueError("input must be (batch_size, data_length)")

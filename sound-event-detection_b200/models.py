@@ -97,7 +97,7 @@ class _Cnn9Base(nn.Module):
         self._generation = [0]
         self._pack_lock = threading.RLock()
         self.precision = "fp16"   # 16-bit operand type of the tensor-core layers: 'fp16' or 'bf16'
-        self.micro_batch = 444   # clips per conv-stack launch group (a multiple of the 148 SMs)
+        self.micro_batch = engine.DEFAULT_MICRO_BATCH   # clips per conv-stack launch group (whole waves of the 148 SMs)
         self.conv_variant = 4   # 4 = CTA-pair kernels + conv_block1 fused on the tensor cores (default); 2 = CTA-pair kernels with
         # conv_block1 as two kernels; 0 = single-CTA patch; 1 = per-tap; 3 = 2 + conv_block1 fused on the CUDA cores (slower)
 

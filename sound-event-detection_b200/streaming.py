@@ -28,7 +28,7 @@ def predict_framewise(model, recording, sample_rate, sample_duration=5, overlap_
     (what `merged` holds after predict.py:349)."""
     if isinstance(model, engine.PackedModel):
         packed = model
-        micro_batch, variant = 444, 4
+        micro_batch, variant = engine.DEFAULT_MICRO_BATCH, 4
     else:
         if model.training:
             raise RuntimeError("inference only -- call .eval()")
@@ -57,7 +57,7 @@ def predict_framewise_many(model, recordings, sample_rate, sample_duration=5, ov
     the same number of windows are merged by one launch.  Returns a list of [1, total_frames, classes] tensors equal,
     bit for bit, to calling predict_framewise per recording."""
     if isinstance(model, engine.PackedModel):
-        packed, micro_batch, variant = model, 444, 4
+        packed, micro_batch, variant = model, engine.DEFAULT_MICRO_BATCH, 4
     else:
         if model.training:
             raise RuntimeError("inference only -- call .eval()")
@@ -124,7 +124,7 @@ def predict_framewise_overlap(model, clips, sample_rate, sample_duration, overla
     reads them in place through an offset table), each file's windows are overlap-added and block-averaged on the
     device.  Returns a list of per-file tensors [1, total_frames, classes] (what `merged` holds after :835)."""
     if isinstance(model, engine.PackedModel):
-        packed, micro_batch, variant = model, 444, 4
+        packed, micro_batch, variant = model, engine.DEFAULT_MICRO_BATCH, 4
     else:
         if model.training:
             raise RuntimeError("inference only -- call .eval()")

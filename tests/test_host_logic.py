@@ -129,6 +129,6 @@ def test_host_micro_batch_plan_tiles_the_batch():
     _, plan = engine.plan_host_micro_batches(1024, False)
     assert [b1 - b0 for b0, b1 in plan[0]] == [37, 37, 74, 111, 185, 296, 284]
     _, plan = engine.plan_host_micro_batches(1024, True)
-    assert [b1 - b0 for b0, b1 in plan[0]] == [37, 111, 296, 444, 136]
+    assert [b1 - b0 for b0, b1 in plan[0]] == [37, 111, 296, 580]
     ranges, plan = engine.plan_host_micro_batches(1024, False, result_parts=2)
     assert ranges == [(0, 839), (839, 1024)] and plan[1] == [(839, 1024)]
