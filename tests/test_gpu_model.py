@@ -7,7 +7,7 @@ import torch
 
 import sed_oracle as so
 from conftest import load_golden, synthetic_sd
-from sed_b200 import models, synth
+from sed_b200 import engine, models, synth
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -76,7 +76,7 @@ def test_batch_shards_are_bit_identical(mt):
     parts = [model(wave[0:2]), model(wave[2:5])]
     model.micro_batch = 2
     mb = model(wave)
-    model.micro_batch = 444
+    model.micro_batch = engine.DEFAULT_MICRO_BATCH
     for k in ("framewise_output", "clipwise_output"):
         cat = torch.cat([p[k] for p in parts], 0)
         assert torch.equal(full[k], cat), k
@@ -193,3 +193,22 @@ def test_second_device_direct():
     with torch.cuda.device(1):
         got = b(wave.to("cuda:1"))["clipwise_output"].cpu()
     assert torch.equal(got, ref)
+
+
+def test_workspace_reuse_across_shapes_and_lengths():
+    """One packed model serves calls of different batch sizes and clip lengths back to back (the activation workspace
+    grows, shrinks to prefixes and is re-sized per clip length): every call gives what a fresh model gives."""
+    mt = "Cnn_9layers_Gru_FrameAtt"
+    model = build(mt)
+    a = synth.synthetic_waveform(3, 80000, seed=21, kind="events").to(DEV)
+    b = synth.synthetic_waveform(150, 32000, seed=22).to(DEV)
+    c = synth.synthetic_waveform(2, 160001, seed=23, kind="events").to(DEV)
+    ref = {}
+    for name, w in (("a", a), ("b", b), ("c", c)):
+        fresh = build(mt)
+        ref[name] = {k: v.clone() for k, v in fresh(w).items()}
+    for name, w in (("a", a), ("b", b), ("a", a), ("c", c), ("b", b[:7]), ("c", c), ("a", a)):
+        out = model(w)
+        n = w.shape[0]
+        for k in ("framewise_output", "clipwise_output", "embedding"):
+            assert torch.equal(out[k], ref[name][k][:n]), (name, k)
