@@ -269,8 +269,8 @@ int conv_first_launch(const float* x, int NB, int H, int W, const float* w9, con
 // shared-memory patch that conv2's implicit-GEMM MMAs read -- the [NB, H, 64, 64] intermediate never exists in HBM.
 // CTA pairs (cta_group::2) as in conv_umma2_kernel: M = 256 = one tile per CTA, each CTA holds half of the weight
 // rows of both layers.  Warp roles: 0 weight TMA, 1 MMA issuer (leader CTA: conv1 of tile i+1, then conv2 of tile i),
-// 2-9 conv2 pooling epilogue, 10-17 two groups of conv1 operand builders (im2col of the one-channel input, hi/lo
-// split) + TMEM drainers working on alternate tiles.
+// 2-3 idle (they complete the control warpgroup that gives its registers away), 4-11 conv2 pooling epilogue, 12-19 two
+// groups of conv1 operand builders (im2col of the one-channel input, hi/lo split) + TMEM drainers on alternate tiles.
 // ---------------------------------------------------------------------------------------------
 namespace c1tc {
 constexpr int SA = 5;                       // conv2 patch stages

@@ -303,6 +303,21 @@ def blocks_to_rows(xb, n, T):
     return xb.permute(1, 3, 0, 2, 4).reshape(nblk * 128, T_, c4 * 4)[:n]
 
 
+def clamp_micro_batch(micro_batch, T):
+    """Cap of a conv launch group for clips of T STFT frames: the requested cap, scaled down for clips longer than
+    10 s so that the activation workspace (14 KB per frame and clip) and the kernels' 32-bit tile arithmetic stay
+    where batch 1036 x 10 s puts them; multiples of 37 clips (whole waves of the persistent grids) when possible."""
+    if micro_batch < 1:
+        raise ValueError("micro_batch must be positive")
+    cap = min(int(micro_batch), max(1, DEFAULT_MICRO_BATCH * 1001 // max(int(T), 1)))
+    # conv_block1 divides tile indices by multiplication: tiles_per_clip * (tiles + 4096) must stay below 2^32
+    per_clip = ((int(T) + 15) // 16) * 8
+    cap = max(1, min(cap, ((1 << 32) // per_clip - 4097) // per_clip))
+    if cap >= 37 and cap < micro_batch:
+        cap -= cap % 37
+    return cap
+
+
 def plan_host_micro_batches(B, int16_input, micro_batch=DEFAULT_MICRO_BATCH, result_parts=1):
     """Micro-batch schedule of forward_host: (parts, plan) with parts = [(begin, end)] clip ranges that each run conv
     stack -> temporal block -> head on their own and plan[i] = the conv micro-batches [(b0, b1)] of part i.
@@ -683,6 +698,7 @@ class PackedModel:
                 trace.append((label, ev))
 
         mark("start", compute)
+        micro_batch = clamp_micro_batch(micro_batch, T)
         parts, plan = plan_host_micro_batches(B, wave_host.dtype == torch.int16, micro_batch, result_parts)
         T = L // self.front.hop + 1
         self._workspace(max(b1 - b0 for spans in plan for b0, b1 in spans), T, need_a1=variant not in (3, 4))
@@ -785,8 +801,9 @@ class PackedModel:
         self._check_frames(T)
 
         def conv_call(slot):
-            for b0 in range(0, n_windows, micro_batch):
-                b1 = min(n_windows, b0 + micro_batch)
+            mb_cap = clamp_micro_batch(micro_batch, T)
+            for b0 in range(0, n_windows, mb_cap):
+                b1 = min(n_windows, b0 + mb_cap)
                 if offsets is not None:
                     self.conv_stack(recording, variant=variant, windows=(b1 - b0, window_samples, offsets[b0:b1]),
                                     **slot(b0, b1))
@@ -812,8 +829,9 @@ class PackedModel:
         stages = {} if return_stages else None
 
         def conv_call(slot):
-            for b0 in range(0, B, micro_batch):
-                b1 = min(B, b0 + micro_batch)
+            mb_cap = clamp_micro_batch(micro_batch, T)
+            for b0 in range(0, B, mb_cap):
+                b1 = min(B, b0 + mb_cap)
                 self.conv_stack(wave[b0:b1], variant=variant,
                                 stages=stages if (return_stages and b0 == 0) else None, **slot(b0, b1))
 

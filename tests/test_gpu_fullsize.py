@@ -85,3 +85,17 @@ def test_too_short_clip_is_rejected():
     pm = engine.PackedModel(synthetic_sd(MT), MT, 512, 160, torch.device(DEV))
     with pytest.raises(ValueError):
         pm.forward(torch.zeros(1, 800, device=DEV))  # T = 6 frames < one pooled step
+
+
+def test_long_clip_batches_are_split_by_the_launch_group_cap():
+    """60 s clips: the launch group shrinks to 148 clips (workspace and tile arithmetic stay where 1036 x 10 s puts
+    them); a batch of 150 therefore runs as 148 + 2 and equals the separately computed pieces."""
+    assert engine.clamp_micro_batch(engine.DEFAULT_MICRO_BATCH, 6001) == 148
+    pm = engine.PackedModel(synthetic_sd(MT), MT, 512, 160, torch.device(DEV))
+    wave = synth.synthetic_waveform(150, 960000, seed=72).to(DEV)
+    out = pm.forward(wave)
+    tail = pm.forward(wave[148:150])
+    head = pm.forward(wave[0:3])
+    assert torch.equal(out["framewise_output"][148:150], tail["framewise_output"])
+    assert torch.equal(out["framewise_output"][0:3], head["framewise_output"])
+    assert torch.isfinite(out["clipwise_output"]).all()

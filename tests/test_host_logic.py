@@ -132,3 +132,18 @@ def test_host_micro_batch_plan_tiles_the_batch():
     assert [b1 - b0 for b0, b1 in plan[0]] == [37, 111, 296, 580]
     ranges, plan = engine.plan_host_micro_batches(1024, False, result_parts=2)
     assert ranges == [(0, 839), (839, 1024)] and plan[1] == [(839, 1024)]
+
+
+def test_micro_batch_cap_scales_with_clip_length():
+    assert engine.clamp_micro_batch(1036, 1001) == 1036          # 10 s: the default launch group
+    assert engine.clamp_micro_batch(1036, 501) == 1036           # shorter clips never exceed the request
+    assert engine.clamp_micro_batch(1036, 6001) == 148           # 60 s: 172 -> whole waves of 37
+    assert engine.clamp_micro_batch(2, 6001) == 2                # explicit small caps are honoured
+    assert engine.clamp_micro_batch(1036, 10 ** 7) == 1
+    for T in (1001, 3001, 6001, 60001):
+        cap = engine.clamp_micro_batch(1036, T)
+        tiles_per_clip = ((T + 15) // 16) * 8
+        assert tiles_per_clip * (cap * tiles_per_clip + 4096) < 2 ** 32   # conv_block1's magic-division guard
+    import pytest
+    with pytest.raises(ValueError):
+        engine.clamp_micro_batch(0, 1001)
