@@ -932,10 +932,13 @@ int linear_launch(const void* a16, long M, int K, const void* w16, const float* 
     int rc = make_map(&tmB, dtype, 2, const_cast<void*>(w16), dims, str, box);
     if (rc) return rc;
   }
-  // the epilogue caches per-channel shift for at most 512 channels: run N in column panels of <= 512
+  // the epilogue caches the bias of at most 1536 columns: wider outputs run in column panels.  One launch for the GRU
+  // input projection (N = 1536): the 12 column slices of an A tile are consecutive work items, so the tile comes from
+  // HBM once instead of once per panel
+  constexpr int kPanel = 1536;
   int rc = SED_OK;
-  for (int n0 = 0; n0 < N && rc == SED_OK; n0 += 512) {
-    const int npanel = (N - n0) < 512 ? (N - n0) : 512;
+  for (int n0 = 0; n0 < N && rc == SED_OK; n0 += kPanel) {
+    const int npanel = (N - n0) < kPanel ? (N - n0) : kPanel;
     CUtensorMap tmBp = tmB;
     if (n0 != 0) {
       const uint64_t dims[2] = {(uint64_t)K, (uint64_t)npanel};

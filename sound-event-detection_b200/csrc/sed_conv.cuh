@@ -55,7 +55,7 @@ struct ConvCfg {
   static constexpr int THREADS = 64 + 32 * EW;
   static constexpr int CPW = BN / 2;                                  // accumulator columns per epilogue warp
   static constexpr int NSTG = (EPI == EPI_STORE) ? (CPW >= 64 ? 2 : 1) : 0;  // 16 KB TMA-store staging tiles
-  static constexpr int SS = BRES ? BN : 512;                          // cached scale/shift entries
+  static constexpr int SS = BRES ? BN : (EPI == EPI_LINEAR ? 1536 : 512);  // cached scale/shift entries
   static constexpr int TAPS = (EPI == EPI_LINEAR) ? 1 : 9;
   static constexpr int NCHUNK = CIN / 64;
   static constexpr int A_STAGE = NT * (PATCH ? kPatchStride : kTileBytes);

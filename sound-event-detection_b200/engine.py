@@ -517,7 +517,7 @@ class PackedModel:
         rc = lib.sed_linear(capi.ptr(a16), M, K, capi.ptr(w16), capi.ptr(bias), N, 1 if relu else 0, capi.ptr(out),
                             capi.ptr(o16), out_layout, self.dtype_code, capi.current_stream(self.device))
         capi.check(rc, "sed_linear")
-        capi._count((N + 511) // 512)
+        capi._count((N + 1535) // 1536)
         return (out, o16) if out16 else out
 
     def temporal(self, feat16, stages=None):
