@@ -357,11 +357,15 @@ conv_block1_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ConvParams 
       hi[t] = static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
       lo[t] = static_cast<uint32_t>(__half_as_ushort(l0)) | (static_cast<uint32_t>(__half_as_ushort(l1)) << 16);
     }
+    // The 29 products hi*w_hi (10), lo*w_hi (9: the bias slot's lo is 0) and hi*w_lo (10) are packed into TWO K=16 steps
+    // (the operand rows use the matching slot order, see build()):
+    //   step 1: A = [hi0..hi9 | lo0..lo5]        B = [wh0..wh9 | wh0..wh5]
+    //   step 2: A = [lo6 lo7 lo8 0 | hi0..hi9 | 0 0]   B = [wh6 wh7 wh8 0 | wl0..wl9 | 0 0]
     const int sw = (r >> 2) & 1;
     *reinterpret_cast<uint4*>(s_b1 + r * 32 + ((0 ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(s_b1 + r * 32 + ((1 ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-    *reinterpret_cast<uint4*>(s_b1 + 1024 + r * 32 + ((0 ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    *reinterpret_cast<uint4*>(s_b1 + 1024 + r * 32 + ((1 ^ sw) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    *reinterpret_cast<uint4*>(s_b1 + r * 32 + ((1 ^ sw) << 4)) = make_uint4(hi[4], hi[0], hi[1], hi[2]);
+    *reinterpret_cast<uint4*>(s_b1 + 1024 + r * 32 + ((0 ^ sw) << 4)) = make_uint4(hi[3], hi[4] & 0xFFFFu, lo[0], lo[1]);
+    *reinterpret_cast<uint4*>(s_b1 + 1024 + r * 32 + ((1 ^ sw) << 4)) = make_uint4(lo[2], lo[3], lo[4], 0u);
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmB);
@@ -429,9 +433,8 @@ conv_block1_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ConvParams 
         for (int mt = 0; mt < 2; ++mt) {
           const uint32_t d = tmem_base + C1_COL0 + st * 128 + mt * 64;
           const uint32_t mo = mt * (4096 >> 4);
-          umma_f16_2sm(d, desc_join(a_h + mo, d32), desc_join(b1_hi_lo, d32), idesc1, 0u);
-          umma_f16_2sm(d, desc_join(a_l + mo, d32), desc_join(b1_hi_lo, d32), idesc1, 1u);
-          umma_f16_2sm(d, desc_join(a_h + mo, d32), desc_join(b1_lo_lo, d32), idesc1, 1u);
+          umma_f16_2sm(d, desc_join(a_h + mo, d32), desc_join(b1_hi_lo, d32), idesc1, 0u);  // K step 1
+          umma_f16_2sm(d, desc_join(a_l + mo, d32), desc_join(b1_lo_lo, d32), idesc1, 1u);  // K step 2
         }
         umma_commit_2sm(&c1_full[st], 3);
         umma_commit_2sm(&op_empty[st], 3);
@@ -548,7 +551,7 @@ conv_block1_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ConvParams 
           for (int dc = 0; dc < 3; ++dc)
             in[dr * 3 + dc] = (rowv) ? win[(prr[mt] + dr) * 12 + prc[mt] + dc] : 0.0f;
         in[9] = rowv ? 1.0f : 0.0f;
-        uint32_t hi[8], lo[8];
+        uint32_t hi[5], lo[5];
 #pragma unroll
         for (int t = 0; t < 5; ++t) {  // packed conversions: hi = rn16(v), lo = rn16(v - hi)
           const __half2 h = __floats2half2_rn(in[2 * t], in[2 * t + 1]);
@@ -557,14 +560,13 @@ conv_block1_tc_kernel(const __grid_constant__ CUtensorMap tmB, const ConvParams 
           hi[t] = *reinterpret_cast<const uint32_t*>(&h);
           lo[t] = *reinterpret_cast<const uint32_t*>(&l);
         }
-#pragma unroll
-        for (int t = 5; t < 8; ++t) hi[t] = lo[t] = 0u;
+        // slot order of the two K steps (see the weight rows above); lo[4] = (lo8, lo of the constant 1) = (lo8, 0)
         const int sw = (row >> 2) & 1;
         uint8_t* rp = hi_base + row * 32;
         *reinterpret_cast<uint4*>(rp + ((0 ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(rp + ((1 ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-        *reinterpret_cast<uint4*>(rp + 8192 + ((0 ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        *reinterpret_cast<uint4*>(rp + 8192 + ((1 ^ sw) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        *reinterpret_cast<uint4*>(rp + ((1 ^ sw) << 4)) = make_uint4(hi[4], lo[0], lo[1], lo[2]);
+        *reinterpret_cast<uint4*>(rp + 8192 + ((0 ^ sw) << 4)) = make_uint4(lo[3], lo[4], hi[0], hi[1]);
+        *reinterpret_cast<uint4*>(rp + 8192 + ((1 ^ sw) << 4)) = make_uint4(hi[2], hi[3], hi[4], 0u);
       }
       fence_proxy_async_smem();
       __syncwarp();
