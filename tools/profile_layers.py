@@ -39,9 +39,9 @@ def main():
     mb = args.mb
     wave = synth.synthetic_waveform(mb, 160000).to(dev)
     T = 1001
-    ws = pm._workspace(mb, T)
     feat = torch.empty((mb, 125, 512), dtype=pm.tdtype, device=dev)
     pm.conv_stack(wave, feat, variant=args.variant)
+    ws = pm._workspace(mb, T, need_a1=True)  # after the call: it may re-allocate to add conv1's intermediate
     stream = capi.current_stream(dev)
     rows = []
     t = timeit(lambda: engine.logmel_forward(pm.front, wave, pm.bn0_scale, pm.bn0_shift, out=ws["logmel"]))
