@@ -41,7 +41,7 @@ struct ConvParams {
   const float* x1;         // [NB, H, W] f32 (log-mel after bn0)
   const float* w1;         // [64][9] f32 conv_block1.conv1 weights with the bn1 scale folded in
   const float* shift1;     // [64] f32 folded bn1 shift
-  int dbg;                 // profiling experiments only (SED_CONV_DBG): 1 = no stores, 2 = no drain, 4 = no MMA, 8 = direct 32-byte stores
+  int dbg;                 // profiling experiments only (SED_CONV_DBG): 1 = no stores, 2 = no drain, 4 = no MMA
 };
 
 constexpr int kPatchBytes = 180 * 128;       // 18 x 10 pixels x 64 ch x 2 B
@@ -114,18 +114,7 @@ SED_DEVICE_INLINE void conv_epilogue_tile(const uint32_t taddr, const int chalf,
             if (EPI != EPI_LINEAR || p.relu) x = fmaxf(x, 0.0f);
             v[j] = x;
           }
-          if (EPI == EPI_STORE && (p.dbg & 8)) {
-            // experiment (SED_CONV_DBG=8): 32-byte stores straight to global memory instead of staging + TMA store
-            if (tile_ok && h < p.H) {
-              uint32_t q[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) q[j] = Elem16<T>::pack2(v[2 * j], v[2 * j + 1]);
-              T* dst = out16 + ((static_cast<size_t>(n) * p.H + h) * p.W + w) * p.cout + ch0 + cc * 16;
-              asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(q[0]), "r"(q[1]), "r"(q[2]),
-                           "r"(q[3]), "r"(q[4]), "r"(q[5]), "r"(q[6]), "r"(q[7])
-                           : "memory");
-            }
-          } else if (EPI == EPI_STORE) {
+          if (EPI == EPI_STORE) {
             // stage this row's 16 channels in the SWIZZLE_128B tile; one TMA store per 64-channel chunk
             if (u == 0) {
               if (stg_leader) bulk_wait_read0();          // previous store has finished reading the tile
