@@ -1,7 +1,7 @@
-"""Per-kernel GPU diagnostics against the CPU oracle (developer tool; the graded checks live in tests/).
+"""Per-kernel GPU diagnostics against the CPU oracle (developer tool beside the graded checks; like them it may use the oracle).
 
-Usage on a GPU box:  python tools/gpu_diag.py            # every stage, each in its own subprocess
-                     python tools/gpu_diag.py --stage conv_tap
+Usage on a GPU box:  python tests/gpu_diag.py            # every stage, each in its own subprocess
+                     python tests/gpu_diag.py --stage conv_tap
 """
 import argparse
 import os
