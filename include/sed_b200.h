@@ -163,10 +163,12 @@ int sed_window_merge_avg(const float* frames, int n_windows, int frames_per_wind
 int sed_events(const float* frames, int n_clips, int n_frames, int classes, const double* high, const double* low,
                const int* n_smooth, const int* n_salt, int max_events, int* events, int* counts, void* stream);
 
-/* Profiling hook: sed_bigru that also records clock64() stamps of CTA 0 for recurrence steps 8..15
- * (stamps: device buffer of 8*12 long long).  Developer tool (tools/gru_stamps.py). */
+#ifdef SED_PROFILE
+/* Developer builds only (make -C sound-event-detection_b200/csrc profile -> libsed_b200_profile.so): sed_bigru that
+ * also records clock64() stamps of CTA 0 for recurrence steps 8..15 (stamps: device buffer of 8*12 long long). */
 int sed_bigru_profile(const float* gi, const void* whh_packed, const float* bhh, int B, int T, float* out,
                       void* workspace, int dtype, long long* stamps, void* stream);
+#endif
 
 /* softmax(q k^T / 8) v for 8 heads of 64.  Replaces ScaledDotProductAttention.forward
  * pytorch/models.py:808-820 and the head split/merge :863-875.

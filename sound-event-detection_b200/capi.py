@@ -46,7 +46,6 @@ SIGNATURES = {
     "sed_linear": ([_p, _l, _i, _p, _p, _i, _i, _p, _p, _i, _i, _p], _i),
     "sed_bigru_workspace_bytes": ([_i], _l),
     "sed_bigru": ([_p, _p, _p, _i, _i, _p, _p, _i, _p], _i),
-    "sed_bigru_profile": ([_p, _p, _p, _i, _i, _p, _p, _i, _p, _p], _i),
     "sed_mha_core": ([_p, _i, _i, _l, _l, _p, _i, _p], _i),
     "sed_attpool_blocks_scratch_bytes": ([_i, _i], _l),
     "sed_attpool_blocks": ([_p, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p], _i),
@@ -81,6 +80,16 @@ def load():
             fn.restype = restype
         _lib = lib
     return _lib
+
+
+def use_profile_library():
+    """Developer tools only: bind the -DSED_PROFILE build (`make -C csrc profile`), which carries the clock-stamp
+    entry `sed_bigru_profile` and honours the SED_*_DBG experiment switches.  Must be called before load()."""
+    global LIB_PATH
+    if _lib is not None:
+        raise SedError("use_profile_library() must be called before the library is loaded")
+    LIB_PATH = os.path.join(_HERE, "libsed_b200_profile.so")
+    SIGNATURES["sed_bigru_profile"] = ([_p, _p, _p, _i, _i, _p, _p, _i, _p, _p], _i)
 
 
 def launches():

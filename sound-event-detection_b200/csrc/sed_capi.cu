@@ -139,11 +139,13 @@ int sed_bigru(const float* gi, const void* whh_packed, const float* bhh, int B, 
   return sed::gru_launch(gi, whh_packed, bhh, B, T, out, workspace, dtype, as_stream(stream));
 }
 
+#ifdef SED_PROFILE
 int sed_bigru_profile(const float* gi, const void* whh_packed, const float* bhh, int B, int T, float* out,
                       void* workspace, int dtype, long long* stamps, void* stream) {
   SED_REQUIRE(gi); SED_REQUIRE(whh_packed); SED_REQUIRE(bhh); SED_REQUIRE(out); SED_REQUIRE(workspace); SED_REQUIRE(stamps);
   return sed::gru_launch(gi, whh_packed, bhh, B, T, out, workspace, dtype, as_stream(stream), stamps);
 }
+#endif
 
 long sed_attpool_blocks_scratch_bytes(int B, int T) {
   return (B > 0 && T > 0) ? static_cast<long>(sed::attpool_blocks_scratch_bytes(B, T)) : 0;

@@ -810,10 +810,12 @@ int conv3x3_launch(const void* x, int NB, int H, int W, int cin, const void* wpa
   p.M = 0; p.ldc = 0; p.relu = 1; p.tblock = 0;
   p.out_sn = (mode == EPI_FREQMEAN && out_sn > 0) ? out_sn : H;
   p.out_sh = (mode == EPI_FREQMEAN && out_sh > 0) ? out_sh : 1;
+#ifdef SED_PROFILE
   {
     const char* e = getenv("SED_CONV_DBG");
     p.dbg = e ? atoi(e) : 0;
   }
+#endif
   if (dtype == 0) return conv3x3_dispatch<__half>(tmA, tmB, tmO, p, cin, cout, mode, variant, stream);
   if (dtype == 1) return conv3x3_dispatch<__nv_bfloat16>(tmA, tmB, tmO, p, cin, cout, mode, variant, stream);
   set_error("conv3x3: dtype must be 0 (fp16) or 1 (bf16)");
@@ -861,10 +863,12 @@ int conv_block1_launch(const float* x, int NB, int H, int W, const float* w1s, c
   p.relu = 1;
   p.out_sn = H; p.out_sh = 1;
   p.x1 = x; p.w1 = w1s; p.shift1 = shift1;
+#ifdef SED_PROFILE
   {
     const char* e = getenv("SED_CONV_DBG");
     p.dbg = e ? atoi(e) : 0;
   }
+#endif
   if (producer == 1) {
     if (dtype != 0 && dtype != 1) {
       set_error("conv_block1: dtype must be 0 (fp16) or 1 (bf16)");

@@ -41,8 +41,17 @@ struct ConvParams {
   const float* x1;         // [NB, H, W] f32 (log-mel after bn0)
   const float* w1;         // [64][9] f32 conv_block1.conv1 weights with the bn1 scale folded in
   const float* shift1;     // [64] f32 folded bn1 shift
-  int dbg;                 // profiling experiments only (SED_CONV_DBG): 1 = no stores, 2 = no drain, 4 = no MMA
+#ifdef SED_PROFILE
+  int dbg;                 // -DSED_PROFILE builds only (SED_CONV_DBG): 1 = no stores, 2 = no drain, 4 = no MMA
+#endif
 };
+
+// profiling switches compile to the constant 0 in the shipped library
+#ifdef SED_PROFILE
+#define SED_CONV_DBG(p, bit) ((p).dbg & (bit))
+#else
+#define SED_CONV_DBG(p, bit) 0
+#endif
 
 constexpr int kPatchBytes = 180 * 128;       // 18 x 10 pixels x 64 ch x 2 B
 constexpr int kPatchStride = 23 * 1024;      // padded so every patch starts 1024-aligned
@@ -428,7 +437,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int t = 0; t < NT; ++t) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                if (!(p.dbg & 4))
+                if (!SED_CONV_DBG(p, 4))
                   umma_f16(d_base + t * BN, desc_join(a_lo + t * a_tile_step + tap_off + k * 2, a_hi),
                            desc_join(b_lo + k * 2, b_hi), idesc, (c | tap | k) ? 1u : 0u);
               }
@@ -466,9 +475,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
-        if (p.dbg & 2) break;
+        if (SED_CONV_DBG(p, 2)) break;
         const int tile = g * NT + t;
-        const bool tile_ok = (tile < p.num_tiles) && !(p.dbg & 1);
+        const bool tile_ok = (tile < p.num_tiles) && !SED_CONV_DBG(p, 1);
         int n = 0, h0 = 0, w0 = 0;
         if (EPI != EPI_LINEAR) tile_coords(tile, n, h0, w0);
         const uint32_t taddr = tmem_base + acc * Cfg::ACC_COLS + t * BN + chalf * CPW +
@@ -692,7 +701,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int t = 0; t < NT; ++t) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                if (!(p.dbg & 4))
+                if (!SED_CONV_DBG(p, 4))
                   umma_f16_2sm(d_base + t * BN, desc_join(a_lo + t * (kPatchStride >> 4) + tap_off + k * 2, a_hi),
                                desc_join(b_lo + k * 2, b_hi), idesc, (c | tap | k) ? 1u : 0u);
               }
@@ -823,9 +832,9 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_after();
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
-        if (p.dbg & 2) break;
+        if (SED_CONV_DBG(p, 2)) break;
         const int tile = (item * 2 + rank) * NT + t;
-        const bool tile_ok = (tile < p.num_tiles) && !(p.dbg & 1);
+        const bool tile_ok = (tile < p.num_tiles) && !SED_CONV_DBG(p, 1);
         int n, h0, w0;
         tile_coords(tile, n, h0, w0);
         const uint32_t taddr = tmem_base + acc * Cfg::ACC_COLS + t * BN + chalf * CPW +

@@ -225,6 +225,9 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
                 const float* __restrict__ mel_val, int n_mels, float amin, float db_offset, int is_log,
                 const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, float* __restrict__ out,
                 int mode, int aligned, int dbg) {
+#ifndef SED_PROFILE
+  dbg = 0;  // the experiment switches fold away in the shipped library
+#endif
   constexpr int WARPS = FrontCfg<NFFT>::WARPS;
   constexpr int FPB = FrontCfg<NFFT>::FPB;
   constexpr int F = NFFT / 2 + 1;
@@ -456,8 +459,11 @@ static int launch_frontend_t(const FrontendArgs& a, cudaStream_t stream) {
                       (a.clip_offset != nullptr || (a.clip_stride * es) % 16 == 0) &&
                       ((static_cast<size_t>(FPB) * a.hop * es) % 16 == 0) && ((NFFT / 2 * es) % 16 == 0) &&
                       ((seg_len * es) % 16 == 0);
-  const char* e_dbg = getenv("SED_FE_DBG");
-  const int dbg = e_dbg ? atoi(e_dbg) : 0;
+  int dbg = 0;
+#ifdef SED_PROFILE
+  const char* e_dbg = getenv("SED_FE_DBG");  // developer experiments: 1 = first FFT pass only, 2 = no mel projection
+  dbg = e_dbg ? atoi(e_dbg) : 0;
+#endif
   frontend_kernel<NFFT, TIn><<<static_cast<unsigned>(blocks), WARPS * 32, smem, stream>>>(
       reinterpret_cast<const TIn*>(a.wave), a.clip_stride, a.clip_offset, a.total_len, a.B, a.L, a.T, a.hop, a.window,
       reinterpret_cast<const float2*>(a.twiddle), a.mel_lo, a.mel_len, a.mel_off, a.mel_val, a.n_mels, a.amin,

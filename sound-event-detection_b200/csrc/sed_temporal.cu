@@ -1,17 +1,27 @@
 // Temporal blocks and the frame-attention head for sm_100a.
 //
 //  * gru_kernel      : persistent bidirectional GRU recurrence (pytorch/models.py:614-615, 670; gate order
-//                      r, z, n).  An 8-CTA cluster owns 128 clips of one direction for all T steps; each CTA
-//                      keeps a 96-row [r|z|n] x 32-unit slice of W_hh resident in shared memory and the f32
-//                      state of its units in registers; h_t is exchanged through L2 + TMA once per step.
+//                      r, z, n).  A 4-CTA cluster owns 128 clips of one direction for all T steps; each CTA
+//                      keeps a 192-row [r|z|n] x 64-unit slice of W_hh resident in shared memory and the f32
+//                      state of its units in registers; h_t is exchanged through distributed shared memory
+//                      (bulk shared->shared::cluster copies) once per step.
 //  * mha_core_kernel : softmax(q k^T / sqrt(64)) v per (clip, head)  (models.py:799-820, 863-875), float32,
-//                      one query row per thread, K/V of the head resident in shared memory.
+//                      one query row per thread, K/V of the head resident in shared memory (reference path of
+//                      the tensor-core attention kernel in sed_attention.cu).
 //  * attpool_kernel  : AttBlock + interpolate + pad_framewise_output (models.py:161-169, 84-95, 65-81).
 #include <cstdio>
 #include <cstdlib>
 
 #include "sed_common.cuh"
 #include "sed_kernels.h"
+
+// Developer experiments (clock stamps, switched-off phases) exist only in a -DSED_PROFILE build (make profile);
+// in the shipped library SED_DBG(x) is the constant 0 and the compiler drops every hook.
+#ifdef SED_PROFILE
+#define SED_DBG(x) (x)
+#else
+#define SED_DBG(x) 0
+#endif
 
 namespace sed {
 
@@ -110,7 +120,8 @@ gru_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ gi
   unsigned int* s_done = reinterpret_cast<unsigned int*>(bars + 11);  // warps that finished their piece of h_t
   float* s_bias = reinterpret_cast<float*>(bars + 12);  // [3][64] b_hh of this CTA's units
   // profiling hook (stamps != nullptr): CTA 0 records clock64() at a few points of steps 8..15
-  const bool prof = stamps != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  const bool prof = SED_DBG(stamps != nullptr && blockIdx.x == 0 && blockIdx.y == 0);
+  dbg = SED_DBG(dbg);
 #define GRU_STAMP(step, slot)                                                       \
   do {                                                                               \
     if (prof && (step) >= 8 && (step) < 16) stamps[((step) - 8) * 12 + (slot)] = clock64(); \
@@ -382,9 +393,11 @@ int gru_launch(const float* gi, const void* whh_packed, const float* bhh, int B,
   }
   dim3 grid(kGruCluster * (Bpad / 128), 2);
   cudaError_t e;
-  const char* e_dbg2 = getenv("SED_GRU_DBG2");  // developer experiments: 1 = no gi loads, 2 = no remote stores, 4 = no out
-  const int dbg = e_dbg2 ? atoi(e_dbg2) : 0;
-  if (getenv("SED_GRU_DBG")) {  // developer aid: how many 8-CTA clusters can be resident at once
+  int dbg = 0;
+#ifdef SED_PROFILE
+  const char* e_dbg2 = getenv("SED_GRU_DBG2");  // developer experiments: 1 = no gi loads, 4 = no out, 8 = no L2 prefetch
+  dbg = e_dbg2 ? atoi(e_dbg2) : 0;
+  if (getenv("SED_GRU_DBG")) {  // developer aid: how many 4-CTA clusters can be resident at once
     cudaFuncSetAttribute(gru_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGruSmem);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(kGruThreads); cfg.dynamicSmemBytes = kGruSmem; cfg.stream = stream;
@@ -393,6 +406,9 @@ int gru_launch(const float* gi, const void* whh_packed, const float* bhh, int B,
     fprintf(stderr, "[sed] gru: max active clusters = %d (%s), grid clusters = %d\n", ncl, cudaGetErrorString(qe),
             (Bpad / 128) * 2);
   }
+#else
+  (void)stamps;
+#endif
   if (dtype == 0) {
     e = cudaFuncSetAttribute(gru_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGruSmem);
     if (e == cudaSuccess)

@@ -9,6 +9,7 @@ from sed_b200 import capi
 def _declared_functions():
     src = open(capi.HEADER_PATH).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"#ifdef SED_PROFILE.*?#endif", "", src, flags=re.S)  # developer-build entries
     decls = re.findall(r"\b(?:int|long|const char\s*\*)\s+(sed_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", src, flags=re.S)
     out = {}
     for name, args in decls:
@@ -27,6 +28,30 @@ def test_every_declared_symbol_is_exported():
     lib = ctypes.CDLL(capi.LIB_PATH)
     for name in decl:
         assert hasattr(lib, name), "missing export " + name
+
+
+def test_every_exported_symbol_is_declared():
+    """library -> header: the shipped ABI has no undeclared `sed_*` entry point (debug / profiling entries live in
+    the -DSED_PROFILE build only) and none of its own code calls getenv."""
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if ln.split()[-1].startswith("sed_")}
+    assert exported, "nm found no sed_* exports"
+    assert exported == set(_declared_functions()), exported ^ set(_declared_functions())
+    csrc = os.path.join(os.path.dirname(capi.LIB_PATH), "csrc")
+    for name in os.listdir(csrc):
+        if not name.endswith((".cu", ".cuh", ".h")):
+            continue
+        depth = 0
+        for ln in open(os.path.join(csrc, name)):
+            t = ln.strip()
+            if t.startswith("#if"):
+                depth += 1 if (depth or "SED_PROFILE" in t and "ifdef" in t) else 0
+            elif t.startswith("#endif") and depth:
+                depth -= 1
+            elif t.startswith("#else") and depth == 1:
+                depth = 0
+            assert depth or "getenv(" not in ln, "%s: getenv outside #ifdef SED_PROFILE: %s" % (name, t)
 
 
 def test_binding_matches_header():

@@ -5,6 +5,7 @@ sys.path.insert(0, ROOT)
 os.environ["SED_GRU_DBG"] = "1"
 import torch
 from sed_b200 import capi, engine, synth
+capi.use_profile_library()  # experiment switches / stamps exist only in the -DSED_PROFILE build
 from tools.profile_layers import timeit
 dev = torch.device("cuda:0")
 lib = capi.load()

@@ -4,6 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from sed_b200 import capi, engine, synth
+capi.use_profile_library()  # experiment switches / stamps exist only in the -DSED_PROFILE build
 dev = torch.device("cuda:0")
 lib = capi.load()
 mt = "Cnn_9layers_Gru_FrameAtt"
