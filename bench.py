@@ -119,12 +119,22 @@ class ClockSampler:
                 "samples": len(sm), "window": "device-resident + end-to-end timed regions"}
 
 
-def cpu_reference_throughput(steps, warmup, batch=32, device="cpu"):
-    """The reference algorithm (oracle port of pytorch/models.py forward) on the host CPU, all cores.  With
-    device="cuda" (`--ref-device cuda`, an extra row, never the reference arm the driver runs) the same float32 torch
-    ops run eagerly on the GPU: the incumbent a user of the reference has today."""
+def reference_modules_available():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_import
+    return ref_import.available()
+
+
+def cpu_reference_throughput(steps, warmup, batch=32, device="cpu", autocast=None, channels_last=False):
+    """The reference's own CPU implementation of the path on the host cores, all threads: the UNMODIFIED reference
+    modules (`/root/reference/pytorch/models.py` where it lies, else the verbatim snapshot oracle/_ref that
+    oracle/snapshot_ref.py wrote -- kind "reference"); without either, the oracle port (kind "port").  With
+    device="cuda" (`--ref-device cuda`, extra rows, never the reference arm the driver runs) the same modules run
+    eagerly on the GPU -- float32 / TF32, or `--ref-autocast bf16` (+ `--ref-channels-last`): the incumbent a user
+    of the reference has today."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch
+    import ref_import
     import sed_oracle
     from sed_b200 import synth
     cores = os.cpu_count() or 1
@@ -132,36 +142,56 @@ def cpu_reference_throughput(steps, warmup, batch=32, device="cpu"):
     sd = synth.synthetic_state_dict(MODEL_TYPE, SR)
     wave = synth.synthetic_waveform(batch, CLIP_SAMPLES, seed=1234)
     on_gpu = device != "cpu"
-    if on_gpu:
-        sd = {k: v.to(device) for k, v in sd.items()}
+    kind = "reference" if ref_import.available() else "port"
+    if kind == "reference":
+        _, ref_models = ref_import.load()
+        model = getattr(ref_models, MODEL_TYPE)(SR, N_FFT, HOP, 64, FMIN, FMAX, 25, "logmel")
+        model.load_state_dict(sd, strict=True)
+        model = model.eval().to(device)
+        if channels_last:
+            model = model.to(memory_format=torch.channels_last)
         wave = wave.to(device)
+
+        def run():
+            with torch.no_grad():
+                if autocast:
+                    with torch.autocast("cuda" if on_gpu else "cpu", dtype=getattr(torch, autocast)):
+                        return model(wave)
+                return model(wave)
+    else:
+        if on_gpu:
+            sd = {k: v.to(device) for k, v in sd.items()}
+            wave = wave.to(device)
+
+        def run():
+            return sed_oracle.model_forward(sd, wave, MODEL_TYPE, N_FFT, HOP)
 
     def sync():
         if on_gpu:
             torch.cuda.synchronize()
 
     for _ in range(warmup):
-        sed_oracle.model_forward(sd, wave, MODEL_TYPE, N_FFT, HOP)
+        run()
     sync()
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        out = sed_oracle.model_forward(sd, wave, MODEL_TYPE, N_FFT, HOP)
+        out = run()
         if on_gpu:
-            out["framewise_output"].cpu()
+            out["framewise_output"].float().cpu()
         sync()
         times.append(time.perf_counter() - t0)
     total = sum(times)
-    where = ("float32 torch eager ops on %s (cudnn tf32 %s)" % (torch.cuda.get_device_name(0),
-                                                                 torch.backends.cudnn.allow_tf32)) if on_gpu else \
-        "float32 torch CPU ops, %d threads" % cores
-    return {"value": batch * steps / total, "unit": "clips/s", "cores": cores, "kind": "port",
+    what = "unmodified reference modules" if kind == "reference" else "oracle port of the reference forward"
+    if on_gpu:
+        where = "%s, torch eager on %s (%s%s, cudnn tf32 %s)" % (
+            what, torch.cuda.get_device_name(0), "autocast " + autocast if autocast else "float32",
+            ", channels_last" if channels_last else "", torch.backends.cudnn.allow_tf32)
+    else:
+        where = "%s, float32 torch CPU ops, %d threads" % (what, cores)
+    return {"value": batch * steps / total, "unit": "clips/s", "cores": cores, "kind": kind,
             "sample": "%d steps of batch %d x 10 s clips, %s" % (steps, batch, where),
             "ms_per_step": 1e3 * total / steps, "batch": batch}
-
-
-def pm_spans(B, micro_batch):
-    return list(range(0, B, micro_batch))
 
 
 def run_reference(args):
@@ -171,27 +201,243 @@ def run_reference(args):
     steps = max(1, args.steps)
     warmup = max(0, args.warmup)
     batch = args.ref_batch
-    cb = cpu_reference_throughput(steps, warmup, batch, args.ref_device)
+    cb = cpu_reference_throughput(steps, warmup, batch, args.ref_device, args.ref_autocast, args.ref_channels_last)
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "clips/s", "n_gpus": args.gpus,
         "gpus_used": 0 if args.ref_device == "cpu" else 1, "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32" if not args.ref_autocast else args.ref_autocast, "data": "synthetic",
         "config": {"workload": "%s logmel 16k batch %d per GPU (BASELINE.json configs[%d]), "
                                "10 s clips, seeded synthetic checkpoint" % (MODEL_TYPE, args.batch, config_index()),
                    "batch_per_gpu": args.batch,
                    "sample": "each step is %d clips of that workload on the host CPU (same clips, same checkpoint)"
                              % batch},
-        "cpu_baseline": {"value": cb["value"], "unit": "clips/s", "cores": cb["cores"], "kind": "port",
+        "cpu_baseline": {"value": cb["value"], "unit": "clips/s", "cores": cb["cores"], "kind": cb["kind"],
                          "sample": cb["sample"]},
         "e2e": {"value": cb["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------------------------
+class Ctx:
+    """Rank / device / collectives of one bench process."""
+
+    def __init__(self, torch, dist, dev, world, rank):
+        self.torch, self.dist, self.dev, self.world, self.rank = torch, dist, dev, world, rank
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.item()
+
+    def timed(self, fn, steps, warmup):
+        """ms per step of fn(i): barrier + synchronize on both sides, CUDA events on the current stream, max over ranks."""
+        for i in range(warmup):
+            fn(i)
+        self.barrier()
+        e0 = self.torch.cuda.Event(enable_timing=True)
+        e1 = self.torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1)) / steps
+
+
+class Gatherer:
+    """Assembly of every rank's framewise / clipwise on rank 0 inside the step.  Default: the pooling-head kernels
+    store straight into rank 0's buffer over NVLink (dist.PeerGather: CUDA-IPC peer memory, completion = one 4-byte
+    all-reduce); `--gather nccl`, or a box without peer access, uses one NCCL gather received in place."""
+
+    def __init__(self, ctx, sdist, n, frames, classes, mode):
+        self.ctx, self.sdist, self.peer, self.how = ctx, sdist, None, "none (1 GPU)"
+        self.into = None
+        if ctx.world == 1:
+            return
+        if mode == "peer":
+            try:
+                self.peer = sdist.PeerGather(n, frames, classes, ctx.dev, dst=0, slots=2)
+                self.how = "peer stores over NVLink into rank 0's buffer (CUDA IPC) + 4-byte all-reduce"
+            except RuntimeError as e:
+                self.how = "nccl gather (peer memory unavailable: %s)" % str(e)[:120]
+        else:
+            self.how = "nccl gather"
+        if self.peer is None and ctx.rank == 0:
+            t = ctx.torch
+            self.into = {"framewise_output": t.empty((ctx.world * n, frames, classes), device=ctx.dev),
+                         "clipwise_output": t.empty((ctx.world * n, classes), device=ctx.dev)}
+
+    def step(self, pm, wave, i, **kw):
+        if self.peer is not None:
+            pm.forward(wave, out=self.peer.local_out(i), **kw)
+            return self.peer.complete(i)
+        out = pm.forward(wave, **kw)
+        if self.ctx.world > 1:
+            return self.sdist.gather_outputs(out, dst=0, into=self.into)
+        return out
+
+    def close(self):
+        if self.peer is not None:
+            self.peer.close()
+
+
+def dp_preflight(torch, models, synth):
+    """Untimed: the drop-in model under torch.nn.DataParallel on two GPUs (the reference's own multi-GPU mechanism,
+    main_strong.py:541) returns bit for bit what one GPU returns."""
+    if torch.cuda.device_count() < 2:
+        return "skipped (1 GPU visible)"
+    try:
+        sd = synth.synthetic_state_dict(MODEL_TYPE, SR)
+        model = getattr(models, MODEL_TYPE)(SR, N_FFT, HOP, 64, FMIN, FMAX, 25, "logmel")
+        model.load_state_dict(sd)
+        model = model.to("cuda:0").eval()
+        x = synth.synthetic_waveform(6, 32000, seed=5, kind="events").to("cuda:0")
+        one = model(x)
+        two = torch.nn.DataParallel(model, device_ids=[0, 1])(x)
+        torch.cuda.synchronize()
+        same = all(torch.equal(one[k], two[k]) for k in ("framewise_output", "clipwise_output"))
+        return "ok" if same else "MISMATCH"
+    except Exception as e:  # noqa: BLE001 -- a preflight must not take the benchmark down
+        return "error: %s" % str(e)[:160]
+
+
+def e2e_rate(ctx, pipe, wave_h, steps):
+    """clips/s per rank through the host pipeline: K submits + K collected results inside the timed region (every
+    step's host->device copy from pinned memory and device->host result copy included; two batches in flight)."""
+    for _ in range(2):
+        pipe.result(pipe.submit(wave_h))
+    ctx.barrier()
+    t0 = time.perf_counter()
+    pipe.submit(wave_h)
+    for _ in range(steps - 1):
+        pipe.submit(wave_h)
+        res = pipe.result()
+    res = pipe.result()
+    ctx.torch.cuda.synchronize(ctx.dev)
+    dt = ctx.max_over_ranks(time.perf_counter() - t0)
+    ctx.barrier()
+    return wave_h.shape[0] * steps / dt, res
+
+
+def bench_config3(ctx, engine, synth, sdist, args):
+    """BASELINE configs[2]: Cnn_9layers_Transformer_FrameAtt, 16 kHz, 4096 clips over 8 GPUs = 512 per GPU; timed from
+    inputs resident on each rank to framewise + clipwise resident on rank 0 (gather included), and without it."""
+    mt = "Cnn_9layers_Transformer_FrameAtt"
+    B = 512
+    pm = engine.PackedModel(synth.synthetic_state_dict(mt, SR), mt, N_FFT, HOP, ctx.dev, precision=args.precision)
+    wave = synth.synthetic_waveform(B, CLIP_SAMPLES, seed=4321, rank=ctx.rank).to(ctx.dev)
+    g = Gatherer(ctx, sdist, B, 1000, 25, args.gather)
+    ms = ctx.timed(lambda i: g.step(pm, wave, i), steps=4, warmup=2)
+    ms_nog = ctx.timed(lambda i: pm.forward(wave), steps=4, warmup=1)
+    g.close()
+    return {"workload": "%s logmel 16k, %d clips per GPU x %d GPUs" % (mt, B, ctx.world), "batch_per_gpu": B,
+            "clips_per_s": ctx.world * B / ms * 1e3, "ms_per_step": ms, "gather": g.how,
+            "clips_per_s_without_gather": ctx.world * B / ms_nog * 1e3, "steps": 4}
+
+
+def bench_config4(ctx, engine, streaming, synth, args, with_cpu):
+    """BASELINE configs[3]: predict.py streaming path at 32 kHz -- 60 s recordings, 5 s windows, 1 s stride (56 windows
+    per recording), frame-wise overlap averaging on the device; recordings sharded over the ranks (no collective).
+    e2e: pinned host int16 recordings in -> merged frames on the host."""
+    torch = ctx.torch
+    sr, files = 32000, 16
+    n_fft, hop, fmin, fmax = synth.PRESETS[sr]
+    pm = engine.PackedModel(synth.synthetic_state_dict(MODEL_TYPE, sr), MODEL_TYPE, n_fft, hop, ctx.dev,
+                            precision=args.precision)
+    host = []
+    for f in range(files):
+        w = synth.synthetic_waveform(1, 60 * sr, seed=100 + f, rank=ctx.rank, kind="events", sample_rate=sr)[0]
+        host.append(torch.round(w * 32767.0).to(torch.int16).pin_memory())
+    recs = [h.to(ctx.dev) for h in host]
+    windows = files * len(streaming.window_starts(60.0, 5, overlap=True))
+    ms = ctx.timed(lambda i: streaming.predict_framewise_many(pm, recs, sr, 5, 1), steps=4, warmup=2)
+
+    def e2e_step(i):
+        dev_recs = [h.to(ctx.dev, non_blocking=True) for h in host]
+        merged = streaming.predict_framewise_many(pm, dev_recs, sr, 5, 1)
+        return [m.cpu() for m in merged]
+
+    for i in range(2):
+        e2e_step(i)
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for i in range(4):
+        out = e2e_step(i)
+    ms_e2e = 1e3 * ctx.max_over_ranks(time.perf_counter() - t0) / 4
+    ctx.barrier()
+    res = {"workload": "%s logmel 32k streaming: %d recordings of 60 s per GPU per call x %d GPUs, 5 s windows / 1 s "
+                       "stride, merge + avg_merge on the device" % (MODEL_TYPE, files, ctx.world),
+           "windows_per_call_per_gpu": windows, "windows_per_s": ctx.world * windows / ms * 1e3,
+           "audio_seconds_per_s": ctx.world * files * 60 / ms * 1e3, "ms_per_call": ms,
+           "e2e_windows_per_s": ctx.world * windows / ms_e2e * 1e3,
+           "e2e_audio_seconds_per_s": ctx.world * files * 60 / ms_e2e * 1e3,
+           "e2e_bytes_per_call": {"h2d": files * 60 * sr * 2, "d2h": sum(m.numel() * 4 for m in out)}}
+    if with_cpu:
+        # the reference's sequential B = 1 window loop (predict.py:297-349) on the host cores: bounded sample
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import stream_oracle
+        torch.set_num_threads(os.cpu_count() or 1)
+        sd = synth.synthetic_state_dict(MODEL_TYPE, sr)
+        audio = (host[0][:15 * sr].float() / 32767.0).numpy()
+        nw = len(streaming.window_starts(15.0, 5, overlap=True))
+        t0 = time.perf_counter()
+        stream_oracle.streaming_predict(sd, audio, MODEL_TYPE, sr, n_fft, hop, 5, 1)
+        dt = time.perf_counter() - t0
+        res["cpu_b1_loop"] = {"windows_per_s": nw / dt, "audio_seconds_per_s": 15.0 / dt, "cores": os.cpu_count(),
+                              "kind": "port", "sample": "one 15 s recording = %d windows of 5 s, batch 1 per window "
+                              "(oracle/stream_oracle.streaming_predict, the loop of predict.py:297-349)" % nw}
+    return res
+
+
+def bench_config5(ctx, engine, synth, peaks, total_clips=1000000):
+    """BASELINE configs[4]: log-mel front-end alone (waveform f32 -> log-mel f32) at 8k / 16k / 32k; a resident
+    592-clip chunk (input + output exceed L2) is looped until `total_clips` clips have gone through all GPUs."""
+    torch = ctx.torch
+    out = {}
+    B = 592
+    iters = max(3, -(-total_clips // (ctx.world * B)))
+    for sr in (8000, 16000, 32000):
+        n_fft, hop, fmin, fmax = synth.PRESETS[sr]
+        sd = synth.synthetic_state_dict(MODEL_TYPE, sr)
+        plan = engine.FrontendPlan(sd["spectrogram_extractor.stft.conv_real.weight"],
+                                   sd["spectrogram_extractor.stft.conv_imag.weight"], n_fft, hop,
+                                   sd["logmel_extractor.melW"], ctx.dev)
+        L = 10 * sr
+        w = synth.synthetic_waveform(B, L, seed=77, rank=ctx.rank).to(ctx.dev)
+        o = torch.empty((B, L // hop + 1, 64), dtype=torch.float32, device=ctx.dev)
+        for _ in range(3):
+            engine.logmel_forward(plan, w, out=o)
+        ctx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            engine.logmel_forward(plan, w, out=o)
+        e1.record()
+        ctx.barrier()
+        ms = ctx.max_over_ranks(e0.elapsed_time(e1))
+        per_clip = 4 * L + 4 * (L // hop + 1) * 64
+        rate = ctx.world * B * iters / ms * 1e3
+        out["%dk" % (sr // 1000)] = {"clips": ctx.world * B * iters, "clips_per_s": rate,
+                                     "algorithmic_GBps_per_gpu": rate / ctx.world * per_clip / 1e9,
+                                     "hbm_frac": rate / ctx.world * per_clip / 1e9 / peaks["hbm_gbs"],
+                                     "bytes_per_clip": per_clip}
+    return {"workload": "log-mel front-end alone, 10 s clips, %d-clip resident chunk looped to >= %d clips over %d "
+                        "GPUs" % (B, total_clips, ctx.world), "hbm_peak_GBps": peaks["hbm_gbs"], "presets": out}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from sed_b200 import capi, engine, synth
+    from sed_b200 import capi, engine, models, streaming, synth
     from sed_b200 import dist as sdist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -212,6 +458,7 @@ def run_b200(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL banners / warnings never reach stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
+    ctx = Ctx(torch, dist, dev, world, rank)
     capi.load()
 
     B = args.batch
@@ -219,25 +466,25 @@ def run_b200(args):
     sd = synth.synthetic_state_dict(MODEL_TYPE, SR)
     pm = engine.PackedModel(sd, MODEL_TYPE, N_FFT, HOP, dev, precision=args.precision)
     wave_host = synth.synthetic_waveform(B, CLIP_SAMPLES, seed=1234, rank=rank).pin_memory()
+    wave_i16 = torch.round(wave_host * 32767.0).to(torch.int16).pin_memory()
     wave = wave_host.to(dev)
+    frames = pm.frames_for((CLIP_SAMPLES // HOP + 1) // 8)
 
-    def step_device():
-        out = pm.forward(wave, micro_batch=args.micro_batch, variant=args.variant)
-        if world > 1:
-            sdist.gather_outputs(out, dst=0)
-        return out
+    # untimed preflight: the reference's own multi-GPU mechanism on the drop-in model
+    dp_check = dp_preflight(torch, models, synth) if rank == 0 else None
+    ctx.barrier()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+    gather = Gatherer(ctx, sdist, B, frames, pm.classes, args.gather)
+
+    def step_device(i):
+        return gather.step(pm, wave, i, micro_batch=args.micro_batch, variant=args.variant)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for _ in range(warmup):
-        step_device()
-    barrier()
+    for i in range(warmup):
+        step_device(i)
+    ctx.barrier()
 
     # ---------------- timed region 1: inputs resident in HBM ----------------
     if rank == 0:
@@ -245,65 +492,58 @@ def run_b200(args):
     capi.reset_launches()
     pm.conv_events = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    ctx.barrier()
     e0.record()
-    for _ in range(steps):
-        step_device()
+    for i in range(steps):
+        step_device(warmup + i)
     e1.record()
-    barrier()
+    ctx.barrier()
     elapsed_ms = e0.elapsed_time(e1)
     launches = capi.launches()
     conv_ms = sum(a.elapsed_time(b) for a, b, _ in pm.conv_events)
     conv_clips = sum(n for _, _, n in pm.conv_events)
     pm.conv_events = None
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = t.item()
+    elapsed_ms = ctx.max_over_ranks(elapsed_ms)
 
-    # ---------------- timed region 2: end to end with HOST buffers ----------------
-    def step_host():
-        out = pm.forward_host(wave_host, micro_batch=args.micro_batch, variant=args.variant)
-        return out
-
-    for _ in range(2):
-        step_host()
-    barrier()
-    t0 = time.perf_counter()
-    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    h0.record()
-    for _ in range(steps):
-        res = step_host()
-    h1.record()
-    barrier()
-    e2e_ms = max(h0.elapsed_time(h1), 0.0)
-    wall_ms = 1e3 * (time.perf_counter() - t0)
-    t = torch.tensor([max(e2e_ms, wall_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = t.item()
+    # ---------------- timed region 2: end to end with HOST buffers, through the host pipeline ----------------
+    # Headline: int16 PCM host input -- the reference's own storage format (utils/utilities.py:78-79); at N = 8 the
+    # float32 variant is bound by this platform's host<->device copy ceiling (profiles/r02_h2d_ceiling.json).
+    pipe = pm.host_pipeline(depth=2, micro_batch=args.micro_batch, variant=args.variant)
+    rate_i16, res = e2e_rate(ctx, pipe, wave_i16, steps)
     d2h = res["clipwise_output"].numel() * 4 + res["framewise_output"].numel() * 4
-
-    # ---------------- extra: the same end-to-end call fed with int16 PCM ----------------
-    wave_i16 = torch.round(wave_host * 32767.0).to(torch.int16).pin_memory()
+    rate_f32, _ = e2e_rate(ctx, pipe, wave_host, steps)
+    # the synchronous single call (copy in, run, copy out; nothing overlapped across calls), for reference
     for _ in range(2):
         pm.forward_host(wave_i16, micro_batch=args.micro_batch, variant=args.variant)
-    barrier()
+    ctx.barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
         pm.forward_host(wave_i16, micro_batch=args.micro_batch, variant=args.variant)
-    barrier()
-    t = torch.tensor([1e3 * (time.perf_counter() - t0)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_i16_ms = t.item()
+    sync_ms = 1e3 * ctx.max_over_ranks(time.perf_counter() - t0)
+    ctx.barrier()
     clocks = None
     if rank == 0:
         sampler.mark_end()
         clocks = sampler.stop()
 
+    # ---------------- the other BASELINE configs: short runs outside the headline regions ----------------
+    peaks = load_peaks()
+    configs = None
+    if not args.no_configs:
+        del wave
+        pm._ws.clear()
+        torch.cuda.empty_cache()
+        configs = {}
+        for name, fn in (("config3_transformer_4096_over_8", lambda: bench_config3(ctx, engine, synth, sdist, args)),
+                         ("config4_streaming_32k", lambda: bench_config4(ctx, engine, streaming, synth, args,
+                                                                         with_cpu=(world == 1 and rank == 0 and
+                                                                                   not args.no_cpu_baseline))),
+                         ("config5_frontend_sweep", lambda: bench_config5(ctx, engine, synth, peaks))):
+            configs[name] = fn()
+            torch.cuda.empty_cache()
+    gather.close()
+
     if rank == 0:
-        peaks = load_peaks()
         traffic = load_conv_traffic()
         value = world * B * steps / (elapsed_ms / 1e3)
         # variant 4 runs conv_block1.conv1 inside the first timed launch: the timed group is the whole conv stack
@@ -316,17 +556,22 @@ def run_b200(args):
             "dtype": args.precision, "data": "synthetic",
             "config": {"workload": "%s logmel 16k batch %d per GPU (BASELINE.json configs[%d]), "
                                    "10 s clips, seeded synthetic checkpoint" % (MODEL_TYPE, B, config_index()),
-                       "batch_per_gpu": B, "micro_batch": args.micro_batch, "parallelism": "dp%d (batch shards, "
-                       "NCCL gather of outputs to rank 0)" % world,
+                       "batch_per_gpu": B, "micro_batch": args.micro_batch, "parallelism": "dp%d (batch shards, no "
+                       "collective on the data path; outputs assembled on rank 0: %s)" % (world, gather.how),
                        "l2": "inputs (%.0f MB/step) and activations (>6 GB/micro-batch) exceed the 126 MB L2" %
                              (B * CLIP_SAMPLES * 4 / 1e6)},
-            "e2e": {"value": world * B * steps / (e2e_ms / 1e3), "unit": "clips/s",
-                    "h2d_bytes_per_step": B * CLIP_SAMPLES * 4, "d2h_bytes_per_step": d2h,
-                    "api": "PackedModel.forward_host (pinned host f32 waveform in, host clipwise/framewise out)",
+            "e2e": {"value": world * rate_i16, "unit": "clips/s",
+                    "h2d_bytes_per_step": B * CLIP_SAMPLES * 2, "d2h_bytes_per_step": d2h,
+                    "api": "HostPipeline.submit/result (sed_b200.pipeline; what sed_b200.pytorch_utils.forward drives): "
+                           "pinned host int16 PCM waveform in (x = q/32767 in the front-end kernel, the reference's "
+                           "HDF5 format), host clipwise/framewise out, two batches in flight",
                     "host_affinity": numa,
-                    "int16_input_value": world * B * steps / (e2e_i16_ms / 1e3),
-                    "int16_h2d_bytes_per_step": B * CLIP_SAMPLES * 2},
+                    "f32_input_value": world * rate_f32, "f32_h2d_bytes_per_step": B * CLIP_SAMPLES * 4,
+                    "synchronous_forward_host_int16_value": world * B * steps / (sync_ms / 1e3),
+                    "platform_ceiling": "profiles/r02_h2d_ceiling.json: 8 ranks doing only these copies reach 344 k "
+                                        "clips/s (int16) / 215 k (float32) on this pool's 8-GPU host"},
             "gpu_launches": launches,
+            "dp_check": dp_check,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": peaks["tflops_sustained"],
                          "unit": "TFLOP/s", "frac": conv_tflops / peaks["tflops_sustained"],
@@ -342,6 +587,8 @@ def run_b200(args):
                          "peak_source": peaks["source"] + ", sustained bf16; burst %.1f" % peaks["tflops_burst"],
                          "launches_timed": n_conv_launch, "conv_ms_per_step": conv_ms / steps},
         }
+        if configs is not None:
+            line["configs"] = configs
         if world == 1 and not args.no_cpu_baseline:
             os.sched_setaffinity(0, full_affinity)  # the CPU baseline gets every host core again
             cb = cpu_reference_throughput(steps=3, warmup=1, batch=args.ref_batch)
@@ -351,6 +598,10 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def pm_spans(B, micro_batch):
+    return list(range(0, B, micro_batch))
 
 
 def main():
@@ -369,7 +620,13 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=32)
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="cpu = the reference arm (default); cuda = extra row: the same torch ops eagerly on the GPU")
+    ap.add_argument("--ref-autocast", default=None, choices=["bfloat16", "float16"],
+                    help="extra row: run the reference modules under torch.autocast (with --ref-device cuda)")
+    ap.add_argument("--ref-channels-last", action="store_true", help="extra row: channels_last reference modules")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short runs of BASELINE configs 3 / 4 / 5")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how rank 0 gets every rank's outputs (peer = head kernels store over NVLink)")
     args = ap.parse_args()
     globals()["MODEL_TYPE"] = args.model_type
     if args.impl == "reference":

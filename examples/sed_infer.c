@@ -150,8 +150,8 @@ int main(int argc, char** argv) {
   const int n_fft = argc > 4 ? atoi(argv[4]) : 512;
   const int hop = argc > 5 ? atoi(argv[5]) : 160;
   const int F = n_fft / 2 + 1, M = 64, DT = SED_DTYPE_F16;
-  if (sed_abi_version() != 11) {
-    fprintf(stderr, "libsed_b200 ABI %d, this driver was written against 11\n", sed_abi_version());
+  if (sed_abi_version() != 12) {
+    fprintf(stderr, "libsed_b200 ABI %d, this driver was written against 12\n", sed_abi_version());
     return 1;
   }
   load_weights(argv[1]);

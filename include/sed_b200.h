@@ -163,6 +163,23 @@ int sed_window_merge_avg(const float* frames, int n_windows, int frames_per_wind
 int sed_events(const float* frames, int n_clips, int n_frames, int classes, const double* high, const double* low,
                const int* n_smooth, const int* n_salt, int max_events, int* events, int* counts, void* stream);
 
+/* ---- Peer-memory result buffers (multi-GPU gather without a collective on the data path) -------------------------
+ * The reference gathers replica outputs on GPU 0 inside torch.nn.DataParallel (pytorch/main_strong.py:541,
+ * pytorch/predict.py:239).  Here the destination rank owns ONE buffer for the results of all ranks; every other rank
+ * (one process per GPU) maps it through CUDA IPC and passes its slice as the `clip` / `frame` output pointers of
+ * sed_attpool* / sed_fcpool, whose stores then travel over NVLink to the destination GPU: the gather is fused into
+ * the pooling head's epilogue.  These five entries are the only ones that allocate; they are explicit alloc / free
+ * calls made by the caller, host-synchronous, and work on the calling thread's current CUDA device.
+ *   sed_peer_alloc : cudaMalloc of `bytes` on the current device (a dedicated allocation, exportable as a whole)
+ *   sed_peer_export: 64-byte IPC handle (HOST buffer) of an allocation made by sed_peer_alloc
+ *   sed_peer_open  : map another process's allocation into this process (peer access enabled lazily)
+ *   sed_peer_close / sed_peer_free: undo sed_peer_open / sed_peer_alloc */
+int sed_peer_alloc(long bytes, void** dev_ptr);
+int sed_peer_free(void* dev_ptr);
+int sed_peer_export(const void* dev_ptr, unsigned char* handle64);
+int sed_peer_open(const unsigned char* handle64, void** dev_ptr);
+int sed_peer_close(void* dev_ptr);
+
 #ifdef SED_PROFILE
 /* Developer builds only (make -C sound-event-detection_b200/csrc profile -> libsed_b200_profile.so): sed_bigru that
  * also records clock64() stamps of CTA 0 for recurrence steps 8..15 (stamps: device buffer of 8*12 long long). */

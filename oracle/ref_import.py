@@ -9,8 +9,20 @@ import importlib
 import os
 import sys
 
-REF_ROOT = os.environ.get("SED_REFERENCE_ROOT", "/root/reference")
-_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_shims")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIMS = os.path.join(_HERE, "_shims")
+
+
+def _find_root():
+    """The reference tree where it lies (build container), else the verbatim snapshot oracle/snapshot_ref.py wrote
+    to oracle/_ref (git-ignored; travels to the GPU box with the working tree)."""
+    for root in (os.environ.get("SED_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if root and os.path.isfile(os.path.join(root, "pytorch", "models.py")):
+            return root
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def available():

@@ -49,6 +49,11 @@ SIGNATURES = {
     "sed_mha_core": ([_p, _i, _i, _l, _l, _p, _i, _p], _i),
     "sed_attpool_blocks_scratch_bytes": ([_i, _i], _l),
     "sed_attpool_blocks": ([_p, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p], _i),
+    "sed_peer_alloc": ([_l, _p], _i),
+    "sed_peer_free": ([_p], _i),
+    "sed_peer_export": ([_p, _p], _i),
+    "sed_peer_open": ([_p, _p], _i),
+    "sed_peer_close": ([_p], _i),
     "sed_attpool": ([_p, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p], _i),
 }
 

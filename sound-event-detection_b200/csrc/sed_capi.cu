@@ -2,10 +2,11 @@
 #include "../../include/sed_b200.h"
 
 #include <cuda_runtime.h>
+#include <string.h>
 
 #include "sed_kernels.h"
 
-#define SED_ABI_VERSION 11
+#define SED_ABI_VERSION 12
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -129,6 +130,53 @@ int sed_linear(const void* a16, long M, int K, const void* w16, const float* bia
                void* out16, int out_layout, int dtype, void* stream) {
   SED_REQUIRE(a16); SED_REQUIRE(w16); SED_REQUIRE(out);
   return sed::linear_launch(a16, M, K, w16, bias, N, relu, out, out16, out_layout, dtype, as_stream(stream));
+}
+
+// ---- peer-memory result buffers (see sed_b200.h) ----
+static int peer_fail(const char* what, cudaError_t e) {
+  sed::set_error("%s: %s", what, cudaGetErrorString(e));
+  cudaGetLastError();
+  return SED_ERR_CUDA;
+}
+
+int sed_peer_alloc(long bytes, void** dev_ptr) {
+  SED_REQUIRE(dev_ptr);
+  if (bytes <= 0) {
+    sed::set_error("sed_peer_alloc: bytes=%ld", bytes);
+    return SED_ERR_BAD_SHAPE;
+  }
+  cudaError_t e = cudaMalloc(dev_ptr, static_cast<size_t>(bytes));
+  return e == cudaSuccess ? SED_OK : peer_fail("sed_peer_alloc", e);
+}
+
+int sed_peer_free(void* dev_ptr) {
+  SED_REQUIRE(dev_ptr);
+  cudaError_t e = cudaFree(dev_ptr);
+  return e == cudaSuccess ? SED_OK : peer_fail("sed_peer_free", e);
+}
+
+int sed_peer_export(const void* dev_ptr, unsigned char* handle64) {
+  SED_REQUIRE(dev_ptr); SED_REQUIRE(handle64);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr));
+  if (e != cudaSuccess) return peer_fail("sed_peer_export", e);
+  memcpy(handle64, &h, 64);
+  return SED_OK;
+}
+
+int sed_peer_open(const unsigned char* handle64, void** dev_ptr) {
+  SED_REQUIRE(handle64); SED_REQUIRE(dev_ptr);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  return e == cudaSuccess ? SED_OK : peer_fail("sed_peer_open", e);
+}
+
+int sed_peer_close(void* dev_ptr) {
+  SED_REQUIRE(dev_ptr);
+  cudaError_t e = cudaIpcCloseMemHandle(dev_ptr);
+  return e == cudaSuccess ? SED_OK : peer_fail("sed_peer_close", e);
 }
 
 long sed_bigru_workspace_bytes(int B) { return B > 0 ? static_cast<long>(sed::gru_workspace_bytes(B)) : 0; }

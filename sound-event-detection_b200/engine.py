@@ -10,6 +10,8 @@ multiple of the persistent grid, and fewer launches mean fewer drain / fill gaps
 batch of 1024 is one launch group with a 14.5 GB activation workspace); the temporal block and the head run once over
 the batch.
 """
+import collections
+import functools
 import math
 import threading
 
@@ -17,6 +19,28 @@ import numpy as np
 import torch
 
 from . import capi
+
+
+def _on_device(fn):
+    """Run a PackedModel method with the model's GPU as the current CUDA device: kernels launched through the C ABI,
+    `cudaFuncSetAttribute` and the SM-count queries act on the CURRENT device, so a model living on cuda:1 must not
+    depend on the caller having selected it (the reference works from any current device)."""
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+    return wrapper
+
+
+def _on_device_of(argname_index):
+    """Same guard for the module-level helpers: the device is the one of positional argument `argname_index`."""
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapper(*args, **kwargs):
+            with torch.cuda.device(args[argname_index].device):
+                return fn(*args, **kwargs)
+        return wrapper
+    return deco
 
 CONV_LAYERS = (
     # name, cin, cout, mode
@@ -175,6 +199,7 @@ def _wave_dtype_code(wave):
     raise TypeError("waveform must be float32 or int16, got %s" % (wave.dtype,))
 
 
+@_on_device_of(1)
 def logmel_forward(plan, wave, bn_scale=None, bn_shift=None, out=None, windows=None):
     """wave [B, L] (f32 or int16 PCM) cuda -> [B, T, n_mels] f32.
 
@@ -216,6 +241,7 @@ def logmel_forward(plan, wave, bn_scale=None, bn_shift=None, out=None, windows=N
     return out
 
 
+@_on_device_of(0)
 def window_merge_avg(frames, overlap_interval, sample_duration):
     """frames [n_windows, frames_per_window, classes] f32 cuda -> merged [1, total_frames, classes]
     (merge + avg_merge, utils/utilities.py:405-446); a 4-D input [n_recordings, n_windows, fpw, classes] merges every
@@ -233,6 +259,7 @@ def window_merge_avg(frames, overlap_interval, sample_duration):
     return merged
 
 
+@_on_device_of(1)
 def spectrogram_forward(plan, wave):
     lib = capi.load()
     B, L = wave.shape
@@ -245,6 +272,7 @@ def spectrogram_forward(plan, wave):
     return out
 
 
+@_on_device_of(1)
 def logmel_rows_forward(plan, spec):
     lib = capi.load()
     F = spec.shape[-1]
@@ -261,6 +289,7 @@ def logmel_rows_forward(plan, spec):
     return out
 
 
+@_on_device_of(0)
 def extract_events(frames, high, low, n_smooth, n_salt, max_events=64):
     """frames [n_clips, n_frames, classes] f32 cuda; per-class thresholds (sequences or scalars).
     Returns (events [n_clips, classes, max_events, 2] int32, counts [n_clips, classes] int32) on the device
@@ -350,6 +379,15 @@ class PackedModel:
     """Weights of one model repacked for the kernels, resident on one device."""
 
     def __init__(self, sd, model_type, n_fft, hop, device, precision="fp16"):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise ValueError("PackedModel needs a CUDA device (no CPU fallback), got %s" % (device,))
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        with torch.cuda.device(device):
+            self._init(sd, model_type, n_fft, hop, device, precision)
+
+    def _init(self, sd, model_type, n_fft, hop, device, precision):
         if precision not in _DTYPES:
             raise ValueError("precision must be 'fp16' or 'bf16'")
         if model_type not in MODEL_PLANS:
@@ -416,23 +454,34 @@ class PackedModel:
             self.classes = int(self.fc_w.shape[0])
             if self.fc_w.shape[1] != 512 or self.classes > 32:
                 raise NotImplementedError("fc head: need Linear(512 -> classes_num <= 32)")
-        self._ws = {}
-        self._lock = threading.Lock()
-        self._host = {}
+        self._ws = collections.OrderedDict()  # T -> workspace entry, least recently used first
+        self._lock = threading.RLock()
+        self._pipelines = {}
+        self._last_stream = None
         self.conv_events = None  # set to [] to collect (start, end) CUDA events around the tensor-core conv launches
 
     # ------------------------------------------------------------------ workspaces
+    WS_CACHE_ENTRIES = 3          # clip lengths whose activation workspace stays allocated
+    WS_CACHE_BYTES = 64 << 30     # ... as long as together they stay below this
+
     def _workspace(self, mb, T, need_a1=False):
-        """Activation buffers of the conv stack for a micro-batch of `mb` clips: views into one allocation per T sized
-        for the largest micro-batch seen (micro-batch sizes vary inside forward_host).  a1, the 8.2 MB/clip output of
-        conv_block1.conv1, only exists for the two-kernel variants of block 1."""
+        """Activation buffers of the conv stack for a micro-batch of `mb` clips: views into one allocation per clip
+        length T, sized for the largest micro-batch seen (micro-batch sizes vary inside forward_host).  A small LRU of
+        clip lengths is kept, so that callers alternating between lengths (10 s evaluation clips and 5 s streaming
+        windows) do not re-allocate ~14.5 GB per switch.  a1, the 8.2 MB/clip output of conv_block1.conv1, only exists
+        for the two-kernel variants of block 1."""
         ent = self._ws.get(T)
         if ent is None or ent["cap"] < mb or (need_a1 and "a1" not in ent["buf"]):
             cap = mb if ent is None else max(mb, ent["cap"])
             need_a1 = need_a1 or (ent is not None and "a1" in ent["buf"])
             dev, td = self.device, self.tdtype
             H1, H2, H3 = T // 2, T // 4, T // 8
-            self._ws = {}  # drop the old allocation first (keep only the most recent T)
+            self._ws.pop(T, None)  # drop this length's old allocation first
+            ent = None
+            per_clip = 4 * T * 64 + 2 * 64 * (H1 * 32 * 3 + H2 * 16 * 6 + H3 * 8 * 12) + (2 * T * 64 * 64 if need_a1 else 0)
+            while self._ws and (len(self._ws) >= self.WS_CACHE_ENTRIES or
+                                sum(e["bytes"] for e in self._ws.values()) + cap * per_clip > self.WS_CACHE_BYTES):
+                self._ws.popitem(last=False)
             buf = {
                 "logmel": torch.empty((cap, T, 64), dtype=torch.float32, device=dev),
                 "p1": torch.empty((cap, H1, 32, 64), dtype=td, device=dev),
@@ -444,11 +493,20 @@ class PackedModel:
             }
             if need_a1:
                 buf["a1"] = torch.empty((cap, T, 64, 64), dtype=td, device=dev)
-            ent = {"cap": cap, "buf": buf}
-            self._ws = {T: ent}
+            ent = {"cap": cap, "buf": buf, "bytes": sum(t.numel() * t.element_size() for t in buf.values())}
+            self._ws[T] = ent
+        self._ws.move_to_end(T)
         return {k: v[:mb] for k, v in ent["buf"].items()}
 
+    def _acquire_stream(self, stream):
+        """The activation workspace is shared by every entry point; when the launching stream changes (forward on
+        the caller's stream, the host pipeline on its own), the new stream waits for the work queued on the old one."""
+        if self._last_stream is not None and self._last_stream != stream:
+            stream.wait_stream(self._last_stream)
+        self._last_stream = stream
+
     # ------------------------------------------------------------------ stages
+    @_on_device
     def conv_stack(self, wave_mb, feat_out, variant=4, stages=None, windows=None, feat32=None, feat_strides=(0, 0)):
         """wave_mb [mb, L] (f32 / int16) -> feat_out [mb, T', 512] 16-bit (freq-mean of conv_block4).
         windows=(mb, L, stride): wave_mb is a 1-D recording read as overlapping windows.
@@ -507,6 +565,7 @@ class PackedModel:
                 if k in ws and not (fused1 and k == "a1"):  # the fused block never materialises a1
                     stages[k] = ws[k].clone()
 
+    @_on_device
     def linear(self, a16, w16, bias, relu=False, out16=False, out_layout=0):
         """out_layout 1: float32 output as 128-row transposed blocks (see sed_b200.h: sed_linear)."""
         lib = capi.load()
@@ -520,6 +579,7 @@ class PackedModel:
         capi._count((N + 1535) // 1536)
         return (out, o16) if out16 else out
 
+    @_on_device
     def temporal(self, feat16, stages=None):
         """feat16 [B, T', 512] 16-bit -> [B, T', 512] f32 (GRU or MultiHead output)."""
         lib = capi.load()
@@ -550,6 +610,7 @@ class PackedModel:
         make = torch.empty if Bp == B else torch.zeros
         return make((Tp, Bp, 512), dtype=self.tdtype, device=self.device)
 
+    @_on_device
     def gru_tmajor(self, feat_t, B, stages=None):
         """feat_t [T', Bp, 512] 16-bit (time-major, batch padded to 128) -> bi-GRU output as 128-clip transposed
         blocks (T'*Bp*512 f32, see blocks_to_rows).  The input projection writes gi in the same layout, which the
@@ -567,6 +628,7 @@ class PackedModel:
             stages["gi_blocks"] = gi
         return out
 
+    @_on_device
     def mha_tmajor(self, feat_t, B, stages=None):
         """feat_t [T', Bp, 512] 16-bit (time-major, batch padded to 128) -> relu(fc(attention)) as 128-clip transposed
         blocks (the layout sed_attpool_blocks consumes)."""
@@ -594,6 +656,7 @@ class PackedModel:
             frames += 100 - frames % 100
         return frames
 
+    @_on_device
     def head(self, x, frames_out, want_cla=True, want_norm_att=False, out=None, n=None, clip0=0):
         """x [B, T', 512] f32 -> (clipwise [B,C], framewise [B,frames_out,C], cla | None, norm_att | None).
         x may also be a 5-D transposed-block tensor (gru_tmajor output) covering n clips."""
@@ -629,6 +692,7 @@ class PackedModel:
         capi._count()
         return clip, frame, None, None
 
+    @_on_device
     def _head_blocks(self, xb, n, frames_out, want_cla, want_norm_att, out, stage=0, clips=None, scratch=None):
         """Pooling head on a transposed-block input.  stage / clips=(begin, count) / scratch expose the two launches
         of sed_attpool_blocks separately (forward_host overlaps result copies with the per-clip pass); `out` tensors
@@ -664,94 +728,49 @@ class PackedModel:
         return x.transpose(1, 2)
 
     # ------------------------------------------------------------------ whole model
-    def forward_host(self, wave_host, micro_batch=DEFAULT_MICRO_BATCH, variant=4, head_chunk=256, result_parts=1, trace=None):
-        """End-to-end call with HOST buffers: `wave_host` [B, L] f32 (pinned for full speed) is copied to
-        the device micro-batch by micro-batch on a copy stream that runs ahead of the compute stream, and
-        `clipwise_output` / `framewise_output` come back as host tensors (the reference callers do
-        `.data.cpu().numpy()` on exactly these, pytorch_utils.py:57-62)."""
-        if wave_host.is_cuda or wave_host.dim() != 2 or wave_host.dtype not in (torch.float32, torch.int16):
-            raise ValueError("forward_host expects a (batch_size, data_length) float32 or int16 CPU tensor")
-        B, L = wave_host.shape
-        key = (B, L, wave_host.dtype)
-        hb = self._host.get(key)
-        T = L // self.front.hop + 1
-        self._check_frames(T)
-        Tp = T // 8
-        frames = self.frames_for(Tp)
-        C = self.classes
-        if hb is None:
-            hb = {"dev": torch.empty((B, L), dtype=wave_host.dtype, device=self.device),
-                  "clip": torch.empty((B, C), dtype=torch.float32).pin_memory(),
-                  "frame": torch.empty((B, frames, C), dtype=torch.float32).pin_memory(),
-                  "clip_dev": torch.empty((B, C), dtype=torch.float32, device=self.device),
-                  "frame_dev": torch.empty((B, frames, C), dtype=torch.float32, device=self.device),
-                  "copy_stream": torch.cuda.Stream(self.device), "d2h_stream": torch.cuda.Stream(self.device)}
-            self._host = {key: hb}
-        cs, ds = hb["copy_stream"], hb["d2h_stream"]
-        compute = torch.cuda.current_stream(self.device)
-        cs.wait_stream(compute)  # the previous call may still be reading the staging buffer
+    def host_pipeline(self, depth=2, micro_batch=DEFAULT_MICRO_BATCH, variant=4, head_chunk=256):
+        """The cached `pipeline.HostPipeline` of this model for the given options (see that class): asynchronous
+        submit / result over host buffers with `depth` batches in flight."""
+        from .pipeline import HostPipeline
+        key = (depth, micro_batch, variant, head_chunk)
+        pipe = self._pipelines.get(key)
+        if pipe is None:
+            pipe = self._pipelines[key] = HostPipeline(self, depth, micro_batch, variant, head_chunk)
+        return pipe
 
-        def mark(label, stream):  # optional timeline for tools/e2e_ab.py: (label, event) pairs on the stream's order
-            if trace is not None:
-                ev = torch.cuda.Event(enable_timing=True)
-                ev.record(stream)
-                trace.append((label, ev))
+    def forward_host(self, wave_host, micro_batch=DEFAULT_MICRO_BATCH, variant=4, head_chunk=256, result_parts=1,
+                     trace=None, copy=False):
+        """One synchronous end-to-end call with HOST buffers: `wave_host` [B, L] f32 or int16 (pinned for full
+        speed) is copied to the device micro-batch by micro-batch on a copy stream that runs ahead of the compute
+        stream, and `clipwise_output` / `framewise_output` come back as host tensors (the reference callers do
+        `.data.cpu().numpy()` on exactly these, pytorch_utils.py:57-62).
 
-        mark("start", compute)
-        micro_batch = clamp_micro_batch(micro_batch, T)
-        parts, plan = plan_host_micro_batches(B, wave_host.dtype == torch.int16, micro_batch, result_parts)
-        T = L // self.front.hop + 1
-        self._workspace(max(b1 - b0 for spans in plan for b0, b1 in spans), T, need_a1=variant not in (3, 4))
-        events = []
-        with torch.cuda.stream(cs):
-            for spans in plan:
-                for (b0, b1) in spans:
-                    hb["dev"][b0:b1].copy_(wave_host[b0:b1], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(cs)
-                    events.append(ev)
-        events = iter(events)
-        with self._lock:
-            for (p0, p1), spans in zip(parts, plan):
-                n = p1 - p0
-                feat16, feat32, slot = self._alloc_features(n, Tp)
-                for (b0, b1) in spans:
-                    compute.wait_event(next(events))
-                    mark("conv %d:%d begin" % (b0, b1), compute)
-                    self.conv_stack(hb["dev"][b0:b1], variant=variant, **slot(b0 - p0, b1 - p0))
-                    mark("conv %d:%d end" % (b0, b1), compute)
-                x = self._temporal_or_features(feat16, feat32, n)
-                mark("temporal %d:%d end" % (p0, p1), compute)
-                out = (hb["clip_dev"][p0:p1], hb["frame_dev"][p0:p1])
-                # pooling head in chunks: the device->host copy of chunk i overlaps the head kernel of chunk i+1
-                blocks = x.dim() == 5 and self.head_kind == "att"
-                if blocks:  # projections of the whole part once, then the per-clip pass chunk by chunk
-                    scratch = torch.empty((capi.load().sed_attpool_blocks_scratch_bytes(n, Tp),), dtype=torch.uint8,
-                                          device=self.device)
-                    self._head_blocks(x, n, frames, False, False, out, stage=1, scratch=scratch)
-                elif x.dim() == 5:
-                    x = blocks_to_rows(x, n, Tp)
-                for c0 in range(0, n, head_chunk):
-                    c1 = min(n, c0 + head_chunk)
-                    if blocks:
-                        self._head_blocks(x, n, frames, False, False, out, stage=2, clips=(c0, c1 - c0),
-                                          scratch=scratch)
-                    else:
-                        self.head(x[c0:c1], frames, want_cla=False, out=(out[0][c0:c1], out[1][c0:c1]))
-                    done = torch.cuda.Event()
-                    done.record(compute)
-                    ds.wait_event(done)
-                    with torch.cuda.stream(ds):
-                        hb["clip"][p0 + c0:p0 + c1].copy_(out[0][c0:c1], non_blocking=True)
-                        hb["frame"][p0 + c0:p0 + c1].copy_(out[1][c0:c1], non_blocking=True)
-                    mark("head %d:%d end" % (p0 + c0, p0 + c1), compute)
-                    mark("d2h %d:%d end" % (p0 + c0, p0 + c1), ds)
-        ds.synchronize()
-        return {"clipwise_output": hb["clip"], "framewise_output": hb["frame"]}
+        Result lifetime: with copy=False (default) the returned tensors are views of pinned staging buffers that
+        rotate over THREE calls -- a result stays valid while the next two calls run and is overwritten by the third;
+        a loop that keeps results longer must copy them (or pass copy=True, which returns fresh tensors like the
+        reference's `.data.cpu()`).  For back-to-back batches use `host_pipeline()`: it overlaps the copies of one
+        batch with the kernels of its neighbours."""
+        pipe = self.host_pipeline(3, micro_batch, variant, head_chunk)
+        pipe.drain()
+        pipe.trace = trace
+        try:
+            ticket = pipe.submit(wave_host, result_parts=result_parts)
+            return pipe.result(ticket, copy=copy)
+        finally:
+            pipe.trace = None
+
+    MAX_POOLED_STEPS = {"mha": 400, "att": 590}  # shared-memory limits of mha_core / the pooling head (K/V, [T'][50])
 
     def _check_frames(self, T):
         if T // 8 < 1:
             raise ValueError("clip too short: %d STFT frames give no pooled time step (need >= 8)" % T)
+        Tp = T // 8
+        if self.temporal_kind == "mha" and Tp > self.MAX_POOLED_STEPS["mha"]:
+            raise ValueError("clip too long for the MultiHead block: %d pooled steps (limit %d = %.0f s at 100 frames/s)"
+                             % (Tp, self.MAX_POOLED_STEPS["mha"], self.MAX_POOLED_STEPS["mha"] * 0.08))
+        if self.head_kind == "att" and Tp > self.MAX_POOLED_STEPS["att"]:
+            raise ValueError("clip too long for the frame-attention head: %d pooled steps (limit %d = %.0f s at 100 "
+                             "frames/s)" % (Tp, self.MAX_POOLED_STEPS["att"], self.MAX_POOLED_STEPS["att"] * 0.08))
 
     def _alloc_features(self, n, Tp):
         """Feature buffers of the conv stack and slot(b0, b1) -> conv_stack keyword arguments for one micro-batch.
@@ -771,21 +790,25 @@ class PackedModel:
             return feat32
         return (self.gru_tmajor if self.temporal_kind == "gru" else self.mha_tmajor)(feat16, n, stages)
 
-    def _run(self, n, Tp, conv_call, stages=None, want_norm_att=False):
+    def _run(self, n, Tp, conv_call, stages=None, want_norm_att=False, out=None):
         """Shared tail of forward / forward_windows: conv stack per micro-batch (conv_call(b0, b1, feat16, feat32,
-        stages)), temporal block and head over the whole batch."""
+        stages)), temporal block and head over the whole batch.  out=(clipwise [n, C], framewise [n, frames, C]):
+        preallocated destinations -- may be slices of a peer GPU's buffer (dist.PeerGather)."""
+        self._acquire_stream(torch.cuda.current_stream(self.device))
         feat16, feat32, slot = self._alloc_features(n, Tp)
         conv_call(slot)
         x = self._temporal_or_features(feat16, feat32, n, stages)
         if x.dim() == 5:
             feat16 = feat16[:, :n].transpose(0, 1)  # clip-major view for the stage dump
         wants_cla = self.model_type in ("Cnn_9layers_Gru_FrameAtt", "Cnn_9layers_FrameAtt")
-        clip, frame, cla, natt = self.head(x, self.frames_for(Tp), want_cla=wants_cla, want_norm_att=want_norm_att, n=n)
+        clip, frame, cla, natt = self.head(x, self.frames_for(Tp), want_cla=wants_cla, want_norm_att=want_norm_att, n=n,
+                                           out=out)
         if x.dim() == 5 and (stages is not None or not wants_cla):
             x = blocks_to_rows(x, n, Tp)  # clip-major view of the GRU output (stage dump / 'embedding' of *_FrameAvg)
         out = {"framewise_output": frame, "clipwise_output": clip, "embedding": self._embedding(x, cla, feat32)}
         return out, feat16, x, natt
 
+    @_on_device
     def forward_windows(self, recording, window_samples, stride_samples, n_windows, micro_batch=DEFAULT_MICRO_BATCH, variant=4,
                         offsets=None):
         """Run the model on `n_windows` overlapping windows of one 1-D recording (f32 or int16, on device):
@@ -814,8 +837,10 @@ class PackedModel:
         with self._lock:
             return self._run(n_windows, T // 8, conv_call)[0]
 
-    def forward(self, wave, micro_batch=DEFAULT_MICRO_BATCH, variant=4, return_stages=False):
-        """wave [B, L] f32 on self.device -> reference output dict (models.py:683-686 / :1072-1075)."""
+    @_on_device
+    def forward(self, wave, micro_batch=DEFAULT_MICRO_BATCH, variant=4, return_stages=False, out=None):
+        """wave [B, L] f32 on self.device -> reference output dict (models.py:683-686 / :1072-1075).
+        out=(clipwise, framewise): write the two result tensors into these preallocated buffers."""
         if wave.dim() != 2:
             raise ValueError("input must be (batch_size, data_length)")
         if wave.device != self.device:
@@ -836,7 +861,7 @@ class PackedModel:
                                 stages=stages if (return_stages and b0 == 0) else None, **slot(b0, b1))
 
         with self._lock:
-            out, feat16, x, natt = self._run(B, T // 8, conv_call, stages, want_norm_att=return_stages)
+            out, feat16, x, natt = self._run(B, T // 8, conv_call, stages, want_norm_att=return_stages, out=out)
         if return_stages:
             stages["feat"] = feat16
             stages["temporal"] = x

@@ -35,9 +35,13 @@ def _worker(rank, world, port, batch, ragged, q):
     out = _fake_forward(shard)
     sizes = [hi - lo for lo, hi in (sdist.shard_bounds(batch, world, r) for r in range(world))]
     res = sdist.gather_outputs(out, dst=0, shard_sizes=sizes if ragged else None)
+    # the same gather received in place into a preallocated result (no concatenation pass)
+    into = {k: torch.full((batch,) + tuple(v.shape[1:]), -1.0) for k, v in out.items()} if rank == 0 else None
+    res2 = sdist.gather_outputs(out, dst=0, shard_sizes=sizes if ragged else None, into=into)
     if rank == 0:
         full = _fake_forward(wave)
         ok = all(torch.equal(res[k], full[k]) for k in full)
+        ok = ok and all(res2[k] is into[k] and torch.equal(into[k], full[k]) for k in full)
         q.put(ok)
     else:
         assert res is None

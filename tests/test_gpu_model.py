@@ -183,6 +183,8 @@ def test_data_parallel_two_gpus_matches_single_gpu():
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_second_device_direct():
+    """A model living on cuda:1 called while cuda:0 is the current device (no `torch.cuda.device` guard by the
+    caller -- the reference works like that): the engine selects the model's device itself."""
     mt = "Cnn_9layers_Transformer_FrameAtt"
     a = build(mt)
     wave = synth.synthetic_waveform(2, 32000, seed=23)
@@ -190,9 +192,87 @@ def test_second_device_direct():
     b = getattr(models, mt)(*ARGS[16000])
     b.load_state_dict(synthetic_sd(mt))
     b = b.to("cuda:1").eval()
-    with torch.cuda.device(1):
-        got = b(wave.to("cuda:1"))["clipwise_output"].cpu()
+    assert torch.cuda.current_device() == 0
+    got = b(wave.to("cuda:1"))["clipwise_output"].cpu()
     assert torch.equal(got, ref)
+    from sed_b200 import engine
+    pm = engine.PackedModel(synthetic_sd(mt), mt, 512, 160, torch.device("cuda:1"))
+    host = pm.forward_host(wave.pin_memory())
+    assert torch.equal(host["clipwise_output"], ref)
+    assert torch.cuda.current_device() == 0
+
+
+def test_forward_host_results_survive_the_next_call():
+    """forward_host hands out rotating pinned buffers: the results of two consecutive calls are both intact (a loop
+    appending them must not see the second overwrite the first); copy=True returns fresh tensors."""
+    from sed_b200 import engine
+    mt = "Cnn_9layers_Gru_FrameAtt"
+    pm = engine.PackedModel(synthetic_sd(mt), mt, 512, 160, torch.device(DEV))
+    w1 = synth.synthetic_waveform(3, 32000, seed=31, kind="events").pin_memory()
+    w2 = synth.synthetic_waveform(3, 32000, seed=32, kind="events").pin_memory()
+    r1 = pm.forward_host(w1)
+    keep = {k: v.clone() for k, v in r1.items()}
+    r2 = pm.forward_host(w2)
+    assert not torch.equal(r1["framewise_output"], r2["framewise_output"])
+    for k in keep:
+        assert torch.equal(r1[k], keep[k]), k
+    d2 = pm.forward(w2.to(DEV))
+    assert torch.equal(r2["framewise_output"], d2["framewise_output"].cpu())
+    fresh = [pm.forward_host(w, copy=True)["clipwise_output"] for w in (w1, w2, w1, w2, w1)]
+    assert torch.equal(fresh[0], keep["clipwise_output"]) and torch.equal(fresh[4], keep["clipwise_output"])
+    assert fresh[0].data_ptr() != fresh[4].data_ptr()
+
+
+def test_host_pipeline_matches_device_entry():
+    """HostPipeline: batches of different sizes / dtypes kept two in flight give, bit for bit, what forward() gives,
+    in submission order; the in-flight limit and the result order are enforced."""
+    from sed_b200 import engine
+    mt = "Cnn_9layers_Gru_FrameAtt"
+    pm = engine.PackedModel(synthetic_sd(mt), mt, 512, 160, torch.device(DEV))
+    batches = [synth.synthetic_waveform(n, 80000, seed=40 + i, kind="events") for i, n in enumerate((5, 3, 5, 7, 5))]
+    batches[2] = torch.round(batches[2] * 32767.0).to(torch.int16)
+    refs = [pm.forward(b.to(DEV)) for b in batches]
+    pipe = pm.host_pipeline(depth=2, micro_batch=4)
+    outs = [{k: v.clone() for k, v in o.items()} for o in pipe.run(b.pin_memory() for b in batches)]
+    assert len(outs) == len(batches) and pipe.in_flight == 0
+    for o, r in zip(outs, refs):
+        assert torch.equal(o["framewise_output"], r["framewise_output"].cpu())
+        assert torch.equal(o["clipwise_output"], r["clipwise_output"].cpu())
+    t0 = pipe.submit(batches[0].pin_memory())
+    t1 = pipe.submit(batches[1].pin_memory())
+    with pytest.raises(RuntimeError):
+        pipe.submit(batches[1].pin_memory())
+    with pytest.raises(RuntimeError):
+        pipe.result(t1)
+    assert torch.equal(pipe.result(t0)["clipwise_output"], refs[0]["clipwise_output"].cpu())
+    assert torch.equal(pipe.result(t1)["clipwise_output"], refs[1]["clipwise_output"].cpu())
+    # a forward() on the caller's stream right after pipeline work shares the workspace safely
+    t2 = pipe.submit(batches[3].pin_memory())
+    again = pm.forward(batches[4].to(DEV))
+    assert torch.equal(again["framewise_output"], refs[4]["framewise_output"])
+    assert torch.equal(pipe.result(t2)["framewise_output"], refs[3]["framewise_output"].cpu())
+
+
+def test_forward_writes_into_caller_buffers():
+    from sed_b200 import engine
+    for mt in ("Cnn_9layers_Gru_FrameAtt", "Cnn_9layers_Transformer_FrameAvg"):
+        pm = engine.PackedModel(synthetic_sd(mt), mt, 512, 160, torch.device(DEV))
+        wave = synth.synthetic_waveform(3, 48000, seed=51, kind="events").to(DEV)
+        ref = pm.forward(wave)
+        clip = torch.full((5, pm.classes), -1.0, device=DEV)
+        frame = torch.full((5,) + tuple(ref["framewise_output"].shape[1:]), -1.0, device=DEV)
+        out = pm.forward(wave, out=(clip[1:4], frame[1:4]))
+        assert out["framewise_output"].data_ptr() == frame[1:4].data_ptr()
+        assert torch.equal(frame[1:4], ref["framewise_output"]) and torch.equal(clip[1:4], ref["clipwise_output"])
+        assert (frame[0] == -1).all() and (frame[4] == -1).all() and (clip[0] == -1).all()
+
+
+def test_clip_length_limits_fail_early():
+    from sed_b200 import engine
+    mt = "Cnn_9layers_Transformer_FrameAtt"
+    pm = engine.PackedModel(synthetic_sd(mt), mt, 512, 160, torch.device(DEV))
+    with pytest.raises(ValueError, match="too long"):
+        pm.forward(torch.zeros(1, 16000 * 40, device=DEV))
 
 
 def test_workspace_reuse_across_shapes_and_lengths():

@@ -134,6 +134,24 @@ def test_host_micro_batch_plan_tiles_the_batch():
     assert ranges == [(0, 839), (839, 1024)] and plan[1] == [(839, 1024)]
 
 
+def test_steady_state_spans_tile_the_batch():
+    from hypothesis import given, settings, strategies as st
+    from sed_b200 import pipeline
+
+    @settings(max_examples=300, deadline=None)
+    @given(B=st.integers(1, 5000), mb=st.integers(1, 1200), span=st.integers(1, 1200))
+    def check(B, mb, span):
+        spans = pipeline.plan_steady_spans(B, mb, span)
+        assert spans[0][0] == 0 and spans[-1][1] == B
+        for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+            assert a1 == b0
+        assert all(0 < b1 - b0 <= mb for b0, b1 in spans)
+
+    check()
+    assert pipeline.plan_steady_spans(1024, 1036, 370) == [(0, 370), (370, 740), (740, 1024)]
+    assert pipeline.plan_steady_spans(2048, 1036, 370)[-1][1] == 2048
+
+
 def test_micro_batch_cap_scales_with_clip_length():
     assert engine.clamp_micro_batch(1036, 1001) == 1036          # 10 s: the default launch group
     assert engine.clamp_micro_batch(1036, 501) == 1036           # shorter clips never exceed the request
