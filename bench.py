@@ -238,7 +238,7 @@ class Ctx:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return t.item()
 
-    def timed(self, fn, steps, warmup):
+    def timed(self, fn, steps, warmup, finish=None):
         """ms per step of fn(i): barrier + synchronize on both sides, CUDA events on the current stream, max over ranks."""
         for i in range(warmup):
             fn(i)
@@ -248,45 +248,92 @@ class Ctx:
         e0.record()
         for i in range(steps):
             fn(warmup + i)
+        if finish is not None:
+            finish()
         e1.record()
         self.barrier()
         return self.max_over_ranks(e0.elapsed_time(e1)) / steps
 
 
 class Gatherer:
-    """Assembly of every rank's framewise / clipwise on rank 0 inside the step.  Default: the pooling-head kernels
-    store straight into rank 0's buffer over NVLink (dist.PeerGather: CUDA-IPC peer memory, completion = one 4-byte
-    all-reduce); `--gather nccl`, or a box without peer access, uses one NCCL gather received in place."""
+    """Assembly of every rank's framewise / clipwise on rank 0 inside the step (dist.PeerGather: rank 0 owns one
+    buffer for all ranks, mapped everywhere through CUDA IPC; completion = one stream-ordered 4-byte all-reduce).
+      push (default)  results are written locally and leave by DMA (sed_peer_copy) on a side stream, so the NVLink
+                      transfer of step k overlaps the kernels of step k+1 without occupying an SM; step k is complete
+                      on rank 0 after the kernels of step k+1 (one step of latency, no loss of throughput)
+      peer            the pooling-head kernels store straight into rank 0's memory over NVLink (fused, no copy)
+      nccl            one NCCL gather received in place (also the fallback where peer memory is unavailable)"""
 
     def __init__(self, ctx, sdist, n, frames, classes, mode):
-        self.ctx, self.sdist, self.peer, self.how = ctx, sdist, None, "none (1 GPU)"
+        self.ctx, self.sdist, self.peer, self.how, self.mode = ctx, sdist, None, "none (1 GPU)", mode
         self.into = None
+        t = ctx.torch
         if ctx.world == 1:
+            self.mode = "none"
             return
-        if mode == "peer":
+        if mode in ("peer", "push"):
             try:
                 self.peer = sdist.PeerGather(n, frames, classes, ctx.dev, dst=0, slots=2)
-                self.how = "peer stores over NVLink into rank 0's buffer (CUDA IPC) + 4-byte all-reduce"
+                self.how = ("results pushed by DMA into rank 0's buffer over NVLink on a side stream (CUDA IPC peer "
+                            "memory), overlapping the next step" if mode == "push" else
+                            "head kernels store over NVLink into rank 0's buffer (CUDA IPC peer memory)") + \
+                    " + 4-byte all-reduce"
             except RuntimeError as e:
+                self.mode = "nccl"
                 self.how = "nccl gather (peer memory unavailable: %s)" % str(e)[:120]
         else:
-            self.how = "nccl gather"
-        if self.peer is None and ctx.rank == 0:
-            t = ctx.torch
+            self.how = "nccl gather received in place"
+        if self.mode == "nccl" and ctx.rank == 0:
             self.into = {"framewise_output": t.empty((ctx.world * n, frames, classes), device=ctx.dev),
                          "clipwise_output": t.empty((ctx.world * n, classes), device=ctx.dev)}
+        if self.mode == "push":
+            self.side = t.cuda.Stream(ctx.dev)
+            self.local = [(t.empty((n, classes), device=ctx.dev), t.empty((n, frames, classes), device=ctx.dev))
+                          for _ in range(2)]
+            self.copied = [None, None]
+            self.pending = None   # step whose results are on their way to rank 0
 
     def step(self, pm, wave, i, **kw):
-        if self.peer is not None:
+        t = self.ctx.torch
+        if self.mode == "peer":
             pm.forward(wave, out=self.peer.local_out(i), **kw)
             return self.peer.complete(i)
+        if self.mode == "push":
+            # step i: kernels on the main stream, then its results leave by DMA on the side stream; the completion of
+            # step i-1 (whose DMA ran under this step's kernels) follows on the main stream.  No collective kernel
+            # ever runs beside the persistent conv kernels (it would hold an SM until the slowest rank arrives).
+            main = t.cuda.current_stream(self.ctx.dev)
+            loc = self.local[i % 2]
+            pm.forward(wave, out=loc, **kw)
+            ready = t.cuda.Event()
+            ready.record(main)
+            self.side.wait_event(ready)
+            with t.cuda.stream(self.side):
+                self.peer.push(loc[0], loc[1], i)
+                self.copied[i % 2] = t.cuda.Event()
+                self.copied[i % 2].record(self.side)
+            res = self._complete(self.pending) if self.pending is not None else None
+            self.pending = i
+            return res
         out = pm.forward(wave, **kw)
-        if self.ctx.world > 1:
+        if self.mode == "nccl":
             return self.sdist.gather_outputs(out, dst=0, into=self.into)
         return out
 
+    def _complete(self, i):
+        self.ctx.torch.cuda.current_stream(self.ctx.dev).wait_event(self.copied[i % 2])
+        return self.peer.complete(i)
+
+    def finish(self):
+        """Complete the last step's transfer on the caller's stream (call before the closing timing event)."""
+        if self.mode == "push" and self.pending is not None:
+            res = self._complete(self.pending)
+            self.pending = None
+            return res
+
     def close(self):
         if self.peer is not None:
+            self.ctx.torch.cuda.synchronize(self.ctx.dev)
             self.peer.close()
 
 
@@ -336,7 +383,7 @@ def bench_config3(ctx, engine, synth, sdist, args):
     pm = engine.PackedModel(synth.synthetic_state_dict(mt, SR), mt, N_FFT, HOP, ctx.dev, precision=args.precision)
     wave = synth.synthetic_waveform(B, CLIP_SAMPLES, seed=4321, rank=ctx.rank).to(ctx.dev)
     g = Gatherer(ctx, sdist, B, 1000, 25, args.gather)
-    ms = ctx.timed(lambda i: g.step(pm, wave, i), steps=4, warmup=2)
+    ms = ctx.timed(lambda i: g.step(pm, wave, i), steps=4, warmup=2, finish=g.finish)
     ms_nog = ctx.timed(lambda i: pm.forward(wave), steps=4, warmup=1)
     g.close()
     return {"workload": "%s logmel 16k, %d clips per GPU x %d GPUs" % (mt, B, ctx.world), "batch_per_gpu": B,
@@ -496,6 +543,7 @@ def run_b200(args):
     e0.record()
     for i in range(steps):
         step_device(warmup + i)
+    gather.finish()
     e1.record()
     ctx.barrier()
     elapsed_ms = e0.elapsed_time(e1)
@@ -513,7 +561,7 @@ def run_b200(args):
     d2h = res["clipwise_output"].numel() * 4 + res["framewise_output"].numel() * 4
     rate_f32, _ = e2e_rate(ctx, pipe, wave_host, steps)
     # the synchronous single call (copy in, run, copy out; nothing overlapped across calls), for reference
-    for _ in range(2):
+    for _ in range(4):  # its three rotating result slots are allocated before the clock starts
         pm.forward_host(wave_i16, micro_batch=args.micro_batch, variant=args.variant)
     ctx.barrier()
     t0 = time.perf_counter()
@@ -625,8 +673,8 @@ def main():
     ap.add_argument("--ref-channels-last", action="store_true", help="extra row: channels_last reference modules")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the short runs of BASELINE configs 3 / 4 / 5")
-    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
-                    help="N > 1: how rank 0 gets every rank's outputs (peer = head kernels store over NVLink)")
+    ap.add_argument("--gather", default="push", choices=["push", "peer", "nccl"],
+                    help="N > 1: how rank 0 gets every rank's outputs (see class Gatherer)")
     args = ap.parse_args()
     globals()["MODEL_TYPE"] = args.model_type
     if args.impl == "reference":

@@ -173,12 +173,16 @@ int sed_events(const float* frames, int n_clips, int n_frames, int classes, cons
  *   sed_peer_alloc : cudaMalloc of `bytes` on the current device (a dedicated allocation, exportable as a whole)
  *   sed_peer_export: 64-byte IPC handle (HOST buffer) of an allocation made by sed_peer_alloc
  *   sed_peer_open  : map another process's allocation into this process (peer access enabled lazily)
- *   sed_peer_close / sed_peer_free: undo sed_peer_open / sed_peer_alloc */
+ *   sed_peer_close / sed_peer_free: undo sed_peer_open / sed_peer_alloc
+ *   sed_peer_copy  : asynchronous copy-engine transfer between any two device pointers visible to this process
+ *                    (local or peer-mapped) on `stream` -- the push variant: results leave over NVLink by DMA while
+ *                    the SMs already run the next batch */
 int sed_peer_alloc(long bytes, void** dev_ptr);
 int sed_peer_free(void* dev_ptr);
 int sed_peer_export(const void* dev_ptr, unsigned char* handle64);
 int sed_peer_open(const unsigned char* handle64, void** dev_ptr);
 int sed_peer_close(void* dev_ptr);
+int sed_peer_copy(void* dst, const void* src, long bytes, void* stream);
 
 #ifdef SED_PROFILE
 /* Developer builds only (make -C sound-event-detection_b200/csrc profile -> libsed_b200_profile.so): sed_bigru that
@@ -228,6 +232,14 @@ int sed_pack_gru_whh(const float* whh_fwd, const float* whh_bwd, void* whh_packe
 
 /* float32 -> 16-bit (round to nearest even) for the nn.Linear / weight_ih operands of sed_linear. */
 int sed_cast_16(const float* src, long n, void* dst, int dtype, void* stream);
+
+/* Range guard of the 16-bit path.  The reference computes in float32 (no range limit); here every conversion of an
+ * activation or weight to 16 bits saturates, so a value beyond the format's range is stored as exactly +-MAX (fp16:
+ * 65504).  Adds to *count (device, 8 bytes, zeroed by the caller) the number of stored values of x[0..n) with
+ * |x| >= MAX or non-finite, i.e. the conversions that clipped.  Used on packed weights at load time and on the
+ * activation buffers by PackedModel.saturation_report (a checkpoint whose BatchNorm statistics do not bound the
+ * activations trips it; results would silently differ from the reference otherwise). */
+int sed_count_saturated16(const void* x, long n, int dtype, unsigned long long* count, void* stream);
 
 /* Front-end constants, HOST pointers: twiddle_host [n_fft][2] f32 = (cos, sin)(-2 pi k / n_fft) computed in float64;
  * the banded form of the loaded mel matrix melW_host [F, n_mels] f32 (LogmelFilterBank.melW, pytorch/stft.py:688-693):

@@ -40,6 +40,7 @@ SIGNATURES = {
     "sed_pack_conv_first": ([_p, _p, _p, _p], _i),
     "sed_pack_gru_whh": ([_p, _p, _p, _i, _p], _i),
     "sed_cast_16": ([_p, _l, _p, _i, _p], _i),
+    "sed_count_saturated16": ([_p, _l, _i, _p, _p], _i),
     "sed_frontend_twiddle": ([_i, _p], _i),
     "sed_band_mel": ([_p, _i, _i, _p, _p, _p, _p, _i, _p], _i),
     "sed_fcpool": ([_p, _i, _i, _p, _p, _i, _i, _i, _p, _p, _p], _i),
@@ -54,6 +55,7 @@ SIGNATURES = {
     "sed_peer_export": ([_p, _p], _i),
     "sed_peer_open": ([_p, _p], _i),
     "sed_peer_close": ([_p], _i),
+    "sed_peer_copy": ([_p, _p, _l, _p], _i),
     "sed_attpool": ([_p, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p], _i),
 }
 

@@ -179,6 +179,16 @@ int sed_peer_close(void* dev_ptr) {
   return e == cudaSuccess ? SED_OK : peer_fail("sed_peer_close", e);
 }
 
+int sed_peer_copy(void* dst, const void* src, long bytes, void* stream) {
+  SED_REQUIRE(dst); SED_REQUIRE(src);
+  if (bytes <= 0) {
+    sed::set_error("sed_peer_copy: bytes=%ld", bytes);
+    return SED_ERR_BAD_SHAPE;
+  }
+  cudaError_t e = cudaMemcpyAsync(dst, src, static_cast<size_t>(bytes), cudaMemcpyDefault, as_stream(stream));
+  return e == cudaSuccess ? SED_OK : peer_fail("sed_peer_copy", e);
+}
+
 long sed_bigru_workspace_bytes(int B) { return B > 0 ? static_cast<long>(sed::gru_workspace_bytes(B)) : 0; }
 
 int sed_bigru(const float* gi, const void* whh_packed, const float* bhh, int B, int T, float* out, void* workspace,
@@ -254,6 +264,11 @@ int sed_pack_gru_whh(const float* whh_fwd, const float* whh_bwd, void* whh_packe
 int sed_cast_16(const float* src, long n, void* dst, int dtype, void* stream) {
   SED_REQUIRE(src); SED_REQUIRE(dst);
   return sed::cast16_launch(src, n, dst, dtype, as_stream(stream));
+}
+
+int sed_count_saturated16(const void* x, long n, int dtype, unsigned long long* count, void* stream) {
+  SED_REQUIRE(x); SED_REQUIRE(count);
+  return sed::count_saturated16_launch(x, n, dtype, count, as_stream(stream));
 }
 
 int sed_frontend_twiddle(int n_fft, float* twiddle_host) {

@@ -78,6 +78,7 @@ int pack_conv3x3_launch(const float* w, int cout, int cin, void* out, int dtype,
 int pack_conv_first_launch(const float* w, const float* scale, float* out, cudaStream_t stream);
 int pack_gru_whh_launch(const float* fwd, const float* bwd, void* out, int dtype, cudaStream_t stream);
 int cast16_launch(const float* src, long n, void* dst, int dtype, cudaStream_t stream);
+int count_saturated16_launch(const void* x, long n, int dtype, unsigned long long* count, cudaStream_t stream);
 int frontend_twiddle_host(int n_fft, float* out);
 int band_mel_host(const float* melW, int F, int M, int* lo, int* len, int* off, float* val, int cap, int* n_val);
 int fcpool_launch(const float* x, int B, int T, const float* w, const float* b, int C, int ratio, int use_max,

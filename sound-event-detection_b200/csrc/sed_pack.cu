@@ -145,6 +145,37 @@ int cast16_launch(const float* src, long n, void* dst, int dtype, cudaStream_t s
   return finish("cast_16");
 }
 
+// ---------------------------------------------------------------- range guard of the 16-bit path
+// Every float32 -> 16-bit conversion of the hot path saturates (cvt.rn.satfinite): a value beyond the format's range
+// is stored as exactly +-MAX (fp16: 65504).  Counting stored values with |x| >= MAX (or non-finite) therefore counts
+// the conversions that clipped -- after the fact, with no work added to the conv epilogues.
+__global__ void count_saturated16_kernel(const uint16_t* __restrict__ x, long n, uint16_t max_bits,
+                                         unsigned long long* __restrict__ count) {
+  unsigned int local = 0;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long>(gridDim.x) * blockDim.x)
+    local += ((x[i] & 0x7FFFu) >= max_bits) ? 1u : 0u;
+  local = __reduce_add_sync(0xffffffffu, local);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, static_cast<unsigned long long>(local));
+}
+
+int count_saturated16_launch(const void* x, long n, int dtype, unsigned long long* count, cudaStream_t stream) {
+  if (n <= 0) {
+    set_error("count_saturated16: n=%ld", n);
+    return SED_ERR_BAD_SHAPE;
+  }
+  if (dtype != SED_DTYPE_F16 && dtype != SED_DTYPE_BF16) {
+    set_error("count_saturated16: dtype must be 0 (fp16) or 1 (bf16)");
+    return SED_ERR_UNSUPPORTED;
+  }
+  const uint16_t max_bits = dtype == SED_DTYPE_F16 ? 0x7BFFu : 0x7F7Fu;
+  long blocks = (n + 256L * 8 - 1) / (256L * 8);
+  if (blocks > 148L * 16) blocks = 148L * 16;
+  count_saturated16_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<const uint16_t*>(x), n,
+                                                                                max_bits, count);
+  return finish("count_saturated16");
+}
+
 // ---------------------------------------------------------------- host-side front-end constants
 int frontend_twiddle_host(int n_fft, float* out) {
   if (n_fft != 256 && n_fft != 512 && n_fft != 1024) {

@@ -558,13 +558,32 @@ __device__ __forceinline__ void attpool_tail(const float* s_e, const float* s_c,
     for (int t = 0; t < Tn; ++t) acc += (s_e[t * kCls + c] / s) * s_c[t * kCls + c];  // models.py:166, 168
     clip[b * kCls + c] = acc;
   }
-  // framewise: repeat each step `ratio` times, pad with the last frame (models.py:93-94, 74-78)
+  // framewise: repeat each step `ratio` times, pad with the last frame (models.py:93-94, 74-78).  The clip's rows
+  // are one contiguous run: 16-byte stores (a warp instruction covers 512 contiguous bytes) -- the destination may
+  // be another GPU's memory (dist.PeerGather), where the number of store requests in flight is what limits the rate.
   float* fr = frame + static_cast<size_t>(b) * frames_out * kCls;
-  for (int i = threadIdx.x; i < frames_out * kCls; i += blockDim.x) {
-    const int f = i / kCls, c = i - f * kCls;
-    int t = f / ratio;
-    if (t > Tn - 1) t = Tn - 1;
-    fr[i] = s_c[t * kCls + c];
+  const int total = frames_out * kCls;
+  if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(fr) & 15) == 0) {
+    float4* fr4 = reinterpret_cast<float4*>(fr);
+    for (int i4 = threadIdx.x; i4 < (total >> 2); i4 += blockDim.x) {
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = 4 * i4 + e;
+        const int f = i / kCls, c = i - f * kCls;
+        int t = f / ratio;
+        if (t > Tn - 1) t = Tn - 1;
+        v[e] = s_c[t * kCls + c];
+      }
+      fr4[i4] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  } else {
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int f = i / kCls, c = i - f * kCls;
+      int t = f / ratio;
+      if (t > Tn - 1) t = Tn - 1;
+      fr[i] = s_c[t * kCls + c];
+    }
   }
   if (cla_t != nullptr) {  // 'embedding' of the GRU model: cla [B, 25, T'] (models.py:686)
     float* o = cla_t + static_cast<size_t>(b) * kCls * Tn;
@@ -843,9 +862,24 @@ fcpool_kernel(const float* __restrict__ x, int Tn, const float* __restrict__ w, 
     clip[bidx * C + c] = use_max ? r : r / static_cast<float>(Tn);
   }
   float* fr = frame + static_cast<size_t>(bidx) * Tn * ratio * C;
-  for (int i = threadIdx.x; i < Tn * ratio * C; i += blockDim.x) {
-    const int f = i / C, c = i - f * C;
-    fr[i] = s_p[(f / ratio) * C + c];
+  const int total = Tn * ratio * C;
+  if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(fr) & 15) == 0) {  // 16-byte stores (see attpool_tail)
+    float4* fr4 = reinterpret_cast<float4*>(fr);
+    for (int i4 = threadIdx.x; i4 < (total >> 2); i4 += blockDim.x) {
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = 4 * i4 + e;
+        const int f = i / C, c = i - f * C;
+        v[e] = s_p[(f / ratio) * C + c];
+      }
+      fr4[i4] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  } else {
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int f = i / C, c = i - f * C;
+      fr[i] = s_p[(f / ratio) * C + c];
+    }
   }
 }
 

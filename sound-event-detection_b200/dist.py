@@ -189,6 +189,18 @@ class PeerGather:
         lo, hi = self.rank * self.n, (self.rank + 1) * self.n
         return clip[lo:hi], frame[lo:hi]
 
+    def push(self, clipwise, framewise, slot):
+        """Copy-engine variant: this rank's finished [n, ...] results (ordinary tensors on its own GPU) go to its slice
+        of the destination's buffer by DMA on the CURRENT stream (sed_peer_copy) -- run it on a side stream and the
+        transfer overlaps the next batch's kernels without occupying an SM."""
+        from . import capi
+        clip, frame = self.local_out(slot)
+        stream = capi.current_stream(self.device)
+        for src, dst in ((clipwise, clip), (framewise, frame)):
+            if not src.is_contiguous() or src.dtype != torch.float32 or tuple(src.shape) != dst.shape:
+                raise ValueError("push expects contiguous float32 results of shape %s" % (dst.shape,))
+            capi.check(self._lib.sed_peer_copy(dst.data_ptr(), src.data_ptr(), src.numel() * 4, stream), "sed_peer_copy")
+
     def complete(self, slot):
         """Stream-ordered completion of step `slot` on every rank.  Returns the assembled dict on `dst` (torch tensors
         aliasing the buffer, valid until the slot is written again), None elsewhere."""

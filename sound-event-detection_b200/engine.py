@@ -454,6 +454,17 @@ class PackedModel:
             self.classes = int(self.fc_w.shape[0])
             if self.fc_w.shape[1] != 512 or self.classes > 32:
                 raise NotImplementedError("fc head: need Linear(512 -> classes_num <= 32)")
+        # range guard: packed 16-bit weights that hit the format's limit (fp16: |w| >= 65504) were clipped
+        self.weight_saturation = {}
+        packed16 = [(CONV_LAYERS[i][0], c[3]) for i, c in enumerate(self.convs)]
+        packed16 += [(n, getattr(self, n)) for n in ("gru_wih", "gru_whh", "mha_wqkv", "mha_wfc") if hasattr(self, n)]
+        for name, t in packed16:
+            self.weight_saturation[name] = self.count_saturated(t)
+        if any(self.weight_saturation.values()):
+            import warnings
+            warnings.warn("sed_b200: %s weights exceed the %s range and were clipped: %s -- outputs will differ from "
+                          "the float32 reference" % (model_type, precision,
+                                                     {k: v for k, v in self.weight_saturation.items() if v}))
         self._ws = collections.OrderedDict()  # T -> workspace entry, least recently used first
         self._lock = threading.RLock()
         self._pipelines = {}
@@ -728,6 +739,33 @@ class PackedModel:
         return x.transpose(1, 2)
 
     # ------------------------------------------------------------------ whole model
+    @_on_device
+    def count_saturated(self, t):
+        """Number of stored 16-bit values of `t` at the format's +-MAX (= conversions that clipped), via the C ABI."""
+        if t.dtype != self.tdtype:
+            raise TypeError("expected a %s tensor" % (self.tdtype,))
+        t = t.contiguous()
+        cnt = torch.zeros(1, dtype=torch.int64, device=self.device)
+        _call("sed_count_saturated16", capi.ptr(t), t.numel(), self.dtype_code, capi.ptr(cnt),
+              capi.current_stream(self.device))
+        capi._count()
+        return int(cnt.item())
+
+    def saturation_report(self, wave, micro_batch=DEFAULT_MICRO_BATCH):
+        """Debug-mode range check of the 16-bit path on real inputs: runs `wave` through the model with every conv
+        activation materialised (block 1 as two kernels, so conv1's output exists in memory) and returns
+        {'weights': {name: count}, 'activations': {stage: count}, 'total': n} -- the number of values that hit the
+        16-bit format's range limit and were clipped (always 0 for a healthy checkpoint; the float32 reference has no
+        such limit, so any non-zero count means the outputs may differ from it).  Weights are checked at pack time
+        too (`self.weight_saturation`)."""
+        out, stages = self.forward(wave, micro_batch=micro_batch, variant=2, return_stages=True)
+        acts = {}
+        for k in ("a1", "p1", "a2", "p2", "a3", "p3", "a4", "feat"):
+            if k in stages and stages[k] is not None and stages[k].dtype == self.tdtype:
+                acts[k] = self.count_saturated(stages[k])
+        total = sum(acts.values()) + sum(self.weight_saturation.values())
+        return {"weights": dict(self.weight_saturation), "activations": acts, "total": total}
+
     def host_pipeline(self, depth=2, micro_batch=DEFAULT_MICRO_BATCH, variant=4, head_chunk=256):
         """The cached `pipeline.HostPipeline` of this model for the given options (see that class): asynchronous
         submit / result over host buffers with `depth` batches in flight."""
@@ -759,18 +797,25 @@ class PackedModel:
         finally:
             pipe.trace = None
 
-    MAX_POOLED_STEPS = {"mha": 400, "att": 590}  # shared-memory limits of mha_core / the pooling head (K/V, [T'][50])
+    # shared-memory limits of the temporal / pooling kernels in pooled steps T' (one step = 80 ms at 100 frames/s):
+    # mha_core keeps K and V of a head resident (512 T' bytes <= 200 KB); sed_attpool keeps the 100 KB of weights plus
+    # [T'][50] f32 (<= 220 KB); sed_attpool_blocks' per-clip pass only the [T'][50] f32
+    MAX_POOLED_STEPS = {"mha": 400, "att": 590, "att_blocks": 1100}
 
     def _check_frames(self, T):
+        """Reject clip lengths the kernels cannot take BEFORE anything is launched, naming the limit."""
         if T // 8 < 1:
             raise ValueError("clip too short: %d STFT frames give no pooled time step (need >= 8)" % T)
         Tp = T // 8
-        if self.temporal_kind == "mha" and Tp > self.MAX_POOLED_STEPS["mha"]:
-            raise ValueError("clip too long for the MultiHead block: %d pooled steps (limit %d = %.0f s at 100 frames/s)"
-                             % (Tp, self.MAX_POOLED_STEPS["mha"], self.MAX_POOLED_STEPS["mha"] * 0.08))
-        if self.head_kind == "att" and Tp > self.MAX_POOLED_STEPS["att"]:
-            raise ValueError("clip too long for the frame-attention head: %d pooled steps (limit %d = %.0f s at 100 "
-                             "frames/s)" % (Tp, self.MAX_POOLED_STEPS["att"], self.MAX_POOLED_STEPS["att"] * 0.08))
+        limits = []
+        if self.temporal_kind == "mha":
+            limits.append(("MultiHead block", self.MAX_POOLED_STEPS["mha"]))
+        if self.head_kind == "att":
+            limits.append(("frame-attention head", self.MAX_POOLED_STEPS["att_blocks" if self.temporal_kind else "att"]))
+        for what, cap in limits:
+            if Tp > cap:
+                raise ValueError("clip too long for the %s: %d pooled steps, limit %d (= %.0f s of audio at 100 "
+                                 "frames/s)" % (what, Tp, cap, cap * 0.08))
 
     def _alloc_features(self, n, Tp):
         """Feature buffers of the conv stack and slot(b0, b1) -> conv_stack keyword arguments for one micro-batch.

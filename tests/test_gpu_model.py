@@ -34,12 +34,15 @@ def test_model_matches_reference_golden(mt, sr):
     assert set(out) == {"framewise_output", "clipwise_output", "embedding"}
     # clips 0-4: tone bursts / noise / low-level noise -> north_star tolerance 2e-3.
     # clip 5: digital silence (log-mel = -100 dB everywhere) sits ~8 sigma outside the range the synthetic
-    # bn0 statistics were calibrated on; 16-bit operand rounding is amplified there, so it gets 2e-2.
+    # bn0 statistics were calibrated on; 16-bit operand rounding is amplified there: bound 4e-3 (measured
+    # 1.4e-3 .. 2.7e-3 over presets and checkpoint seeds, tests/test_gpu_decisions.py).
     for k in ("framewise_output", "clipwise_output"):
         got = out[k].cpu().numpy()
         assert got.shape == g[k].shape and got.dtype == np.float32
         assert np.abs(got[:5] - g[k][:5]).max() <= 2e-3, (k, np.abs(got[:5] - g[k][:5]).max())
-        assert np.abs(got[5] - g[k][5]).max() <= 2e-2, (k, np.abs(got[5] - g[k][5]).max())
+        print("\n%s %dk %s: max|dp| clips 0-4 %.2e, silence clip %.2e" % (mt, sr // 1000, k, np.abs(got[:5] - g[k][:5]).max(),
+                                                                           np.abs(got[5] - g[k][5]).max()))
+        assert np.abs(got[5] - g[k][5]).max() <= 4e-3, (k, np.abs(got[5] - g[k][5]).max())
     emb = out["embedding"].cpu().numpy()
     assert emb.shape == g["embedding"].shape
     tol = 2e-3 if "Gru" in mt else 2e-2  # Transformer embedding = un-squashed ReLU features (|x| up to ~5)
@@ -157,7 +160,7 @@ def test_fused_conv_block1_matches_the_two_kernel_path(variant):
     for k in ("framewise_output", "clipwise_output"):
         got = out3[k].cpu().numpy()
         assert np.abs(got[:5] - g[k][:5]).max() <= 2e-3, (k, np.abs(got[:5] - g[k][:5]).max())
-        assert np.abs(got[5] - g[k][5]).max() <= 2e-2
+        assert np.abs(got[5] - g[k][5]).max() <= 4e-3, np.abs(got[5] - g[k][5]).max()
     # odd sizes: 5 s clips (T = 501), batch that is not a multiple of anything
     wave5 = synth.synthetic_waveform(3, 80000, seed=77, kind="events").to(DEV)
     a = pm.forward(wave5, variant=2)["framewise_output"]

@@ -36,8 +36,12 @@ def _worker(rank, world, port, q):
     frames = pm.frames_for((48000 // 160 + 1) // 8)
     peer = sdist.PeerGather(n, frames, pm.classes, dev, dst=0, slots=2)
     ok = True
-    for step in range(3):  # slots are reused round-robin
-        pm.forward(mine, out=peer.local_out(step))
+    for step in range(4):  # slots are reused round-robin; even steps: fused peer stores, odd steps: DMA push
+        if step % 2 == 0:
+            pm.forward(mine, out=peer.local_out(step))
+        else:
+            loc = pm.forward(mine)
+            peer.push(loc["clipwise_output"], loc["framewise_output"], step)
         res = peer.complete(step)
         if rank == 0:
             ref = pm.forward(full.to(dev))

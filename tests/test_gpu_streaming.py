@@ -79,7 +79,7 @@ def test_streaming_short_recording_and_32k_preset():
     assert err[:330].max() <= 2e-3          # the 3.3 s of signal: north_star tolerance (measured 5e-4)
     # frames past the recording are digital silence (log-mel = -100 dB, far outside the synthetic bn0 calibration):
     # 16-bit operand rounding is amplified there (measured 2e-3), same bound as the silent clip of the model goldens
-    assert err[330:].max() <= 2e-2
+    assert err[330:].max() <= 4e-3, err[330:].max()
 
 
 def test_windowed_frontend_reads_in_place():
