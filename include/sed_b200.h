@@ -199,6 +199,23 @@ int sed_bigru_profile(const float* gi, const void* whh_packed, const float* bhh,
 int sed_mha_core(const float* qkv, int B, int T, long row_stride_t, long row_stride_b, void* out16, int dtype,
                  void* stream);
 
+/* The same attention on the tensor cores, for T <= 128 pooled steps (clips up to 10.24 s): per (clip, head)
+ * S = Q K^T and O = P V are tcgen05 MMAs with S / O in TMEM and the softmax in registers; operands arrive by TMA
+ * straight from the 16-bit output of the QKV projection, so no float32 q | k | v tensor exists.  Replaces
+ * pytorch/models.py:808-820, 863-875 like sed_mha_core.
+ *   qkv16 [T * Bp, 1536] 16-bit, row of (step t, clip b) = t * Bp + b (time-major over the batch padded to Bp),
+ *   columns [q | k | v]; qk_lo16 [T * Bp, 1024] 16-bit or NULL: the residuals q - q16 | k - k16 written by
+ *   sed_linear_split16 -- with them the logits are accumulated as q_hi k_hi + q_lo k_hi + q_hi k_lo (float32-grade:
+ *   the softmax exponentiates them, so operand rounding there is amplified by the logit magnitude);
+ *   ctx16 [T * Bp, 512] 16-bit in the same row order (rows of clips >= B are left untouched). */
+int sed_mha_attention(const void* qkv16, const void* qk_lo16, int B, int T, long Bp, void* ctx16, int dtype,
+                      void* stream);
+
+/* sed_linear without activation whose result leaves as split 16-bit operands: out_hi [M, N] = the rounded values,
+ * out_lo [M, lo_cols] = (value - out_hi) rounded, for the first lo_cols columns (a multiple of 128, N <= 1536). */
+int sed_linear_split16(const void* a16, long M, int K, const void* w16, const float* bias, int N, void* out_hi,
+                       void* out_lo, int lo_cols, int dtype, void* stream);
+
 /* Frame-attention pooling + framewise interpolation/padding.
  * Replaces AttBlock.forward pytorch/models.py:161-169, interpolate :84-95, pad_framewise_output :65-81.
  *   x [B, T, 512] f32; w_att/w_cla [25][512]; b_att/b_cla [25];

@@ -48,6 +48,8 @@ SIGNATURES = {
     "sed_bigru_workspace_bytes": ([_i], _l),
     "sed_bigru": ([_p, _p, _p, _i, _i, _p, _p, _i, _p], _i),
     "sed_mha_core": ([_p, _i, _i, _l, _l, _p, _i, _p], _i),
+    "sed_mha_attention": ([_p, _p, _i, _i, _l, _p, _i, _p], _i),
+    "sed_linear_split16": ([_p, _l, _i, _p, _p, _i, _p, _p, _i, _i, _p], _i),
     "sed_attpool_blocks_scratch_bytes": ([_i, _i], _l),
     "sed_attpool_blocks": ([_p, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p], _i),
     "sed_peer_alloc": ([_l, _p], _i),

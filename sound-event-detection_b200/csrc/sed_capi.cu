@@ -128,7 +128,8 @@ int sed_conv_block1(const float* x, int NB, int H, int W, const float* w1_scaled
 
 int sed_linear(const void* a16, long M, int K, const void* w16, const float* bias, int N, int relu, float* out,
                void* out16, int out_layout, int dtype, void* stream) {
-  SED_REQUIRE(a16); SED_REQUIRE(w16); SED_REQUIRE(out);
+  SED_REQUIRE(a16); SED_REQUIRE(w16);
+  if (out == nullptr) SED_REQUIRE(out16);
   return sed::linear_launch(a16, M, K, w16, bias, N, relu, out, out16, out_layout, dtype, as_stream(stream));
 }
 
@@ -204,6 +205,18 @@ int sed_bigru_profile(const float* gi, const void* whh_packed, const float* bhh,
   return sed::gru_launch(gi, whh_packed, bhh, B, T, out, workspace, dtype, as_stream(stream), stamps);
 }
 #endif
+
+int sed_mha_attention(const void* qkv16, const void* qk_lo16, int B, int T, long Bp, void* ctx16, int dtype,
+                      void* stream) {
+  SED_REQUIRE(qkv16); SED_REQUIRE(ctx16);
+  return sed::mha_tc_launch(qkv16, qk_lo16, B, T, Bp, ctx16, dtype, as_stream(stream));
+}
+
+int sed_linear_split16(const void* a16, long M, int K, const void* w16, const float* bias, int N, void* out_hi,
+                       void* out_lo, int lo_cols, int dtype, void* stream) {
+  SED_REQUIRE(a16); SED_REQUIRE(w16); SED_REQUIRE(out_hi); SED_REQUIRE(out_lo);
+  return sed::linear_launch(a16, M, K, w16, bias, N, 0, nullptr, out_hi, 0, dtype, as_stream(stream), out_lo, lo_cols);
+}
 
 long sed_attpool_blocks_scratch_bytes(int B, int T) {
   return (B > 0 && T > 0) ? static_cast<long>(sed::attpool_blocks_scratch_bytes(B, T)) : 0;

@@ -910,10 +910,18 @@ extern "C" int sed_debug_c1_stamps(long long* host_out) {
 #endif
 
 int linear_launch(const void* a16, long M, int K, const void* w16, const float* bias, int N, int relu, float* out,
-                  void* out16, int out_layout, int dtype, cudaStream_t stream) {
+                  void* out16, int out_layout, int dtype, cudaStream_t stream, void* out_lo, int lo_cols) {
+  if (out_lo != nullptr && (out16 == nullptr || lo_cols <= 0 || lo_cols > N || (lo_cols % 128) != 0 || N > 1536)) {
+    set_error("linear: the 16-bit residual output needs the 16-bit output, lo_cols a multiple of 128 <= N <= 1536");
+    return SED_ERR_BAD_SHAPE;
+  }
   if (out_layout != 0 && (out_layout != 1 || out16 != nullptr || (M % 128) != 0)) {
     set_error("linear: out_layout must be 0 (row-major) or 1 (128-row transposed blocks: M %% 128 == 0, no 16-bit copy)");
     return SED_ERR_UNSUPPORTED;
+  }
+  if (out == nullptr && (out16 == nullptr || out_layout != 0)) {
+    set_error("linear: a NULL float32 output needs the 16-bit output and the row-major layout");
+    return SED_ERR_NULL;
   }
   if (M <= 0 || (N % 128) != 0 || N > 512 * 8) {
     set_error("linear: bad shape M=%ld N=%d K=%d", M, N, K);
@@ -959,9 +967,10 @@ int linear_launch(const void* a16, long M, int K, const void* w16, const float* 
     p.nslices = npanel / 128;
     p.scale = nullptr;
     p.shift = bias ? bias + n0 : nullptr;
-    p.out = out_layout ? out + (size_t)n0 * 128 : out + n0;  // transposed blocks: float4 column n0/4 = +n0/4*128*4 floats
+    p.out = out == nullptr ? nullptr : out_layout ? out + (size_t)n0 * 128 : out + n0;  // transposed blocks: float4 column n0/4 = +n0/4*128*4 floats
     p.out2 = out16 ? (void*)((char*)out16 + (size_t)n0 * 2) : nullptr;
     p.M = (int)M; p.ldc = N; p.relu = relu; p.tblock = out_layout;
+    p.out3 = out_lo; p.lo_cols = lo_cols;
     p.out_sn = 0; p.out_sh = 0;
     if (K == 512) {
       rc = dtype == 0 ? launch_cfg<__half, 512, 128, 1, false, false, EPI_LINEAR, 4, 4>(tmA, tmBp, tmA, p, stream)

@@ -36,6 +36,8 @@ struct ConvParams {
   void* out2;              // EPI 3: optional 16-bit copy [M, ldc]; EPI 2: optional f32 copy [NB,H,cout] (may be null)
   int M, ldc, relu;        // linear only
   int tblock;              // linear only: 1 = store float32 output as 128-row transposed blocks [tile][ldc/4][128][4]
+  void* out3;              // linear only, optional: 16-bit residual (value - its 16-bit rounding) of columns < lo_cols,
+  int lo_cols;             //   [M, lo_cols]: hi + lo carry ~21 bits of the float32 result (split-precision operands)
   long out_sn, out_sh;     // EPI 2: output row of (image n, row h) = n*out_sn + h*out_sh (default H, 1)
   // fused conv_block1 (FUSE1): the A operand is computed in the kernel from the 1-channel input
   const float* x1;         // [NB, H, W] f32 (log-mel after bn0)
@@ -213,7 +215,9 @@ SED_DEVICE_INLINE void conv_epilogue_tile(const uint32_t taddr, const int chalf,
           } else {  // EPI_LINEAR
             const long row = static_cast<long>(tile) * 128 + m;
             if (tile_ok && row < p.M) {
-              if (p.tblock) {
+              if (p.out == nullptr) {
+                // 16-bit output only (the QKV projection feeding the tensor-core attention kernel)
+              } else if (p.tblock) {
                 // 128-row transposed blocks: float4 column c4 of row m of tile `tile` sits at
                 // ((tile * ldc/4 + c4) * 128 + m): a warp (32 consecutive rows) writes 512 contiguous bytes
                 float4* dst4 = reinterpret_cast<float4*>(p.out) +
@@ -236,6 +240,17 @@ SED_DEVICE_INLINE void conv_epilogue_tile(const uint32_t taddr, const int chalf,
                 T* d2 = reinterpret_cast<T*>(p.out2) + row * p.ldc + ch0 + cc * 16;
                 reinterpret_cast<uint4*>(d2)[0] = q0;
                 reinterpret_cast<uint4*>(d2)[1] = q1;
+                if (p.out3 && ch0 + cc * 16 < p.lo_cols) {
+                  const uint32_t hi[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                  uint32_t lo[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    lo[j] = Elem16<T>::pack2(v[2 * j] - Elem16<T>::to_float(static_cast<uint16_t>(hi[j] & 0xFFFFu)),
+                                             v[2 * j + 1] - Elem16<T>::to_float(static_cast<uint16_t>(hi[j] >> 16)));
+                  T* d3 = reinterpret_cast<T*>(p.out3) + row * p.lo_cols + ch0 + cc * 16;
+                  reinterpret_cast<uint4*>(d3)[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                  reinterpret_cast<uint4*>(d3)[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                }
               }
             }
           }

@@ -46,7 +46,7 @@ int conv_block1_launch(const float* x, int NB, int H, int W, const float* w1s, c
                        cudaStream_t stream);
 
 int linear_launch(const void* a16, long M, int K, const void* w16, const float* bias, int N, int relu, float* out,
-                  void* out16, int out_layout, int dtype, cudaStream_t stream);
+                  void* out16, int out_layout, int dtype, cudaStream_t stream, void* out_lo = nullptr, int lo_cols = 0);
 
 size_t gru_workspace_bytes(int B);
 int gru_launch(const float* gi, const void* whh_packed, const float* bhh, int B, int T, float* out, void* workspace,
@@ -60,6 +60,9 @@ int events_launch(const float* frames, int n_clips, int n_frames, int classes, c
                   cudaStream_t stream);
 
 int mha_core_launch(const float* qkv, int B, int T, long rs_t, long rs_b, void* out16, int dtype, cudaStream_t stream);
+
+int mha_tc_launch(const void* qkv16, const void* qk_lo16, int B, int T, long Bp, void* ctx16, int dtype,
+                  cudaStream_t stream);
 
 int attpool_launch(const float* x, int B, int T, const float* w_att, const float* b_att, const float* w_cla,
                    const float* b_cla, int ratio, int frames_out, float* clip, float* frame, float* cla_t,

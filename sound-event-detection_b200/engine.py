@@ -577,17 +577,20 @@ class PackedModel:
                     stages[k] = ws[k].clone()
 
     @_on_device
-    def linear(self, a16, w16, bias, relu=False, out16=False, out_layout=0):
-        """out_layout 1: float32 output as 128-row transposed blocks (see sed_b200.h: sed_linear)."""
+    def linear(self, a16, w16, bias, relu=False, out16=False, out_layout=0, f32=True):
+        """out_layout 1: float32 output as 128-row transposed blocks (see sed_b200.h: sed_linear).
+        f32=False (with out16=True): only the 16-bit output is written."""
         lib = capi.load()
         M, K = a16.shape
         N = w16.shape[0]
-        out = torch.empty((M, N), dtype=torch.float32, device=self.device)
+        out = torch.empty((M, N), dtype=torch.float32, device=self.device) if f32 else None
         o16 = torch.empty((M, N), dtype=self.tdtype, device=self.device) if out16 else None
         rc = lib.sed_linear(capi.ptr(a16), M, K, capi.ptr(w16), capi.ptr(bias), N, 1 if relu else 0, capi.ptr(out),
                             capi.ptr(o16), out_layout, self.dtype_code, capi.current_stream(self.device))
         capi.check(rc, "sed_linear")
         capi._count((N + 1535) // 1536)
+        if not f32:
+            return o16
         return (out, o16) if out16 else out
 
     @_on_device
@@ -604,16 +607,9 @@ class PackedModel:
             return blocks_to_rows(self.gru_tmajor(feat_t, B, stages), B, Tp)
         if self.temporal_kind != "mha":
             raise RuntimeError("%s has no temporal block" % self.model_type)
-        qkv = self.linear(flat, self.mha_wqkv, self.mha_bqkv)
-        ctx = torch.empty((B * Tp, 512), dtype=self.tdtype, device=self.device)
-        rc = lib.sed_mha_core(capi.ptr(qkv), B, Tp, 0, 0, capi.ptr(ctx), self.dtype_code, stream)
-        capi.check(rc, "sed_mha_core")
-        capi._count()
-        out = self.linear(ctx, self.mha_wfc, self.mha_bfc, relu=True)
-        if stages is not None:
-            stages["qkv"] = qkv
-            stages["ctx"] = ctx
-        return out.view(B, Tp, 512)
+        feat_t = self.alloc_feat_tmajor(B, Tp)
+        feat_t[:, :B].copy_(feat16.transpose(0, 1))
+        return blocks_to_rows(self.mha_tmajor(feat_t, B, stages), B, Tp)
 
     def alloc_feat_tmajor(self, B, Tp):
         """[T', Bp, 512] 16-bit feature buffer, Bp = B rounded up to 128 clips (padding rows zero)."""
@@ -639,19 +635,40 @@ class PackedModel:
             stages["gi_blocks"] = gi
         return out
 
+    MHA_TC_MAX_STEPS = 128  # the tensor-core attention kernel holds one 128-step tile of keys per (clip, head)
+    mha_split = True        # q, k as split 16-bit operands (hi + lo): float32-grade logits in the tensor-core kernel
+
     @_on_device
-    def mha_tmajor(self, feat_t, B, stages=None):
+    def mha_tmajor(self, feat_t, B, stages=None, tensor_core=True):
         """feat_t [T', Bp, 512] 16-bit (time-major, batch padded to 128) -> relu(fc(attention)) as 128-clip transposed
-        blocks (the layout sed_attpool_blocks consumes)."""
+        blocks (the layout sed_attpool_blocks consumes).  T' <= 128 (clips up to 10.24 s): q | k | v leave the
+        projection as 16-bit rows and feed sed_mha_attention (tcgen05 QK^T / PV, softmax in registers); longer clips
+        take the float32 kernel sed_mha_core, which tiles nothing and keeps K / V of a head in shared memory."""
         lib = capi.load()
         Tp, Bp, _ = feat_t.shape
-        qkv = self.linear(feat_t.view(Tp * Bp, 512), self.mha_wqkv, self.mha_bqkv)
         ctx = torch.empty((Tp * Bp, 512), dtype=self.tdtype, device=self.device)
         if Bp != B:
-            ctx.zero_()  # rows of padding clips are not produced by the attention kernel
-        rc = lib.sed_mha_core(capi.ptr(qkv), B, Tp, Bp, 1, capi.ptr(ctx), self.dtype_code,
-                              capi.current_stream(self.device))
-        capi.check(rc, "sed_mha_core")
+            ctx.zero_()  # rows of padding clips are not produced by the attention kernels
+        if tensor_core and Tp <= self.MHA_TC_MAX_STEPS:
+            stream = capi.current_stream(self.device)
+            qkv = torch.empty((Tp * Bp, 1536), dtype=self.tdtype, device=self.device)
+            qk_lo = torch.empty((Tp * Bp, 1024), dtype=self.tdtype, device=self.device) if self.mha_split else None
+            if self.mha_split:
+                rc = lib.sed_linear_split16(capi.ptr(feat_t), Tp * Bp, 512, capi.ptr(self.mha_wqkv), capi.ptr(self.mha_bqkv),
+                                            1536, capi.ptr(qkv), capi.ptr(qk_lo), 1024, self.dtype_code, stream)
+                capi.check(rc, "sed_linear_split16")
+            else:
+                rc = lib.sed_linear(capi.ptr(feat_t), Tp * Bp, 512, capi.ptr(self.mha_wqkv), capi.ptr(self.mha_bqkv), 1536,
+                                    0, None, capi.ptr(qkv), 0, self.dtype_code, stream)
+                capi.check(rc, "sed_linear")
+            capi._count()
+            rc = lib.sed_mha_attention(capi.ptr(qkv), capi.ptr(qk_lo), B, Tp, Bp, capi.ptr(ctx), self.dtype_code, stream)
+            capi.check(rc, "sed_mha_attention")
+        else:
+            qkv = self.linear(feat_t.view(Tp * Bp, 512), self.mha_wqkv, self.mha_bqkv)
+            rc = lib.sed_mha_core(capi.ptr(qkv), B, Tp, Bp, 1, capi.ptr(ctx), self.dtype_code,
+                                  capi.current_stream(self.device))
+            capi.check(rc, "sed_mha_core")
         capi._count()
         out = self.linear(ctx, self.mha_wfc, self.mha_bfc, relu=True, out_layout=1)
         if stages is not None:

@@ -153,6 +153,78 @@ def test_multihead_matches_oracle(B, T):
     assert (got - ref).abs().max().item() < 2e-3 * max(ref.abs().max().item(), 1.0)
 
 
+@pytest.mark.parametrize("B,T", [(3, 125), (130, 62), (2, 128), (1, 1), (5, 17)])
+def test_tensor_core_attention_matches_float32_kernel_and_torch(B, T):
+    """sed_mha_attention (tcgen05 QK^T / PV, 16-bit q | k | v | P) against softmax(q k^T / 8) v in float64 on the same
+    16-bit inputs, and against the float32 kernel sed_mha_core; time-major rows over a batch padded to 128."""
+    lib = capi.load()
+    Bp = (B + 127) // 128 * 128
+    g = torch.Generator().manual_seed(B * 31 + T)
+    qkv = (torch.randn(T, Bp, 1536, generator=g) * 1.5).half()
+    qkv_d = qkv.to(DEV)
+    ctx = torch.full((T * Bp, 512), float("nan"), dtype=torch.float16, device=DEV)
+    capi.check(lib.sed_mha_attention(capi.ptr(qkv_d), None, B, T, Bp, capi.ptr(ctx), 0, capi.current_stream(DEV)),
+               "sed_mha_attention")
+    x = qkv[:, :B].double().permute(1, 0, 2)                              # [B, T, 1536]
+    q, k, v = (x[..., i * 512:(i + 1) * 512].reshape(B, T, 8, 64).permute(0, 2, 1, 3) for i in range(3))
+    ref = torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1) @ v          # [B, 8, T, 64]
+    ref = ref.permute(2, 0, 1, 3).reshape(T, B, 512)
+    got = ctx.view(T, Bp, 512)[:, :B].float().cpu()
+    assert torch.isfinite(got).all()
+    # 16-bit P and the 16-bit store of the context: ~1e-3 relative
+    assert (got.double() - ref).abs().max().item() <= 4e-3 * max(1.0, ref.abs().max().item())
+    if Bp != B:
+        assert torch.isnan(ctx.view(T, Bp, 512)[:, B:].float()).all()       # rows of padding clips are not written
+    ctx32 = torch.zeros((T * Bp, 512), dtype=torch.float16, device=DEV)
+    qkv32 = qkv_d.float().contiguous()
+    capi.check(lib.sed_mha_core(capi.ptr(qkv32), B, T, Bp, 1, capi.ptr(ctx32), 0, capi.current_stream(DEV)), "sed_mha_core")
+    old = ctx32.view(T, Bp, 512)[:, :B].float().cpu()
+    assert (got - old).abs().max().item() <= 4e-3 * max(1.0, ref.abs().max().item())
+
+
+def test_split_precision_projection_and_logits():
+    """sed_linear_split16: hi + lo reproduce the float32 projection to ~2^-21; with the residual tiles the attention
+    kernel's result follows float32 q, k (large logits: the case plain 16-bit operands lose)."""
+    lib = capi.load()
+    B, T, Bp = 3, 125, 128
+    g = torch.Generator().manual_seed(77)
+    x = (torch.randn(T * Bp, 512, generator=g)).half()
+    w = (torch.randn(1536, 512, generator=g) * 0.2).half()      # logits of magnitude ~ 40
+    bias = torch.randn(1536, generator=g)
+    hi = torch.empty((T * Bp, 1536), dtype=torch.float16, device=DEV)
+    lo = torch.empty((T * Bp, 1024), dtype=torch.float16, device=DEV)
+    xd, wd, bd = x.to(DEV), w.to(DEV), bias.to(DEV)
+    capi.check(lib.sed_linear_split16(capi.ptr(xd), T * Bp, 512, capi.ptr(wd), capi.ptr(bd), 1536, capi.ptr(hi),
+                                      capi.ptr(lo), 1024, 0, capi.current_stream(DEV)), "sed_linear_split16")
+    ref = x.double() @ w.double().t() + bias.double()
+    assert (hi.double().cpu() - ref).abs().max() <= 1e-3 * ref.abs().max()
+    both = hi[:, :1024].double().cpu() + lo.double().cpu()
+    assert (both - ref[:, :1024]).abs().max() <= 2e-6 * ref.abs().max()
+    r3 = ref.view(T, Bp, 1536)[:, :B].permute(1, 0, 2)
+    q, k = (r3[..., i * 512:(i + 1) * 512].reshape(B, T, 8, 64).permute(0, 2, 1, 3) for i in range(2))
+    v = hi.view(T, Bp, 1536)[:, :B, 1024:].double().cpu().permute(1, 0, 2).reshape(B, T, 8, 64).permute(0, 2, 1, 3)
+    want = (torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1) @ v).permute(2, 0, 1, 3).reshape(T, B, 512)
+    errs = []
+    for lo_arg in (lo, None):
+        ctx = torch.zeros((T * Bp, 512), dtype=torch.float16, device=DEV)
+        capi.check(lib.sed_mha_attention(capi.ptr(hi), capi.ptr(lo_arg), B, T, Bp, capi.ptr(ctx), 0,
+                                         capi.current_stream(DEV)), "sed_mha_attention")
+        errs.append((ctx.view(T, Bp, 512)[:, :B].double().cpu() - want).abs().max().item())
+    print("\nattention vs float64 logits: split %.2e, plain 16-bit q/k %.2e" % tuple(errs))
+    assert errs[0] <= 4e-3 * max(1.0, want.abs().max().item())
+    assert errs[0] < errs[1]
+
+
+def test_long_clips_take_the_float32_attention_kernel():
+    mt = "Cnn_9layers_Transformer_FrameAtt"
+    sd = synthetic_sd(mt)
+    pm = engine.PackedModel(sd, mt, 512, 160, DEV)
+    x = torch.relu(torch.randn(2, 200, 512, generator=torch.Generator().manual_seed(9)) * 0.5).half()
+    got = pm.temporal(x.to(DEV)).cpu()
+    ref = so.multihead(x.float(), sd)
+    assert (got - ref).abs().max().item() < 2e-3 * max(ref.abs().max().item(), 1.0)
+
+
 @pytest.mark.parametrize("B,T,frames", [(3, 125, 1000), (2, 62, 500), (2, 62, 496), (1, 1, 100)])
 def test_attpool_matches_oracle(B, T, frames):
     mt = "Cnn_9layers_Gru_FrameAtt"

