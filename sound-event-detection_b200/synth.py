@@ -78,8 +78,12 @@ def _bn_fold(sd, prefix):
     return scale, shift
 
 
-def synthetic_state_dict(model_type, sample_rate=16000, seed=0, calib_seconds=3.0, calib_clips=2, classes_num=25):
-    """Reference-layout `state_dict` (float32 CPU tensors) with calibrated BN statistics."""
+def synthetic_state_dict(model_type, sample_rate=16000, seed=0, calib_seconds=3.0, calib_clips=2, classes_num=25,
+                         calib_silence=False):
+    """Reference-layout `state_dict` (float32 CPU tensors) with calibrated BN statistics.
+    calib_silence=True adds a half-silent clip to the calibration batch, so that the statistics of every BatchNorm
+    cover digital silence the way a checkpoint trained on real recordings does (the default calibration batch has no
+    silent stretch: silence then sits ~8 sigma outside bn0's range, the regime tests/test_gpu_decisions.py examines)."""
     if model_type not in _PLANS:
         raise ValueError("unsupported model_type %r" % (model_type,))
     temporal, head = _PLANS[model_type]
@@ -112,6 +116,10 @@ def synthetic_state_dict(model_type, sample_rate=16000, seed=0, calib_seconds=3.
     L = int(calib_seconds * sample_rate)
     wave = torch.cat([synthetic_waveform(calib_clips, L, seed=977 + seed, kind="events", sample_rate=sample_rate),
                       synthetic_waveform(1, L, seed=978 + seed, kind="noise")], 0)
+    if calib_silence:
+        half = synthetic_waveform(1, L, seed=979 + seed, kind="events", sample_rate=sample_rate)
+        half[:, :L // 2] = 0.0
+        wave = torch.cat([wave, half], 0)
 
     def calibrate(prefix, x, dims):
         mean = x.mean(dim=dims)
