@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of the three ways rank 0 gets every rank's outputs (bench.py --gather push|peer|nccl), N = $1 GPUs
 N=${1:-2}
-for mode in push peer nccl; do
+for mode in ${MODES:-push peer nccl}; do
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2952$N \
     bench.py --gpus $N --steps 10 --warmup 3 --no-configs --no-cpu-baseline --gather $mode \
     > gpurun_out/r02_gather_${mode}_n$N.json 2> gpurun_out/r02_gather_${mode}_n$N.err
