@@ -27,7 +27,10 @@ struct FrontCfg {
   // one is transformed.
   static constexpr int FPB = (NFFT == 1024) ? 16 : 32;
   static constexpr int MELV = 1024;  // banded mel weights cached in shared memory (falls back to global beyond)
-  static constexpr bool WIN_REGS = (NFFT <= 512);  // window taps of the first pass live in registers
+  // window taps of the first pass: shared memory (one conflict-free LDS per tap).  A register copy does not survive
+  // the 128-register cap of two resident blocks: the compiler re-loaded it from global memory for every frame pair
+  // (ncu source view: 4.7 % of all instructions, long-scoreboard stalls)
+  static constexpr bool WIN_REGS = false;
   static constexpr int MIN_BLOCKS = (NFFT == 1024) ? 1 : 2;
 };
 
@@ -123,6 +126,16 @@ __device__ __forceinline__ float load_sample_global(const short* p) { return sta
 __device__ __forceinline__ void store_raw(float* p, float v) { *p = v; }
 __device__ __forceinline__ void store_raw(short* p, float v) { *p = static_cast<short>(v); }
 
+// 10*log10(max(x, amin)) - db_offset (stft.py:726-727) as one MUFU.LG2 and one FMA.  lg2.approx is accurate to 2^-22
+// (absolute inside (0.5, 2), relative elsewhere): at most 2.4e-5 dB over the whole range, against a tolerance of
+// 1e-4 * max(|dB|, 1).  Values at or below amin return `db_floor`, the float32 value of 10*log10(amin) - db_offset the
+// host computed with the reference's own operations (digital silence is exactly -100 dB).
+__device__ __forceinline__ float power_to_db(float x, float amin, float db_offset, float db_floor) {
+  float l;
+  asm("lg2.approx.f32 %0, %1;" : "=f"(l) : "f"(x));
+  return x > amin ? fmaf(l, 3.010299956639812f, -db_offset) : db_floor;
+}
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
@@ -201,12 +214,22 @@ __device__ __forceinline__ void stage_segment(TIn* __restrict__ dst, const TIn* 
     const int nvec = seg_len * static_cast<int>(sizeof(TIn)) / 16;
     for (int i = threadIdx.x; i < nvec; i += blockDim.x) cp_async16(d + 16 * i, src + 16 * i);
   } else {
-    for (int s = threadIdx.x; s < seg_len; s += blockDim.x) {
-      long i = q0 + s;
-      if (i < 0) i = -i;
-      if (i >= L) i = 2L * (L - 1) - i;
-      const float v = (i >= 0 && i < L && clip_base + i < total_len) ? load_sample_global(w + i) : 0.0f;
-      store_raw(dst + s, v);
+    // edge segments (first / last chunk of a clip: 2 of ~32 items): four independent loads in flight per thread
+    for (int s0 = threadIdx.x; s0 < seg_len; s0 += 4 * blockDim.x) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int s = s0 + u * blockDim.x;
+        long i = q0 + s;
+        if (i < 0) i = -i;
+        if (i >= L) i = 2L * (L - 1) - i;
+        v[u] = (s < seg_len && i >= 0 && i < L && clip_base + i < total_len) ? load_sample_global(w + i) : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int s = s0 + u * blockDim.x;
+        if (s < seg_len) store_raw(dst + s, v[u]);
+      }
     }
   }
   cp_async_commit();
@@ -232,6 +255,7 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
   constexpr int FPB = FrontCfg<NFFT>::FPB;
   constexpr int F = NFFT / 2 + 1;
   constexpr int BUF = NFFT;  // swizzled in place (see pidx)
+  const float db_floor = 10.0f * log10f(amin) - db_offset;  // once per thread: the value every clamped bin takes
   constexpr bool WINREG = FrontCfg<NFFT>::WIN_REGS;
   constexpr int R0 = Sched<NFFT>::R0;
   constexpr int NS1 = R0, NS2 = R0 * 8, NS3 = R0 * 64;  // strides of the radix-8 passes after the first
@@ -366,6 +390,18 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
           if (mel_in_smem) {
             const float* mv = s_melv + off;
             int i = 0;
+            for (; i + 3 < len; i += 4) {  // four bins per trip (same summation order as two trips of the loop below)
+              const float2 p = Pm[i], q = Pm[i + 1], p2 = Pm[i + 2], q2 = Pm[i + 3];
+              const float w0 = mv[i], w1 = mv[i + 1], w2 = mv[i + 2], w3 = mv[i + 3];
+              a0 = fmaf(p.x, w0, a0);
+              b0 = fmaf(p.y, w0, b0);
+              a1 = fmaf(q.x, w1, a1);
+              b1 = fmaf(q.y, w1, b1);
+              a0 = fmaf(p2.x, w2, a0);
+              b0 = fmaf(p2.y, w2, b0);
+              a1 = fmaf(q2.x, w3, a1);
+              b1 = fmaf(q2.y, w3, b1);
+            }
             for (; i + 1 < len; i += 2) {
               const float2 p = Pm[i], q = Pm[i + 1];
               const float w0 = mv[i], w1 = mv[i + 1];
@@ -391,8 +427,8 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
           }
           float ya = a0 + a1, yb = b0 + b1;
           if (is_log) {  // stft.py:726-727
-            ya = 10.0f * log10f(fmaxf(ya, amin)) - db_offset;
-            yb = 10.0f * log10f(fmaxf(yb, amin)) - db_offset;
+            ya = power_to_db(ya, amin, db_offset, db_floor);
+            yb = power_to_db(yb, amin, db_offset, db_floor);
           }
           if (bn_scale != nullptr) {  // models.py:642-644
             const float sc = bn_scale[m], sh = bn_shift[m];
