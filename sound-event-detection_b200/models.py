@@ -9,6 +9,7 @@ the reference forward (SpecAugment / mixup / timeshift, models.py:647-661) are n
 """
 import math
 import threading
+import weakref
 
 import torch
 import torch.nn as nn
@@ -96,6 +97,7 @@ class _Cnn9Base(nn.Module):
         self._packed = {}
         self._generation = [0]
         self._pack_lock = threading.RLock()
+        self._master_ref = [weakref.ref(self)]  # DataParallel replicas copy __dict__: they find the master through it
         self.precision = "fp16"   # 16-bit operand type of the tensor-core layers: 'fp16' or 'bf16'
         self.micro_batch = engine.DEFAULT_MICRO_BATCH   # clips per conv-stack launch group (whole waves of the 148 SMs)
         self.conv_variant = 4   # 4 = CTA-pair kernels + conv_block1 fused on the tensor cores (default); 2 = CTA-pair kernels with
@@ -121,11 +123,13 @@ class _Cnn9Base(nn.Module):
         state["_packed"] = {}
         state["_generation"] = [0]
         state.pop("_pack_lock", None)
+        state.pop("_master_ref", None)
         return state
 
     def __setstate__(self, state):
         self.__dict__.update(state)
         self._pack_lock = threading.RLock()
+        self._master_ref = [weakref.ref(self)]
 
     def _full_state(self):
         """state_dict()-like view that also works on DataParallel replicas, whose parameters are plain attributes
@@ -139,15 +143,23 @@ class _Cnn9Base(nn.Module):
                     sd[(prefix + "." if prefix else "") + k] = v
         return sd
 
+    def _signature(self):
+        """Cheap fingerprint of every parameter / buffer: storage pointer and in-place version counter.  In-place edits
+        (`p.data.copy_()`, `p.mul_()` under no_grad, manual BatchNorm-statistics updates) bump `_version`, `.to()` /
+        `load_state_dict` change pointers or versions: either way the packed copies are rebuilt on the next call."""
+        master = self._master_ref[0]() or self  # a replica's own tensors are fresh broadcast copies on every call
+        return (self._generation[0],) + tuple((v.data_ptr(), v._version) for v in master._full_state().values())
+
     def _packed_for(self, device):
         key = (device.type, device.index, self.precision)
+        sig = self._signature()
         hit = self._packed.get(key)
-        if hit is None or hit[0] != self._generation[0]:
+        if hit is None or hit[0] != sig:
             with self._pack_lock:  # DataParallel runs one thread per replica; they share _packed by reference
                 hit = self._packed.get(key)
-                if hit is None or hit[0] != self._generation[0]:
-                    hit = (self._generation[0], engine.PackedModel(self._full_state(), self.MODEL_TYPE, self.window_size,
-                                                                   self.hop_size, device, self.precision))
+                if hit is None or hit[0] != sig:
+                    hit = (sig, engine.PackedModel(self._full_state(), self.MODEL_TYPE, self.window_size,
+                                                   self.hop_size, device, self.precision))
                     self._packed[key] = hit
         return hit[1]
 

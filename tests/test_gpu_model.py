@@ -122,6 +122,35 @@ def test_reload_invalidates_packed_weights():
     assert (b.cpu() - ref).abs().max() <= 2e-3
 
 
+def test_in_place_parameter_edits_invalidate_packed_weights():
+    """`p.data.copy_()` / `p.mul_()` / manual BatchNorm-statistics updates change no module attribute; the packed copies
+    follow them through the parameters' version counters -- also under DataParallel, whose replicas are rebuilt per call."""
+    mt = "Cnn_9layers_Gru_FrameAtt"
+    model = build(mt)
+    wave = synth.synthetic_waveform(2, 32000, seed=5, kind="events").to(DEV)
+    a = model(wave)["clipwise_output"].clone()
+    assert torch.equal(model(wave)["clipwise_output"], a)                      # unchanged weights: cached pack re-used
+    packed = model._packed_for(torch.device(DEV))
+    assert model._packed_for(torch.device(DEV)) is packed
+    with torch.no_grad():
+        model.att_block.cla.bias.mul_(0.5)
+        model.bn0.running_mean.add_(1.0)
+    sd2 = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    b = model(wave)["clipwise_output"]
+    assert model._packed_for(torch.device(DEV)) is not packed
+    ref = so.model_forward(sd2, wave.cpu(), mt, 512, 160)["clipwise_output"]
+    assert not torch.equal(a, b) and (b.cpu() - ref).abs().max() <= 2e-3
+    dp = torch.nn.DataParallel(model, device_ids=[0])
+    c = dp(wave)["clipwise_output"]
+    assert torch.equal(c, b)
+    with torch.no_grad():
+        model.att_block.cla.bias.add_(0.25)
+    d = dp(wave)["clipwise_output"]
+    sd3 = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    ref3 = so.model_forward(sd3, wave.cpu(), mt, 512, 160)["clipwise_output"]
+    assert not torch.equal(d, c) and (d.cpu() - ref3).abs().max() <= 2e-3
+
+
 def test_host_buffer_entry_matches_device_entry():
     from sed_b200 import engine
     mt = "Cnn_9layers_Gru_FrameAtt"
