@@ -273,14 +273,17 @@ class Gatherer:
             return
         if mode in ("peer", "push"):
             try:
-                self.peer = sdist.PeerGather(n, frames, classes, ctx.dev, dst=0, slots=2)
+                self.peer = sdist.PeerGather(n, frames, classes, ctx.dev, dst=0, slots=4)
+                done = ("flag words behind the data (stream memory operations; no collective, no per-step lockstep)"
+                        if self.peer.use_flags else "4-byte all-reduce")
                 self.how = ("results pushed by DMA into rank 0's buffer over NVLink on a side stream (CUDA IPC peer "
                             "memory), overlapping the next step" if mode == "push" else
-                            "head kernels store over NVLink into rank 0's buffer (CUDA IPC peer memory)") + \
-                    " + 4-byte all-reduce"
+                            "head kernels store over NVLink into rank 0's buffer (CUDA IPC peer memory)") + "; completion: " + done
             except RuntimeError as e:
                 self.mode = "nccl"
                 self.how = "nccl gather (peer memory unavailable: %s)" % str(e)[:120]
+        elif mode == "none":
+            self.how = "NOT assembled (diagnostic: every rank keeps its own outputs)"
         else:
             self.how = "nccl gather received in place"
         if self.mode == "nccl" and ctx.rank == 0:
@@ -288,30 +291,36 @@ class Gatherer:
                          "clipwise_output": t.empty((ctx.world * n, classes), device=ctx.dev)}
         if self.mode == "push":
             self.side = t.cuda.Stream(ctx.dev)
+            self.nloc = 4
             self.local = [(t.empty((n, classes), device=ctx.dev), t.empty((n, frames, classes), device=ctx.dev))
-                          for _ in range(2)]
-            self.copied = [None, None]
+                          for _ in range(self.nloc)]
+            self.copied = [None] * self.nloc
             self.pending = None   # step whose results are on their way to rank 0
 
     def step(self, pm, wave, i, **kw):
         t = self.ctx.torch
         if self.mode == "peer":
+            self.peer.wait_turn(i)
             pm.forward(wave, out=self.peer.local_out(i), **kw)
+            self.peer.signal(i)
             return self.peer.complete(i)
         if self.mode == "push":
-            # step i: kernels on the main stream, then its results leave by DMA on the side stream; the completion of
-            # step i-1 (whose DMA ran under this step's kernels) follows on the main stream.  No collective kernel
-            # ever runs beside the persistent conv kernels (it would hold an SM until the slowest rank arrives).
+            # step i: kernels on the main stream, then its results leave by DMA on the side stream (behind them the
+            # completion flag); rank 0 completes step i-1 (whose DMA ran under this step's kernels) on its main stream.
+            # No collective kernel ever runs beside the persistent conv kernels and no rank waits for another one
+            # except rank 0 for what it consumes.
             main = t.cuda.current_stream(self.ctx.dev)
-            loc = self.local[i % 2]
+            loc = self.local[i % self.nloc]
+            if self.copied[i % self.nloc] is not None:
+                main.wait_event(self.copied[i % self.nloc])  # the DMA of step i - nloc has read this buffer
             pm.forward(wave, out=loc, **kw)
             ready = t.cuda.Event()
             ready.record(main)
             self.side.wait_event(ready)
             with t.cuda.stream(self.side):
                 self.peer.push(loc[0], loc[1], i)
-                self.copied[i % 2] = t.cuda.Event()
-                self.copied[i % 2].record(self.side)
+                self.copied[i % self.nloc] = t.cuda.Event()
+                self.copied[i % self.nloc].record(self.side)
             res = self._complete(self.pending) if self.pending is not None else None
             self.pending = i
             return res
@@ -321,7 +330,8 @@ class Gatherer:
         return out
 
     def _complete(self, i):
-        self.ctx.torch.cuda.current_stream(self.ctx.dev).wait_event(self.copied[i % 2])
+        if not self.peer.use_flags:  # the all-reduce fallback needs this rank's transfer ordered before it
+            self.ctx.torch.cuda.current_stream(self.ctx.dev).wait_event(self.copied[i % self.nloc])
         return self.peer.complete(i)
 
     def finish(self):
@@ -673,7 +683,7 @@ def main():
     ap.add_argument("--ref-channels-last", action="store_true", help="extra row: channels_last reference modules")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the short runs of BASELINE configs 3 / 4 / 5")
-    ap.add_argument("--gather", default="push", choices=["push", "peer", "nccl"],
+    ap.add_argument("--gather", default="push", choices=["push", "peer", "nccl", "none"],
                     help="N > 1: how rank 0 gets every rank's outputs (see class Gatherer)")
     args = ap.parse_args()
     globals()["MODEL_TYPE"] = args.model_type

@@ -183,6 +183,12 @@ int sed_peer_export(const void* dev_ptr, unsigned char* handle64);
 int sed_peer_open(const unsigned char* handle64, void** dev_ptr);
 int sed_peer_close(void* dev_ptr);
 int sed_peer_copy(void* dst, const void* src, long bytes, void* stream);
+/* Stream-ordered 32-bit flags (driver stream memory operations; no kernel runs, no SM is occupied) on LOCAL device
+ * memory: a producer rank writes step + 1 into a local word and copies the word into the consumer's flag array with
+ * sed_peer_copy behind its data; the consumer's stream waits until the flag is cyclically >= the value.  With them the
+ * ranks never meet in a collective: each runs at its own pace, only the consumer waits for what it consumes. */
+int sed_stream_write32(void* dev_ptr, unsigned int value, void* stream);
+int sed_stream_wait_geq32(void* dev_ptr, unsigned int value, void* stream);
 
 #ifdef SED_PROFILE
 /* Developer builds only (make -C sound-event-detection_b200/csrc profile -> libsed_b200_profile.so): sed_bigru that

@@ -58,6 +58,8 @@ SIGNATURES = {
     "sed_peer_open": ([_p, _p], _i),
     "sed_peer_close": ([_p], _i),
     "sed_peer_copy": ([_p, _p, _l, _p], _i),
+    "sed_stream_write32": ([_p, ctypes.c_uint, _p], _i),
+    "sed_stream_wait_geq32": ([_p, ctypes.c_uint, _p], _i),
     "sed_attpool": ([_p, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p], _i),
 }
 

@@ -1,6 +1,7 @@
 // extern "C" boundary: see include/sed_b200.h for the contract of every entry.
 #include "../../include/sed_b200.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <string.h>
 
@@ -188,6 +189,48 @@ int sed_peer_copy(void* dst, const void* src, long bytes, void* stream) {
   }
   cudaError_t e = cudaMemcpyAsync(dst, src, static_cast<size_t>(bytes), cudaMemcpyDefault, as_stream(stream));
   return e == cudaSuccess ? SED_OK : peer_fail("sed_peer_copy", e);
+}
+
+// stream-ordered 32-bit flag write / wait (driver stream memory operations): no kernel, no SM
+typedef CUresult (*StreamValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static StreamValue32Fn stream_value_fn(const char* name) {
+  void* fp = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint(name, &fp, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  return reinterpret_cast<StreamValue32Fn>(fp);
+}
+
+int sed_stream_write32(void* dev_ptr, unsigned int value, void* stream) {
+  SED_REQUIRE(dev_ptr);
+  static StreamValue32Fn fn = stream_value_fn("cuStreamWriteValue32");
+  if (!fn) {
+    sed::set_error("sed_stream_write32: cuStreamWriteValue32 unavailable");
+    return SED_ERR_DRIVER;
+  }
+  CUresult r = fn(reinterpret_cast<CUstream>(stream), reinterpret_cast<CUdeviceptr>(dev_ptr), value,
+                  CU_STREAM_WRITE_VALUE_DEFAULT);
+  if (r != CUDA_SUCCESS) {
+    sed::set_error("sed_stream_write32: driver error %d", static_cast<int>(r));
+    return SED_ERR_DRIVER;
+  }
+  return SED_OK;
+}
+
+int sed_stream_wait_geq32(void* dev_ptr, unsigned int value, void* stream) {
+  SED_REQUIRE(dev_ptr);
+  static StreamValue32Fn fn = stream_value_fn("cuStreamWaitValue32");
+  if (!fn) {
+    sed::set_error("sed_stream_wait_geq32: cuStreamWaitValue32 unavailable");
+    return SED_ERR_DRIVER;
+  }
+  CUresult r = fn(reinterpret_cast<CUstream>(stream), reinterpret_cast<CUdeviceptr>(dev_ptr), value,
+                  CU_STREAM_WAIT_VALUE_GEQ);
+  if (r != CUDA_SUCCESS) {
+    sed::set_error("sed_stream_wait_geq32: driver error %d", static_cast<int>(r));
+    return SED_ERR_DRIVER;
+  }
+  return SED_OK;
 }
 
 long sed_bigru_workspace_bytes(int B) { return B > 0 ? static_cast<long>(sed::gru_workspace_bytes(B)) : 0; }

@@ -34,23 +34,30 @@ def _worker(rank, world, port, q):
     full = synth.synthetic_waveform(world * n, 48000, seed=61, kind="events")
     mine = full[rank * n:(rank + 1) * n].to(dev)
     frames = pm.frames_for((48000 // 160 + 1) // 8)
-    peer = sdist.PeerGather(n, frames, pm.classes, dev, dst=0, slots=2)
     ok = True
-    for step in range(4):  # slots are reused round-robin; even steps: fused peer stores, odd steps: DMA push
-        if step % 2 == 0:
-            pm.forward(mine, out=peer.local_out(step))
-        else:
-            loc = pm.forward(mine)
-            peer.push(loc["clipwise_output"], loc["framewise_output"], step)
-        res = peer.complete(step)
-        if rank == 0:
-            ref = pm.forward(full.to(dev))
-            torch.cuda.synchronize()
-            ok = ok and torch.equal(res["framewise_output"], ref["framewise_output"])
-            ok = ok and torch.equal(res["clipwise_output"], ref["clipwise_output"])
-        else:
-            assert res is None
+    for use_flags in (True, False):  # flag-based completion, then the all-reduce fallback
+        peer = sdist.PeerGather(n, frames, pm.classes, dev, dst=0, slots=3, use_flags=use_flags)
+        if use_flags and not peer.use_flags:
+            print("stream memory operations unavailable on this box: flags not exercised")
+        for step in range(7):  # slots are reused round-robin; even steps: fused peer stores, odd steps: DMA push
+            if step % 2 == 0:
+                peer.wait_turn(step)
+                pm.forward(mine, out=peer.local_out(step))
+                peer.signal(step)
+            else:
+                loc = pm.forward(mine)
+                peer.push(loc["clipwise_output"], loc["framewise_output"], step)
+            res = peer.complete(step)
+            if rank == 0:
+                ref = pm.forward(full.to(dev))
+                torch.cuda.synchronize()
+                ok = ok and torch.equal(res["framewise_output"], ref["framewise_output"])
+                ok = ok and torch.equal(res["clipwise_output"], ref["clipwise_output"])
+            else:
+                assert res is None
+        torch.cuda.synchronize()
         dist.barrier()
+        peer.close()
     out = pm.forward(mine)
     into = {"framewise_output": torch.empty((world * n, frames, pm.classes), device=dev),
             "clipwise_output": torch.empty((world * n, pm.classes), device=dev)} if rank == 0 else None
@@ -59,7 +66,6 @@ def _worker(rank, world, port, q):
         torch.cuda.synchronize()
         ok = ok and torch.equal(got["framewise_output"], ref["framewise_output"])
         q.put(bool(ok))
-    peer.close()
     dist.barrier()
     dist.destroy_process_group()
 
