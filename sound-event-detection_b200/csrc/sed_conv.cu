@@ -972,7 +972,13 @@ int linear_launch(const void* a16, long M, int K, const void* w16, const float* 
     p.M = (int)M; p.ldc = N; p.relu = relu; p.tblock = out_layout;
     p.out3 = out_lo; p.lo_cols = lo_cols;
     p.out_sn = 0; p.out_sh = 0;
-    if (K == 512) {
+    if (K == 512 && M >= 128 * 296) {
+      // large M (the GRU input projection / QKV projection of a whole batch): the kernel is bound by L2 -> shared
+      // memory operand traffic (A 128 KB + B 128 KB per 128 x 128 tile = 125 B/clk/SM); two row tiles per work item
+      // share every B block (94 B/clk/SM)
+      rc = dtype == 0 ? launch_cfg<__half, 512, 128, 2, false, false, EPI_LINEAR, 4, 4>(tmA, tmBp, tmA, p, stream)
+                      : launch_cfg<__nv_bfloat16, 512, 128, 2, false, false, EPI_LINEAR, 4, 4>(tmA, tmBp, tmA, p, stream);
+    } else if (K == 512) {
       rc = dtype == 0 ? launch_cfg<__half, 512, 128, 1, false, false, EPI_LINEAR, 4, 4>(tmA, tmBp, tmA, p, stream)
                       : launch_cfg<__nv_bfloat16, 512, 128, 1, false, false, EPI_LINEAR, 4, 4>(tmA, tmBp, tmA, p, stream);
     } else {
