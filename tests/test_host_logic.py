@@ -165,3 +165,30 @@ def test_micro_batch_cap_scales_with_clip_length():
     import pytest
     with pytest.raises(ValueError):
         engine.clamp_micro_batch(0, 1001)
+
+
+def test_peer_view_addressing():
+    """dist._PeerView: the pointer arithmetic behind a rank's slice of the destination's result buffer."""
+    from sed_b200.dist import _PeerView
+    v = _PeerView(1 << 20, (8 * 1024, 1000, 25))
+    mine = v[3 * 1024:4 * 1024]
+    assert mine.shape == (1024, 1000, 25)
+    assert mine.data_ptr() == (1 << 20) + 3 * 1024 * 1000 * 25 * 4
+    assert mine[10:12].data_ptr() == mine.data_ptr() + 10 * 100000 and mine[10:12].shape == (2, 1000, 25)
+    cai = mine.__cuda_array_interface__
+    assert cai["shape"] == (1024, 1000, 25) and cai["typestr"] == "<f4" and cai["data"] == (mine.data_ptr(), False)
+    import pytest
+    with pytest.raises(IndexError):
+        v[::2]
+    with pytest.raises(IndexError):
+        v[3]
+
+
+def test_saturation_and_stream_entries_reject_null_without_a_gpu():
+    from sed_b200 import capi
+    lib = capi.load()
+    assert lib.sed_count_saturated16(None, 16, 0, None, None) == 4
+    assert lib.sed_stream_write32(None, 1, None) == 4 and lib.sed_stream_wait_geq32(None, 1, None) == 4
+    assert lib.sed_peer_copy(None, None, 4, None) == 4 and lib.sed_peer_alloc(0, None) == 4
+    assert lib.sed_mha_attention(None, None, 1, 1, 128, None, 0, None) == 4
+    assert lib.sed_linear_split16(None, 128, 512, None, None, 1536, None, None, 1024, 0, None) == 4
