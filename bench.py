@@ -678,7 +678,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=32)
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="cpu = the reference arm (default); cuda = extra row: the same torch ops eagerly on the GPU")
-    ap.add_argument("--ref-autocast", default=None, choices=["bfloat16", "float16"],
+    ap.add_argument("--ref-autocast", default=None, choices=["bf16", "bfloat16", "fp16", "float16"],
                     help="extra row: run the reference modules under torch.autocast (with --ref-device cuda)")
     ap.add_argument("--ref-channels-last", action="store_true", help="extra row: channels_last reference modules")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -686,6 +686,7 @@ def main():
     ap.add_argument("--gather", default="push", choices=["push", "peer", "nccl", "none"],
                     help="N > 1: how rank 0 gets every rank's outputs (see class Gatherer)")
     args = ap.parse_args()
+    args.ref_autocast = {"bf16": "bfloat16", "fp16": "float16"}.get(args.ref_autocast, args.ref_autocast)
     globals()["MODEL_TYPE"] = args.model_type
     if args.impl == "reference":
         run_reference(args)
