@@ -6,7 +6,7 @@
 //
 // The reference evaluates the DFT as a dense [n_fft x (n_fft/2+1)] contraction (0.53 GFLOP per 10 s
 // clip at 16 kHz).  Here two consecutive real frames are packed as one complex sequence and pushed
-// through an in-shared-memory Stockham FFT (radix-4 passes + one radix-2 pass), 25x fewer flops, in
+// through an in-shared-memory Stockham FFT (three passes of radix 4 / 8 / 16), 25x fewer flops, in
 // float32 with float64-derived twiddles -- the accuracy class of the reference's float32 conv1d, which
 // the 1e-4 log-mel tolerance needs (single-pass 16-bit tensor-core DFTs do not reach it).  The window
 // is read from the loaded conv_real kernel (row 0), so a checkpoint's window is honoured; the host
@@ -84,6 +84,38 @@ __device__ __forceinline__ void butterfly<8>(float2 (&v)[8]) {
   for (int k = 0; k < 4; ++k) {
     v[2 * k] = a[k];
     v[2 * k + 1] = b[k];
+  }
+}
+
+template <>
+__device__ __forceinline__ void butterfly<16>(float2 (&v)[16]) {
+  // n = 4a + i, k = m + 4p:  X[m + 4p] = sum_i W4^{ip} W16^{im} sum_a x[4a + i] W4^{am}
+  constexpr float kC1 = 0.92387953251128675613f, kS1 = 0.38268343236508977173f;  // cos, sin(pi / 8)
+  constexpr float kS = 0.70710678118654752440f;
+  float2 u[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t[4] = {v[i], v[i + 4], v[i + 8], v[i + 12]};
+    butterfly<4>(t);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) u[i][m] = t[m];
+  }
+  // u[i][m] *= W16^{i m},  W16 = exp(-2 pi i / 16)
+  u[1][1] = cmul(u[1][1], make_float2(kC1, -kS1));
+  u[1][2] = make_float2((u[1][2].x + u[1][2].y) * kS, (u[1][2].y - u[1][2].x) * kS);      // W16^2 = W8
+  u[1][3] = cmul(u[1][3], make_float2(kS1, -kC1));
+  u[2][1] = make_float2((u[2][1].x + u[2][1].y) * kS, (u[2][1].y - u[2][1].x) * kS);      // W16^2
+  u[2][2] = make_float2(u[2][2].y, -u[2][2].x);                                            // W16^4 = -i
+  u[2][3] = make_float2((u[2][3].y - u[2][3].x) * kS, -(u[2][3].x + u[2][3].y) * kS);     // W16^6
+  u[3][1] = cmul(u[3][1], make_float2(kS1, -kC1));                                         // W16^3
+  u[3][2] = make_float2((u[3][2].y - u[3][2].x) * kS, -(u[3][2].x + u[3][2].y) * kS);     // W16^6
+  u[3][3] = cmul(u[3][3], make_float2(-kC1, kS1));                                         // W16^9 = -W16^1
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    float2 t[4] = {u[0][m], u[1][m], u[2][m], u[3][m]};
+    butterfly<4>(t);
+#pragma unroll
+    for (int pq = 0; pq < 4; ++pq) v[m + 4 * pq] = t[pq];
   }
 }
 
@@ -189,11 +221,12 @@ __device__ __forceinline__ void fft_pass(float2* __restrict__ buf, const PassTw<
   __syncwarp();
 }
 
-// Radix schedule of the N-point transform: 256 = 4*8*8, 512 = 8*8*8, 1024 = 2*8*8*8.
+// Radix schedule of the N-point transform, three passes each: 256 = 4*8*8, 512 = 8*8*8, 1024 = 8*8*16 (the earlier
+// 2*8*8*8 cost a fourth trip through shared memory for a radix-2 pass).
 template <int N> struct Sched;
-template <> struct Sched<256> { static constexpr int R0 = 4; };
-template <> struct Sched<512> { static constexpr int R0 = 8; };
-template <> struct Sched<1024> { static constexpr int R0 = 2; };
+template <> struct Sched<256> { static constexpr int R0 = 4, R1 = 8, R2 = 8; };
+template <> struct Sched<512> { static constexpr int R0 = 8, R1 = 8, R2 = 8; };
+template <> struct Sched<1024> { static constexpr int R0 = 8, R1 = 8, R2 = 16; };
 
 // Stage the raw waveform segment [q0, q0 + seg_len) of clip b (reflect padding at the clip ends, stft.py:236-237;
 // zero beyond total_len, pad_truncate_sequence utils/utilities.py:66-70) into shared memory.  Interior, 16-byte
@@ -257,8 +290,9 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
   constexpr int BUF = NFFT;  // swizzled in place (see pidx)
   const float db_floor = 10.0f * log10f(amin) - db_offset;  // once per thread: the value every clamped bin takes
   constexpr bool WINREG = FrontCfg<NFFT>::WIN_REGS;
-  constexpr int R0 = Sched<NFFT>::R0;
-  constexpr int NS1 = R0, NS2 = R0 * 8, NS3 = R0 * 64;  // strides of the radix-8 passes after the first
+  constexpr int R0 = Sched<NFFT>::R0, R1 = Sched<NFFT>::R1, R2 = Sched<NFFT>::R2;
+  static_assert(R0 * R1 * R2 == NFFT, "radix schedule");
+  constexpr int NS1 = R0, NS2 = R0 * R1;  // strides of the second and third pass
   extern __shared__ float4 smem_f4[];
   const int seg_len = (FPB - 1) * hop + NFFT;
   const int seg_bytes = ((seg_len * static_cast<int>(sizeof(TIn)) + 15) & ~15);
@@ -298,12 +332,10 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
 
   // per-lane constants of the transform, loaded once per persistent warp
   PassTw<NFFT, R0, 1> tw0;  // first pass: no twiddles
-  PassTw<NFFT, 8, NS1> tw1;
-  PassTw<NFFT, 8, NS2> tw2;
-  PassTw<NFFT, 8, (NFFT == 1024) ? NS3 : 1> tw3;  // fourth pass exists for 1024 only
+  PassTw<NFFT, R1, NS1> tw1;
+  PassTw<NFFT, R2, NS2> tw2;
   tw1.init(twiddle, lane);
   tw2.init(twiddle, lane);
-  tw3.init(twiddle, lane);
   float wreg[NFFT / 32];
   if (WINREG) {
     constexpr int NB0 = NFFT / R0, BPL0 = NB0 / 32;
@@ -335,11 +367,8 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
       // ---- 2 real frames -> 1 complex FFT of size NFFT (Stockham autosort, natural-order output) ----
       fft_pass<NFFT, R0, 1, true, WINREG, TIn>(buf, tw0, s_tw, seg_a, seg_b, s_win, wreg, lane);
       if (!(dbg & 1)) {
-        fft_pass<NFFT, 8, NS1, false, WINREG, TIn>(buf, tw1, s_tw, seg_a, seg_b, s_win, wreg, lane);
-        fft_pass<NFFT, 8, NS2, false, WINREG, TIn>(buf, tw2, s_tw, seg_a, seg_b, s_win, wreg, lane);
-        if (NFFT == 1024)
-          fft_pass<NFFT, 8, (NFFT == 1024) ? NS3 : 1, false, WINREG, TIn>(buf, tw3, s_tw, seg_a, seg_b, s_win, wreg,
-                                                                           lane);
+        fft_pass<NFFT, R1, NS1, false, WINREG, TIn>(buf, tw1, s_tw, seg_a, seg_b, s_win, wreg, lane);
+        fft_pass<NFFT, R2, NS2, false, WINREG, TIn>(buf, tw2, s_tw, seg_a, seg_b, s_win, wreg, lane);
       }
       // ---- split the two real spectra and take the power (stft.py:663), in place: P[0..F) = |A|^2,
       //      P[F..2F) = |B|^2 overwrite the spectrum after every lane has read its bins ----
