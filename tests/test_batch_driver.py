@@ -78,3 +78,22 @@ def test_driver_on_the_b200_model_matches_oracle(int16):
     ref = so.model_forward(synthetic_sd(MT), wave, MT, 512, 160)
     assert np.abs(out["framewise_output"] - ref["framewise_output"].numpy()).max() <= 2e-3
     assert np.abs(out["clipwise_output"] - ref["clipwise_output"].numpy()).max() <= 2e-3
+
+
+@pytest.mark.gpu
+def test_driver_generic_path_flushes_in_bounded_groups():
+    """A wrapped model (torch.nn.DataParallel has no packed engine behind it) takes the generic loop: outputs stay on the
+    device for at most `flush_every` batches; results equal the pipelined path bit for bit."""
+    from sed_b200 import models
+    model = getattr(models, MT)(16000, 512, 160, 64, 25, 7000, 25, "logmel")
+    model.load_state_dict(synthetic_sd(MT))
+    model = model.to("cuda:0")
+    loader = make_loader(5, 2, 32000)
+    piped = pu.forward(model, loader)
+    wrapped = torch.nn.DataParallel(model, device_ids=[0])
+    for flush_every in (1, 2, 8):
+        plain = pu.forward(wrapped, loader, flush_every=flush_every)
+        assert list(plain.keys()) == list(piped.keys())
+        for k in ("clipwise_output", "framewise_output"):
+            assert np.array_equal(plain[k], piped[k]), (flush_every, k)
+    assert np.array_equal(piped["audio_name"], np.concatenate([b["audio_name"] for b in loader]))
