@@ -100,6 +100,112 @@ def predict_framewise_many(model, recordings, sample_rate, sample_duration=5, ov
     return merged
 
 
+class HostStreamer:
+    """predict_framewise_many for recordings that live in HOST memory, end to end: the recordings of a call are laid
+    out in one pinned buffer (zero padded up to the end of their last window), travel with ONE host->device copy, the
+    window offset table is built on the host, and the merged frames of all recordings come back with one device->host
+    copy per window-count group.  Two staging slots alternate, so the copy in of call k+1 can be queued while call k
+    computes (`submit` returns at once, `result` blocks for the oldest call).  Replaces the per-file, per-window loop of
+    pytorch/predict.py:264-349, which reads each window back to the host before it runs the next one."""
+
+    def __init__(self, model, sample_rate, sample_duration=5, overlap_value=1):
+        self.model, self.sr, self.dur, self.ov = model, int(sample_rate), int(sample_duration), overlap_value
+        self.packed = model if isinstance(model, engine.PackedModel) else None
+        self.slots = [dict(), dict()]
+        self.calls = 0
+        self.pending = []
+        self.copy_stream = None
+
+    def _packed(self, device):
+        if self.packed is not None:
+            return self.packed, engine.DEFAULT_MICRO_BATCH, 4
+        if self.model.training:
+            raise RuntimeError("inference only -- call .eval()")
+        return self.model._packed_for(device), self.model.micro_batch, self.model.conv_variant
+
+    def submit(self, recordings, device):
+        """recordings: list of 1-D CPU tensors (float32 or int16 PCM, one dtype).  Queues the call; returns a ticket."""
+        device = torch.device(device)
+        packed, micro_batch, variant = self._packed(device)
+        dtype = recordings[0].dtype
+        if any(r.dim() != 1 or r.is_cuda or r.dtype != dtype for r in recordings) or dtype not in (torch.float32, torch.int16):
+            raise ValueError("recordings must be 1-D float32 or int16 CPU tensors of one dtype")
+        window_samples = self.sr * self.dur
+        counts, seg_len = [], []
+        for r in recordings:
+            starts = window_starts(r.numel() / float(self.sr), self.dur, overlap=True)
+            counts.append(len(starts))
+            need = max(r.numel(), starts[-1] * self.sr + window_samples)
+            seg_len.append((need + 7) // 8 * 8)
+        total = sum(seg_len)
+        slot = self.slots[self.calls % 2]
+        if "done" in slot:
+            slot["done"].synchronize()
+        with torch.cuda.device(device):
+            if self.copy_stream is None:
+                self.copy_stream = torch.cuda.Stream(device)
+            key = (total, dtype, len(recordings))
+            if slot.get("key") != key:
+                slot["host"] = torch.zeros(total, dtype=dtype).pin_memory()
+                slot["dev"] = torch.empty(total, dtype=dtype, device=device)
+                slot["off_host"] = torch.zeros(sum(counts), dtype=torch.int64).pin_memory()
+                slot["off_dev"] = torch.empty(sum(counts), dtype=torch.int64, device=device)
+                slot["key"] = key
+                slot["out"] = {}
+            host, base, offs = slot["host"], 0, []
+            for r, nw, sl in zip(recordings, counts, seg_len):
+                host[base:base + r.numel()].copy_(r)
+                if r.numel() < sl:
+                    host[base + r.numel():base + sl].zero_()
+                offs.extend(base + k * self.sr for k in range(nw))
+                base += sl
+            slot["off_host"].copy_(torch.tensor(offs, dtype=torch.int64))
+            compute = torch.cuda.current_stream(device)
+            cs = self.copy_stream  # the slot's previous call has finished (host-synchronised above): copy at once,
+            with torch.cuda.stream(cs):  # under the kernels of the call queued before this one
+                slot["dev"].copy_(host, non_blocking=True)
+                slot["off_dev"].copy_(slot["off_host"], non_blocking=True)
+            compute.wait_stream(cs)
+            with torch.no_grad():
+                out = packed.forward_windows(slot["dev"], window_samples, 0, len(offs), micro_batch=micro_batch,
+                                             variant=variant, offsets=slot["off_dev"])
+                frames = out["framewise_output"]
+                oi = int(100 * self.ov)
+                groups, first = {}, 0
+                for f, nw in enumerate(counts):
+                    groups.setdefault(nw, []).append((f, first))
+                    first += nw
+                results = []
+                for nw, members in sorted(groups.items()):
+                    if all(members[i + 1][1] == members[i][1] + nw for i in range(len(members) - 1)):
+                        group = frames[members[0][1]:members[0][1] + nw * len(members)]  # contiguous rows: a view
+                    else:
+                        rows = torch.tensor([fst + k for _, fst in members for k in range(nw)], dtype=torch.int64).to(device)
+                        group = frames.index_select(0, rows)
+                    merged = engine.window_merge_avg(group.view(len(members), nw, frames.shape[1], frames.shape[2]), oi, self.dur)
+                    host_out = slot["out"].get(tuple(merged.shape))
+                    if host_out is None:
+                        host_out = slot["out"][tuple(merged.shape)] = torch.empty(merged.shape, dtype=torch.float32).pin_memory()
+                    host_out.copy_(merged, non_blocking=True)
+                    results.append((members, host_out))
+            slot["done"] = torch.cuda.Event()
+            slot["done"].record(compute)
+        self.calls += 1
+        self.pending.append((slot, results, len(recordings)))
+        return self.calls - 1
+
+    def result(self):
+        """Merged frames of the oldest queued call: list of [1, total_frames, classes] CPU tensors, one per recording
+        (views of the slot's pinned buffers: valid until two further calls have been submitted)."""
+        slot, results, n = self.pending.pop(0)
+        slot["done"].synchronize()
+        merged = [None] * n
+        for members, host_out in results:
+            for j, (f, _) in enumerate(members):
+                merged[f] = host_out[j:j + 1]
+        return merged
+
+
 def overlap_window_counts(audio_durations, sample_duration, overlap_value):
     """Windows the loop of main_strong.py:786-834 runs per file: start k*overlap_value for k = 0 and every k with
     k*overlap_value + sample_duration <= audio_duration (the `while end <= audio_duration` rule, end updated after

@@ -138,3 +138,24 @@ def test_many_recordings_in_one_batch_equal_per_recording_calls():
         one = streaming.predict_framewise(model, r, sr, 5, 1)
         assert m.shape == one.shape
         assert torch.equal(m, one)
+
+
+def test_host_streamer_equals_device_entry():
+    """HostStreamer (recordings in host memory, one copy each way, two calls in flight) returns bit for bit what
+    predict_framewise gives per recording on the device -- recordings of different lengths, float32 and int16."""
+    mt = "Cnn_9layers_Gru_FrameAtt"
+    sr = 16000
+    model = build(mt, sr)
+    lens = (int(7.3 * sr), 12 * sr, 12 * sr, int(5.0 * sr), int(3.1 * sr))
+    recs = [synth.synthetic_waveform(1, n, seed=60 + i, kind="events", sample_rate=sr)[0] for i, n in enumerate(lens)]
+    st = streaming.HostStreamer(model, sr, 5, 1)
+    for dtype in (torch.float32, torch.int16):
+        host = [r if dtype == torch.float32 else torch.round(r * 32767.0).to(torch.int16) for r in recs]
+        want = [streaming.predict_framewise(model, h.to(DEV), sr, 5, 1).cpu() for h in host]
+        st.submit([h.pin_memory() for h in host], DEV)
+        st.submit([h.pin_memory() for h in host[::-1]], DEV)
+        got, got_rev = st.result(), st.result()
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
+        for a, b in zip(got_rev, want[::-1]):
+            assert torch.equal(a, b)
