@@ -12,6 +12,7 @@
 // is read from the loaded conv_real kernel (row 0), so a checkpoint's window is honoured; the host
 // wrapper verifies that the loaded kernels are a windowed DFT before selecting this path.
 // The mel projection uses the loaded melW in banded form (first/last non-zero per mel bin).
+#include <atomic>
 #include <cstdlib>
 
 #include "sed_common.cuh"
@@ -280,7 +281,7 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
                 const int* __restrict__ mel_lo, const int* __restrict__ mel_len, const int* __restrict__ mel_off,
                 const float* __restrict__ mel_val, int n_mels, float amin, float db_offset, int is_log,
                 const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, float* __restrict__ out,
-                int mode, int aligned, int dbg) {
+                int mode, int aligned, int dbg, int* __restrict__ work_counter) {
 #ifndef SED_PROFILE
   dbg = 0;  // the experiment switches fold away in the shipped library
 #endif
@@ -346,11 +347,16 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
   }
 
   float2* buf = s_buf + warp * BUF;
+  // Work items are claimed dynamically (block b starts with item b, every further item comes from an atomic counter):
+  // a block that starts late -- its SM was still busy with another stream's kernel -- simply claims fewer items, so
+  // the launch ends when the work is done, not when the slowest static share is.
+  __shared__ int s_next[2];
   int sel = 0;
-  for (; item < items; item += gridDim.x, sel ^= 1) {
+  for (int nxt = 0; item < items; item = nxt, sel ^= 1) {
     cp_async_wait_all();
-    __syncthreads();  // this item's segment is visible; every warp has finished the previous item
-    const int nxt = item + gridDim.x;
+    if (threadIdx.x == 0) s_next[sel] = static_cast<int>(gridDim.x) + atomicAdd(work_counter, 1);
+    __syncthreads();  // this item's segment and the claimed item are visible; every warp has finished the previous item
+    nxt = s_next[sel];
     if (nxt < items)
       stage_segment<NFFT, TIn>(sel ? s_stage0 : s_stage1, wave, clip_stride, clip_offset, total_len, L, hop, seg_len,
                                nxt, chunks, aligned != 0);
@@ -492,6 +498,10 @@ __global__ void logmel_rows_kernel(const float* __restrict__ spec, long rows, in
   }
 }
 
+// claim counters of the launches in flight (one per launch, round robin; zeroed on the launch's stream)
+__device__ int g_frontend_work_counters[64];
+static std::atomic<unsigned> g_frontend_launch_seq{0};
+
 template <int NFFT, typename TIn>
 static int launch_frontend_t(const FrontendArgs& a, cudaStream_t stream) {
   constexpr int WARPS = FrontCfg<NFFT>::WARPS;
@@ -529,10 +539,15 @@ static int launch_frontend_t(const FrontendArgs& a, cudaStream_t stream) {
   const char* e_dbg = getenv("SED_FE_DBG");  // developer experiments: 1 = first FFT pass only, 2 = no mel projection
   dbg = e_dbg ? atoi(e_dbg) : 0;
 #endif
+  int* counters = nullptr;
+  if (cudaGetSymbolAddress(reinterpret_cast<void**>(&counters), g_frontend_work_counters) != cudaSuccess)
+    return SED_ERR_CUDA;
+  int* counter = counters + (g_frontend_launch_seq.fetch_add(1) & 63u);
+  if (cudaMemsetAsync(counter, 0, sizeof(int), stream) != cudaSuccess) return SED_ERR_CUDA;
   frontend_kernel<NFFT, TIn><<<static_cast<unsigned>(blocks), WARPS * 32, smem, stream>>>(
       reinterpret_cast<const TIn*>(a.wave), a.clip_stride, a.clip_offset, a.total_len, a.B, a.L, a.T, a.hop, a.window,
       reinterpret_cast<const float2*>(a.twiddle), a.mel_lo, a.mel_len, a.mel_off, a.mel_val, a.n_mels, a.amin,
-      a.db_offset, a.is_log, a.bn_scale, a.bn_shift, a.out, a.mode, aligned, dbg);
+      a.db_offset, a.is_log, a.bn_scale, a.bn_shift, a.out, a.mode, aligned, dbg, counter);
   return cudaGetLastError() == cudaSuccess ? SED_OK : SED_ERR_CUDA;
 }
 

@@ -41,13 +41,17 @@ def run(steps, overlap, prio):
     return outs
 
 
-for name, overlap, prio in (("sequential", False, 0), ("overlap, same priority", True, 0), ("overlap, tail high priority", True, -1),
-                            ("sequential", False, 0)):
-    run(3, overlap, prio)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    outs = run(10, overlap, prio)
-    e1.record()
-    torch.cuda.synchronize()
-    print("%-30s %.3f ms/step  (checksum %.6f)" % (name, e0.elapsed_time(e1) / 10, outs[1][0].double().sum().item()))
+import statistics
+res = {"sequential": [], "overlap, tail high priority": []}
+for rep in range(5):
+    for name, overlap, prio in (("sequential", False, 0), ("overlap, tail high priority", True, -1)):
+        run(3, overlap, prio)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        outs = run(20, overlap, prio)
+        e1.record()
+        torch.cuda.synchronize()
+        res[name].append(e0.elapsed_time(e1) / 20)
+for name, v in res.items():
+    print("%-30s median %.3f ms/step   runs %s" % (name, statistics.median(v), " ".join("%.2f" % x for x in v)))
