@@ -101,10 +101,10 @@ def predict_framewise_many(model, recordings, sample_rate, sample_duration=5, ov
 
 
 class HostStreamer:
-    """predict_framewise_many for recordings that live in HOST memory, end to end: the recordings of a call are laid
-    out in one pinned buffer (zero padded up to the end of their last window), travel with ONE host->device copy, the
-    window offset table is built on the host, and the merged frames of all recordings come back with one device->host
-    copy per window-count group.  Two staging slots alternate, so the copy in of call k+1 can be queued while call k
+    """predict_framewise_many for recordings that live in HOST memory, end to end: every recording of a call is copied
+    by DMA from the caller's (pinned) buffer straight to its place in one flat device buffer (zero padded up to the end
+    of its last window by a device memset; nothing is repacked on the host), the window offset table is built on the
+    host, and the merged frames of all recordings come back with one device->host copy per window-count group.  Two staging slots alternate, so the copy in of call k+1 can be queued while call k
     computes (`submit` returns at once, `result` blocks for the oldest call).  Replaces the per-file, per-window loop of
     pytorch/predict.py:264-349, which reads each window back to the host before it runs the next one."""
 
@@ -146,24 +146,28 @@ class HostStreamer:
                 self.copy_stream = torch.cuda.Stream(device)
             key = (total, dtype, len(recordings))
             if slot.get("key") != key:
-                slot["host"] = torch.zeros(total, dtype=dtype).pin_memory()
                 slot["dev"] = torch.empty(total, dtype=dtype, device=device)
                 slot["off_host"] = torch.zeros(sum(counts), dtype=torch.int64).pin_memory()
                 slot["off_dev"] = torch.empty(sum(counts), dtype=torch.int64, device=device)
                 slot["key"] = key
                 slot["out"] = {}
-            host, base, offs = slot["host"], 0, []
-            for r, nw, sl in zip(recordings, counts, seg_len):
-                host[base:base + r.numel()].copy_(r)
-                if r.numel() < sl:
-                    host[base + r.numel():base + sl].zero_()
+            base, offs = 0, []
+            for nw, sl in zip(counts, seg_len):
                 offs.extend(base + k * self.sr for k in range(nw))
                 base += sl
             slot["off_host"].copy_(torch.tensor(offs, dtype=torch.int64))
+            slot["src"] = list(recordings)  # keeps pinned sources alive until their asynchronous copies have run
             compute = torch.cuda.current_stream(device)
             cs = self.copy_stream  # the slot's previous call has finished (host-synchronised above): copy at once,
             with torch.cuda.stream(cs):  # under the kernels of the call queued before this one
-                slot["dev"].copy_(host, non_blocking=True)
+                # the DMA engine does the layout: every recording goes straight from the caller's (pinned) buffer to its
+                # place in the flat device buffer -- no host-side repacking; the zero padding is a device memset
+                base = 0
+                for r, sl in zip(recordings, seg_len):
+                    slot["dev"][base:base + r.numel()].copy_(r, non_blocking=True)
+                    if r.numel() < sl:
+                        slot["dev"][base + r.numel():base + sl].zero_()
+                    base += sl
                 slot["off_dev"].copy_(slot["off_host"], non_blocking=True)
             compute.wait_stream(cs)
             with torch.no_grad():
