@@ -27,12 +27,15 @@ struct FrontCfg {
   // (clip, chunk of FPB frames); the waveform segment of the next item is staged with cp.async while the current
   // one is transformed.
   static constexpr int FPB = (NFFT == 1024) ? 16 : 32;
-  static constexpr int MELV = 1024;  // banded mel weights cached in shared memory (falls back to global beyond)
-  // window taps of the first pass: shared memory (one conflict-free LDS per tap).  A register copy does not survive
-  // the 128-register cap of two resident blocks: the compiler re-loaded it from global memory for every frame pair
-  // (ncu source view: 4.7 % of all instructions, long-scoreboard stalls)
-  static constexpr bool WIN_REGS = false;
   static constexpr int MIN_BLOCKS = (NFFT == 1024) ? 1 : 2;
+  // Mel projection: every band is cut into segments of SEG consecutive bins, one lane per segment, 32 segments per
+  // round (see build_mel_schedule).  SEG is odd, so the 64-bit power reads of neighbouring segments of a band fall
+  // into different banks; the values below give the fewest rows (rounds * SEG) for the reference's three presets
+  // (8 kHz: 9 rows for 219 non-zero weights, 16 kHz: 21 for 436, 32 kHz: 36 for 866).  Other mel matrices only change
+  // the number of rounds; beyond SEGS_MAX segments the projection falls back to one lane per band.
+  static constexpr int SEG = (NFFT == 256) ? 3 : (NFFT == 512) ? 7 : 9;
+  // segment sums live behind the power spectrum in the warp's own buffer: (NFFT - F) float2 slots are free
+  static constexpr int SEGS_MAX = (NFFT == 256) ? 96 : 160;
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -42,7 +45,24 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 // Shared-memory FFT buffers are XOR-swizzled (low four bits of the complex index ^= bits 3..6): the unit-stride reads of
 // a Stockham pass stay conflict-free and its strided autosort writes spread over the banks.  Simulated 64-bit
 // wavefronts per 512-point transform: 212 against 324 with one-in-eight padding (ideal 196); 1024: 612 vs 964.
-__device__ __forceinline__ int pidx(int i) { return i ^ ((i >> 3) & 15); }
+__host__ __device__ constexpr int pidx(int i) { return i ^ ((i >> 3) & 15); }
+
+// pidx is linear over XOR, and every index a pass touches is (a part that depends on the lane) + (a compile-time part)
+// with disjoint bits: element (lanepart + c) lives at pidx(lanepart) ^ pidx(c).  `base` = byte address of
+// pidx(lanepart) in a 128-byte aligned buffer; the low four index bits of pidx(c) are XORed in, the rest is an
+// immediate offset -- one LOP3 (or nothing) per access instead of the shift / and / xor / scale chain.
+__device__ __forceinline__ uint32_t eaddr(uint32_t base, int c) {
+  const int p = pidx(c);
+  return (base ^ static_cast<uint32_t>((p & 15) << 3)) + static_cast<uint32_t>((p & ~15) << 3);
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f2(uint32_t addr, float2 v) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
 
 template <int R>
 __device__ __forceinline__ void butterfly(float2 (&v)[R]);
@@ -175,38 +195,43 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// One Stockham pass of radix R over N complex points, IN PLACE in (padded) shared memory, executed by one warp:
+// One Stockham pass of radix R over N complex points, IN PLACE in the swizzled shared-memory buffer of one warp:
 // every lane first pulls the inputs of all its butterflies into registers, the warp synchronises, then the
-// autosorted outputs are written back.  FIRST: inputs come from the windowed frame pair instead (re = frame a,
-// im = frame b), staged as raw input samples.
-template <int N, int R, int Ns, bool FIRST, bool WINREG, typename TIn>
-__device__ __forceinline__ void fft_pass(float2* __restrict__ buf, const PassTw<N, R, Ns>& tws,
-                                         const float2* __restrict__ s_tw, const TIn* __restrict__ seg_a,
-                                         const TIn* __restrict__ seg_b, const float* __restrict__ s_win,
-                                         const float (&wreg)[N / 32], int lane) {
+// autosorted outputs are written back.  Element indices, per lane (j = lane + 32 q is the butterfly, i = q + BPL r):
+//   inputs   j + r * NB                      = lane + 32 i                     -> eaddr(ld_base, 32 i)
+//   outputs  (j / Ns) Ns R + j % Ns + r Ns   = j0(lane) + (r Ns + 32 R q)      -> eaddr(st_base, r Ns + 32 R q)
+// with ld_base / st_base the byte addresses of pidx(lane) / pidx(j0(lane)) (PassAddr).
+// FIRST: inputs come from the windowed frame pair instead (re = frame a, im = frame b), staged as raw input samples.
+// LAST (Ns >= 32): nothing is written back -- the outputs stay in registers as X[lane + 32 i] = v[i % BPL][i / BPL]
+// for the power split.
+template <int N, int R, int Ns, bool FIRST, bool LAST, typename TIn>
+__device__ __forceinline__ void fft_pass(float2 (&v)[N / R / 32][R], uint32_t ld_base, uint32_t st_base,
+                                         const PassTw<N, R, Ns>& tws, const float2* __restrict__ s_tw,
+                                         const TIn* __restrict__ seg_a, const TIn* __restrict__ seg_b,
+                                         const float* __restrict__ s_win, int lane) {
   constexpr int NB = N / R;
   constexpr int BPL = NB / 32;  // butterflies per lane
-  float2 v[BPL][R];
+  static_assert(!LAST || Ns >= 32, "the last pass must leave X[lane + 32 i] in the lane");
+  static_assert(LAST || Ns <= 32, "store addressing: j / Ns must split into lane / Ns + q * 32 / Ns");
 #pragma unroll
   for (int q = 0; q < BPL; ++q) {
-    const int j = lane + 32 * q;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int idx = j + r * NB;
+      const int i = q + BPL * r;
       if (FIRST) {
-        const float w = WINREG ? wreg[q * R + r] : s_win[idx];
+        const int idx = lane + 32 * i;
+        const float w = s_win[idx];
         v[q][r] = make_float2(w * load_sample(seg_a + idx), w * load_sample(seg_b + idx));
       } else {
-        v[q][r] = buf[pidx(idx)];
+        v[q][r] = lds_f2(eaddr(ld_base, 32 * i));
       }
     }
   }
   __syncwarp();
 #pragma unroll
   for (int q = 0; q < BPL; ++q) {
-    const int j = lane + 32 * q;
-    const int k = j % Ns;
     if (Ns > 1) {
+      const int k = (lane + 32 * q) % Ns;
 #pragma unroll
       for (int r = 1; r < R; ++r) {
         const float2 w = PassTw<N, R, Ns>::IN_REGS ? tws.t[PassTw<N, R, Ns>::NK == 1 ? 0 : q][r - 1]
@@ -215,11 +240,19 @@ __device__ __forceinline__ void fft_pass(float2* __restrict__ buf, const PassTw<
       }
     }
     butterfly<R>(v[q]);
-    const int j0 = (j / Ns) * Ns * R + k;
+    if (!LAST) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) buf[pidx(j0 + r * Ns)] = v[q][r];
+      for (int r = 0; r < R; ++r) sts_f2(eaddr(st_base, r * Ns + 32 * R * q), v[q][r]);
+    }
   }
-  __syncwarp();
+  if (!LAST) __syncwarp();
+}
+
+// byte address of pidx(j0(lane)) for the stores of a pass (see fft_pass); buf_addr is 128-byte aligned
+template <int R, int Ns>
+__device__ __forceinline__ uint32_t pass_store_base(uint32_t buf_addr, int lane) {
+  const int j0 = (lane / Ns) * Ns * R + lane % Ns;
+  return buf_addr + 8u * static_cast<uint32_t>(pidx(j0));
 }
 
 // Radix schedule of the N-point transform, three passes each: 256 = 4*8*8, 512 = 8*8*8, 1024 = 8*8*16 (the earlier
@@ -269,6 +302,78 @@ __device__ __forceinline__ void stage_segment(TIn* __restrict__ dst, const TIn* 
   cp_async_commit();
 }
 
+// Mel projection schedule, built once per persistent block from the banded matrix (stft.py:709 restricted to the
+// non-zero weights).  Band m (bins lo_m .. lo_m + len_m) is cut into ceil(len_m / SEG) segments of SEG consecutive bins;
+// segments are numbered band after band, segment s belongs to lane s % 32 of round s / 32.  Per segment: the first bin
+// it reads (moved down where lo + SEG would pass the last bin F - 1; the weights move with it) and SEG weights, zero
+// where the segment sticks out of its band -- every lane runs the same SEG multiply-adds per round, no divergence, and
+// the wide high-frequency bands are spread over several lanes instead of serialising the warp.
+//   s_band[m]  = first segment | segments << 16
+//   s_seglo[s] = first bin read by segment s          (s < 32 * rounds; unused lanes read bin 0 with zero weights)
+//   s_segw[(round * SEG + i) * 32 + lane] = weight of bin s_seglo[s] + i
+// Returns the number of segments, or -1 when they do not fit (SEGS_MAX): the caller then projects one lane per band.
+template <int NFFT>
+__device__ __forceinline__ int build_mel_schedule(const int* __restrict__ mel_lo, const int* __restrict__ mel_len,
+                                                  const int* __restrict__ mel_off, const float* __restrict__ mel_val,
+                                                  int n_mels, int* __restrict__ s_band, int* __restrict__ s_seglo,
+                                                  int* __restrict__ s_segmj, float* __restrict__ s_segw,
+                                                  int* __restrict__ s_total) {
+  constexpr int SEG = FrontCfg<NFFT>::SEG, SEGS_MAX = FrontCfg<NFFT>::SEGS_MAX, F = NFFT / 2 + 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) {  // exclusive scan of the segment counts, 32 bands at a time
+    int carry = 0;
+    for (int m0 = 0; m0 < n_mels; m0 += 32) {
+      const int m = m0 + lane;
+      const int np = (m < n_mels) ? (max(mel_len[m], 0) + SEG - 1) / SEG : 0;
+      int incl = np;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      if (m < n_mels) s_band[m] = (carry + incl - np) | (np << 16);
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) *s_total = carry;
+  }
+  __syncthreads();
+  const int nseg = *s_total;
+  if (nseg > SEGS_MAX || nseg >= 65536) return -1;
+  const int slots = ((nseg + 31) / 32) * 32;
+  for (int s = threadIdx.x; s < slots; s += blockDim.x) s_segmj[s] = -1;
+  __syncthreads();
+  for (int m = threadIdx.x; m < n_mels; m += blockDim.x) {
+    const int first = s_band[m] & 0xffff, np = s_band[m] >> 16;
+    for (int j = 0; j < np; ++j) s_segmj[first + j] = m | (j << 16);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < slots * SEG; e += blockDim.x) {
+    const int s = e / SEG, i = e - s * SEG;
+    const int mj = s_segmj[s];
+    float w = 0.0f;
+    int start = 0;
+    if (mj >= 0) {
+      const int m = mj & 0xffff, j = mj >> 16;
+      const int lo = mel_lo[m], len = mel_len[m];
+      start = min(lo + j * SEG, F - SEG);
+      const int rel = start + i - lo;  // position of this bin inside the band
+      if (rel >= j * SEG && rel < min((j + 1) * SEG, len)) w = mel_val[mel_off[m] + rel];
+    }
+    s_segw[((s >> 5) * SEG + i) * 32 + (s & 31)] = w;
+    if (i == 0) s_seglo[s] = start;
+  }
+  __syncthreads();
+  return nseg;
+}
+
+// Bytes of the block's constant tables and FFT buffers (everything in front of the two staging buffers), counted from
+// the 128-byte aligned start of the dynamic shared memory; a multiple of 16.
+template <int NFFT>
+__host__ __device__ constexpr int frontend_fixed_smem(int n_mels) {
+  return ((8 * NFFT * (FrontCfg<NFFT>::WARPS + 1) + 4 * NFFT + 4 * FrontCfg<NFFT>::SEGS_MAX * FrontCfg<NFFT>::SEG +
+           8 * FrontCfg<NFFT>::SEGS_MAX + 4 * ((n_mels + 1) & ~1) + 8 * n_mels) + 15) & ~15;
+}
+
 // mode 0: out = log-mel (+ optional bn0 affine) [B, T, n_mels];  mode 1: out = power spectrogram [B, T, F]
 // Clip b starts at wave + b * clip_stride (or wave + clip_offset[b] when a table is given) and is L samples long; samples at or beyond total_len (counted from
 // `wave`) read as zero.  clip_stride < L gives overlapping windows of one long recording (predict.py:297-307)
@@ -281,30 +386,33 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
                 const int* __restrict__ mel_lo, const int* __restrict__ mel_len, const int* __restrict__ mel_off,
                 const float* __restrict__ mel_val, int n_mels, float amin, float db_offset, int is_log,
                 const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, float* __restrict__ out,
-                int mode, int aligned, int dbg, int* __restrict__ work_counter) {
-#ifndef SED_PROFILE
-  dbg = 0;  // the experiment switches fold away in the shipped library
-#endif
+                int mode, int aligned, int* __restrict__ work_counter) {
   constexpr int WARPS = FrontCfg<NFFT>::WARPS;
   constexpr int FPB = FrontCfg<NFFT>::FPB;
+  constexpr int SEG = FrontCfg<NFFT>::SEG, SEGS_MAX = FrontCfg<NFFT>::SEGS_MAX;
   constexpr int F = NFFT / 2 + 1;
-  constexpr int BUF = NFFT;  // swizzled in place (see pidx)
+  constexpr int NS = NFFT / 32, H = NS / 2;  // spectrum values per lane after the last pass; half of them
   const float db_floor = 10.0f * log10f(amin) - db_offset;  // once per thread: the value every clamped bin takes
-  constexpr bool WINREG = FrontCfg<NFFT>::WIN_REGS;
   constexpr int R0 = Sched<NFFT>::R0, R1 = Sched<NFFT>::R1, R2 = Sched<NFFT>::R2;
   static_assert(R0 * R1 * R2 == NFFT, "radix schedule");
   constexpr int NS1 = R0, NS2 = R0 * R1;  // strides of the second and third pass
+  constexpr int BPL2 = NFFT / R2 / 32;
+  static_assert(F + SEGS_MAX <= NFFT, "segment sums must fit behind the power spectrum");
   extern __shared__ float4 smem_f4[];
   const int seg_len = (FPB - 1) * hop + NFFT;
   const int seg_bytes = ((seg_len * static_cast<int>(sizeof(TIn)) + 15) & ~15);
   uint8_t* sp = reinterpret_cast<uint8_t*>(smem_f4);
-  TIn* s_stage0 = reinterpret_cast<TIn*>(sp);
-  TIn* s_stage1 = reinterpret_cast<TIn*>(sp + seg_bytes);
-  float2* s_buf = reinterpret_cast<float2*>(sp + 2 * seg_bytes);     // [WARPS][NFFT]
-  float2* s_tw = s_buf + WARPS * BUF;                                 // [NFFT]
+  sp += (128u - (smem_u32(sp) & 127u)) & 127u;                        // the swizzled addressing XORs address bits 3..6
+  float2* s_buf = reinterpret_cast<float2*>(sp);                      // [WARPS][NFFT]
+  float2* s_tw = s_buf + WARPS * NFFT;                                // [NFFT]
   float* s_win = reinterpret_cast<float*>(s_tw + NFFT);               // [NFFT]
-  float* s_melv = s_win + NFFT;                                       // [MELV] banded mel weights
-  int* s_meli = reinterpret_cast<int*>(s_melv + FrontCfg<NFFT>::MELV);  // [3][n_mels] lo, len, off
+  float* s_segw = s_win + NFFT;                                       // [SEGS_MAX / 32 * SEG][32] segment weights
+  int* s_seglo = reinterpret_cast<int*>(s_segw + SEGS_MAX * SEG);     // [SEGS_MAX]
+  int* s_segmj = s_seglo + SEGS_MAX;                                  // [SEGS_MAX] (band, piece) while building
+  int* s_band = s_segmj + SEGS_MAX;                                   // [n_mels] first segment | segments << 16
+  float2* s_bn = reinterpret_cast<float2*>(s_band + ((n_mels + 1) & ~1));  // [n_mels] bn0 (scale, shift)
+  TIn* s_stage0 = reinterpret_cast<TIn*>(sp + frontend_fixed_smem<NFFT>(n_mels));  // 16-byte aligned (cp.async)
+  TIn* s_stage1 = reinterpret_cast<TIn*>(reinterpret_cast<uint8_t*>(s_stage0) + seg_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunks = (T + FPB - 1) / FPB;
@@ -314,22 +422,20 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
     stage_segment<NFFT, TIn>(s_stage0, wave, clip_stride, clip_offset, total_len, L, hop, seg_len, item, chunks,
                              aligned != 0);
 
+  __shared__ int s_next[2];
+  __shared__ int s_total;
   for (int i = threadIdx.x; i < NFFT; i += blockDim.x) {
     s_win[i] = window[i];
     s_tw[i] = twiddle[i];
   }
-  int mel_total = 0;
+  int nseg = -1;
   if (mode == 0) {
-    mel_total = mel_off[n_mels - 1] + mel_len[n_mels - 1];
-    for (int i = threadIdx.x; i < n_mels; i += blockDim.x) {
-      s_meli[i] = mel_lo[i];
-      s_meli[n_mels + i] = mel_len[i];
-      s_meli[2 * n_mels + i] = mel_off[i];
-    }
-    if (mel_total <= FrontCfg<NFFT>::MELV)
-      for (int i = threadIdx.x; i < mel_total; i += blockDim.x) s_melv[i] = mel_val[i];
+    for (int i = threadIdx.x; i < n_mels; i += blockDim.x)
+      s_bn[i] = bn_scale != nullptr ? make_float2(bn_scale[i], bn_shift[i]) : make_float2(1.0f, 0.0f);
+    nseg = build_mel_schedule<NFFT>(mel_lo, mel_len, mel_off, mel_val, n_mels, s_band, s_seglo, s_segmj, s_segw,
+                                    &s_total);
   }
-  const bool mel_in_smem = mel_total <= FrontCfg<NFFT>::MELV;
+  const int rounds = (nseg + 31) >> 5;  // 0 when the schedule does not fit: one lane per band, weights from global
 
   // per-lane constants of the transform, loaded once per persistent warp
   PassTw<NFFT, R0, 1> tw0;  // first pass: no twiddles
@@ -337,20 +443,19 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
   PassTw<NFFT, R2, NS2> tw2;
   tw1.init(twiddle, lane);
   tw2.init(twiddle, lane);
-  float wreg[NFFT / 32];
-  if (WINREG) {
-    constexpr int NB0 = NFFT / R0, BPL0 = NB0 / 32;
-#pragma unroll
-    for (int q = 0; q < BPL0; ++q)
-#pragma unroll
-      for (int r = 0; r < R0; ++r) wreg[q * R0 + r] = __ldg(window + lane + 32 * q + r * NB0);
-  }
 
-  float2* buf = s_buf + warp * BUF;
+  float2* buf = s_buf + warp * NFFT;
+  const uint32_t buf_addr = smem_u32(buf);
+  const uint32_t ld_base = buf_addr + 8u * static_cast<uint32_t>(pidx(lane));
+  const uint32_t st_base0 = pass_store_base<R0, 1>(buf_addr, lane);
+  const uint32_t st_base1 = pass_store_base<R1, NS1>(buf_addr, lane);
+  float2* P2 = buf;             // P2[k] = (|A_k|^2, |B_k|^2): both frames of the pair side by side, k < F
+  float2* part = buf + F;       // segment sums of the mel projection
+  const int src_lane = (32 - lane) & 31;
+
   // Work items are claimed dynamically (block b starts with item b, every further item comes from an atomic counter):
   // a block that starts late -- its SM was still busy with another stream's kernel -- simply claims fewer items, so
   // the launch ends when the work is done, not when the slowest static share is.
-  __shared__ int s_next[2];
   int sel = 0;
   for (int nxt = 0; item < items; item = nxt, sel ^= 1) {
     cp_async_wait_all();
@@ -370,41 +475,40 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
       const TIn* seg_a = s_seg + (2 * pair) * hop;
       const TIn* seg_b = seg_a + hop;
 
-      // ---- 2 real frames -> 1 complex FFT of size NFFT (Stockham autosort, natural-order output) ----
-      fft_pass<NFFT, R0, 1, true, WINREG, TIn>(buf, tw0, s_tw, seg_a, seg_b, s_win, wreg, lane);
-      if (!(dbg & 1)) {
-        fft_pass<NFFT, R1, NS1, false, WINREG, TIn>(buf, tw1, s_tw, seg_a, seg_b, s_win, wreg, lane);
-        fft_pass<NFFT, R2, NS2, false, WINREG, TIn>(buf, tw2, s_tw, seg_a, seg_b, s_win, wreg, lane);
+      // ---- 2 real frames -> 1 complex FFT of size NFFT (Stockham autosort); the last pass stays in registers ----
+      {
+        float2 v0[NFFT / R0 / 32][R0];
+        fft_pass<NFFT, R0, 1, true, false, TIn>(v0, ld_base, st_base0, tw0, s_tw, seg_a, seg_b, s_win, lane);
       }
-      // ---- split the two real spectra and take the power (stft.py:663), in place: P[0..F) = |A|^2,
-      //      P[F..2F) = |B|^2 overwrite the spectrum after every lane has read its bins ----
-      constexpr int KPL = (F + 31) / 32;
-      float pa[KPL], pb[KPL];
-#pragma unroll
-      for (int i = 0; i < KPL; ++i) {
-        const int k = lane + 32 * i;
-        if (k < F) {
-          const float2 zk = buf[pidx(k & (NFFT - 1))];
-          const float2 zn = buf[pidx((NFFT - k) & (NFFT - 1))];
-          const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
-          const float br = 0.5f * (zk.y + zn.y), bi = 0.5f * (zn.x - zk.x);
-          pa[i] = ar * ar + ai * ai;
-          pb[i] = br * br + bi * bi;
-        }
+      {
+        float2 v1[NFFT / R1 / 32][R1];
+        fft_pass<NFFT, R1, NS1, false, false, TIn>(v1, ld_base, st_base1, tw1, s_tw, seg_a, seg_b, s_win, lane);
       }
-      __syncwarp();
-      float2* P2 = buf;  // P2[k] = (|A_k|^2, |B_k|^2): both frames of the pair side by side
+      float2 X[BPL2][R2];  // X[lane + 32 i] = X[i % BPL2][i / BPL2]
+      fft_pass<NFFT, R2, NS2, false, true, TIn>(X, ld_base, 0u, tw2, s_tw, seg_a, seg_b, s_win, lane);
+
+      // ---- split the two real spectra and take the power (stft.py:663).  Bin k = lane + 32 i (i < H) needs
+      //      Z[N - k]: slot NS - 1 - i of lane 32 - lane (one shuffle per component); lane 0 pairs with itself
+      //      (slot (NS - i) % NS).  The warp has passed the barrier behind the last pass's reads, so P2 can overwrite
+      //      the buffer. ----
 #pragma unroll
-      for (int i = 0; i < KPL; ++i) {
-        const int k = lane + 32 * i;
-        if (k < F) P2[k] = make_float2(pa[i], pb[i]);
+      for (int i = 0; i < H; ++i) {
+        const float2 zk = X[i % BPL2][i / BPL2];
+        const float2 up = X[(NS - 1 - i) % BPL2][(NS - 1 - i) / BPL2];
+        float2 zn = make_float2(__shfl_sync(0xffffffffu, up.x, src_lane), __shfl_sync(0xffffffffu, up.y, src_lane));
+        if (lane == 0) zn = X[((NS - i) % NS) % BPL2][((NS - i) % NS) / BPL2];
+        const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
+        const float br = 0.5f * (zk.y + zn.y), bi = 0.5f * (zn.x - zk.x);
+        P2[lane + 32 * i] = make_float2(ar * ar + ai * ai, br * br + bi * bi);
+      }
+      if (lane == 0) {  // Nyquist bin N / 2 = 32 H: its own partner, so A = re, B = im
+        const float2 z = X[H % BPL2][H / BPL2];
+        P2[NFFT / 2] = make_float2(z.x * z.x, z.y * z.y);
       }
       __syncwarp();
 
       const bool has_b = fa + 1 < T;
-      if (dbg & 2) {
-        if (lane == 0) out[(static_cast<size_t>(b) * T + fa) * n_mels] = P2[3].x + P2[3].y;
-      } else if (mode == 1) {
+      if (mode == 1) {
         float* o = out + (static_cast<size_t>(b) * T + fa) * F;
         for (int k = lane; k < F; k += 32) {
           const float2 p = P2[k];
@@ -413,63 +517,48 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
         }
       } else {
         float* o = out + (static_cast<size_t>(b) * T + fa) * n_mels;
-        // bins are visited as (lane, n_mels-1-lane, lane+32, ...): narrow low bands pair with wide high bands;
-        // both frames of the pair share every weight load
-        for (int mi = lane; mi < n_mels; mi += 32) {
-          const int pr = mi >> 5;
-          const int m = (pr & 1) ? (n_mels - 1 - (mi - 32 * pr) - 32 * (pr >> 1)) : (lane + 32 * (pr >> 1));
-          if (m < 0 || m >= n_mels) continue;
-          const int lo = s_meli[m], len = s_meli[n_mels + m], off = s_meli[2 * n_mels + m];
-          const float2* Pm = P2 + lo;
-          float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;  // stft.py:709 restricted to the band of non-zero weights
-          if (mel_in_smem) {
-            const float* mv = s_melv + off;
-            int i = 0;
-            for (; i + 3 < len; i += 4) {  // four bins per trip (same summation order as two trips of the loop below)
-              const float2 p = Pm[i], q = Pm[i + 1], p2 = Pm[i + 2], q2 = Pm[i + 3];
-              const float w0 = mv[i], w1 = mv[i + 1], w2 = mv[i + 2], w3 = mv[i + 3];
-              a0 = fmaf(p.x, w0, a0);
-              b0 = fmaf(p.y, w0, b0);
-              a1 = fmaf(q.x, w1, a1);
-              b1 = fmaf(q.y, w1, b1);
-              a0 = fmaf(p2.x, w2, a0);
-              b0 = fmaf(p2.y, w2, b0);
-              a1 = fmaf(q2.x, w3, a1);
-              b1 = fmaf(q2.y, w3, b1);
-            }
-            for (; i + 1 < len; i += 2) {
-              const float2 p = Pm[i], q = Pm[i + 1];
-              const float w0 = mv[i], w1 = mv[i + 1];
-              a0 = fmaf(p.x, w0, a0);
-              b0 = fmaf(p.y, w0, b0);
-              a1 = fmaf(q.x, w1, a1);
-              b1 = fmaf(q.y, w1, b1);
-            }
-            if (i < len) {
-              const float2 p = Pm[i];
-              const float w0 = mv[i];
-              a0 = fmaf(p.x, w0, a0);
-              b0 = fmaf(p.y, w0, b0);
+        // ---- mel projection, one lane per segment: SEG multiply-adds per round for both frames of the pair ----
+        for (int r = 0; r < rounds; ++r) {
+          const float2* Pm = P2 + s_seglo[32 * r + lane];
+          const float* wr = s_segw + r * (SEG * 32) + lane;
+          float a0 = 0.0f, b0 = 0.0f;
+#pragma unroll
+          for (int i = 0; i < SEG; ++i) {
+            const float2 p = Pm[i];
+            const float w = wr[32 * i];
+            a0 = fmaf(p.x, w, a0);
+            b0 = fmaf(p.y, w, b0);
+          }
+          part[32 * r + lane] = make_float2(a0, b0);
+        }
+        __syncwarp();
+        for (int m = lane; m < n_mels; m += 32) {
+          float ya = 0.0f, yb = 0.0f;
+          if (rounds > 0) {
+            const int first = s_band[m] & 0xffff, np = s_band[m] >> 16;
+            for (int j = 0; j < np; ++j) {  // ascending segments: the summation order is fixed
+              const float2 t = part[first + j];
+              ya += t.x;
+              yb += t.y;
             }
           } else {
-            const float* mv = mel_val + off;
+            const float2* Pm = P2 + mel_lo[m];
+            const float* mv = mel_val + mel_off[m];
+            const int len = mel_len[m];
             for (int i = 0; i < len; ++i) {
               const float2 p = Pm[i];
-              const float w0 = __ldg(mv + i);
-              a0 = fmaf(p.x, w0, a0);
-              b0 = fmaf(p.y, w0, b0);
+              const float w = __ldg(mv + i);
+              ya = fmaf(p.x, w, ya);
+              yb = fmaf(p.y, w, yb);
             }
           }
-          float ya = a0 + a1, yb = b0 + b1;
           if (is_log) {  // stft.py:726-727
             ya = power_to_db(ya, amin, db_offset, db_floor);
             yb = power_to_db(yb, amin, db_offset, db_floor);
           }
-          if (bn_scale != nullptr) {  // models.py:642-644
-            const float sc = bn_scale[m], sh = bn_shift[m];
-            ya = fmaf(ya, sc, sh);
-            yb = fmaf(yb, sc, sh);
-          }
+          const float2 sc = s_bn[m];  // models.py:642-644 (identity when no bn0 is fused)
+          ya = fmaf(ya, sc.x, sc.y);
+          yb = fmaf(yb, sc.x, sc.y);
           o[m] = ya;
           if (has_b) o[n_mels + m] = yb;
         }
@@ -508,8 +597,8 @@ static int launch_frontend_t(const FrontendArgs& a, cudaStream_t stream) {
   constexpr int FPB = FrontCfg<NFFT>::FPB;
   const int seg_len = (FPB - 1) * a.hop + NFFT;
   const int seg_bytes = (seg_len * static_cast<int>(sizeof(TIn)) + 15) & ~15;
-  const size_t smem = 2 * static_cast<size_t>(seg_bytes) + sizeof(float2) * (WARPS * NFFT + NFFT) +
-                      sizeof(float) * (NFFT + FrontCfg<NFFT>::MELV) + sizeof(int) * 3 * (a.n_mels > 0 ? a.n_mels : 1);
+  const size_t smem = 128 + static_cast<size_t>(frontend_fixed_smem<NFFT>(a.n_mels > 0 ? a.n_mels : 0)) +
+                      2 * static_cast<size_t>(seg_bytes);
   if (smem > 227 * 1024) return SED_ERR_UNSUPPORTED;
   static int sm_count = 0;
   if (sm_count == 0) {
@@ -534,11 +623,6 @@ static int launch_frontend_t(const FrontendArgs& a, cudaStream_t stream) {
                       (a.clip_offset != nullptr || (a.clip_stride * es) % 16 == 0) &&
                       ((static_cast<size_t>(FPB) * a.hop * es) % 16 == 0) && ((NFFT / 2 * es) % 16 == 0) &&
                       ((seg_len * es) % 16 == 0);
-  int dbg = 0;
-#ifdef SED_PROFILE
-  const char* e_dbg = getenv("SED_FE_DBG");  // developer experiments: 1 = first FFT pass only, 2 = no mel projection
-  dbg = e_dbg ? atoi(e_dbg) : 0;
-#endif
   int* counters = nullptr;
   if (cudaGetSymbolAddress(reinterpret_cast<void**>(&counters), g_frontend_work_counters) != cudaSuccess)
     return SED_ERR_CUDA;
@@ -547,7 +631,7 @@ static int launch_frontend_t(const FrontendArgs& a, cudaStream_t stream) {
   frontend_kernel<NFFT, TIn><<<static_cast<unsigned>(blocks), WARPS * 32, smem, stream>>>(
       reinterpret_cast<const TIn*>(a.wave), a.clip_stride, a.clip_offset, a.total_len, a.B, a.L, a.T, a.hop, a.window,
       reinterpret_cast<const float2*>(a.twiddle), a.mel_lo, a.mel_len, a.mel_off, a.mel_val, a.n_mels, a.amin,
-      a.db_offset, a.is_log, a.bn_scale, a.bn_shift, a.out, a.mode, aligned, dbg, counter);
+      a.db_offset, a.is_log, a.bn_scale, a.bn_shift, a.out, a.mode, aligned, counter);
   return cudaGetLastError() == cudaSuccess ? SED_OK : SED_ERR_CUDA;
 }
 
