@@ -36,6 +36,8 @@ struct FrontCfg {
   static constexpr int SEG = (NFFT == 256) ? 3 : (NFFT == 512) ? 7 : 9;
   // segment sums live behind the power spectrum in the warp's own buffer: (NFFT - F) float2 slots are free
   static constexpr int SEGS_MAX = (NFFT == 256) ? 96 : 160;
+  // segments of one band summed without a loop (widest band of the presets: 8 / 20 / 47 bins = 3 / 3 / 6 segments)
+  static constexpr int NP_UNROLL = (NFFT == 1024) ? 6 : 3;
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -64,25 +66,45 @@ __device__ __forceinline__ void sts_f2(uint32_t addr, float2 v) {
   asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
 }
 
+// complex add / sub as ONE packed instruction (FADD2 on a 64-bit register pair, sm_100): same IEEE results as two FADD
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+  unsigned long long x, y, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(x), "l"(y));
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(d));
+  return r;
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+  unsigned long long x, y, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(b.x), "f"(b.y));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(x), "l"(y));
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(d));
+  return r;
+}
+
 template <int R>
 __device__ __forceinline__ void butterfly(float2 (&v)[R]);
 
 template <>
 __device__ __forceinline__ void butterfly<2>(float2 (&v)[2]) {
   const float2 a0 = v[0], a1 = v[1];
-  v[0] = make_float2(a0.x + a1.x, a0.y + a1.y);
-  v[1] = make_float2(a0.x - a1.x, a0.y - a1.y);
+  v[0] = cadd(a0, a1);
+  v[1] = csub(a0, a1);
 }
 
 template <>
 __device__ __forceinline__ void butterfly<4>(float2 (&v)[4]) {
-  const float2 a0 = make_float2(v[0].x + v[2].x, v[0].y + v[2].y);
-  const float2 a1 = make_float2(v[0].x - v[2].x, v[0].y - v[2].y);
-  const float2 a2 = make_float2(v[1].x + v[3].x, v[1].y + v[3].y);
-  const float2 a3 = make_float2(v[1].x - v[3].x, v[1].y - v[3].y);
-  v[0] = make_float2(a0.x + a2.x, a0.y + a2.y);
+  const float2 a0 = cadd(v[0], v[2]);
+  const float2 a1 = csub(v[0], v[2]);
+  const float2 a2 = cadd(v[1], v[3]);
+  const float2 a3 = csub(v[1], v[3]);
+  v[0] = cadd(a0, a2);
   v[1] = make_float2(a1.x + a3.y, a1.y - a3.x);  // a1 - i*a3
-  v[2] = make_float2(a0.x - a2.x, a0.y - a2.y);
+  v[2] = csub(a0, a2);
   v[3] = make_float2(a1.x - a3.y, a1.y + a3.x);  // a1 + i*a3
 }
 
@@ -92,8 +114,8 @@ __device__ __forceinline__ void butterfly<8>(float2 (&v)[8]) {
   float2 a[4], b[4];
 #pragma unroll
   for (int n = 0; n < 4; ++n) {
-    a[n] = make_float2(v[n].x + v[n + 4].x, v[n].y + v[n + 4].y);
-    b[n] = make_float2(v[n].x - v[n + 4].x, v[n].y - v[n + 4].y);
+    a[n] = cadd(v[n], v[n + 4]);
+    b[n] = csub(v[n], v[n + 4]);
   }
   // b[n] *= W8^n  (W8 = exp(-2 pi i / 8))
   b[1] = make_float2((b[1].x + b[1].y) * kS, (b[1].y - b[1].x) * kS);
@@ -189,11 +211,13 @@ __device__ __forceinline__ float power_to_db(float x, float amin, float db_offse
   return x > amin ? fmaf(l, 3.010299956639812f, -db_offset) : db_floor;
 }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+// global -> shared bulk copy (one instruction for a whole segment; completes bytes on an mbarrier)
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // One Stockham pass of radix R over N complex points, IN PLACE in the swizzled shared-memory buffer of one warp:
 // every lane first pulls the inputs of all its butterflies into registers, the warp synchronises, then the
@@ -264,11 +288,13 @@ template <> struct Sched<1024> { static constexpr int R0 = 8, R1 = 8, R2 = 16; }
 
 // Stage the raw waveform segment [q0, q0 + seg_len) of clip b (reflect padding at the clip ends, stft.py:236-237;
 // zero beyond total_len, pad_truncate_sequence utils/utilities.py:66-70) into shared memory.  Interior, 16-byte
-// aligned segments go through cp.async; edge segments through guarded loads.
+// aligned segments are ONE bulk copy issued by thread 0 (returns true: the consumer waits on `bar`); edge segments go
+// through guarded loads of all threads (returns false: the block barrier in front of the consumer orders them).  The
+// caller has passed a block barrier since the last generic-proxy access to `dst`.
 template <int NFFT, typename TIn>
-__device__ __forceinline__ void stage_segment(TIn* __restrict__ dst, const TIn* __restrict__ wave, long clip_stride,
-                                              const long* __restrict__ clip_offset, long total_len, int L, int hop,
-                                              int seg_len, int item, int chunks, bool aligned) {
+__device__ __forceinline__ bool stage_segment(TIn* __restrict__ dst, uint64_t* bar, const TIn* __restrict__ wave,
+                                              long clip_stride, const long* __restrict__ clip_offset, long total_len,
+                                              int L, int hop, int seg_len, int item, int chunks, bool aligned) {
   constexpr int FPB = FrontCfg<NFFT>::FPB;
   const int b = item / chunks, c = item - b * chunks;
   const long clip_base = clip_offset ? clip_offset[b] : static_cast<long>(b) * clip_stride;
@@ -276,30 +302,32 @@ __device__ __forceinline__ void stage_segment(TIn* __restrict__ dst, const TIn* 
   const long q0 = static_cast<long>(c) * FPB * hop - NFFT / 2;
   const TIn* w = wave + clip_base;
   if (aligned && q0 >= 0 && q0 + seg_len <= L && clip_base + q0 + seg_len <= total_len) {
-    const char* src = reinterpret_cast<const char*>(w + q0);
-    char* d = reinterpret_cast<char*>(dst);
-    const int nvec = seg_len * static_cast<int>(sizeof(TIn)) / 16;
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) cp_async16(d + 16 * i, src + 16 * i);
-  } else {
-    // edge segments (first / last chunk of a clip: 2 of ~32 items): four independent loads in flight per thread
-    for (int s0 = threadIdx.x; s0 < seg_len; s0 += 4 * blockDim.x) {
-      float v[4];
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = static_cast<uint32_t>(seg_len) * static_cast<uint32_t>(sizeof(TIn));
+      fence_proxy_async_smem();  // the buffer's previous readers used the generic proxy
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(dst, w + q0, bytes, bar);
+    }
+    return true;
+  }
+  // edge segments (first / last chunk of a clip: 2 of ~32 items): four independent loads in flight per thread
+  for (int s0 = threadIdx.x; s0 < seg_len; s0 += 4 * blockDim.x) {
+    float v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int s = s0 + u * blockDim.x;
-        long i = q0 + s;
-        if (i < 0) i = -i;
-        if (i >= L) i = 2L * (L - 1) - i;
-        v[u] = (s < seg_len && i >= 0 && i < L && clip_base + i < total_len) ? load_sample_global(w + i) : 0.0f;
-      }
+    for (int u = 0; u < 4; ++u) {
+      const int s = s0 + u * blockDim.x;
+      long i = q0 + s;
+      if (i < 0) i = -i;
+      if (i >= L) i = 2L * (L - 1) - i;
+      v[u] = (s < seg_len && i >= 0 && i < L && clip_base + i < total_len) ? load_sample_global(w + i) : 0.0f;
+    }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int s = s0 + u * blockDim.x;
-        if (s < seg_len) store_raw(dst + s, v[u]);
-      }
+    for (int u = 0; u < 4; ++u) {
+      const int s = s0 + u * blockDim.x;
+      if (s < seg_len) store_raw(dst + s, v[u]);
     }
   }
-  cp_async_commit();
+  return false;
 }
 
 // Mel projection schedule, built once per persistent block from the banded matrix (stft.py:709 restricted to the
@@ -347,20 +375,40 @@ __device__ __forceinline__ int build_mel_schedule(const int* __restrict__ mel_lo
     for (int j = 0; j < np; ++j) s_segmj[first + j] = m | (j << 16);
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < slots * SEG; e += blockDim.x) {
-    const int s = e / SEG, i = e - s * SEG;
+  // First bin each segment reads.  A segment that is shorter than SEG may start anywhere between (its last bin + 1 -
+  // SEG) and its first bin; the 64-bit reads of a half-warp are conflict-free when their starts differ mod 16, so
+  // every lane that shares its residue with a lower lane of its half-warp moves down one bin at a time while it can
+  // (the reference's 16 kHz matrix: 91 -> 63 wavefronts per frame pair, 42 without any conflict).
+  for (int r = warp; r < slots / 32; r += blockDim.x >> 5) {
+    const int s = 32 * r + lane;
     const int mj = s_segmj[s];
-    float w = 0.0f;
-    int start = 0;
+    int start = 0, lowest = 0;
     if (mj >= 0) {
       const int m = mj & 0xffff, j = mj >> 16;
       const int lo = mel_lo[m], len = mel_len[m];
       start = min(lo + j * SEG, F - SEG);
-      const int rel = start + i - lo;  // position of this bin inside the band
-      if (rel >= j * SEG && rel < min((j + 1) * SEG, len)) w = mel_val[mel_off[m] + rel];
+      lowest = max(lo + min((j + 1) * SEG, len) - SEG, 0);
+    }
+    for (int it = 0; it < SEG; ++it) {
+      const unsigned peers = __match_any_sync(0xffffffffu, (start & 15) | (lane & 16) | (mj >= 0 ? 0 : 32 + lane));
+      const int first = __ffs(peers) - 1;
+      const int first_start = __shfl_sync(0xffffffffu, start, first);
+      if (lane != first && start != first_start && start > lowest) --start;
+    }
+    const int anchor = __shfl_sync(0xffffffffu, start, lane & 16);  // unused lanes re-read a neighbour's address
+    s_seglo[s] = (mj >= 0) ? start : anchor;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < slots * SEG; e += blockDim.x) {
+    const int s = e / SEG, i = e - s * SEG;
+    const int mj = s_segmj[s];
+    float w = 0.0f;
+    if (mj >= 0) {
+      const int m = mj & 0xffff, j = mj >> 16;
+      const int rel = s_seglo[s] + i - mel_lo[m];  // position of this bin inside the band
+      if (rel >= j * SEG && rel < min((j + 1) * SEG, mel_len[m])) w = mel_val[mel_off[m] + rel];
     }
     s_segw[((s >> 5) * SEG + i) * 32 + (s & 31)] = w;
-    if (i == 0) s_seglo[s] = start;
   }
   __syncthreads();
   return nseg;
@@ -390,6 +438,7 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
   constexpr int WARPS = FrontCfg<NFFT>::WARPS;
   constexpr int FPB = FrontCfg<NFFT>::FPB;
   constexpr int SEG = FrontCfg<NFFT>::SEG, SEGS_MAX = FrontCfg<NFFT>::SEGS_MAX;
+  constexpr int NP_UNROLL = FrontCfg<NFFT>::NP_UNROLL;
   constexpr int F = NFFT / 2 + 1;
   constexpr int NS = NFFT / 32, H = NS / 2;  // spectrum values per lane after the last pass; half of them
   const float db_floor = 10.0f * log10f(amin) - db_offset;  // once per thread: the value every clamped bin takes
@@ -411,19 +460,26 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
   int* s_segmj = s_seglo + SEGS_MAX;                                  // [SEGS_MAX] (band, piece) while building
   int* s_band = s_segmj + SEGS_MAX;                                   // [n_mels] first segment | segments << 16
   float2* s_bn = reinterpret_cast<float2*>(s_band + ((n_mels + 1) & ~1));  // [n_mels] bn0 (scale, shift)
-  TIn* s_stage0 = reinterpret_cast<TIn*>(sp + frontend_fixed_smem<NFFT>(n_mels));  // 16-byte aligned (cp.async)
+  TIn* s_stage0 = reinterpret_cast<TIn*>(sp + frontend_fixed_smem<NFFT>(n_mels));  // 16-byte aligned (bulk copy)
   TIn* s_stage1 = reinterpret_cast<TIn*>(reinterpret_cast<uint8_t*>(s_stage0) + seg_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunks = (T + FPB - 1) / FPB;
   const int items = B * chunks;
-  int item = blockIdx.x;
-  if (item < items)
-    stage_segment<NFFT, TIn>(s_stage0, wave, clip_stride, clip_offset, total_len, L, hop, seg_len, item, chunks,
-                             aligned != 0);
-
   __shared__ int s_next[2];
   __shared__ int s_total;
+  __shared__ __align__(8) uint64_t s_bar[2];  // one per staging buffer: bytes of the bulk copy in flight
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  int item = blockIdx.x;
+  bool cur_bulk = false;  // block-uniform: this item's segment arrives through s_bar[sel]
+  if (item < items)
+    cur_bulk = stage_segment<NFFT, TIn>(s_stage0, &s_bar[0], wave, clip_stride, clip_offset, total_len, L, hop, seg_len,
+                                        item, chunks, aligned != 0);
   for (int i = threadIdx.x; i < NFFT; i += blockDim.x) {
     s_win[i] = window[i];
     s_tw[i] = twiddle[i];
@@ -457,14 +513,20 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
   // a block that starts late -- its SM was still busy with another stream's kernel -- simply claims fewer items, so
   // the launch ends when the work is done, not when the slowest static share is.
   int sel = 0;
-  for (int nxt = 0; item < items; item = nxt, sel ^= 1) {
-    cp_async_wait_all();
+  uint32_t phase = 0;  // bit s: parity of s_bar[s]'s next completion
+  bool nxt_bulk = false;
+  for (int nxt = 0; item < items; item = nxt, sel ^= 1, cur_bulk = nxt_bulk) {
     if (threadIdx.x == 0) s_next[sel] = static_cast<int>(gridDim.x) + atomicAdd(work_counter, 1);
-    __syncthreads();  // this item's segment and the claimed item are visible; every warp has finished the previous item
+    __syncthreads();  // the claimed item and an edge segment's stores are visible; every warp has finished the previous item
     nxt = s_next[sel];
+    nxt_bulk = false;
     if (nxt < items)
-      stage_segment<NFFT, TIn>(sel ? s_stage0 : s_stage1, wave, clip_stride, clip_offset, total_len, L, hop, seg_len,
-                               nxt, chunks, aligned != 0);
+      nxt_bulk = stage_segment<NFFT, TIn>(sel ? s_stage0 : s_stage1, &s_bar[sel ^ 1], wave, clip_stride, clip_offset,
+                                          total_len, L, hop, seg_len, nxt, chunks, aligned != 0);
+    if (cur_bulk) {
+      mbar_wait(&s_bar[sel], (phase >> sel) & 1u);
+      phase ^= 1u << sel;
+    }
     const TIn* s_seg = sel ? s_stage1 : s_stage0;
     const int b = item / chunks;
     const int f_base = (item - b * chunks) * FPB;
@@ -497,9 +559,10 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
         const float2 up = X[(NS - 1 - i) % BPL2][(NS - 1 - i) / BPL2];
         float2 zn = make_float2(__shfl_sync(0xffffffffu, up.x, src_lane), __shfl_sync(0xffffffffu, up.y, src_lane));
         if (lane == 0) zn = X[((NS - i) % NS) % BPL2][((NS - i) % NS) / BPL2];
-        const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
-        const float br = 0.5f * (zk.y + zn.y), bi = 0.5f * (zn.x - zk.x);
-        P2[lane + 32 * i] = make_float2(ar * ar + ai * ai, br * br + bi * bi);
+        // A = (zk + conj(zn)) / 2, B = (zk - conj(zn)) / 2i; the halves are folded into one exact scale by 1/4
+        const float ar = zk.x + zn.x, ai = zk.y - zn.y;
+        const float br = zk.y + zn.y, bi = zn.x - zk.x;
+        P2[lane + 32 * i] = make_float2(0.25f * fmaf(ai, ai, ar * ar), 0.25f * fmaf(bi, bi, br * br));
       }
       if (lane == 0) {  // Nyquist bin N / 2 = 32 H: its own partner, so A = re, B = im
         const float2 z = X[H % BPL2][H / BPL2];
@@ -536,8 +599,19 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
           float ya = 0.0f, yb = 0.0f;
           if (rounds > 0) {
             const int first = s_band[m] & 0xffff, np = s_band[m] >> 16;
-            for (int j = 0; j < np; ++j) {  // ascending segments: the summation order is fixed
-              const float2 t = part[first + j];
+            const float2* pm = part + first;
+            // ascending segments: the summation order is fixed.  The first NP_UNROLL are predicated (no loop for the
+            // reference's presets), wider bands continue in a loop.
+#pragma unroll
+            for (int j = 0; j < NP_UNROLL; ++j) {
+              if (j < np) {
+                const float2 t = pm[j];
+                ya += t.x;
+                yb += t.y;
+              }
+            }
+            for (int j = NP_UNROLL; j < np; ++j) {
+              const float2 t = pm[j];
               ya += t.x;
               yb += t.y;
             }
@@ -617,7 +691,7 @@ static int launch_frontend_t(const FrontendArgs& a, cudaStream_t stream) {
   const long items = static_cast<long>(a.B) * ((a.T + FPB - 1) / FPB);
   long blocks = static_cast<long>(sm_count) * per_sm;
   if (blocks > items) blocks = items;
-  // cp.async staging needs 16-byte aligned interior segments
+  // bulk-copy staging needs 16-byte aligned interior segments
   const size_t es = sizeof(TIn);
   const int aligned = (reinterpret_cast<uintptr_t>(a.wave) % 16 == 0) &&
                       (a.clip_offset != nullptr || (a.clip_stride * es) % 16 == 0) &&
