@@ -22,11 +22,14 @@ namespace sed {
 
 template <int NFFT>
 struct FrontCfg {
-  static constexpr int WARPS = 8;
-  // frames per work item (even: frames are transformed in pairs).  A persistent block loops over work items =
-  // (clip, chunk of FPB frames); the waveform segment of the next item is staged with cp.async while the current
-  // one is transformed.
-  static constexpr int FPB = (NFFT == 1024) ? 16 : 32;
+  // 1024: one block of 12 warps per SM (8 KB of FFT buffer and 168 registers per warp); 256 / 512: two blocks of 8
+  static constexpr int WARPS = (NFFT == 1024) ? 12 : 8;
+  // frames per work item (even: frames are transformed in pairs) for 4-byte samples; 2-byte PCM takes twice as many
+  // in the same staging space (fpb()).  A persistent block loops over work items = (clip, chunk of frames); the
+  // waveform segment of the next item arrives by bulk copy while the current one is transformed.
+  static constexpr int FPB = (NFFT == 1024) ? 24 : 32;
+  template <typename TIn>
+  static constexpr int fpb() { return FPB * (sizeof(TIn) == 2 ? 2 : 1); }
   static constexpr int MIN_BLOCKS = (NFFT == 1024) ? 1 : 2;
   // Mel projection: every band is cut into segments of SEG consecutive bins, one lane per segment, 32 segments per
   // round (see build_mel_schedule).  SEG is odd, so the 64-bit power reads of neighbouring segments of a band fall
@@ -38,6 +41,8 @@ struct FrontCfg {
   static constexpr int SEGS_MAX = (NFFT == 256) ? 96 : 160;
   // segments of one band summed without a loop (widest band of the presets: 8 / 20 / 47 bins = 3 / 3 / 6 segments)
   static constexpr int NP_UNROLL = (NFFT == 1024) ? 6 : 3;
+  // rounds of the presets (91 / 94 / 127 segments); this count runs fully unrolled, any other in a loop
+  static constexpr int ROUNDS_UNROLL = (NFFT == 1024) ? 4 : 3;
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -295,7 +300,7 @@ template <int NFFT, typename TIn>
 __device__ __forceinline__ bool stage_segment(TIn* __restrict__ dst, uint64_t* bar, const TIn* __restrict__ wave,
                                               long clip_stride, const long* __restrict__ clip_offset, long total_len,
                                               int L, int hop, int seg_len, int item, int chunks, bool aligned) {
-  constexpr int FPB = FrontCfg<NFFT>::FPB;
+  constexpr int FPB = FrontCfg<NFFT>::template fpb<TIn>();
   const int b = item / chunks, c = item - b * chunks;
   const long clip_base = clip_offset ? clip_offset[b] : static_cast<long>(b) * clip_stride;
   aligned = aligned && ((clip_base * static_cast<long>(sizeof(TIn))) & 15) == 0;
@@ -338,7 +343,8 @@ __device__ __forceinline__ bool stage_segment(TIn* __restrict__ dst, uint64_t* b
 // the wide high-frequency bands are spread over several lanes instead of serialising the warp.
 //   s_band[m]  = first segment | segments << 16
 //   s_seglo[s] = first bin read by segment s          (s < 32 * rounds; unused lanes read bin 0 with zero weights)
-//   s_segw[(round * SEG + i) * 32 + lane] = weight of bin s_seglo[s] + i
+//   s_segw[(round * SEG + i) * 32 + lane] = weight of bin s_seglo[s] + i, times 1/4 (the power split of the log-mel
+//                                            path leaves 4 |X|^2 in P2; the scale is exact)
 // Returns the number of segments, or -1 when they do not fit (SEGS_MAX): the caller then projects one lane per band.
 template <int NFFT>
 __device__ __forceinline__ int build_mel_schedule(const int* __restrict__ mel_lo, const int* __restrict__ mel_len,
@@ -406,7 +412,7 @@ __device__ __forceinline__ int build_mel_schedule(const int* __restrict__ mel_lo
     if (mj >= 0) {
       const int m = mj & 0xffff, j = mj >> 16;
       const int rel = s_seglo[s] + i - mel_lo[m];  // position of this bin inside the band
-      if (rel >= j * SEG && rel < min((j + 1) * SEG, mel_len[m])) w = mel_val[mel_off[m] + rel];
+      if (rel >= j * SEG && rel < min((j + 1) * SEG, mel_len[m])) w = 0.25f * mel_val[mel_off[m] + rel];
     }
     s_segw[((s >> 5) * SEG + i) * 32 + (s & 31)] = w;
   }
@@ -426,7 +432,7 @@ __host__ __device__ constexpr int frontend_fixed_smem(int n_mels) {
 // Clip b starts at wave + b * clip_stride (or wave + clip_offset[b] when a table is given) and is L samples long; samples at or beyond total_len (counted from
 // `wave`) read as zero.  clip_stride < L gives overlapping windows of one long recording (predict.py:297-307)
 // without materialising them.
-template <int NFFT, typename TIn>
+template <int NFFT, typename TIn, int MODE>
 __global__ void __launch_bounds__(FrontCfg<NFFT>::WARPS * 32, FrontCfg<NFFT>::MIN_BLOCKS)
 frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __restrict__ clip_offset, long total_len,
                 int B, int L, int T, int hop,
@@ -434,11 +440,12 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
                 const int* __restrict__ mel_lo, const int* __restrict__ mel_len, const int* __restrict__ mel_off,
                 const float* __restrict__ mel_val, int n_mels, float amin, float db_offset, int is_log,
                 const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, float* __restrict__ out,
-                int mode, int aligned, int* __restrict__ work_counter) {
+                int aligned, int* __restrict__ work_counter) {
   constexpr int WARPS = FrontCfg<NFFT>::WARPS;
-  constexpr int FPB = FrontCfg<NFFT>::FPB;
+  constexpr int FPB = FrontCfg<NFFT>::template fpb<TIn>();
   constexpr int SEG = FrontCfg<NFFT>::SEG, SEGS_MAX = FrontCfg<NFFT>::SEGS_MAX;
   constexpr int NP_UNROLL = FrontCfg<NFFT>::NP_UNROLL;
+  constexpr int RU = FrontCfg<NFFT>::ROUNDS_UNROLL;
   constexpr int F = NFFT / 2 + 1;
   constexpr int NS = NFFT / 32, H = NS / 2;  // spectrum values per lane after the last pass; half of them
   const float db_floor = 10.0f * log10f(amin) - db_offset;  // once per thread: the value every clamped bin takes
@@ -485,7 +492,7 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
     s_tw[i] = twiddle[i];
   }
   int nseg = -1;
-  if (mode == 0) {
+  if (MODE == 0) {
     for (int i = threadIdx.x; i < n_mels; i += blockDim.x)
       s_bn[i] = bn_scale != nullptr ? make_float2(bn_scale[i], bn_shift[i]) : make_float2(1.0f, 0.0f);
     nseg = build_mel_schedule<NFFT>(mel_lo, mel_len, mel_off, mel_val, n_mels, s_band, s_seglo, s_segmj, s_segw,
@@ -562,16 +569,19 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
         // A = (zk + conj(zn)) / 2, B = (zk - conj(zn)) / 2i; the halves are folded into one exact scale by 1/4
         const float ar = zk.x + zn.x, ai = zk.y - zn.y;
         const float br = zk.y + zn.y, bi = zn.x - zk.x;
-        P2[lane + 32 * i] = make_float2(0.25f * fmaf(ai, ai, ar * ar), 0.25f * fmaf(bi, bi, br * br));
+        // (the log-mel path keeps 4 |.|^2 and carries the 1/4 in its mel weights)
+        constexpr float kQ = (MODE == 0) ? 1.0f : 0.25f;
+        P2[lane + 32 * i] = make_float2(kQ * fmaf(ai, ai, ar * ar), kQ * fmaf(bi, bi, br * br));
       }
       if (lane == 0) {  // Nyquist bin N / 2 = 32 H: its own partner, so A = re, B = im
+        constexpr float kN = (MODE == 0) ? 4.0f : 1.0f;
         const float2 z = X[H % BPL2][H / BPL2];
-        P2[NFFT / 2] = make_float2(z.x * z.x, z.y * z.y);
+        P2[NFFT / 2] = make_float2(kN * z.x * z.x, kN * z.y * z.y);
       }
       __syncwarp();
 
       const bool has_b = fa + 1 < T;
-      if (mode == 1) {
+      if (MODE == 1) {
         float* o = out + (static_cast<size_t>(b) * T + fa) * F;
         for (int k = lane; k < F; k += 32) {
           const float2 p = P2[k];
@@ -581,18 +591,41 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
       } else {
         float* o = out + (static_cast<size_t>(b) * T + fa) * n_mels;
         // ---- mel projection, one lane per segment: SEG multiply-adds per round for both frames of the pair ----
-        for (int r = 0; r < rounds; ++r) {
-          const float2* Pm = P2 + s_seglo[32 * r + lane];
-          const float* wr = s_segw + r * (SEG * 32) + lane;
-          float a0 = 0.0f, b0 = 0.0f;
+        if (rounds == RU) {  // the presets: every round unrolled, all loads in flight, RU independent chains per frame
+          float a0[RU], b0[RU];
+          const float2* Pm[RU];
+#pragma unroll
+          for (int r = 0; r < RU; ++r) {
+            Pm[r] = P2 + s_seglo[32 * r + lane];
+            a0[r] = 0.0f;
+            b0[r] = 0.0f;
+          }
 #pragma unroll
           for (int i = 0; i < SEG; ++i) {
-            const float2 p = Pm[i];
-            const float w = wr[32 * i];
-            a0 = fmaf(p.x, w, a0);
-            b0 = fmaf(p.y, w, b0);
+#pragma unroll
+            for (int r = 0; r < RU; ++r) {
+              const float2 p = Pm[r][i];
+              const float w = s_segw[(r * SEG + i) * 32 + lane];
+              a0[r] = fmaf(p.x, w, a0[r]);
+              b0[r] = fmaf(p.y, w, b0[r]);
+            }
           }
-          part[32 * r + lane] = make_float2(a0, b0);
+#pragma unroll
+          for (int r = 0; r < RU; ++r) part[32 * r + lane] = make_float2(a0[r], b0[r]);
+        } else {
+          for (int r = 0; r < rounds; ++r) {
+            const float2* Pm = P2 + s_seglo[32 * r + lane];
+            const float* wr = s_segw + r * (SEG * 32) + lane;
+            float a0 = 0.0f, b0 = 0.0f;
+#pragma unroll
+            for (int i = 0; i < SEG; ++i) {
+              const float2 p = Pm[i];
+              const float w = wr[32 * i];
+              a0 = fmaf(p.x, w, a0);
+              b0 = fmaf(p.y, w, b0);
+            }
+            part[32 * r + lane] = make_float2(a0, b0);
+          }
         }
         __syncwarp();
         for (int m = lane; m < n_mels; m += 32) {
@@ -621,7 +654,7 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
             const int len = mel_len[m];
             for (int i = 0; i < len; ++i) {
               const float2 p = Pm[i];
-              const float w = __ldg(mv + i);
+              const float w = 0.25f * __ldg(mv + i);
               ya = fmaf(p.x, w, ya);
               yb = fmaf(p.y, w, yb);
             }
@@ -665,10 +698,10 @@ __global__ void logmel_rows_kernel(const float* __restrict__ spec, long rows, in
 __device__ int g_frontend_work_counters[64];
 static std::atomic<unsigned> g_frontend_launch_seq{0};
 
-template <int NFFT, typename TIn>
+template <int NFFT, typename TIn, int MODE>
 static int launch_frontend_t(const FrontendArgs& a, cudaStream_t stream) {
   constexpr int WARPS = FrontCfg<NFFT>::WARPS;
-  constexpr int FPB = FrontCfg<NFFT>::FPB;
+  constexpr int FPB = FrontCfg<NFFT>::template fpb<TIn>();
   const int seg_len = (FPB - 1) * a.hop + NFFT;
   const int seg_bytes = (seg_len * static_cast<int>(sizeof(TIn)) + 15) & ~15;
   const size_t smem = 128 + static_cast<size_t>(frontend_fixed_smem<NFFT>(a.n_mels > 0 ? a.n_mels : 0)) +
@@ -682,10 +715,10 @@ static int launch_frontend_t(const FrontendArgs& a, cudaStream_t stream) {
       sm_count = 148;
   }
   cudaError_t e =
-      cudaFuncSetAttribute(frontend_kernel<NFFT, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(frontend_kernel<NFFT, TIn, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return SED_ERR_CUDA;
   int per_sm = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frontend_kernel<NFFT, TIn>, WARPS * 32, smem) !=
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frontend_kernel<NFFT, TIn, MODE>, WARPS * 32, smem) !=
           cudaSuccess || per_sm < 1)
     per_sm = 1;
   const long items = static_cast<long>(a.B) * ((a.T + FPB - 1) / FPB);
@@ -702,17 +735,18 @@ static int launch_frontend_t(const FrontendArgs& a, cudaStream_t stream) {
     return SED_ERR_CUDA;
   int* counter = counters + (g_frontend_launch_seq.fetch_add(1) & 63u);
   if (cudaMemsetAsync(counter, 0, sizeof(int), stream) != cudaSuccess) return SED_ERR_CUDA;
-  frontend_kernel<NFFT, TIn><<<static_cast<unsigned>(blocks), WARPS * 32, smem, stream>>>(
+  frontend_kernel<NFFT, TIn, MODE><<<static_cast<unsigned>(blocks), WARPS * 32, smem, stream>>>(
       reinterpret_cast<const TIn*>(a.wave), a.clip_stride, a.clip_offset, a.total_len, a.B, a.L, a.T, a.hop, a.window,
       reinterpret_cast<const float2*>(a.twiddle), a.mel_lo, a.mel_len, a.mel_off, a.mel_val, a.n_mels, a.amin,
-      a.db_offset, a.is_log, a.bn_scale, a.bn_shift, a.out, a.mode, aligned, counter);
+      a.db_offset, a.is_log, a.bn_scale, a.bn_shift, a.out, aligned, counter);
   return cudaGetLastError() == cudaSuccess ? SED_OK : SED_ERR_CUDA;
 }
 
 template <int NFFT>
 static int launch_frontend(const FrontendArgs& a, cudaStream_t stream) {
-  if (a.wave_dtype == 1) return launch_frontend_t<NFFT, short>(a, stream);
-  return launch_frontend_t<NFFT, float>(a, stream);
+  if (a.mode == 1)
+    return a.wave_dtype == 1 ? launch_frontend_t<NFFT, short, 1>(a, stream) : launch_frontend_t<NFFT, float, 1>(a, stream);
+  return a.wave_dtype == 1 ? launch_frontend_t<NFFT, short, 0>(a, stream) : launch_frontend_t<NFFT, float, 0>(a, stream);
 }
 
 int frontend_launch(const FrontendArgs& a, cudaStream_t stream) {
