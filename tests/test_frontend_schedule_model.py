@@ -1,0 +1,188 @@
+"""CPU model of the index arithmetic inside `csrc/sed_frontend.cu` (no GPU needed).
+
+The front-end kernel relies on three pieces of integer bookkeeping that are easy to get wrong and impossible to see in
+a tolerance test: (1) swizzled shared-memory addresses formed as (per-lane base) XOR / + (compile-time constant),
+(2) the lane / register-slot pairing of the power split after the last FFT pass, (3) the segment schedule of the mel
+projection built by `build_mel_schedule`.  This file restates each of them in numpy exactly as the kernel computes
+them and checks them against first principles (the plain swizzle function, numpy's FFT, a dense matmul)."""
+import numpy as np
+import pytest
+
+from sed_b200 import melbank, synth
+
+SCHED = {256: (4, 8, 8), 512: (8, 8, 8), 1024: (8, 8, 16)}          # Sched<N> in the kernel
+SEG = {256: 3, 512: 7, 1024: 9}                                     # FrontCfg<N>::SEG
+SEGS_MAX = {256: 96, 512: 160, 1024: 160}                           # FrontCfg<N>::SEGS_MAX
+
+
+def pidx(i):
+    return i ^ ((i >> 3) & 15)
+
+
+def eaddr(base, c):
+    p = pidx(c)
+    return (base ^ ((p & 15) << 3)) + ((p & ~15) << 3)
+
+
+@pytest.mark.parametrize("n_fft", [256, 512, 1024])
+def test_pass_addresses_equal_the_plain_swizzle(n_fft):
+    r0, r1, r2 = SCHED[n_fft]
+    buf = 128 * 37  # any 128-byte aligned shared-memory address
+    for pi, (R, Ns) in enumerate(((r0, 1), (r1, r0), (r2, r0 * r1))):
+        NB = n_fft // R
+        BPL = NB // 32
+        for lane in range(32):
+            ld_base = buf + 8 * pidx(lane)
+            st_base = buf + 8 * pidx((lane // Ns) * Ns * R + lane % Ns) if Ns <= 32 else None
+            for q in range(BPL):
+                j = lane + 32 * q
+                for r in range(R):
+                    i = q + BPL * r
+                    assert j + r * NB == lane + 32 * i                       # input index of butterfly j, leg r
+                    if pi > 0:
+                        assert eaddr(ld_base, 32 * i) == buf + 8 * pidx(j + r * NB)
+                    out = (j // Ns) * Ns * R + j % Ns + r * Ns                # Stockham autosort output index
+                    if pi < 2:
+                        assert eaddr(st_base, r * Ns + 32 * R * q) == buf + 8 * pidx(out)
+                    else:
+                        assert out == lane + 32 * i                          # last pass: X[lane + 32 i] stays in the lane
+
+
+@pytest.mark.parametrize("n_fft", [256, 512, 1024])
+def test_power_split_pairing(n_fft):
+    rng = np.random.default_rng(n_fft)
+    a, b = rng.standard_normal(n_fft), rng.standard_normal(n_fft)
+    Z = np.fft.fft(a + 1j * b)
+    NS, H = n_fft // 32, n_fft // 64
+    X = [[Z[lane + 32 * i] for i in range(NS)] for lane in range(32)]
+    P = np.zeros((n_fft // 2 + 1, 2))
+    for lane in range(32):
+        src = (32 - lane) & 31
+        for i in range(H):
+            zk = X[lane][i]
+            zn = X[src][NS - 1 - i]                  # the shuffle
+            if lane == 0:
+                zn = X[0][(NS - i) % NS]              # lane 0 pairs with itself
+            ar, ai = zk.real + zn.real, zk.imag - zn.imag
+            br, bi = zk.imag + zn.imag, zn.real - zk.real
+            P[lane + 32 * i] = (0.25 * (ar * ar + ai * ai), 0.25 * (br * br + bi * bi))
+        if lane == 0:
+            z = X[0][H]
+            P[n_fft // 2] = (z.real ** 2, z.imag ** 2)
+    assert np.allclose(P[:, 0], np.abs(np.fft.rfft(a)) ** 2)
+    assert np.allclose(P[:, 1], np.abs(np.fft.rfft(b)) ** 2)
+
+
+def band(W):
+    F, M = W.shape
+    lo, ln, off, vals, pos = np.zeros(M, int), np.zeros(M, int), np.zeros(M, int), [], 0
+    for m in range(M):
+        nz = np.nonzero(W[:, m])[0]
+        if nz.size:
+            lo[m], ln[m] = nz[0], nz[-1] - nz[0] + 1
+        off[m] = pos
+        vals.append(W[lo[m]:lo[m] + ln[m], m])
+        pos += ln[m]
+    return lo, ln, off, (np.concatenate(vals) if pos else np.zeros(1))
+
+
+def build_schedule(n_fft, lo, ln, off, val, n_mels):
+    """build_mel_schedule of the kernel, statement for statement (the warp-synchronous window search included)."""
+    seg, F = SEG[n_fft], n_fft // 2 + 1
+    npm = [(max(ln[m], 0) + seg - 1) // seg for m in range(n_mels)]
+    first = np.concatenate([[0], np.cumsum(npm)[:-1]]).astype(int)
+    nseg = int(sum(npm))
+    if nseg > SEGS_MAX[n_fft]:
+        return None
+    slots = ((nseg + 31) // 32) * 32
+    segmj = [None] * slots
+    for m in range(n_mels):
+        for j in range(npm[m]):
+            segmj[first[m] + j] = (m, j)
+    seglo = np.zeros(slots, int)
+    for r in range(slots // 32):
+        start, lowest = [0] * 32, [0] * 32
+        for lane in range(32):
+            if segmj[32 * r + lane] is not None:
+                m, j = segmj[32 * r + lane]
+                start[lane] = min(lo[m] + j * seg, F - seg)
+                lowest[lane] = max(lo[m] + min((j + 1) * seg, ln[m]) - seg, 0)
+        for _ in range(seg):
+            key = [(start[l] & 15) | (l & 16) | (0 if segmj[32 * r + l] is not None else 32 + l) for l in range(32)]
+            new = list(start)
+            for l in range(32):
+                f = key.index(key[l])                                         # lowest lane with the same key
+                if l != f and start[l] != start[f] and start[l] > lowest[l]:
+                    new[l] = start[l] - 1
+            start = new
+        for lane in range(32):
+            seglo[32 * r + lane] = start[lane] if segmj[32 * r + lane] is not None else start[lane & 16]
+    segw = np.zeros(slots * seg)
+    for s in range(slots):
+        for i in range(seg):
+            w = 0.0
+            if segmj[s] is not None:
+                m, j = segmj[s]
+                rel = seglo[s] + i - lo[m]
+                if j * seg <= rel < min((j + 1) * seg, ln[m]):
+                    w = val[off[m] + rel]
+            segw[((s >> 5) * seg + i) * 32 + (s & 31)] = w
+    return nseg, first, npm, seglo, segw
+
+
+def run_schedule(n_fft, sched, P, n_mels):
+    seg = SEG[n_fft]
+    nseg, first, npm, seglo, segw = sched
+    rounds = (nseg + 31) >> 5
+    part = np.zeros(32 * rounds)
+    for r in range(rounds):
+        for lane in range(32):
+            acc = 0.0
+            for i in range(seg):
+                k = seglo[32 * r + lane] + i
+                assert 0 <= k < n_fft // 2 + 1                                 # every read stays inside the spectrum
+                acc += P[k] * segw[(r * seg + i) * 32 + lane]
+            part[32 * r + lane] = acc
+    return np.array([part[first[m]:first[m] + npm[m]].sum() for m in range(n_mels)])
+
+
+@pytest.mark.parametrize("sr", [8000, 16000, 32000])
+@pytest.mark.parametrize("n_mels", [40, 64, 128])
+def test_mel_schedule_equals_dense_projection(sr, n_mels):
+    n_fft, _, fmin, fmax = synth.PRESETS[sr]
+    W = np.asarray(melbank.mel_filterbank(sr, n_fft, n_mels, fmin, fmax), dtype=np.float64)
+    if W.shape[0] == n_mels:
+        W = W.T
+    lo, ln, off, val = band(W)
+    sched = build_schedule(n_fft, lo, ln, off, val, n_mels)
+    if sched is None:      # too many segments: the kernel projects one lane per band instead
+        assert int(np.ceil(ln / SEG[n_fft]).sum()) > SEGS_MAX[n_fft]
+        return
+    P = np.random.default_rng(sr + n_mels).random(n_fft // 2 + 1)
+    assert np.allclose(run_schedule(n_fft, sched, P, n_mels), P @ W, rtol=1e-12, atol=1e-15)
+    if n_mels == 64:       # the shipped presets run the fully unrolled path (FrontCfg::ROUNDS_UNROLL)
+        assert (sched[0] + 31) // 32 == (4 if n_fft == 1024 else 3)
+        assert max(sched[2]) <= (6 if n_fft == 1024 else 3)                    # FrontCfg::NP_UNROLL
+
+
+@pytest.mark.parametrize("n_fft", [256, 512, 1024])
+def test_mel_schedule_random_banded_matrices(n_fft):
+    rng = np.random.default_rng(n_fft + 1)
+    F = n_fft // 2 + 1
+    for _ in range(60):
+        M = int(rng.integers(1, 70))
+        W = np.zeros((F, M))
+        for m in range(M):
+            if rng.random() < 0.1:
+                continue                                                       # empty band
+            n = int(rng.integers(1, 12))
+            a = F - n if rng.random() < 0.2 else int(rng.integers(0, F - n + 1))  # some bands touch the last bin
+            W[a:a + n, m] = rng.random(n) + 0.1
+            if n > 2 and rng.random() < 0.3:
+                W[a + 1, m] = 0.0                                              # interior zero weight
+        lo, ln, off, val = band(W)
+        sched = build_schedule(n_fft, lo, ln, off, val, M)
+        if sched is None:
+            continue
+        P = rng.random(F)
+        assert np.allclose(run_schedule(n_fft, sched, P, M), P @ W, rtol=1e-12, atol=1e-15)

@@ -45,6 +45,23 @@ def test_logmel_matches_oracle_long_and_ragged(sr):
         assert logmel_close(got, ref).all(), (sr, L, np.abs(got - ref).max())
 
 
+@pytest.mark.parametrize("sr,n_mels", [(8000, 128), (16000, 128), (16000, 40), (32000, 128), (32000, 40)])
+def test_logmel_other_mel_matrices(sr, n_mels):
+    """Mel matrices other than the shipped 64-band ones leave the unrolled fast path of the projection: more or fewer
+    rounds of segments (loop instead of the unrolled rounds), bands wider than the unrolled band sum, and -- when the
+    segments do not fit (8 kHz / 32 kHz at 128 bands) -- one lane per band with the weights read from global memory."""
+    n_fft, hop, fmin, fmax = synth.PRESETS[sr]
+    melW = melbank.mel_filterbank(sr, n_fft, n_mels, fmin, fmax)
+    plan, (wr, wi, _) = _plan(sr, melW)
+    L = sr * 2 + 3
+    wave = torch.cat([synth.synthetic_waveform(2, L, seed=n_mels, kind="noise"),
+                      synth.synthetic_waveform(1, L, seed=n_mels + 1, kind="events")])
+    got = engine.logmel_forward(plan, wave.to(DEV)).cpu().numpy()
+    ref = so.logmel(so.spectrogram(wave, wr, wi, n_fft, hop), melW)[:, 0].numpy()
+    assert got.shape == ref.shape == (3, L // hop + 1, n_mels)
+    assert logmel_close(got, ref).all(), (sr, n_mels, np.abs(got - ref).max())
+
+
 def test_logmel_vs_float64_fft_is_at_least_as_close_as_the_reference():
     g = load_golden("frontend_16k.npz")
     plan, _ = _plan(16000, torch.from_numpy(g["melW"]))
