@@ -167,6 +167,48 @@ __device__ __forceinline__ void butterfly<16>(float2 (&v)[16]) {
   }
 }
 
+template <>
+__device__ __forceinline__ void butterfly<32>(float2 (&v)[32]) {
+  // decimation in frequency: a[n] = v[n] + v[n + 16], b[n] = (v[n] - v[n + 16]) W32^n; X[2k] = DFT16(a)[k],
+  // X[2k + 1] = DFT16(b)[k]
+  constexpr float kC[16] = {1.0f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                            0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f,
+                            0.19509032201612826785f, 0.0f, -0.19509032201612826785f, -0.38268343236508977173f,
+                            -0.55557023301960222474f, -0.70710678118654752440f, -0.83146961230254523708f,
+                            -0.92387953251128675613f, -0.98078528040323044913f};  // cos(pi n / 16)
+  constexpr float kSn[16] = {0.0f, 0.19509032201612826785f, 0.38268343236508977173f, 0.55557023301960222474f,
+                             0.70710678118654752440f, 0.83146961230254523708f, 0.92387953251128675613f,
+                             0.98078528040323044913f, 1.0f, 0.98078528040323044913f, 0.92387953251128675613f,
+                             0.83146961230254523708f, 0.70710678118654752440f, 0.55557023301960222474f,
+                             0.38268343236508977173f, 0.19509032201612826785f};  // sin(pi n / 16)
+  constexpr float kS = 0.70710678118654752440f;
+  float2 a[16], b[16];
+#pragma unroll
+  for (int n = 0; n < 16; ++n) {
+    a[n] = cadd(v[n], v[n + 16]);
+    b[n] = csub(v[n], v[n + 16]);
+  }
+#pragma unroll
+  for (int n = 1; n < 16; ++n) {
+    if (n == 4) {
+      b[n] = make_float2((b[n].x + b[n].y) * kS, (b[n].y - b[n].x) * kS);        // W32^4 = W8
+    } else if (n == 8) {
+      b[n] = make_float2(b[n].y, -b[n].x);                                        // W32^8 = -i
+    } else if (n == 12) {
+      b[n] = make_float2((b[n].y - b[n].x) * kS, -(b[n].x + b[n].y) * kS);       // W32^12 = W8^3
+    } else {
+      b[n] = cmul(b[n], make_float2(kC[n], -kSn[n]));                             // W32^n = cos - i sin
+    }
+  }
+  butterfly<16>(a);
+  butterfly<16>(b);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    v[2 * k] = a[k];
+    v[2 * k + 1] = b[k];
+  }
+}
+
 // Per-lane twiddles of one Stockham pass (radix R, stride Ns) of an N-point transform.  They depend only on the
 // lane, not on the frame, so a persistent warp keeps them in registers; the widest case (N = 1024, Ns = 128) reads
 // the shared-memory table instead.
@@ -296,11 +338,10 @@ template <> struct Sched<1024> { static constexpr int R0 = 8, R1 = 8, R2 = 16; }
 // aligned segments are ONE bulk copy issued by thread 0 (returns true: the consumer waits on `bar`); edge segments go
 // through guarded loads of all threads (returns false: the block barrier in front of the consumer orders them).  The
 // caller has passed a block barrier since the last generic-proxy access to `dst`.
-template <int NFFT, typename TIn>
+template <int NFFT, int FPB, typename TIn>
 __device__ __forceinline__ bool stage_segment(TIn* __restrict__ dst, uint64_t* bar, const TIn* __restrict__ wave,
                                               long clip_stride, const long* __restrict__ clip_offset, long total_len,
                                               int L, int hop, int seg_len, int item, int chunks, bool aligned) {
-  constexpr int FPB = FrontCfg<NFFT>::template fpb<TIn>();
   const int b = item / chunks, c = item - b * chunks;
   const long clip_base = clip_offset ? clip_offset[b] : static_cast<long>(b) * clip_stride;
   aligned = aligned && ((clip_base * static_cast<long>(sizeof(TIn))) & 15) == 0;
@@ -423,8 +464,8 @@ __device__ __forceinline__ int build_mel_schedule(const int* __restrict__ mel_lo
 // Bytes of the block's constant tables and FFT buffers (everything in front of the two staging buffers), counted from
 // the 128-byte aligned start of the dynamic shared memory; a multiple of 16.
 template <int NFFT>
-__host__ __device__ constexpr int frontend_fixed_smem(int n_mels) {
-  return ((8 * NFFT * (FrontCfg<NFFT>::WARPS + 1) + 4 * NFFT + 4 * FrontCfg<NFFT>::SEGS_MAX * FrontCfg<NFFT>::SEG +
+__host__ __device__ constexpr int frontend_fixed_smem(int n_mels, int buf_elems = FrontCfg<NFFT>::WARPS * NFFT) {
+  return ((8 * (buf_elems + NFFT) + 4 * NFFT + 4 * FrontCfg<NFFT>::SEGS_MAX * FrontCfg<NFFT>::SEG +
            8 * FrontCfg<NFFT>::SEGS_MAX + 4 * ((n_mels + 1) & ~1) + 8 * n_mels) + 15) & ~15;
 }
 
@@ -485,7 +526,7 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
   int item = blockIdx.x;
   bool cur_bulk = false;  // block-uniform: this item's segment arrives through s_bar[sel]
   if (item < items)
-    cur_bulk = stage_segment<NFFT, TIn>(s_stage0, &s_bar[0], wave, clip_stride, clip_offset, total_len, L, hop, seg_len,
+    cur_bulk = stage_segment<NFFT, FPB, TIn>(s_stage0, &s_bar[0], wave, clip_stride, clip_offset, total_len, L, hop, seg_len,
                                         item, chunks, aligned != 0);
   for (int i = threadIdx.x; i < NFFT; i += blockDim.x) {
     s_win[i] = window[i];
@@ -528,7 +569,7 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
     nxt = s_next[sel];
     nxt_bulk = false;
     if (nxt < items)
-      nxt_bulk = stage_segment<NFFT, TIn>(sel ? s_stage0 : s_stage1, &s_bar[sel ^ 1], wave, clip_stride, clip_offset,
+      nxt_bulk = stage_segment<NFFT, FPB, TIn>(sel ? s_stage0 : s_stage1, &s_bar[sel ^ 1], wave, clip_stride, clip_offset,
                                           total_len, L, hop, seg_len, nxt, chunks, aligned != 0);
     if (cur_bulk) {
       mbar_wait(&s_bar[sel], (phase >> sel) & 1u);
@@ -675,6 +716,303 @@ frontend_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __re
   }
 }
 
+// =====================================================================================================================
+// Two-pass kernel (serves n_fft 1024; generic over 256 / 512 / 1024, see SED_FE_TWO_PASS): ONE trip of the spectrum
+// through shared memory instead of two.
+//
+// N = RA * 32 (RA = 8 / 16 / 32).  With n = n2 + 32 n1 and k = k1 + RA k2:
+//     X[k1 + RA k2] = sum_n2 W32^(n2 k2) { W_N^(n2 k1) sum_n1 x[n2 + 32 n1] W_RA^(n1 k1) }
+// Pass A: lane n2 takes the RA-point DFT over n1 (inputs lane + 32 n1: unit stride across the warp) and multiplies by its
+// own twiddles W_N^(lane k1) (RA - 1 register pairs).  Pass B: a 32-point DFT over n2 without any twiddle -- one per
+// (transform, k1), so a warp carries T = 32 / RA transforms (2 T real frames) at a time and lane f RA + k1 owns butterfly
+// k1 of transform f.  In between, value (f, k1, n2) sits at element 32 (f RA + k1) + (n2 ^ ((f RA + k1) & 15)): row =
+// the pass-B lane, the XOR makes both the stores of pass A (fixed row, 32 lanes) and the loads of pass B (fixed n2, 16
+// rows per half-warp) conflict-free.  Pass B leaves X_f[k1 + RA k2], k2 = 0..31, in the lane; bin k <= N/2 needs
+// Z[N - k] = slot 31 - k2 of lane (f, RA - k1) (k1 = 0: the lane itself, slot (32 - k2) % 32) -- one shuffle per
+// component as in the three-pass kernel.  Per frame pair this costs 64 shared-memory wavefronts for the transform
+// instead of 128, and the window taps and mel weights are loaded once for T transforms.
+template <int NFFT>
+struct Front2Cfg {
+  static constexpr int RA = NFFT / 32;        // radix of pass A
+  static constexpr int T = 32 / RA;           // transforms (frame pairs) per warp and iteration
+  static constexpr int WARPS = 12;            // one block per SM (8 KB of buffer per warp)
+  static constexpr int BUF = 1024;            // complex elements per warp: T transforms of NFFT points
+  static constexpr int GROUP = 2 * T;         // frames per warp and iteration
+  template <typename TIn>
+  static constexpr int fpb() { return WARPS * GROUP * (sizeof(TIn) == 2 ? 2 : 1); }
+  // transform t keeps its power spectrum (and the segment sums behind it) in its own NFFT elements of the buffer; at
+  // RA = 8 two transforms share a half-warp, so odd ones start 8 elements later (conflict-free P2 stores)
+  static constexpr int p2_base(int t) { return t * NFFT + ((RA == 8) ? 8 * (t & 1) : 0); }
+};
+
+template <int NFFT, typename TIn, int MODE>
+__global__ void __launch_bounds__(Front2Cfg<NFFT>::WARPS * 32, 1)
+frontend2_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __restrict__ clip_offset, long total_len,
+                 int B, int L, int T, int hop,
+                 const float* __restrict__ window, const float2* __restrict__ twiddle,
+                 const int* __restrict__ mel_lo, const int* __restrict__ mel_len, const int* __restrict__ mel_off,
+                 const float* __restrict__ mel_val, int n_mels, float amin, float db_offset, int is_log,
+                 const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, float* __restrict__ out,
+                 int aligned, int* __restrict__ work_counter) {
+  using C2 = Front2Cfg<NFFT>;
+  constexpr int WARPS = C2::WARPS, RA = C2::RA, NT = C2::T, GROUP = C2::GROUP, BUF = C2::BUF;
+  constexpr int FPB = C2::template fpb<TIn>();
+  constexpr int SEG = FrontCfg<NFFT>::SEG, SEGS_MAX = FrontCfg<NFFT>::SEGS_MAX;
+  constexpr int NP_UNROLL = FrontCfg<NFFT>::NP_UNROLL;
+  constexpr int RU = FrontCfg<NFFT>::ROUNDS_UNROLL;
+  constexpr int F = NFFT / 2 + 1;
+  static_assert(RA * 32 == NFFT && NT * NFFT == BUF, "two-pass geometry");
+  static_assert(C2::p2_base(NT - 1) + F + SEGS_MAX <= NT * NFFT, "power spectrum + segment sums fit the transform's part");
+  const float db_floor = 10.0f * log10f(amin) - db_offset;
+  extern __shared__ float4 smem_f4[];
+  const int seg_len = (FPB - 1) * hop + NFFT;
+  const int seg_bytes = ((seg_len * static_cast<int>(sizeof(TIn)) + 15) & ~15);
+  uint8_t* sp = reinterpret_cast<uint8_t*>(smem_f4);
+  sp += (128u - (smem_u32(sp) & 127u)) & 127u;
+  float2* s_buf = reinterpret_cast<float2*>(sp);                      // [WARPS][BUF]
+  float2* s_tw = s_buf + WARPS * BUF;                                 // [NFFT] (only read while the block starts)
+  float* s_win = reinterpret_cast<float*>(s_tw + NFFT);               // [NFFT]
+  float* s_segw = s_win + NFFT;
+  int* s_seglo = reinterpret_cast<int*>(s_segw + SEGS_MAX * SEG);
+  int* s_segmj = s_seglo + SEGS_MAX;
+  int* s_band = s_segmj + SEGS_MAX;
+  float2* s_bn = reinterpret_cast<float2*>(s_band + ((n_mels + 1) & ~1));
+  TIn* s_stage0 = reinterpret_cast<TIn*>(sp + frontend_fixed_smem<NFFT>(n_mels, WARPS * BUF));
+  TIn* s_stage1 = reinterpret_cast<TIn*>(reinterpret_cast<uint8_t*>(s_stage0) + seg_bytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunks = (T + FPB - 1) / FPB;
+  const int items = B * chunks;
+  __shared__ int s_next[2];
+  __shared__ int s_total;
+  __shared__ __align__(8) uint64_t s_bar[2];
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  int item = blockIdx.x;
+  bool cur_bulk = false;
+  if (item < items)
+    cur_bulk = stage_segment<NFFT, FPB, TIn>(s_stage0, &s_bar[0], wave, clip_stride, clip_offset, total_len, L, hop,
+                                             seg_len, item, chunks, aligned != 0);
+  for (int i = threadIdx.x; i < NFFT; i += blockDim.x) s_win[i] = window[i];
+  int nseg = -1;
+  if (MODE == 0) {
+    for (int i = threadIdx.x; i < n_mels; i += blockDim.x)
+      s_bn[i] = bn_scale != nullptr ? make_float2(bn_scale[i], bn_shift[i]) : make_float2(1.0f, 0.0f);
+    nseg = build_mel_schedule<NFFT>(mel_lo, mel_len, mel_off, mel_val, n_mels, s_band, s_seglo, s_segmj, s_segw,
+                                    &s_total);
+  }
+  const int rounds = (nseg + 31) >> 5;
+
+  // pass-A twiddles of this lane: W_N^(lane k1), k1 = 1 .. RA - 1
+  float2 twa[RA - 1];
+#pragma unroll
+  for (int k1 = 1; k1 < RA; ++k1) twa[k1 - 1] = twiddle[(lane * k1) & (NFFT - 1)];
+
+  float2* buf = s_buf + warp * BUF;
+  const uint32_t buf_addr = smem_u32(buf);
+  const uint32_t st_base = buf_addr + 8u * static_cast<uint32_t>(lane);                    // pass A: element n2 = lane of a row
+  const uint32_t ld_base = buf_addr + 256u * static_cast<uint32_t>(lane) + 8u * static_cast<uint32_t>(lane & 15);  // pass B: own row
+  const int k1b = lane & (RA - 1), tb = lane / RA;                                         // pass-B role of this lane
+  const int src_lane = (lane & ~(RA - 1)) | ((RA - k1b) & (RA - 1));
+  float2* P2own = buf + C2::p2_base(0) + tb * NFFT + ((RA == 8) ? 8 * (tb & 1) : 0) + k1b;  // + RA k2
+
+  int sel = 0;
+  uint32_t phase = 0;
+  bool nxt_bulk = false;
+  for (int nxt = 0; item < items; item = nxt, sel ^= 1, cur_bulk = nxt_bulk) {
+    if (threadIdx.x == 0) s_next[sel] = static_cast<int>(gridDim.x) + atomicAdd(work_counter, 1);
+    __syncthreads();
+    nxt = s_next[sel];
+    nxt_bulk = false;
+    if (nxt < items)
+      nxt_bulk = stage_segment<NFFT, FPB, TIn>(sel ? s_stage0 : s_stage1, &s_bar[sel ^ 1], wave, clip_stride,
+                                               clip_offset, total_len, L, hop, seg_len, nxt, chunks, aligned != 0);
+    if (cur_bulk) {
+      mbar_wait(&s_bar[sel], (phase >> sel) & 1u);
+      phase ^= 1u << sel;
+    }
+    const TIn* s_seg = sel ? s_stage1 : s_stage0;
+    const int b = item / chunks;
+    const int f_base = (item - b * chunks) * FPB;
+
+    for (int grp = warp; grp < FPB / GROUP; grp += WARPS) {
+      const int fa0 = f_base + GROUP * grp;  // first frame of this warp's 2 T frames
+      if (fa0 >= T) break;
+
+      // ---- pass A: per transform the RA-point DFT over n1 of the windowed frame pair, twiddle, store to row (t, k1) ----
+      {
+        float wv[RA];
+#pragma unroll
+        for (int n1 = 0; n1 < RA; ++n1) wv[n1] = s_win[lane + 32 * n1];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const TIn* seg_a = s_seg + (GROUP * grp + 2 * t) * hop + lane;
+          const TIn* seg_b = seg_a + hop;
+          float2 v[RA];
+#pragma unroll
+          for (int n1 = 0; n1 < RA; ++n1)
+            v[n1] = make_float2(wv[n1] * load_sample(seg_a + 32 * n1), wv[n1] * load_sample(seg_b + 32 * n1));
+          butterfly<RA>(v);
+#pragma unroll
+          for (int k1 = 0; k1 < RA; ++k1) {
+            const int row = t * RA + k1;
+            const float2 y = (k1 == 0) ? v[0] : cmul(v[k1], twa[k1 - 1]);
+            sts_f2((st_base ^ static_cast<uint32_t>(8 * (row & 15))) + static_cast<uint32_t>(256 * row), y);
+          }
+        }
+      }
+      __syncwarp();
+
+      // ---- pass B: 32-point DFT over n2 of this lane's row ----
+      float2 X[32];
+#pragma unroll
+      for (int n2 = 0; n2 < 32; ++n2)
+        X[n2] = lds_f2((ld_base ^ static_cast<uint32_t>(8 * (n2 & 15))) + static_cast<uint32_t>(8 * (n2 & 16)));
+      __syncwarp();  // every row has been read: the buffer can take the power spectra
+      butterfly<32>(X);
+
+      // ---- split the two real spectra and take the power (stft.py:663): bin k = k1 + RA k2, k2 < 16 ----
+#pragma unroll
+      for (int k2 = 0; k2 < 16; ++k2) {
+        const float2 zk = X[k2];
+        const float2 up = X[31 - k2];
+        float2 zn = make_float2(__shfl_sync(0xffffffffu, up.x, src_lane), __shfl_sync(0xffffffffu, up.y, src_lane));
+        if (k1b == 0) zn = X[(32 - k2) & 31];
+        const float ar = zk.x + zn.x, ai = zk.y - zn.y;
+        const float br = zk.y + zn.y, bi = zn.x - zk.x;
+        constexpr float kQ = (MODE == 0) ? 1.0f : 0.25f;  // the log-mel path carries the 1/4 in its mel weights
+        P2own[RA * k2] = make_float2(kQ * fmaf(ai, ai, ar * ar), kQ * fmaf(bi, bi, br * br));
+      }
+      if (k1b == 0) {  // Nyquist bin N / 2 = RA * 16
+        constexpr float kN = (MODE == 0) ? 4.0f : 1.0f;
+        const float2 z = X[16];
+        P2own[RA * 16] = make_float2(kN * z.x * z.x, kN * z.y * z.y);
+      }
+      __syncwarp();
+
+      if (MODE == 1) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const int fa = fa0 + 2 * t;
+          if (fa >= T) break;
+          const float2* P2 = buf + C2::p2_base(t);
+          float* o = out + (static_cast<size_t>(b) * T + fa) * F;
+          for (int k = lane; k < F; k += 32) {
+            const float2 p = P2[k];
+            o[k] = p.x;
+            if (fa + 1 < T) o[F + k] = p.y;
+          }
+        }
+      } else {
+        // ---- mel projection, one lane per segment; seglo and weights are loaded once for the T transforms ----
+        if (rounds == RU) {
+          float a0[RU][NT], b0[RU][NT];
+          int slo[RU];
+#pragma unroll
+          for (int r = 0; r < RU; ++r) {
+            slo[r] = s_seglo[32 * r + lane];
+#pragma unroll
+            for (int t = 0; t < NT; ++t) a0[r][t] = b0[r][t] = 0.0f;
+          }
+#pragma unroll
+          for (int i = 0; i < SEG; ++i) {
+#pragma unroll
+            for (int r = 0; r < RU; ++r) {
+              const float w = s_segw[(r * SEG + i) * 32 + lane];
+#pragma unroll
+              for (int t = 0; t < NT; ++t) {
+                const float2 p = buf[C2::p2_base(t) + slo[r] + i];
+                a0[r][t] = fmaf(p.x, w, a0[r][t]);
+                b0[r][t] = fmaf(p.y, w, b0[r][t]);
+              }
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < RU; ++r)
+#pragma unroll
+            for (int t = 0; t < NT; ++t) buf[C2::p2_base(t) + F + 32 * r + lane] = make_float2(a0[r][t], b0[r][t]);
+        } else {
+          for (int r = 0; r < rounds; ++r) {
+            const int slo = s_seglo[32 * r + lane];
+            const float* wr = s_segw + r * (SEG * 32) + lane;
+            float a0[NT], b0[NT];
+#pragma unroll
+            for (int t = 0; t < NT; ++t) a0[t] = b0[t] = 0.0f;
+#pragma unroll
+            for (int i = 0; i < SEG; ++i) {
+              const float w = wr[32 * i];
+#pragma unroll
+              for (int t = 0; t < NT; ++t) {
+                const float2 p = buf[C2::p2_base(t) + slo + i];
+                a0[t] = fmaf(p.x, w, a0[t]);
+                b0[t] = fmaf(p.y, w, b0[t]);
+              }
+            }
+#pragma unroll
+            for (int t = 0; t < NT; ++t) buf[C2::p2_base(t) + F + 32 * r + lane] = make_float2(a0[t], b0[t]);
+          }
+        }
+        __syncwarp();
+        for (int m = lane; m < n_mels; m += 32) {
+          int first = 0, np = 0;
+          if (rounds > 0) {
+            first = s_band[m] & 0xffff;
+            np = s_band[m] >> 16;
+          }
+          const float2 sc = s_bn[m];  // models.py:642-644 (identity when no bn0 is fused)
+#pragma unroll
+          for (int t = 0; t < NT; ++t) {
+            const int fa = fa0 + 2 * t;
+            if (fa >= T) break;
+            float ya = 0.0f, yb = 0.0f;
+            if (rounds > 0) {
+              const float2* pm = buf + C2::p2_base(t) + F + first;
+              // ascending segments: the summation order is fixed
+#pragma unroll
+              for (int j = 0; j < NP_UNROLL; ++j) {
+                if (j < np) {
+                  const float2 s = pm[j];
+                  ya += s.x;
+                  yb += s.y;
+                }
+              }
+              for (int j = NP_UNROLL; j < np; ++j) {
+                const float2 s = pm[j];
+                ya += s.x;
+                yb += s.y;
+              }
+            } else {
+              const float2* Pm = buf + C2::p2_base(t) + mel_lo[m];
+              const float* mv = mel_val + mel_off[m];
+              const int len = mel_len[m];
+              for (int i = 0; i < len; ++i) {
+                const float2 p = Pm[i];
+                const float w = 0.25f * __ldg(mv + i);
+                ya = fmaf(p.x, w, ya);
+                yb = fmaf(p.y, w, yb);
+              }
+            }
+            if (is_log) {  // stft.py:726-727
+              ya = power_to_db(ya, amin, db_offset, db_floor);
+              yb = power_to_db(yb, amin, db_offset, db_floor);
+            }
+            ya = fmaf(ya, sc.x, sc.y);
+            yb = fmaf(yb, sc.x, sc.y);
+            float* o = out + (static_cast<size_t>(b) * T + fa) * n_mels;
+            o[m] = ya;
+            if (fa + 1 < T) o[n_mels + m] = yb;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // Standalone LogmelFilterBank.forward (stft.py:698-718): rows [R, F] -> [R, n_mels]
 __global__ void logmel_rows_kernel(const float* __restrict__ spec, long rows, int F, const int* __restrict__ mel_lo,
                                    const int* __restrict__ mel_len, const int* __restrict__ mel_off,
@@ -698,13 +1036,33 @@ __global__ void logmel_rows_kernel(const float* __restrict__ spec, long rows, in
 __device__ int g_frontend_work_counters[64];
 static std::atomic<unsigned> g_frontend_launch_seq{0};
 
+// Which kernel serves an n_fft (compile-time switch, so that only the kernels in use are instantiated).  Measured on one
+// box, ms per 148 clips of 10 s (profiles/r02_frontend_ab_v4_vs_two_pass.log): n_fft 1024 three-pass 0.291, two-pass
+// 0.249 (both 12 warps per SM); n_fft 512 three-pass 0.134 (16 warps at 127 registers), two-pass 0.140 (12 warps at
+// 148-160 registers: the 32 spectrum values of pass B do not fit a 128-register budget); n_fft 256 0.092 / 0.092
+// (int16 0.092 / 0.101).  Build with -DSED_FE_TWO_PASS(N)=1 to run the two-pass kernel everywhere.
+#ifndef SED_FE_TWO_PASS
+#define SED_FE_TWO_PASS(NFFT) ((NFFT) == 1024)
+#endif
+template <int NFFT, typename TIn, int MODE, bool TWO_PASS>
+struct FrontKernel {
+  static auto get() { return frontend_kernel<NFFT, TIn, MODE>; }
+};
+template <int NFFT, typename TIn, int MODE>
+struct FrontKernel<NFFT, TIn, MODE, true> {
+  static auto get() { return frontend2_kernel<NFFT, TIn, MODE>; }
+};
+
 template <int NFFT, typename TIn, int MODE>
 static int launch_frontend_t(const FrontendArgs& a, cudaStream_t stream) {
-  constexpr int WARPS = FrontCfg<NFFT>::WARPS;
-  constexpr int FPB = FrontCfg<NFFT>::template fpb<TIn>();
+  constexpr bool TWO_PASS = SED_FE_TWO_PASS(NFFT);
+  constexpr int WARPS = TWO_PASS ? Front2Cfg<NFFT>::WARPS : FrontCfg<NFFT>::WARPS;
+  constexpr int FPB = TWO_PASS ? Front2Cfg<NFFT>::template fpb<TIn>() : FrontCfg<NFFT>::template fpb<TIn>();
+  constexpr int BUF_ELEMS = TWO_PASS ? Front2Cfg<NFFT>::WARPS * Front2Cfg<NFFT>::BUF : FrontCfg<NFFT>::WARPS * NFFT;
+  auto kernel = FrontKernel<NFFT, TIn, MODE, TWO_PASS>::get();
   const int seg_len = (FPB - 1) * a.hop + NFFT;
   const int seg_bytes = (seg_len * static_cast<int>(sizeof(TIn)) + 15) & ~15;
-  const size_t smem = 128 + static_cast<size_t>(frontend_fixed_smem<NFFT>(a.n_mels > 0 ? a.n_mels : 0)) +
+  const size_t smem = 128 + static_cast<size_t>(frontend_fixed_smem<NFFT>(a.n_mels > 0 ? a.n_mels : 0, BUF_ELEMS)) +
                       2 * static_cast<size_t>(seg_bytes);
   if (smem > 227 * 1024) return SED_ERR_UNSUPPORTED;
   static int sm_count = 0;
@@ -714,12 +1072,10 @@ static int launch_frontend_t(const FrontendArgs& a, cudaStream_t stream) {
     if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0)
       sm_count = 148;
   }
-  cudaError_t e =
-      cudaFuncSetAttribute(frontend_kernel<NFFT, TIn, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return SED_ERR_CUDA;
   int per_sm = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frontend_kernel<NFFT, TIn, MODE>, WARPS * 32, smem) !=
-          cudaSuccess || per_sm < 1)
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS * 32, smem) != cudaSuccess || per_sm < 1)
     per_sm = 1;
   const long items = static_cast<long>(a.B) * ((a.T + FPB - 1) / FPB);
   long blocks = static_cast<long>(sm_count) * per_sm;
@@ -735,7 +1091,7 @@ static int launch_frontend_t(const FrontendArgs& a, cudaStream_t stream) {
     return SED_ERR_CUDA;
   int* counter = counters + (g_frontend_launch_seq.fetch_add(1) & 63u);
   if (cudaMemsetAsync(counter, 0, sizeof(int), stream) != cudaSuccess) return SED_ERR_CUDA;
-  frontend_kernel<NFFT, TIn, MODE><<<static_cast<unsigned>(blocks), WARPS * 32, smem, stream>>>(
+  kernel<<<static_cast<unsigned>(blocks), WARPS * 32, smem, stream>>>(
       reinterpret_cast<const TIn*>(a.wave), a.clip_stride, a.clip_offset, a.total_len, a.B, a.L, a.T, a.hop, a.window,
       reinterpret_cast<const float2*>(a.twiddle), a.mel_lo, a.mel_len, a.mel_off, a.mel_val, a.n_mels, a.amin,
       a.db_offset, a.is_log, a.bn_scale, a.bn_shift, a.out, aligned, counter);

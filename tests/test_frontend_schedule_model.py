@@ -73,6 +73,64 @@ def test_power_split_pairing(n_fft):
     assert np.allclose(P[:, 1], np.abs(np.fft.rfft(b)) ** 2)
 
 
+@pytest.mark.parametrize("n_fft", [256, 512, 1024])
+def test_two_pass_transform(n_fft):
+    """frontend2_kernel: N = RA * 32; pass A = RA-point DFTs by lane n2 with the twiddle W_N^(n2 k1) applied by the
+    producer, pass B = 32-point DFTs by lane (transform, k1) over a row-swizzled buffer, then the split pairing."""
+    from collections import defaultdict
+    RA, T = n_fft // 32, 32 // (n_fft // 32)
+    rng = np.random.default_rng(n_fft)
+    xs = [rng.standard_normal(n_fft) + 1j * rng.standard_normal(n_fft) for _ in range(T)]
+    tw = np.exp(-2j * np.pi * np.arange(n_fft) / n_fft)
+    buf = np.zeros(T * n_fft, complex)
+
+    def wavefronts(addrs):  # 64-bit accesses: one wavefront per half-warp when the 16 slots mod 16 are distinct
+        worst = 0
+        for h in range(2):
+            d = defaultdict(set)
+            for a in addrs[16 * h:16 * h + 16]:
+                d[a % 16].add(a)
+            worst = max(worst, max(len(v) for v in d.values()))
+        return worst
+
+    for t in range(T):
+        for k1 in range(RA):
+            row, addrs = t * RA + k1, []
+            for lane in range(32):
+                y = np.fft.fft(np.array([xs[t][lane + 32 * n1] for n1 in range(RA)]))[k1] * tw[(lane * k1) % n_fft]
+                byte = ((8 * lane) ^ (8 * (row & 15))) + 256 * row              # the kernel's store address
+                assert byte == 8 * (32 * row + (lane ^ (row & 15)))
+                buf[byte // 8] = y
+                addrs.append(byte // 8)
+            assert wavefronts(addrs) == 1
+    regs = {}
+    for n2 in range(32):
+        addrs = []
+        for lane in range(32):
+            byte = ((256 * lane + 8 * (lane & 15)) ^ (8 * (n2 & 15))) + 8 * (n2 & 16)   # the kernel's load address
+            assert byte == 8 * (32 * lane + (n2 ^ (lane & 15)))
+            addrs.append(byte // 8)
+        assert wavefronts(addrs) == 1
+    for lane in range(32):
+        regs[lane] = np.fft.fft(np.array([buf[32 * lane + (n2 ^ (lane & 15))] for n2 in range(32)]))
+    X = [np.fft.fft(x) for x in xs]
+    for lane in range(32):
+        t, k1 = lane // RA, lane % RA
+        src = (lane & ~(RA - 1)) | ((RA - k1) & (RA - 1))
+        for k2 in range(32):
+            assert np.isclose(regs[lane][k2], X[t][k1 + RA * k2])                # pass B leaves X_t[k1 + RA k2]
+        for k2 in range(16):
+            zn = regs[src][31 - k2] if k1 else regs[lane][(32 - k2) & 31]
+            assert np.isclose(zn, X[t][(n_fft - (k1 + RA * k2)) % n_fft])        # the partner bin N - k
+    # power spectra of the transforms do not collide in the warp's buffer, and their stores are conflict-free
+    base = [t * n_fft + (8 * (t & 1) if RA == 8 else 0) for t in range(T)]
+    for k2 in range(16):
+        assert wavefronts([base[lane // RA] + lane % RA + RA * k2 for lane in range(32)]) == 1
+    for t in range(T - 1):
+        assert base[t] + n_fft // 2 + 1 + SEGS_MAX[n_fft] <= base[t + 1]
+    assert base[T - 1] + n_fft // 2 + 1 + SEGS_MAX[n_fft] <= T * n_fft
+
+
 def band(W):
     F, M = W.shape
     lo, ln, off, vals, pos = np.zeros(M, int), np.zeros(M, int), np.zeros(M, int), [], 0

@@ -59,7 +59,13 @@ def test_logmel_other_mel_matrices(sr, n_mels):
     got = engine.logmel_forward(plan, wave.to(DEV)).cpu().numpy()
     ref = so.logmel(so.spectrogram(wave, wr, wi, n_fft, hop), melW)[:, 0].numpy()
     assert got.shape == ref.shape == (3, L // hop + 1, n_mels)
-    assert logmel_close(got, ref).all(), (sr, n_mels, np.abs(got - ref).max())
+    # Narrow bands at -80 dB expose the float32 rounding noise of the reference's own conv1d DFT (it is 1.5e-2 dB
+    # away from exact arithmetic in one bin of the 32 kHz / 128-band case): where the reference misses the float64
+    # transform by more than the tolerance, agreeing with the float64 transform is what "matching" can mean.
+    f64 = so.logmel_float64_fft(wave.numpy().astype(np.float64), n_fft, hop, melW.numpy())
+    ok = logmel_close(got, ref) | (~logmel_close(ref, f64) & logmel_close(got, f64))
+    assert ok.all(), (sr, n_mels, np.abs(got - ref).max())
+    assert logmel_close(got, ref).mean() > 0.9999
 
 
 def test_logmel_vs_float64_fft_is_at_least_as_close_as_the_reference():
