@@ -735,7 +735,11 @@ template <int NFFT>
 struct Front2Cfg {
   static constexpr int RA = NFFT / 32;        // radix of pass A
   static constexpr int T = 32 / RA;           // transforms (frame pairs) per warp and iteration
-  static constexpr int WARPS = 12;            // one block per SM (8 KB of buffer per warp)
+  // One block per SM (8 KB of buffer per warp).  1024: 12 warps, pass-A twiddles in registers (168 registers);
+  // 256 / 512: 16 warps inside a 128-register budget -- the twiddles are then read from a lane-major shared-memory
+  // table right before they are used (TW_SMEM)
+  static constexpr int WARPS = (NFFT == 1024) ? 12 : 16;
+  static constexpr bool TW_SMEM = (NFFT != 1024);
   static constexpr int BUF = 1024;            // complex elements per warp: T transforms of NFFT points
   static constexpr int GROUP = 2 * T;         // frames per warp and iteration
   template <typename TIn>
@@ -808,9 +812,15 @@ frontend2_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __r
   const int rounds = (nseg + 31) >> 5;
 
   // pass-A twiddles of this lane: W_N^(lane k1), k1 = 1 .. RA - 1
-  float2 twa[RA - 1];
+  // (TW_SMEM: s_tw[(k1 - 1) * 32 + lane], filled here; otherwise registers)
+  float2 twa[C2::TW_SMEM ? 1 : RA - 1];
+  if (C2::TW_SMEM) {
+    for (int i = threadIdx.x; i < (RA - 1) * 32; i += blockDim.x)
+      s_tw[i] = twiddle[((i & 31) * ((i >> 5) + 1)) & (NFFT - 1)];
+  } else {
 #pragma unroll
-  for (int k1 = 1; k1 < RA; ++k1) twa[k1 - 1] = twiddle[(lane * k1) & (NFFT - 1)];
+    for (int k1 = 1; k1 < RA; ++k1) twa[k1 - 1] = twiddle[(lane * k1) & (NFFT - 1)];
+  }
 
   float2* buf = s_buf + warp * BUF;
   const uint32_t buf_addr = smem_u32(buf);
@@ -860,7 +870,7 @@ frontend2_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __r
 #pragma unroll
           for (int k1 = 0; k1 < RA; ++k1) {
             const int row = t * RA + k1;
-            const float2 y = (k1 == 0) ? v[0] : cmul(v[k1], twa[k1 - 1]);
+            const float2 y = (k1 == 0) ? v[0] : cmul(v[k1], C2::TW_SMEM ? s_tw[(k1 - 1) * 32 + lane] : twa[k1 - 1]);
             sts_f2((st_base ^ static_cast<uint32_t>(8 * (row & 15))) + static_cast<uint32_t>(256 * row), y);
           }
         }
@@ -1036,11 +1046,18 @@ __global__ void logmel_rows_kernel(const float* __restrict__ spec, long rows, in
 __device__ int g_frontend_work_counters[64];
 static std::atomic<unsigned> g_frontend_launch_seq{0};
 
-// Which kernel serves an n_fft (compile-time switch, so that only the kernels in use are instantiated).  Measured on one
-// box, ms per 148 clips of 10 s (profiles/r02_frontend_ab_v4_vs_two_pass.log): n_fft 1024 three-pass 0.291, two-pass
-// 0.249 (both 12 warps per SM); n_fft 512 three-pass 0.134 (16 warps at 127 registers), two-pass 0.140 (12 warps at
-// 148-160 registers: the 32 spectrum values of pass B do not fit a 128-register budget); n_fft 256 0.092 / 0.092
-// (int16 0.092 / 0.101).  Build with -DSED_FE_TWO_PASS(N)=1 to run the two-pass kernel everywhere.
+// Which kernel serves an n_fft.  Measured on one box, ms per 148 clips of 10 s (profiles/r02_frontend_ab_*.log):
+//   n_fft 1024: three-pass 0.291, two-pass 0.249 (both 12 warps per SM)                          -> two-pass
+//   n_fft 512 : three-pass 0.134 (2 blocks x 8 warps, 127 registers); two-pass 0.140 with the twiddles in registers
+//               (12 warps, 148-160 registers) and 0.141 with the twiddles in shared memory (16 warps, 121-126
+//               registers)                                                                        -> three-pass
+//   n_fft 256 : 0.092 / 0.090 (int16 0.091 / 0.098)                                              -> three-pass
+// At 512 the two-pass kernel executes 7 % fewer instructions and 19 % fewer shared-memory wavefronts than the
+// three-pass one and is still slower (profiles/r02_ncu_full_frontend_two_pass_512.json): its 16 warps sit in ONE block
+// whose item barrier keeps them in phase -- all load, then all compute (barrier stalls 0.89 per issue against 0.44,
+// math-pipe throttle 0.82 against 0.16) -- where two independent blocks of 8 warps interleave their phases.
+// The two-pass kernel needs 8 KB of buffer per warp; where its shared memory does not fit (large hop) the three-pass
+// kernel takes over.  -DSED_FE_TWO_PASS(N)=1 builds a library that uses the two-pass kernel at every size.
 #ifndef SED_FE_TWO_PASS
 #define SED_FE_TWO_PASS(NFFT) ((NFFT) == 1024)
 #endif
@@ -1053,9 +1070,8 @@ struct FrontKernel<NFFT, TIn, MODE, true> {
   static auto get() { return frontend2_kernel<NFFT, TIn, MODE>; }
 };
 
-template <int NFFT, typename TIn, int MODE>
-static int launch_frontend_t(const FrontendArgs& a, cudaStream_t stream) {
-  constexpr bool TWO_PASS = SED_FE_TWO_PASS(NFFT);
+template <int NFFT, typename TIn, int MODE, bool TWO_PASS>
+static int launch_frontend_v(const FrontendArgs& a, cudaStream_t stream) {
   constexpr int WARPS = TWO_PASS ? Front2Cfg<NFFT>::WARPS : FrontCfg<NFFT>::WARPS;
   constexpr int FPB = TWO_PASS ? Front2Cfg<NFFT>::template fpb<TIn>() : FrontCfg<NFFT>::template fpb<TIn>();
   constexpr int BUF_ELEMS = TWO_PASS ? Front2Cfg<NFFT>::WARPS * Front2Cfg<NFFT>::BUF : FrontCfg<NFFT>::WARPS * NFFT;
@@ -1096,6 +1112,15 @@ static int launch_frontend_t(const FrontendArgs& a, cudaStream_t stream) {
       reinterpret_cast<const float2*>(a.twiddle), a.mel_lo, a.mel_len, a.mel_off, a.mel_val, a.n_mels, a.amin,
       a.db_offset, a.is_log, a.bn_scale, a.bn_shift, a.out, aligned, counter);
   return cudaGetLastError() == cudaSuccess ? SED_OK : SED_ERR_CUDA;
+}
+
+template <int NFFT, typename TIn, int MODE>
+static int launch_frontend_t(const FrontendArgs& a, cudaStream_t stream) {
+  if (SED_FE_TWO_PASS(NFFT)) {
+    const int rc = launch_frontend_v<NFFT, TIn, MODE, true>(a, stream);
+    if (rc != SED_ERR_UNSUPPORTED) return rc;
+  }
+  return launch_frontend_v<NFFT, TIn, MODE, false>(a, stream);
 }
 
 template <int NFFT>
