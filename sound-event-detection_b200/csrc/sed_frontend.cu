@@ -20,17 +20,35 @@
 
 namespace sed {
 
+// Block shapes (compile-time knobs of the A/B runs in profiles/r02_frontend_ab_block_shapes.log).  The warps of a block
+// meet at one barrier per work item and therefore run in phase -- all load, then all compute; several SMALL blocks per SM
+// interleave their phases.  Same warps per SM, ms per 148 clips of 10 s on one box: n_fft 512 2 x 8 warps 0.136 -> 4 x 4
+// warps 0.129; n_fft 256 0.093 -> 0.089; n_fft 1024 (two-pass kernel) 1 x 12 warps 0.249 -> 2 x 6 warps 0.214.
+#ifndef SED_FE_WARPS3
+#define SED_FE_WARPS3 4   // three-pass kernel, n_fft 256 / 512: warps per block ...
+#define SED_FE_BLOCKS3 4  // ... and blocks per SM
+#endif
+#ifndef SED_FE_WARPS2_1024
+#define SED_FE_WARPS2_1024 6   // two-pass kernel, n_fft 1024: warps per block ...
+#define SED_FE_BLOCKS2_1024 2  // ... and blocks per SM
+#endif
+#ifndef SED_FE_WARPS2
+#define SED_FE_WARPS2 4   // two-pass kernel, n_fft 256 / 512 (not the default kernel for these sizes)
+#define SED_FE_BLOCKS2 3
+#endif
+
 template <int NFFT>
 struct FrontCfg {
-  // 1024: one block of 12 warps per SM (8 KB of FFT buffer and 168 registers per warp); 256 / 512: two blocks of 8
-  static constexpr int WARPS = (NFFT == 1024) ? 12 : 8;
-  // frames per work item (even: frames are transformed in pairs) for 4-byte samples; 2-byte PCM takes twice as many
-  // in the same staging space (fpb()).  A persistent block loops over work items = (clip, chunk of frames); the
-  // waveform segment of the next item arrives by bulk copy while the current one is transformed.
-  static constexpr int FPB = (NFFT == 1024) ? 24 : 32;
+  // 256 / 512: SED_FE_BLOCKS3 blocks of SED_FE_WARPS3 warps (16 warps per SM at 127 registers); 1024 (only where the
+  // two-pass kernel's buffers do not fit): one block of 12 warps
+  static constexpr int WARPS = (NFFT == 1024) ? 12 : SED_FE_WARPS3;
+  // frames per work item (even: frames are transformed in pairs) for 4-byte samples: two pairs per warp; 2-byte PCM
+  // takes twice as many in the same staging space (fpb()).  A persistent block loops over work items = (clip, chunk of
+  // frames); the waveform segment of the next item arrives by bulk copy while the current one is transformed.
+  static constexpr int FPB = (NFFT == 1024) ? 24 : 4 * SED_FE_WARPS3;
   template <typename TIn>
   static constexpr int fpb() { return FPB * (sizeof(TIn) == 2 ? 2 : 1); }
-  static constexpr int MIN_BLOCKS = (NFFT == 1024) ? 1 : 2;
+  static constexpr int MIN_BLOCKS = (NFFT == 1024) ? 1 : SED_FE_BLOCKS3;
   // Mel projection: every band is cut into segments of SEG consecutive bins, one lane per segment, 32 segments per
   // round (see build_mel_schedule).  SEG is odd, so the 64-bit power reads of neighbouring segments of a band fall
   // into different banks; the values below give the fewest rows (rounds * SEG) for the reference's three presets
@@ -735,10 +753,11 @@ template <int NFFT>
 struct Front2Cfg {
   static constexpr int RA = NFFT / 32;        // radix of pass A
   static constexpr int T = 32 / RA;           // transforms (frame pairs) per warp and iteration
-  // One block per SM (8 KB of buffer per warp).  1024: 12 warps, pass-A twiddles in registers (168 registers);
-  // 256 / 512: 16 warps inside a 128-register budget -- the twiddles are then read from a lane-major shared-memory
-  // table right before they are used (TW_SMEM)
-  static constexpr int WARPS = (NFFT == 1024) ? 12 : 16;
+  // 8 KB of buffer per warp.  1024: 2 blocks of 6 warps per SM, pass-A twiddles in registers (168 registers); 256 / 512:
+  // the twiddles are read from a lane-major shared-memory table right before they are used (TW_SMEM), which keeps the
+  // kernel inside a 128-register budget
+  static constexpr int WARPS = (NFFT == 1024) ? SED_FE_WARPS2_1024 : SED_FE_WARPS2;
+  static constexpr int MIN_BLOCKS = (NFFT == 1024) ? SED_FE_BLOCKS2_1024 : SED_FE_BLOCKS2;
   static constexpr bool TW_SMEM = (NFFT != 1024);
   static constexpr int BUF = 1024;            // complex elements per warp: T transforms of NFFT points
   static constexpr int GROUP = 2 * T;         // frames per warp and iteration
@@ -750,7 +769,7 @@ struct Front2Cfg {
 };
 
 template <int NFFT, typename TIn, int MODE>
-__global__ void __launch_bounds__(Front2Cfg<NFFT>::WARPS * 32, 1)
+__global__ void __launch_bounds__(Front2Cfg<NFFT>::WARPS * 32, Front2Cfg<NFFT>::MIN_BLOCKS)
 frontend2_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __restrict__ clip_offset, long total_len,
                  int B, int L, int T, int hop,
                  const float* __restrict__ window, const float2* __restrict__ twiddle,
@@ -1047,15 +1066,13 @@ __device__ int g_frontend_work_counters[64];
 static std::atomic<unsigned> g_frontend_launch_seq{0};
 
 // Which kernel serves an n_fft.  Measured on one box, ms per 148 clips of 10 s (profiles/r02_frontend_ab_*.log):
-//   n_fft 1024: three-pass 0.291, two-pass 0.249 (both 12 warps per SM)                          -> two-pass
-//   n_fft 512 : three-pass 0.134 (2 blocks x 8 warps, 127 registers); two-pass 0.140 with the twiddles in registers
-//               (12 warps, 148-160 registers) and 0.141 with the twiddles in shared memory (16 warps, 121-126
-//               registers)                                                                        -> three-pass
-//   n_fft 256 : 0.092 / 0.090 (int16 0.091 / 0.098)                                              -> three-pass
+//   n_fft 1024: three-pass 0.291, two-pass 0.249 (both one block of 12 warps), two-pass 2 x 6 warps 0.214 -> two-pass
+//   n_fft 512 : three-pass 0.134 (2 x 8 warps) / 0.129 (4 x 4 warps); two-pass 0.140 (1 x 12 warps, twiddles in
+//               registers), 0.141 (1 x 16 warps, twiddles in shared memory), 0.129 (3 x 4 warps)    -> three-pass
+//   n_fft 256 : three-pass 0.089, two-pass 0.087 (int16 0.088 / 0.100)                             -> three-pass
 // At 512 the two-pass kernel executes 7 % fewer instructions and 19 % fewer shared-memory wavefronts than the
-// three-pass one and is still slower (profiles/r02_ncu_full_frontend_two_pass_512.json): its 16 warps sit in ONE block
-// whose item barrier keeps them in phase -- all load, then all compute (barrier stalls 0.89 per issue against 0.44,
-// math-pipe throttle 0.82 against 0.16) -- where two independent blocks of 8 warps interleave their phases.
+// three-pass one (profiles/r02_ncu_full_frontend_two_pass_512.json) and only draws level with it: at 12 warps per SM it
+// has a quarter less latency hiding than the three-pass kernel's 16.
 // The two-pass kernel needs 8 KB of buffer per warp; where its shared memory does not fit (large hop) the three-pass
 // kernel takes over.  -DSED_FE_TWO_PASS(N)=1 builds a library that uses the two-pass kernel at every size.
 #ifndef SED_FE_TWO_PASS
