@@ -482,8 +482,9 @@ __device__ __forceinline__ int build_mel_schedule(const int* __restrict__ mel_lo
 // Bytes of the block's constant tables and FFT buffers (everything in front of the two staging buffers), counted from
 // the 128-byte aligned start of the dynamic shared memory; a multiple of 16.
 template <int NFFT>
-__host__ __device__ constexpr int frontend_fixed_smem(int n_mels, int buf_elems = FrontCfg<NFFT>::WARPS * NFFT) {
-  return ((8 * (buf_elems + NFFT) + 4 * NFFT + 4 * FrontCfg<NFFT>::SEGS_MAX * FrontCfg<NFFT>::SEG +
+__host__ __device__ constexpr int frontend_fixed_smem(int n_mels, int buf_elems = FrontCfg<NFFT>::WARPS * NFFT,
+                                                      int tw_elems = NFFT) {
+  return ((8 * (buf_elems + tw_elems) + 4 * NFFT + 4 * FrontCfg<NFFT>::SEGS_MAX * FrontCfg<NFFT>::SEG +
            8 * FrontCfg<NFFT>::SEGS_MAX + 4 * ((n_mels + 1) & ~1) + 8 * n_mels) + 15) & ~15;
 }
 
@@ -793,14 +794,15 @@ frontend2_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __r
   uint8_t* sp = reinterpret_cast<uint8_t*>(smem_f4);
   sp += (128u - (smem_u32(sp) & 127u)) & 127u;
   float2* s_buf = reinterpret_cast<float2*>(sp);                      // [WARPS][BUF]
-  float2* s_tw = s_buf + WARPS * BUF;                                 // [NFFT] (only read while the block starts)
-  float* s_win = reinterpret_cast<float*>(s_tw + NFFT);               // [NFFT]
+  constexpr int TW_ELEMS = C2::TW_SMEM ? NFFT : 0;                    // lane-major pass-A twiddles (TW_SMEM only)
+  float2* s_tw = s_buf + WARPS * BUF;
+  float* s_win = reinterpret_cast<float*>(s_tw + TW_ELEMS);           // [NFFT]
   float* s_segw = s_win + NFFT;
   int* s_seglo = reinterpret_cast<int*>(s_segw + SEGS_MAX * SEG);
   int* s_segmj = s_seglo + SEGS_MAX;
   int* s_band = s_segmj + SEGS_MAX;
   float2* s_bn = reinterpret_cast<float2*>(s_band + ((n_mels + 1) & ~1));
-  TIn* s_stage0 = reinterpret_cast<TIn*>(sp + frontend_fixed_smem<NFFT>(n_mels, WARPS * BUF));
+  TIn* s_stage0 = reinterpret_cast<TIn*>(sp + frontend_fixed_smem<NFFT>(n_mels, WARPS * BUF, TW_ELEMS));
   TIn* s_stage1 = reinterpret_cast<TIn*>(reinterpret_cast<uint8_t*>(s_stage0) + seg_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1095,7 +1097,9 @@ static int launch_frontend_v(const FrontendArgs& a, cudaStream_t stream) {
   auto kernel = FrontKernel<NFFT, TIn, MODE, TWO_PASS>::get();
   const int seg_len = (FPB - 1) * a.hop + NFFT;
   const int seg_bytes = (seg_len * static_cast<int>(sizeof(TIn)) + 15) & ~15;
-  const size_t smem = 128 + static_cast<size_t>(frontend_fixed_smem<NFFT>(a.n_mels > 0 ? a.n_mels : 0, BUF_ELEMS)) +
+  constexpr int TW_ELEMS = (TWO_PASS && !Front2Cfg<NFFT>::TW_SMEM) ? 0 : NFFT;
+  const size_t smem = 128 +
+                      static_cast<size_t>(frontend_fixed_smem<NFFT>(a.n_mels > 0 ? a.n_mels : 0, BUF_ELEMS, TW_ELEMS)) +
                       2 * static_cast<size_t>(seg_bytes);
   if (smem > 227 * 1024) return SED_ERR_UNSUPPORTED;
   static int sm_count = 0;
