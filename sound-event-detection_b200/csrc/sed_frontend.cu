@@ -6,12 +6,21 @@
 //
 // The reference evaluates the DFT as a dense [n_fft x (n_fft/2+1)] contraction (0.53 GFLOP per 10 s
 // clip at 16 kHz).  Here two consecutive real frames are packed as one complex sequence and pushed
-// through an in-shared-memory Stockham FFT (three passes of radix 4 / 8 / 16), 25x fewer flops, in
-// float32 with float64-derived twiddles -- the accuracy class of the reference's float32 conv1d, which
-// the 1e-4 log-mel tolerance needs (single-pass 16-bit tensor-core DFTs do not reach it).  The window
-// is read from the loaded conv_real kernel (row 0), so a checkpoint's window is honoured; the host
-// wrapper verifies that the loaded kernels are a windowed DFT before selecting this path.
-// The mel projection uses the loaded melW in banded form (first/last non-zero per mel bin).
+// through an in-shared-memory FFT, 25x fewer flops, in float32 with float64-derived twiddles -- the
+// accuracy class of the reference's float32 conv1d, which the 1e-4 log-mel tolerance needs (single-pass
+// 16-bit tensor-core DFTs do not reach it).  The window is read from the loaded conv_real kernel (row 0),
+// so a checkpoint's window is honoured; the host wrapper verifies that the loaded kernels are a windowed
+// DFT before selecting this path.  The mel projection uses the loaded melW in banded form (first/last
+// non-zero per mel bin), cut into equal segments per persistent block (build_mel_schedule).
+//
+// Two kernels share everything but the transform:
+//   frontend_kernel   n_fft 256 / 512: three Stockham passes (4 x 8 x 8, 8 x 8 x 8) over a swizzled buffer, the
+//                     last one left in registers; four blocks of four warps per SM
+//   frontend2_kernel  n_fft 1024: 32 x 32 in two passes, twiddles applied by the producing lane, ONE trip through
+//                     shared memory; two blocks of six warps per SM
+// Both end with X[.] of a frame pair spread over the warp's registers, split the two real spectra with one shuffle
+// per component, and run the same mel projection / dB conversion / bn0 epilogue.  DESIGN.md K1 has the measurements
+// behind every choice; tests/test_frontend_schedule_model.py restates the index arithmetic on the CPU.
 #include <atomic>
 #include <cstdlib>
 
