@@ -244,3 +244,57 @@ def test_mel_schedule_random_banded_matrices(n_fft):
             continue
         P = rng.random(F)
         assert np.allclose(run_schedule(n_fft, sched, P, M), P @ W, rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize("sr", [8000, 16000, 32000])
+def test_kernel_arithmetic_in_float32_meets_the_reference_fixture(sr):
+    """The kernel's arithmetic end to end, in numpy float32: two real frames packed into one complex transform, the
+    power split with its folded 1/4, the segment mel schedule with quarter weights, 10*log10 through log2 -- against
+    the log-mel fixture the unmodified reference produced (tests/golden/frontend_*.npz) at the north-star tolerance."""
+    from conftest import load_golden, logmel_close
+    n_fft, hop, _, _ = synth.PRESETS[sr]
+    g = load_golden("frontend_%dk.npz" % (sr // 1000))
+    x = (g["wave_i16"].astype(np.float64) / 32767.0).astype(np.float32)       # the correctly rounded q / 32767
+    melW = g["melW"].astype(np.float64)
+    lo, ln, off, val = band(melW)
+    sched = build_schedule(n_fft, lo, ln, off, (0.25 * val.astype(np.float32)).astype(np.float32), 64)
+    assert sched is not None
+    nseg, first, npm, seglo, segw = sched
+    seg = SEG[n_fft]
+    rounds = (nseg + 31) >> 5
+    win = (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(n_fft) / n_fft)).astype(np.float32)   # periodic Hann (stft.py:192-195)
+    pad = np.pad(x, ((0, 0), (n_fft // 2, n_fft // 2)), mode="reflect")
+    T = x.shape[1] // hop + 1
+    out = np.zeros((x.shape[0], T, 64), np.float32)
+    F = n_fft // 2 + 1
+    k = np.arange(F)
+    for b in range(x.shape[0]):
+        for fa in range(0, T, 2):
+            fb = min(fa + 1, T - 1)
+            a = pad[b, fa * hop:fa * hop + n_fft] * win
+            c = pad[b, fb * hop:fb * hop + n_fft] * win
+            Z = np.fft.fft((a + 1j * c).astype(np.complex64)).astype(np.complex64)
+            zk, zn = Z[k % n_fft], Z[(n_fft - k) % n_fft]
+            ar, ai = zk.real + zn.real, zk.imag - zn.imag
+            br, bi = zk.imag + zn.imag, zn.real - zk.real
+            P4 = np.stack([ai * ai + ar * ar, bi * bi + br * br], 1).astype(np.float32)     # 4 |A|^2, 4 |B|^2
+            part = np.zeros((32 * rounds, 2), np.float32)
+            for r in range(rounds):
+                for lane in range(32):
+                    s = 32 * r + lane
+                    acc = np.zeros(2, np.float32)
+                    for i in range(seg):
+                        acc = (acc + P4[seglo[s] + i] * np.float32(segw[(r * seg + i) * 32 + lane])).astype(np.float32)
+                    part[s] = acc
+            for m in range(64):
+                y = np.zeros(2, np.float32)
+                for j in range(npm[m]):
+                    y = (y + part[first[m] + j]).astype(np.float32)
+                db = np.where(y > 1e-10, np.float32(3.010299956639812) * np.log2(np.maximum(y, 1e-30)).astype(np.float32),
+                              np.float32(-100.0)).astype(np.float32)
+                out[b, fa, m] = db[0]
+                if fa + 1 < T:
+                    out[b, fa + 1, m] = db[1]
+    ok = logmel_close(out, g["logmel"], rtol=1e-4)
+    assert ok.all(), "violations %.3e, max |d| %.3e dB" % (1 - ok.mean(), np.abs(out - g["logmel"]).max())
+    assert np.all(out[3] == -100.0)  # the silent clip of the fixture
