@@ -1,3 +1,12 @@
+"""Per-source-line attribution of an `ncu --set full --import-source on` capture (developer tool).
+
+    ncu -i rep.ncu-rep --page source --csv > source.csv                       # SASS-level page of ONE kernel
+    cuobjdump -xelf all build/sed_frontend.o && nvdisasm --print-line-info *.cubin > lines.txt    # needs -lineinfo
+    python tools/ncu_source_attribution.py source.csv lines.txt Li512EfLi0E [units]
+
+joins the SASS addresses of the report with the line table of the same binary (third argument: a substring of the
+kernel's mangled name) and prints, per source line, instructions, stall samples and shared-memory wavefronts per
+unit (default: 74074 frame pairs = 148 clips of 10 s at hop 160)."""
 import csv,re,sys,collections
 rep_csv, lines_txt, kern = sys.argv[1], sys.argv[2], sys.argv[3]
 txt=open(lines_txt).read().split('\n')
