@@ -787,6 +787,8 @@ frontend2_kernel(const TIn* __restrict__ wave, long clip_stride, const long* __r
                  const float* __restrict__ mel_val, int n_mels, float amin, float db_offset, int is_log,
                  const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, float* __restrict__ out,
                  int aligned, int* __restrict__ work_counter) {
+  // Shared-memory carve-up, block start-up, work-item loop and the mel / dB / bn0 epilogue run parallel to
+  // frontend_kernel line by line (there for one transform per warp, here for NT); only the transform differs.
   using C2 = Front2Cfg<NFFT>;
   constexpr int WARPS = C2::WARPS, RA = C2::RA, NT = C2::T, GROUP = C2::GROUP, BUF = C2::BUF;
   constexpr int FPB = C2::template fpb<TIn>();
